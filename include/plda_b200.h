@@ -1,0 +1,160 @@
+/* plda_b200 -- C ABI of the B200-native PLDA / LDA hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one method of the
+ * reference's native object `libplda.MPlda` (src/pldamodule.cpp) or one method of the
+ * reference's pure-Python `LDA` class (python/liblda/lda.py).  Plain C types only
+ * (pointers + sizes); no CUDA or torch types.  All functions return 0 on success and
+ * a negative PLDA_E_* status otherwise; plda_last_error() returns the message of the
+ * last failure on the calling thread.  There is NO CPU fallback: without a sm_100
+ * device plda_create()/lda_create() fail with PLDA_E_CUDA.
+ *
+ * Conventions
+ *   - matrices are row-major; `ld*` are row pitches in ELEMENTS
+ *   - dtype: PLDA_F64 (reference contract: C-contiguous float64, kaldi-utils.hpp:99-111)
+ *            or PLDA_F32 (superset)
+ *   - `loc`: PLDA_HOST pointers are copied in/out by the call (the reference deep-copies
+ *            its inputs too, src/pldamodule.cpp:72,120,202,264-265); PLDA_DEVICE pointers
+ *            are used in place on the handle's device
+ *   - labels are 64-bit unsigned (src/pldamodule.cpp:74,139), always HOST for *_fit /
+ *     *_transform (they are 8 bytes per row)
+ *   - calls on one handle are serialised internally; distinct handles are independent
+ */
+#ifndef PLDA_B200_H_
+#define PLDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLDA_OK 0
+#define PLDA_E_INVALID (-1)   /* bad argument                                             */
+#define PLDA_E_CUDA (-2)      /* CUDA failure / no device                                  */
+#define PLDA_E_NOTFITTED (-3) /* model not fitted / set                                    */
+#define PLDA_E_VALUE (-4)     /* the reference raises ValueError here (e.g. one speaker)   */
+#define PLDA_E_INTERNAL (-5)
+
+#define PLDA_F64 0
+#define PLDA_F32 1
+#define PLDA_HOST 0
+#define PLDA_DEVICE 1
+
+/* precision of the dense contractions */
+#define PLDA_PREC_BF16X3 0 /* tcgen05, split-bf16 x3, fp32 accumulate (default)            */
+#define PLDA_PREC_FP64 1   /* exact mode: fp64 SIMT kernels                                */
+
+typedef struct plda_handle_s* plda_handle_t;
+typedef struct lda_handle_s* lda_handle_t;
+
+const char* plda_last_error(void);
+const char* plda_version(void);
+
+/* ---- lifetime: replaces Plda_new / MPLDA_dealloc (src/pldamodule.cpp:297-316) ---------- */
+int plda_create(int device, plda_handle_t* out);
+int plda_destroy(plda_handle_t h);
+int plda_set_precision(plda_handle_t h, int precision);
+/* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
+int plda_set_stream(plda_handle_t h, void* cuda_stream);
+int plda_synchronize(plda_handle_t h);
+/* number of plda_b200 kernels launched through this handle so far (bench "gpu_launches") */
+int plda_launch_count(plda_handle_t h, int64_t* out);
+
+/* ---- fit: replaces MPlda_fit (src/pldamodule.cpp:42-109) ------------------------------- *
+ * x: [n x d]; labels: [n] uint64 (any values; the reference requires dense 0..K-1, :88-92 --
+ * dense labels give identical results).  iters = EM iterations (default 10 in the reference).
+ * Errors: PLDA_E_VALUE if only one distinct label (:83-86).                                 */
+int plda_fit(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+             const uint64_t* labels, int iters);
+/* timing breakdown of the last fit in milliseconds: [0] ingest+stats pass, [1] EM iterations,
+ * [2] GetOutput, [3] total; [4] EM iterations run */
+int plda_fit_timings(plda_handle_t h, double out[5]);
+
+/* model access (Kaldi Plda{mean_, transform_, psi_}); HOST fp64 buffers: mean[d], transform[d*d], psi[d] */
+int plda_dim(plda_handle_t h, int64_t* d);
+int plda_get_model(plda_handle_t h, double* mean, double* transform, double* psi);
+int plda_set_model(plda_handle_t h, int64_t d, const double* mean, const double* transform, const double* psi);
+/* final EM covariances (within, between) [d*d] each, HOST fp64 -- for parity checks */
+int plda_get_covariances(plda_handle_t h, double* within, double* between);
+/* Plda::SmoothWithinClassCovariance (src/pldamodule.cpp:158-160); mutates the model like the reference */
+int plda_smooth(plda_handle_t h, double factor);
+
+/* ---- transform: replaces Mplda_transform (src/pldamodule.cpp:111-194) ------------------- *
+ * Groups rows by label (ascending label order = std::map order, :164), averages, applies
+ * Plda::TransformIvector with num_examples = group size.  targetdim = 0 keeps d outputs;
+ * targetdim = r keeps the r leading (largest-psi) directions (defined semantics; the
+ * reference's own plumbing is broken).
+ * Outputs (HOST, caller-allocated for the worst case of n groups):
+ *   out_labels[n_out], out_counts[n_out], out_vecs[n_out x out_dim] fp64                    */
+int plda_transform(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                   const uint64_t* labels, int64_t targetdim, uint64_t* out_labels, int64_t* out_counts,
+                   double* out_vecs, int64_t* n_out);
+/* batched variant without grouping: row r is one vector averaged over counts[r] utterances
+ * (counts HOST int32, NULL = all ones).  out: [n x out_dim] of out_dtype at out_loc.         */
+int plda_transform_rows(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                        const int32_t* counts, int32_t const_count, int64_t targetdim, void* out, int64_t ldo,
+                        int out_dtype, int out_loc);
+
+/* ---- score: replaces MPlda_score (src/pldamodule.cpp:258-277) --------------------------- *
+ * One (enrol, test) pair, already transformed, HOST fp64 [dim]; z-normalised iff model_id was
+ * seen by plda_norm (:269-273).  Result is rounded through float32 like Py_BuildValue("f").  */
+int plda_score_pair(plda_handle_t h, uint64_t model_id, int64_t n_enrol, const double* enrol, const double* test,
+                    int64_t dim, float* out);
+/* All-pairs grid: out[e, t] = LLR(enrol_e (n = counts[e]), test_t)  [ne x nt] fp32.
+ * enrol [ne x dim], test [nt x dim] (dtype/loc as given); enrol_counts HOST int32 [ne];
+ * enrol_ids HOST uint64 [ne] or NULL: if given, rows whose id was seen by plda_norm are z-normalised. */
+int plda_score_grid(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                    const uint64_t* enrol_ids, const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype,
+                    int loc, float* out, int64_t ldo, int out_loc);
+
+/* ---- norm: replaces MPlda_norm (src/pldamodule.cpp:196-256) ------------------------------ *
+ * bkg: [m x d] RAW (untransformed) background vectors; each selected row is transformed with
+ * num_examples = m (sic, :224) and scored as LLR(bkg, n=1, enrol_k) against every enrol vector
+ * (:235); mean and population std per enrol id are stored (first insert wins, :245,250).
+ * numutts = 0 -> all rows; otherwise a seeded random subset of that size (:204-213).          */
+int plda_norm(plda_handle_t h, const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc,
+              const uint64_t* enrol_ids, const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype,
+              int enrol_loc, int64_t numutts, uint64_t seed);
+int plda_znorm_size(plda_handle_t h, int64_t* n);
+int plda_znorm_get(plda_handle_t h, uint64_t* ids, double* mean, double* stdv, int64_t capacity, int64_t* n);
+int plda_znorm_clear(plda_handle_t h);
+/* restore tables saved with plda_znorm_get (first insert wins, like plda_norm) */
+int plda_znorm_set(plda_handle_t h, const uint64_t* ids, const double* mean, const double* stdv, int64_t n);
+
+/* ---- LDA: replaces python/liblda/lda.py (LDA.fit svd :178-221, decision_function :253-279,
+ *      predict_log_proba :306-325) ---------------------------------------------------------- */
+int lda_create(int device, lda_handle_t* out);
+int lda_destroy(lda_handle_t h);
+int lda_set_precision(lda_handle_t h, int precision);
+int lda_launch_count(lda_handle_t h, int64_t* out);
+int lda_synchronize(lda_handle_t h);
+/* labels: HOST int64 [n] (any values; classes = sorted unique, lda.py:118); priors NULL = empirical */
+int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                const int64_t* labels, const double* priors, int64_t n_priors);
+int lda_num_classes(lda_handle_t h, int64_t* k, int64_t* d);
+int lda_get_coef(lda_handle_t h, double* coef /* [k*d] */, double* intercept /* [k] */, int64_t* classes /* [k] */);
+int lda_set_coef(lda_handle_t h, int64_t k, int64_t d, const double* coef, const double* intercept);
+/* out[nt x k] fp32: decision values (log_proba = 0) or row log-softmax of them (log_proba = 1) */
+int lda_predict(lda_handle_t h, const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int log_proba,
+                float* out, int64_t ldo, int out_loc);
+
+/* ---- memory helpers for callers that want resident data without torch --------------------- */
+int plda_device_malloc(int device, size_t bytes, void** out);
+int plda_device_free(int device, void* p);
+int plda_host_malloc_pinned(size_t bytes, void** out);
+int plda_host_free_pinned(void* p);
+int plda_memcpy(void* dst, const void* src, size_t bytes, int kind /* 0 h2d, 1 d2h, 2 d2d */);
+
+/* ---- kernel-level entry used by the parity tests: C[m x n] = A[m x k] * B[n x k]^T (HOST fp64 in,
+ *      HOST fp32 out) through the tensor-core kernel (ksplit <= 1: fused-store path; > 1: split-K) */
+int plda_test_gemm(plda_handle_t h, const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit,
+                   float* out);
+/* fp64 d x d helpers exposed for tests: op 0 = cholesky (lower), 1 = lower-triangular inverse,
+ * 2 = symmetric eig (out = eigenvectors as columns, out2 = eigenvalues descending) */
+int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLDA_B200_H_ */

@@ -1,0 +1,257 @@
+// extern "C" boundary (include/plda_b200.h): converts C++ exceptions into status codes and a
+// thread-local last-error string, serialises calls per handle.
+#include "../../include/plda_b200.h"
+
+#include <string.h>
+
+#include "engine.h"
+
+struct plda_handle_s {
+  pb::PldaEngine eng;
+  explicit plda_handle_s(int dev) : eng(dev) {}
+};
+struct lda_handle_s {
+  pb::LdaEngine eng;
+  explicit lda_handle_s(int dev) : eng(dev) {}
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return PLDA_OK;
+  } catch (const pb::Error& e) {
+    g_last_error = e.what();
+    // a sticky CUDA error (e.g. a trapped kernel) must not be silently reused
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of host memory";
+    return PLDA_E_INTERNAL;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return PLDA_E_INTERNAL;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return PLDA_E_INTERNAL;
+  }
+}
+
+template <typename H, typename F>
+int with_handle(H h, F&& f) {
+  if (h == nullptr) {
+    g_last_error = "null handle";
+    return PLDA_E_INVALID;
+  }
+  return guarded([&] {
+    std::lock_guard<std::mutex> lock(h->eng.mu);
+    PB_CUDA(cudaSetDevice(h->eng.ctx.device));
+    f(h->eng);
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* plda_last_error(void) { return g_last_error.c_str(); }
+const char* plda_version(void) { return "plda_b200 0.1.0 (sm_100a)"; }
+
+int plda_create(int device, plda_handle_t* out) {
+  if (out == nullptr) { g_last_error = "null output pointer"; return PLDA_E_INVALID; }
+  *out = nullptr;
+  return guarded([&] { *out = new plda_handle_s(device); });
+}
+int plda_destroy(plda_handle_t h) {
+  if (h == nullptr) return PLDA_OK;
+  return guarded([&] { cudaSetDevice(h->eng.ctx.device); delete h; });
+}
+int plda_set_precision(plda_handle_t h, int precision) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(precision == PLDA_PREC_BF16X3 || precision == PLDA_PREC_FP64, pb::kInvalidArg, "unknown precision");
+    e.precision = precision;
+  });
+}
+int plda_set_stream(plda_handle_t h, void* cuda_stream) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.ctx.sync();
+    if (cuda_stream == nullptr) {
+      if (!e.ctx.owns_stream) {
+        PB_CUDA(cudaStreamCreateWithFlags(&e.ctx.stream, cudaStreamNonBlocking));
+        e.ctx.owns_stream = true;
+      }
+    } else {
+      if (e.ctx.owns_stream && e.ctx.stream) cudaStreamDestroy(e.ctx.stream);
+      e.ctx.stream = static_cast<cudaStream_t>(cuda_stream);
+      e.ctx.owns_stream = false;
+    }
+  });
+}
+int plda_synchronize(plda_handle_t h) { return with_handle(h, [&](pb::PldaEngine& e) { e.ctx.sync(); }); }
+int plda_launch_count(plda_handle_t h, int64_t* out) {
+  return with_handle(h, [&](pb::PldaEngine& e) { *out = e.ctx.launches.load(); });
+}
+
+int plda_fit(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+             const uint64_t* labels, int iters) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.fit(x, n, d, ldx, dtype, loc, labels, iters); });
+}
+int plda_fit_timings(plda_handle_t h, double out[5]) {
+  return with_handle(h, [&](pb::PldaEngine& e) { memcpy(out, e.fit_ms, sizeof(e.fit_ms)); });
+}
+int plda_dim(plda_handle_t h, int64_t* d) {
+  return with_handle(h, [&](pb::PldaEngine& e) { *d = e.model.ready ? e.model.d : 0; });
+}
+int plda_get_model(plda_handle_t h, double* mean, double* transform, double* psi) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.get_model(mean, transform, psi); });
+}
+int plda_set_model(plda_handle_t h, int64_t d, const double* mean, const double* transform, const double* psi) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.set_model(d, mean, transform, psi); });
+}
+int plda_get_covariances(plda_handle_t h, double* within, double* between) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.get_covariances(within, between); });
+}
+int plda_smooth(plda_handle_t h, double factor) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.smooth(factor); });
+}
+
+int plda_transform(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                   const uint64_t* labels, int64_t targetdim, uint64_t* out_labels, int64_t* out_counts,
+                   double* out_vecs, int64_t* n_out) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(out_labels && out_counts && out_vecs && n_out, pb::kInvalidArg, "transform: null output");
+    e.transform_grouped(x, n, d, ldx, dtype, loc, labels, targetdim, out_labels, out_counts, out_vecs, n_out);
+  });
+}
+int plda_transform_rows(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                        const int32_t* counts, int32_t const_count, int64_t targetdim, void* out, int64_t ldo,
+                        int out_dtype, int out_loc) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(out != nullptr || n == 0, pb::kInvalidArg, "transform_rows: null output");
+    e.transform_rows(x, n, d, ldx, dtype, loc, counts, const_count, targetdim, out, ldo, out_dtype, out_loc);
+  });
+}
+
+int plda_score_pair(plda_handle_t h, uint64_t model_id, int64_t n_enrol, const double* enrol, const double* test,
+                    int64_t dim, float* out) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(enrol && test && out, pb::kInvalidArg, "score: null pointer");
+    e.score_pair(model_id, n_enrol, enrol, test, dim, out);
+  });
+}
+int plda_score_grid(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                    const uint64_t* enrol_ids, const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype,
+                    int loc, float* out, int64_t ldo, int out_loc) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.score_grid(enrol, ne, ld_enrol, enrol_counts, enrol_ids, test, nt, ld_test, dim, dtype, loc, out, ldo, out_loc);
+  });
+}
+int plda_norm(plda_handle_t h, const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc,
+              const uint64_t* enrol_ids, const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype,
+              int enrol_loc, int64_t numutts, uint64_t seed) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.norm(bkg, m, d, ldb, dtype, loc, enrol_ids, enrol, ne, ld_enrol, dim, enrol_dtype, enrol_loc, numutts, seed);
+  });
+}
+int plda_znorm_size(plda_handle_t h, int64_t* n) {
+  return with_handle(h, [&](pb::PldaEngine& e) { *n = static_cast<int64_t>(e.znorm.size()); });
+}
+int plda_znorm_get(plda_handle_t h, uint64_t* ids, double* mean, double* stdv, int64_t capacity, int64_t* n) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    int64_t i = 0;
+    for (const auto& kv : e.znorm) {
+      if (i >= capacity) break;
+      ids[i] = kv.first;
+      mean[i] = kv.second.first;
+      stdv[i] = kv.second.second;
+      ++i;
+    }
+    *n = i;
+  });
+}
+int plda_znorm_set(plda_handle_t h, const uint64_t* ids, const double* mean, const double* stdv, int64_t n) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(n == 0 || (ids && mean && stdv), pb::kInvalidArg, "znorm_set: null pointer");
+    for (int64_t i = 0; i < n; ++i) e.znorm.emplace(ids[i], std::make_pair(mean[i], stdv[i]));
+  });
+}
+int plda_znorm_clear(plda_handle_t h) { return with_handle(h, [&](pb::PldaEngine& e) { e.znorm.clear(); }); }
+
+int lda_create(int device, lda_handle_t* out) {
+  if (out == nullptr) { g_last_error = "null output pointer"; return PLDA_E_INVALID; }
+  *out = nullptr;
+  return guarded([&] { *out = new lda_handle_s(device); });
+}
+int lda_destroy(lda_handle_t h) {
+  if (h == nullptr) return PLDA_OK;
+  return guarded([&] { cudaSetDevice(h->eng.ctx.device); delete h; });
+}
+int lda_set_precision(lda_handle_t h, int precision) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    PB_CHECK(precision == PLDA_PREC_BF16X3 || precision == PLDA_PREC_FP64, pb::kInvalidArg, "unknown precision");
+    e.precision = precision;
+  });
+}
+int lda_launch_count(lda_handle_t h, int64_t* out) {
+  return with_handle(h, [&](pb::LdaEngine& e) { *out = e.ctx.launches.load(); });
+}
+int lda_synchronize(lda_handle_t h) { return with_handle(h, [&](pb::LdaEngine& e) { e.ctx.sync(); }); }
+int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                const int64_t* labels, const double* priors, int64_t n_priors) {
+  return with_handle(h, [&](pb::LdaEngine& e) { e.fit_svd(x, n, d, ldx, dtype, loc, labels, priors, n_priors); });
+}
+int lda_num_classes(lda_handle_t h, int64_t* k, int64_t* d) {
+  return with_handle(h, [&](pb::LdaEngine& e) { *k = e.ready ? e.k : 0; *d = e.ready ? e.d : 0; });
+}
+int lda_get_coef(lda_handle_t h, double* coef, double* intercept, int64_t* classes) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    PB_CHECK(e.ready, pb::kNotFitted, "This LDA instance is not fitted yet");
+    if (coef) memcpy(coef, e.h_coef.data(), e.h_coef.size() * sizeof(double));
+    if (intercept) memcpy(intercept, e.h_intercept.data(), e.h_intercept.size() * sizeof(double));
+    if (classes) memcpy(classes, e.h_classes.data(), e.h_classes.size() * sizeof(int64_t));
+  });
+}
+int lda_set_coef(lda_handle_t h, int64_t k, int64_t d, const double* coef, const double* intercept) {
+  return with_handle(h, [&](pb::LdaEngine& e) { e.set_coef(k, d, coef, intercept); });
+}
+int lda_predict(lda_handle_t h, const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int log_proba,
+                float* out, int64_t ldo, int out_loc) {
+  return with_handle(h, [&](pb::LdaEngine& e) { e.predict(x, nt, d, ldx, dtype, loc, log_proba, out, ldo, out_loc); });
+}
+
+int plda_device_malloc(int device, size_t bytes, void** out) {
+  return guarded([&] {
+    PB_CUDA(cudaSetDevice(device));
+    PB_CUDA(cudaMalloc(out, bytes == 0 ? 1 : bytes));
+  });
+}
+int plda_device_free(int device, void* p) {
+  return guarded([&] {
+    PB_CUDA(cudaSetDevice(device));
+    PB_CUDA(cudaFree(p));
+  });
+}
+int plda_host_malloc_pinned(size_t bytes, void** out) {
+  return guarded([&] { PB_CUDA(cudaMallocHost(out, bytes == 0 ? 1 : bytes)); });
+}
+int plda_host_free_pinned(void* p) { return guarded([&] { PB_CUDA(cudaFreeHost(p)); }); }
+int plda_memcpy(void* dst, const void* src, size_t bytes, int kind) {
+  return guarded([&] {
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    PB_CUDA(cudaMemcpy(dst, src, bytes, k));
+  });
+}
+
+int plda_test_gemm(plda_handle_t h, const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit,
+                   float* out) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.test_gemm(a, b, m, n, k, ksplit, out); });
+}
+int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.test_linalg(op, a, d, out, out2); });
+}
+
+}  // extern "C"

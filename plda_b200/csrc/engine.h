@@ -1,0 +1,111 @@
+// PldaEngine / LdaEngine: device-resident state behind the opaque C-ABI handles.
+#pragma once
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.h"
+
+namespace pb {
+
+// Stages a caller matrix on the device: HOST -> copied into an owned buffer, DEVICE -> used in place.
+struct Staged {
+  const void* ptr = nullptr;
+  int64_t ld = 0;
+  bool is_f32 = false;
+  DevBuf<uint8_t> own;
+};
+
+struct PldaModel {
+  int64_t d = 0;
+  bool ready = false;
+  DevBuf<double> mean, transform, psi, within, between;
+  SplitBuf a_split;              // rows of transform_ as split-bf16 (K-major) for the tensor GEMM
+  std::vector<double> h_psi;     // host mirror for cheap validation
+};
+
+class PldaEngine {
+ public:
+  explicit PldaEngine(int device) : ctx(device) {}
+  Context ctx;
+  std::mutex mu;
+  int precision = 0;
+  PldaModel model;
+  std::unordered_map<uint64_t, std::pair<double, double>> znorm;   // id -> (mean, std)  (meanz/stdvz, pldamodule.cpp:33)
+  double fit_ms[5] = {0, 0, 0, 0, 0};
+
+  void set_model(int64_t d, const double* mean, const double* transform, const double* psi);
+  void get_model(double* mean, double* transform, double* psi);
+  void get_covariances(double* within, double* between);
+  void smooth(double factor);
+  void fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels, int iters);
+  void transform_grouped(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,
+                         int64_t targetdim, uint64_t* out_labels, int64_t* out_counts, double* out_vecs,
+                         int64_t* n_out);
+  void transform_rows(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int32_t* counts,
+                      int32_t const_count, int64_t targetdim, void* out, int64_t ldo, int out_dtype, int out_loc);
+  void score_pair(uint64_t id, int64_t n_enrol, const double* enrol, const double* test, int64_t dim, float* out);
+  void score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* counts, const uint64_t* ids,
+                  const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc, float* out,
+                  int64_t ldo, int out_loc);
+  void norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc, const uint64_t* enrol_ids,
+            const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype, int enrol_loc,
+            int64_t numutts, uint64_t seed);
+  void test_gemm(const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit, float* out);
+  void test_linalg(int op, const double* a, int64_t d, double* out, double* out2);
+
+ private:
+  void require_model() const { PB_CHECK(model.ready, kNotFitted, "PLDA model is not fitted (call fit or set_model)"); }
+  void refresh_model_operands();
+  void stage(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype, int loc, Staged& s);
+  // device rows [n x d] (centred by the model mean) -> transformed + length-normalised rows
+  void transform_device_rows(const void* x, bool is_f32, int64_t n, int64_t d, int64_t ld, const double* sub,
+                             const int32_t* counts_dev, int32_t const_count, int64_t dim, double* out64, int64_t ld64,
+                             float* out32, int64_t ld32);
+  void em_iteration(int64_t k, int64_t d, const double* scatter, const SplitBuf& mc_split, const double* mc_f64,
+                    const int32_t* counts_dev, double w_count, double b_count, bool warm);
+  void joint_diagonalise(int64_t d, bool warm);
+
+  // persistent workspaces (grow-only)
+  SplitBuf ws_l, ws_r, ws_x, ws_xt, ws_pt, ws_qt, ws_mc;
+  DevBuf<float> ws_row, ws_col, ws_out[2], ws_y, ws_zmean, ws_zinv, ws_partial, ws_u;
+  DevBuf<double> ws_rsum, ws_rsq, ws_f64a, ws_f64b, ws_f64c, ws_gram, ws_row64, ws_col64;
+  DevBuf<int32_t> ws_counts, ws_grp, ws_gcounts;
+  Segments segs;
+  EigWork eig;
+  // EM state (d x d, fp64)
+  DevBuf<double> em_c, em_t1, em_bp, em_u, em_a, em_ainv, em_psi, em_tmp, em_tmp2, em_bs, em_ws, em_db, em_dw;
+  DevBuf<int> em_info;
+  bool em_have_basis = false;
+};
+
+class LdaEngine {
+ public:
+  explicit LdaEngine(int device) : ctx(device) {}
+  Context ctx;
+  std::mutex mu;
+  int precision = 0;
+  int64_t k = 0, d = 0;
+  bool ready = false;
+  std::vector<double> h_coef, h_intercept;
+  std::vector<int64_t> h_classes;
+  DevBuf<double> coef, intercept;
+  SplitBuf coef_split;
+  DevBuf<float> intercept_f32;
+
+  void fit_svd(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
+               const double* priors, int64_t n_priors);
+  void set_coef(int64_t k, int64_t d, const double* coef, const double* intercept);
+  void predict(const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int log_proba, float* out,
+               int64_t ldo, int out_loc);
+
+ private:
+  void refresh_operands();
+  SplitBuf ws_x;
+  DevBuf<float> ws_out[2], ws_lmax, ws_lsum, ws_neglse;
+  DevBuf<double> ws_gram;
+  DevBuf<uint8_t> ws_in;
+};
+
+}  // namespace pb

@@ -1,0 +1,235 @@
+// PldaEngine::fit -- stats pass, EM iterations in the jointly-diagonalising basis, GetOutput.
+//
+// Reference call stack replaced:
+//   MPlda_fit (src/pldamodule.cpp:42-109)
+//     -> PldaStats::AddSamples per speaker with weight 1/n_s (:94-98), Sort (:100)
+//     -> PldaEstimator::Estimate (:102-106): EstimateOneIter x iters, GetOutput
+#include <chrono>
+
+#include "engine.h"
+
+namespace pb {
+namespace {
+
+__global__ void scale_vec_kernel(double* __restrict__ v, int n, const double* __restrict__ denom) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = v[i] / *denom;
+}
+
+__global__ void symmetrise_kernel(double* __restrict__ a, int d) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(d) * d) return;
+  const int i = static_cast<int>(idx / d), j = static_cast<int>(idx % d);
+  if (j < i) {
+    const double v = 0.5 * (a[idx] + a[static_cast<long long>(j) * d + i]);
+    a[idx] = v;
+    a[static_cast<long long>(j) * d + i] = v;
+  }
+}
+
+double ms_between(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return static_cast<double>(ms);
+}
+
+}  // namespace
+
+// C = chol(W); T1 = C^-1; B' = T1 B T1^T; B' = U diag(psi) U^T; A = U^T T1; A^-1 = C U
+// (PldaEstimator::GetOutput / ComputeNormalizingTransform).  Leaves A in em_a, A^-1 in em_ainv, psi in em_psi.
+void PldaEngine::joint_diagonalise(int64_t d, bool warm) {
+  const size_t dd = static_cast<size_t>(d) * d;
+  em_c.reserve(dd); em_t1.reserve(dd); em_bp.reserve(dd); em_u.reserve(dd); em_a.reserve(dd); em_ainv.reserve(dd);
+  em_psi.reserve(d); em_tmp.reserve(dd); em_info.reserve(1);
+  PB_CUDA(cudaMemcpyAsync(em_c.get(), model.within.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  cholesky_lower(ctx, em_c.get(), d, em_info.get());
+  tri_inverse_lower(ctx, em_c.get(), em_t1.get(), d);
+  // B' = T1 B T1^T
+  gemm_f64(ctx, false, false, d, d, d, 1.0, em_t1.get(), d, model.between.get(), d, 0.0, em_tmp.get(), d);
+  gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp.get(), d, em_t1.get(), d, 0.0, em_bp.get(), d);
+  symmetrise_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(em_bp.get(), static_cast<int>(d));
+  ctx.count_launch();
+  // eigenvectors as ROWS of em_u (= U^T), eigenvalues descending, floored at 0
+  eig_sym_jacobi(ctx, em_bp.get(), d, (warm && em_have_basis) ? em_u.get() : nullptr, em_psi.get(), em_tmp.get(), eig,
+                 nullptr);
+  PB_CUDA(cudaMemcpyAsync(em_u.get(), em_tmp.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  em_have_basis = true;
+  gemm_f64(ctx, false, false, d, d, d, 1.0, em_u.get(), d, em_t1.get(), d, 0.0, em_a.get(), d);     // A = U^T T1
+  gemm_f64(ctx, false, true, d, d, d, 1.0, em_c.get(), d, em_u.get(), d, 0.0, em_ainv.get(), d);    // A^-1 = C U
+}
+
+void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const SplitBuf& mc_split,
+                              const double* mc_f64, const int32_t* counts_dev, double w_count, double b_count,
+                              bool warm) {
+  const size_t dd = static_cast<size_t>(d) * d;
+  joint_diagonalise(d, warm);
+  em_bs.reserve(dd); em_ws.reserve(dd); em_db.reserve(d); em_dw.reserve(d); em_tmp2.reserve(dd);
+  if (precision == 1) {
+    // exact mode: everything fp64
+    ws_f64a.reserve(k * d);   // U
+    ws_f64b.reserve(k * d);   // P
+    ws_f64c.reserve(k * d);   // Q
+    gemm_f64(ctx, false, true, k, d, d, 1.0, mc_f64, d, em_a.get(), d, 0.0, ws_f64a.get(), d);
+    em_posterior_f64(ctx, ws_f64a.get(), k, d, counts_dev, em_psi.get(), ws_f64b.get(), ws_f64c.get(), em_db.get(),
+                     em_dw.get());
+    gemm_f64(ctx, true, false, d, d, k, 1.0, ws_f64b.get(), d, ws_f64b.get(), d, 0.0, em_bs.get(), d);   // P^T P
+    gemm_f64(ctx, true, false, d, d, k, 1.0, ws_f64c.get(), d, ws_f64c.get(), d, 0.0, em_ws.get(), d);   // Q^T Q
+  } else {
+    // U = Mc A^T on tcgen05
+    SplitBuf& a_split = ws_x;
+    split_rows(ctx, em_a.get(), false, d, d, d, nullptr, nullptr, nullptr, a_split);
+    const int64_t ldu = round_up(d, 4);
+    ws_u.reserve(k * ldu);
+    GemmEpilogue epi;
+    epi.out = ws_u.get();
+    epi.ldo = ldu;
+    gemm_bf16x3(ctx, mc_split.view(), a_split.view(), k, d, d, epi);
+    em_posterior_t(ctx, ws_u.get(), ldu, k, d, counts_dev, em_psi.get(), ws_pt, ws_qt, em_db.get(), em_dw.get());
+    // two weighted SYRKs over the class axis (split-K), fp64 reduction of the partials
+    const int ks = choose_ksplit(ctx, d, d, k);
+    const int eff = effective_ksplit(ctx, d, d, k, ks);
+    const int64_t mpad = round_up(d, 128), npad = round_up(d, 4);
+    ws_partial.reserve(static_cast<size_t>(eff) * mpad * npad);
+    gemm_bf16x3_splitk(ctx, ws_pt.view(), ws_pt.view(), d, d, k, ks, ws_partial.get());
+    reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, em_bs.get(), d, 1.0, true);
+    gemm_bf16x3_splitk(ctx, ws_qt.view(), ws_qt.view(), d, d, k, ks, ws_partial.get());
+    reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, em_ws.get(), d, 1.0, true);
+  }
+  // add the diagonal terms (no scaling yet)
+  add_diag_scale(ctx, em_bs.get(), em_db.get(), d, 1.0, nullptr);
+  add_diag_scale(ctx, em_ws.get(), em_dw.get(), d, 1.0, nullptr);
+  // back to the original basis:  X -> A^-1 X A^-T
+  gemm_f64(ctx, false, false, d, d, d, 1.0, em_ainv.get(), d, em_bs.get(), d, 0.0, em_tmp2.get(), d);
+  gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp2.get(), d, em_ainv.get(), d, 0.0, model.between.get(), d);
+  gemm_f64(ctx, false, false, d, d, d, 1.0, em_ainv.get(), d, em_ws.get(), d, 0.0, em_tmp2.get(), d);
+  gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp2.get(), d, em_ainv.get(), d, 0.0, model.within.get(), d);
+  // W = (S + .)/W_count ;  B = ./B_count      (EstimateFromStats)
+  add_diag_scale(ctx, model.between.get(), nullptr, d, 1.0 / b_count, nullptr);
+  add_diag_scale(ctx, model.within.get(), nullptr, d, 1.0, scatter);
+  add_diag_scale(ctx, model.within.get(), nullptr, d, 1.0 / w_count, nullptr);
+  const unsigned sb = static_cast<unsigned>(ceil_div(d * d, 256));
+  symmetrise_kernel<<<sb, 256, 0, ctx.stream>>>(model.between.get(), static_cast<int>(d));
+  symmetrise_kernel<<<sb, 256, 0, ctx.stream>>>(model.within.get(), static_cast<int>(d));
+  ctx.count_launch(2);
+}
+
+void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,
+                     int iters) {
+  PB_CHECK(n > 0 && d > 0, kInvalidArg, "fit: empty input");
+  PB_CHECK(d <= 1024, kInvalidArg, "fit: feature dimension above 1024 is not supported");
+  PB_CHECK(labels != nullptr, kInvalidArg, "fit: labels are required");
+  PB_CHECK(iters >= 0, kInvalidArg, "fit: iters must be >= 0");
+  cudaEvent_t ev[4];
+  for (auto& e : ev) PB_CUDA(cudaEventCreate(&e));
+  const size_t dd = static_cast<size_t>(d) * d;
+  PB_CUDA(cudaEventRecord(ev[0], ctx.stream));
+
+  // ---- stats pass (PldaStats::AddSamples for every speaker) ----
+  Staged sx;
+  stage(x, n, d, ldx, dtype, loc, sx);
+  DevBuf<uint64_t> lab(n);
+  PB_CUDA(cudaMemcpyAsync(lab.get(), labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+  build_segments(ctx, lab.get(), n, segs);                                  // K1
+  const int64_t k = segs.nseg;
+  if (k < 2) {
+    for (auto& e : ev) cudaEventDestroy(e);
+    throw Error(kValueError,
+                "Number of speakers is 1. Aborting PLDA esimation, at least two speakers are required!");
+  }
+  DevBuf<double> means(static_cast<size_t>(k) * d);
+  DevBuf<int32_t> counts(k);
+  segment_sums(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get());        // K2
+  segment_finalize_means(ctx, means.get(), d, segs, counts.get());
+  DevBuf<double> scatter(dd);
+  if (precision == 1) {
+    ws_gram.reserve(static_cast<size_t>(n) * d);
+    center_scale_f64(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_gram.get());
+    gemm_f64(ctx, true, false, d, d, n, 1.0, ws_gram.get(), d, ws_gram.get(), d, 0.0, scatter.get(), d);
+  } else {
+    center_scale_split_t(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_xt);   // K3 operand
+    const int ks = choose_ksplit(ctx, d, d, n);
+    const int eff = effective_ksplit(ctx, d, d, n, ks);
+    const int64_t mpad = round_up(d, 128), npad = round_up(d, 4);
+    ws_partial.reserve(static_cast<size_t>(eff) * mpad * npad);
+    gemm_bf16x3_splitk(ctx, ws_xt.view(), ws_xt.view(), d, d, n, ks, ws_partial.get());   // K3: S = X~^T X~
+    reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, scatter.get(), d, 1.0, true);
+  }
+  // sum_ = sum_s w_s m_s, class_weight = sum_s w_s ; mu = sum_/class_weight
+  DevBuf<double> class_weight(1);
+  model.d = d;
+  model.mean.reserve(d);
+  class_weighted_sum(ctx, means.get(), counts.get(), k, d, model.mean.get(), class_weight.get());
+  scale_vec_kernel<<<static_cast<unsigned>(ceil_div(d, 128)), 128, 0, ctx.stream>>>(model.mean.get(), static_cast<int>(d),
+                                                                                  class_weight.get());
+  ctx.count_launch();
+  double h_cw = 0.0;
+  PB_CUDA(cudaMemcpyAsync(&h_cw, class_weight.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  // centred class means (constant across iterations)
+  DevBuf<double> mc(static_cast<size_t>(k) * d);
+  convert_to_f64(ctx, means.get(), false, k, d, d, mc.get(), d, model.mean.get());
+  if (precision != 1) split_rows(ctx, mc.get(), false, k, d, d, nullptr, nullptr, nullptr, ws_mc);
+  PB_CUDA(cudaEventRecord(ev[1], ctx.stream));
+  ctx.sync();
+  // example_weight = sum w_s n_s = K;  W_count = (K - class_weight) + class_weight = K;  B_count = class_weight
+  const double w_count = static_cast<double>(k);
+  const double b_count = h_cw;
+
+  // ---- EM (InitParameters: W = B = I) ----
+  model.within.reserve(dd);
+  model.between.reserve(dd);
+  set_identity(ctx, model.within.get(), d);
+  set_identity(ctx, model.between.get(), d);
+  em_have_basis = false;
+  for (int it = 0; it < iters; ++it)
+    em_iteration(k, d, scatter.get(), ws_mc, mc.get(), counts.get(), w_count, b_count, /*warm=*/it > 0);
+  PB_CUDA(cudaEventRecord(ev[2], ctx.stream));
+
+  // ---- GetOutput ----
+  joint_diagonalise(d, iters > 0);
+  int h_info = 0;
+  PB_CUDA(cudaMemcpyAsync(&h_info, em_info.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  model.transform.reserve(dd);
+  model.psi.reserve(d);
+  PB_CUDA(cudaMemcpyAsync(model.transform.get(), em_a.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(model.psi.get(), em_psi.get(), d * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  PB_CUDA(cudaEventRecord(ev[3], ctx.stream));
+  ctx.sync();
+  fit_ms[0] = ms_between(ev[0], ev[1]);
+  fit_ms[1] = ms_between(ev[1], ev[2]);
+  fit_ms[2] = ms_between(ev[2], ev[3]);
+  fit_ms[3] = ms_between(ev[0], ev[3]);
+  fit_ms[4] = iters;
+  for (auto& e : ev) cudaEventDestroy(e);
+  PB_CHECK(h_info == 0, kInternal, "within-class covariance is not positive definite (Cholesky failed at column " +
+                                      std::to_string(h_info) + ")");
+  refresh_model_operands();
+}
+
+void PldaEngine::test_linalg(int op, const double* a, int64_t d, double* out, double* out2) {
+  const size_t dd = static_cast<size_t>(d) * d;
+  DevBuf<double> da(dd), db(dd), dv(d);
+  DevBuf<int> info(1);
+  PB_CUDA(cudaMemcpyAsync(da.get(), a, dd * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  if (op == 0) {
+    cholesky_lower(ctx, da.get(), d, info.get());
+    PB_CUDA(cudaMemcpyAsync(out, da.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  } else if (op == 1) {
+    tri_inverse_lower(ctx, da.get(), db.get(), d);
+    PB_CUDA(cudaMemcpyAsync(out, db.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  } else if (op == 2) {
+    int sweeps = 0;
+    eig_sym_jacobi(ctx, da.get(), d, nullptr, dv.get(), db.get(), eig, &sweeps);
+    // return eigenvectors as columns
+    std::vector<double> vt(dd);
+    PB_CUDA(cudaMemcpyAsync(vt.data(), db.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(out2, dv.get(), d * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    for (int64_t p = 0; p < d; ++p)
+      for (int64_t i = 0; i < d; ++i) out[i * d + p] = vt[p * d + i];
+  } else {
+    throw Error(kInvalidArg, "test_linalg: unknown op");
+  }
+  ctx.sync();
+}
+
+}  // namespace pb

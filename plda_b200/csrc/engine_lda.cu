@@ -1,0 +1,314 @@
+// LdaEngine: the reference's pure-Python LDA (python/liblda/lda.py) on the device.
+//   fit_svd  <- LDA.fit + _solve_svd (lda.py:106-138, 178-221).  The two SVDs are replaced by
+//              symmetric eigendecompositions of the corresponding Gram matrices (X^T X = V S^2 V^T):
+//              identical scalings up to column signs, which coef/intercept do not depend on.
+//   predict  <- decision_function (lda.py:253-279) and predict_log_proba (lda.py:306-325).
+#include <algorithm>
+#include <cmath>
+
+#include "engine.h"
+
+namespace pb {
+namespace {
+
+__global__ void lse_combine_kernel(const float* __restrict__ lmax, const float* __restrict__ lsum, long long m,
+                                   int n_tiles, float* __restrict__ neg_lse) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= m) return;
+  float mx = -INFINITY;
+  for (int t = 0; t < n_tiles; ++t) mx = fmaxf(mx, lmax[i * n_tiles + t]);
+  float s = 0.f;
+  for (int t = 0; t < n_tiles; ++t) s += lsum[i * n_tiles + t] * __expf(lmax[i * n_tiles + t] - mx);
+  neg_lse[i] = -(mx + __logf(s));
+}
+
+// exact-mode row log-softmax on an fp64 grid (+ intercept), fp32 out; one block per row
+__global__ void __launch_bounds__(256)
+lda_epilogue_f64_kernel(const double* __restrict__ z, long long nt, long long k, const double* __restrict__ intercept,
+                        int log_proba, float* __restrict__ out, long long ldo) {
+  __shared__ double red[256];
+  const long long r = blockIdx.x;
+  const double* row = z + r * k;
+  double mx = -INFINITY;
+  for (long long c = threadIdx.x; c < k; c += blockDim.x) mx = fmax(mx, row[c] + intercept[c]);
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  mx = red[0];
+  __syncthreads();
+  double sum = 0.0;
+  for (long long c = threadIdx.x; c < k; c += blockDim.x) sum += exp(row[c] + intercept[c] - mx);
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double lse = log_proba ? mx + log(red[0]) : 0.0;
+  for (long long c = threadIdx.x; c < k; c += blockDim.x)
+    out[r * ldo + c] = static_cast<float>(row[c] + intercept[c] - lse);
+}
+
+}  // namespace
+
+void lse_combine(Context& ctx, const float* lmax, const float* lsum, int64_t m, int n_tiles, float* neg_lse) {
+  lse_combine_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, ctx.stream>>>(lmax, lsum, m, n_tiles, neg_lse);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void LdaEngine::refresh_operands() {
+  coef.reserve(k * d);
+  intercept.reserve(k);
+  PB_CUDA(cudaMemcpyAsync(coef.get(), h_coef.data(), k * d * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(intercept.get(), h_intercept.data(), k * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  split_rows(ctx, coef.get(), false, k, d, d, nullptr, nullptr, nullptr, coef_split);
+  const int64_t col_ld = round_up(k, 32);
+  std::vector<float> f(col_ld, 0.f);
+  for (int64_t i = 0; i < k; ++i) f[i] = static_cast<float>(h_intercept[i]);
+  intercept_f32.reserve(col_ld);
+  PB_CUDA(cudaMemcpyAsync(intercept_f32.get(), f.data(), col_ld * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+  ctx.sync();
+  ready = true;
+}
+
+void LdaEngine::set_coef(int64_t k_, int64_t d_, const double* c, const double* b) {
+  PB_CHECK(k_ > 0 && d_ > 0 && c && b, kInvalidArg, "lda_set_coef: bad arguments");
+  k = k_;
+  d = d_;
+  h_coef.assign(c, c + k * d);
+  h_intercept.assign(b, b + k);
+  h_classes.resize(k);
+  for (int64_t i = 0; i < k; ++i) h_classes[i] = i;
+  refresh_operands();
+}
+
+void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                        const double* priors_in, int64_t n_priors) {
+  PB_CHECK(n > 1 && d_ > 0 && d_ <= 1024, kInvalidArg, "lda_fit: need n > 1 and 0 < d <= 1024");
+  PB_CHECK(labels != nullptr && x != nullptr, kInvalidArg, "lda_fit: null input");
+  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+  const double tol = 1e-4;
+  const bool is_f32 = dtype == 1;
+  const size_t es = is_f32 ? 4 : 8;
+  // stage rows
+  const void* xd = x;
+  int64_t ld = ldx;
+  if (loc == 0) {
+    ws_in.reserve(static_cast<size_t>(n) * d_ * es);
+    PB_CUDA(cudaMemcpy2DAsync(ws_in.get(), d_ * es, x, ldx * es, d_ * es, n, cudaMemcpyHostToDevice, ctx.stream));
+    xd = ws_in.get();
+    ld = d_;
+  }
+  // order-preserving map of signed labels to uint64 keys (classes = np.unique(labels), lda.py:118)
+  std::vector<uint64_t> keys(n);
+  for (int64_t i = 0; i < n; ++i) keys[i] = static_cast<uint64_t>(labels[i]) ^ (1ull << 63);
+  DevBuf<uint64_t> dkeys(n);
+  PB_CUDA(cudaMemcpyAsync(dkeys.get(), keys.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+  Segments segs;
+  build_segments(ctx, dkeys.get(), n, segs);
+  const int64_t kk = segs.nseg;
+  PB_CHECK(kk >= 2, kValueError, "lda_fit: at least two classes are required");
+  PB_CHECK(n > kk, kValueError, "lda_fit: need more samples than classes");
+  DevBuf<double> means(static_cast<size_t>(kk) * d_);
+  DevBuf<int32_t> counts(kk);
+  segment_sums(ctx, xd, is_f32, d_, ld, segs, means.get());
+  segment_finalize_means(ctx, means.get(), d_, segs, counts.get());
+  // within scatter  Sw = xc^T xc  (unscaled)
+  const size_t dd = static_cast<size_t>(d_) * d_;
+  DevBuf<double> sw(dd);
+  if (precision == 1) {
+    ws_gram.reserve(static_cast<size_t>(n) * d_);
+    center_scale_f64(ctx, xd, is_f32, d_, ld, segs, means.get(), false, ws_gram.get());
+    gemm_f64(ctx, true, false, d_, d_, n, 1.0, ws_gram.get(), d_, ws_gram.get(), d_, 0.0, sw.get(), d_);
+  } else {
+    SplitBuf xt;
+    center_scale_split_t(ctx, xd, is_f32, d_, ld, segs, means.get(), false, xt);
+    const int ks = choose_ksplit(ctx, d_, d_, n);
+    const int eff = effective_ksplit(ctx, d_, d_, n, ks);
+    DevBuf<float> partial(static_cast<size_t>(eff) * round_up(d_, 128) * round_up(d_, 4));
+    gemm_bf16x3_splitk(ctx, xt.view(), xt.view(), d_, d_, n, ks, partial.get());
+    reduce_partials_f64(ctx, partial.get(), eff, d_, d_, sw.get(), d_, 1.0, true);
+  }
+  // The remaining algebra is K x d and d x d: bring the small pieces to the host-visible side only for the
+  // rank decisions (two scalar thresholds); the matrices themselves stay on the device.
+  std::vector<double> h_sw(dd), h_means(static_cast<size_t>(kk) * d_);
+  std::vector<int32_t> h_counts(kk);
+  std::vector<uint64_t> h_keys(kk);
+  PB_CUDA(cudaMemcpyAsync(h_sw.data(), sw.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(h_means.data(), means.get(), kk * d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(h_counts.data(), counts.get(), kk * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(h_keys.data(), segs.seg_label.get(), kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  // priors (lda.py:119-127)
+  std::vector<double> pri(kk);
+  if (priors_in != nullptr) {
+    PB_CHECK(n_priors == kk, kInvalidArg, "lda_fit: priors length does not match the number of classes");
+    for (int64_t i = 0; i < kk; ++i) pri[i] = priors_in[i];
+  } else {
+    for (int64_t i = 0; i < kk; ++i) pri[i] = static_cast<double>(h_counts[i]) / static_cast<double>(n);
+  }
+  double psum = 0.0;
+  for (double v : pri) psum += v;
+  if (psum != 1.0) for (double& v : pri) v /= psum;
+  // xbar = priors . means ; std_j = sqrt(Sw_jj / n)  (xc has zero column mean) ; fac = 1/(n - K)
+  std::vector<double> xbar(d_, 0.0), stdv(d_);
+  for (int64_t c = 0; c < kk; ++c)
+    for (int64_t j = 0; j < d_; ++j) xbar[j] += pri[c] * h_means[c * d_ + j];
+  for (int64_t j = 0; j < d_; ++j) {
+    double s = std::sqrt(h_sw[j * d_ + j] / static_cast<double>(n));
+    stdv[j] = s == 0.0 ? 1.0 : s;
+  }
+  const double fac = 1.0 / static_cast<double>(n - kk);
+  // G1 = fac * D^-1 Sw D^-1  -> eig on device
+  std::vector<double> g1(dd);
+  for (int64_t i = 0; i < d_; ++i)
+    for (int64_t j = 0; j < d_; ++j) g1[i * d_ + j] = fac * h_sw[i * d_ + j] / (stdv[i] * stdv[j]);
+  DevBuf<double> dg(dd), dvt(dd), dlam(d_);
+  EigWork ew;
+  PB_CUDA(cudaMemcpyAsync(dg.get(), g1.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  eig_sym_jacobi(ctx, dg.get(), d_, nullptr, dlam.get(), dvt.get(), ew, nullptr);
+  std::vector<double> lam(d_), vt(dd);
+  PB_CUDA(cudaMemcpyAsync(lam.data(), dlam.get(), d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(vt.data(), dvt.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  int64_t rank = 0;
+  for (int64_t i = 0; i < d_; ++i) if (std::sqrt(lam[i]) > tol) ++rank;     // S > tol (lda.py:202)
+  PB_CHECK(rank > 0, kValueError, "lda_fit: within-class scatter has rank 0");
+  // scalings[j, r] = V[r, j] / std_j / S_r     [d x rank]
+  std::vector<double> scal(static_cast<size_t>(d_) * rank);
+  for (int64_t r = 0; r < rank; ++r) {
+    const double s = std::sqrt(lam[r]);
+    for (int64_t j = 0; j < d_; ++j) scal[j * rank + r] = vt[r * d_ + j] / stdv[j] / s;
+  }
+  // X2 = diag(sqrt(n p fac)) (means - xbar) scalings      [K x rank]   (device GEMM)
+  std::vector<double> mcw(static_cast<size_t>(kk) * d_), mc(static_cast<size_t>(kk) * d_);
+  for (int64_t c = 0; c < kk; ++c) {
+    const double w = std::sqrt(static_cast<double>(n) * pri[c] * fac);
+    for (int64_t j = 0; j < d_; ++j) {
+      mc[c * d_ + j] = h_means[c * d_ + j] - xbar[j];
+      mcw[c * d_ + j] = w * mc[c * d_ + j];
+    }
+  }
+  DevBuf<double> dmcw(kk * d_), dmc(kk * d_), dscal(d_ * rank), dx2(kk * rank), dg2(rank * rank);
+  PB_CUDA(cudaMemcpyAsync(dmcw.get(), mcw.data(), kk * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(dmc.get(), mc.data(), kk * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(dscal.get(), scal.data(), d_ * rank * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  gemm_f64(ctx, false, false, kk, rank, d_, 1.0, dmcw.get(), d_, dscal.get(), rank, 0.0, dx2.get(), rank);
+  gemm_f64(ctx, true, false, rank, rank, kk, 1.0, dx2.get(), rank, dx2.get(), rank, 0.0, dg2.get(), rank);   // X2^T X2
+  DevBuf<double> dvt2(rank * rank), dlam2(rank);
+  eig_sym_jacobi(ctx, dg2.get(), rank, nullptr, dlam2.get(), dvt2.get(), ew, nullptr);
+  std::vector<double> lam2(rank);
+  PB_CUDA(cudaMemcpyAsync(lam2.data(), dlam2.get(), rank * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  const double s0 = std::sqrt(lam2[0]);
+  int64_t rank2 = 0;
+  for (int64_t i = 0; i < rank; ++i) if (std::sqrt(lam2[i]) > tol * s0) ++rank2;   // lda.py:212
+  PB_CHECK(rank2 > 0, kValueError, "lda_fit: between-class scatter has rank 0");
+  // _scalings = scalings V2[:, :rank2]  (rows of dvt2 are eigenvectors) -> [d x rank2]
+  DevBuf<double> dscal2(d_ * rank2), dcoefp(kk * rank2), dcoef(kk * d_);
+  gemm_f64(ctx, false, true, d_, rank2, rank, 1.0, dscal.get(), rank, dvt2.get(), rank, 0.0, dscal2.get(), rank2);
+  // coef_proj = (means - xbar) _scalings ; coef = coef_proj _scalings^T
+  gemm_f64(ctx, false, false, kk, rank2, d_, 1.0, dmc.get(), d_, dscal2.get(), rank2, 0.0, dcoefp.get(), rank2);
+  gemm_f64(ctx, false, true, kk, d_, rank2, 1.0, dcoefp.get(), rank2, dscal2.get(), rank2, 0.0, dcoef.get(), d_);
+  std::vector<double> coefp(static_cast<size_t>(kk) * rank2);
+  h_coef.resize(static_cast<size_t>(kk) * d_);
+  PB_CUDA(cudaMemcpyAsync(coefp.data(), dcoefp.get(), kk * rank2 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(h_coef.data(), dcoef.get(), kk * d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  h_intercept.resize(kk);
+  h_classes.resize(kk);
+  for (int64_t c = 0; c < kk; ++c) {
+    double s = 0.0;
+    for (int64_t r = 0; r < rank2; ++r) s += coefp[c * rank2 + r] * coefp[c * rank2 + r];
+    double dot = 0.0;
+    for (int64_t j = 0; j < d_; ++j) dot += xbar[j] * h_coef[c * d_ + j];
+    h_intercept[c] = -0.5 * s + std::log(pri[c]) - dot;
+    h_classes[c] = static_cast<int64_t>(h_keys[c] ^ (1ull << 63));
+  }
+  k = kk;
+  d = d_;
+  refresh_operands();
+}
+
+void LdaEngine::predict(const void* x, int64_t nt, int64_t d_, int64_t ldx, int dtype, int loc, int log_proba,
+                        float* out, int64_t ldo, int out_loc) {
+  PB_CHECK(ready, kNotFitted, "This LDA instance is not fitted yet");
+  if (d_ != d)
+    throw Error(kValueError, "X has " + std::to_string(d_) + " features per sample; expecting " + std::to_string(d));
+  PB_CHECK(ldo >= k, kInvalidArg, "lda_predict: output pitch too small");
+  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+  if (nt == 0) return;
+  const bool is_f32 = dtype == 1;
+  const size_t es = is_f32 ? 4 : 8;
+  const int64_t ldo_dev = out_loc == 1 ? ldo : round_up(k, 4);
+  // row chunks keep the staging buffers bounded (the full 1M x 5k fp32 grid is 20 GB)
+  int64_t chunk = nt;
+  if (out_loc == 0 || loc == 0 || precision == 1) {
+    const int64_t budget = (precision == 1 ? (256ll << 20) : (1ll << 30)) / 4;
+    chunk = std::min<int64_t>(nt, std::max<int64_t>(128, (budget / ldo_dev) / 128 * 128));
+  }
+  const int64_t col_ld = round_up(k, 32);
+  for (int64_t r0 = 0; r0 < nt; r0 += chunk) {
+    const int64_t rows = std::min(chunk, nt - r0);
+    const void* xd;
+    int64_t ld;
+    if (loc == 0) {
+      ws_in.reserve(static_cast<size_t>(rows) * d * es);
+      PB_CUDA(cudaMemcpy2DAsync(ws_in.get(), d * es, static_cast<const uint8_t*>(x) + r0 * ldx * es, ldx * es, d * es,
+                                rows, cudaMemcpyHostToDevice, ctx.stream));
+      xd = ws_in.get();
+      ld = d;
+    } else {
+      xd = static_cast<const uint8_t*>(x) + r0 * ldx * es;
+      ld = ldx;
+    }
+    float* dst = out_loc == 1 ? out + r0 * ldo : nullptr;
+    if (out_loc == 0) {
+      ws_out[0].reserve(static_cast<size_t>(rows) * ldo_dev);
+      dst = ws_out[0].get();
+    }
+    if (precision == 1) {
+      ws_gram.reserve(static_cast<size_t>(rows) * (d + k));
+      double* xf = ws_gram.get();
+      double* z = xf + rows * d;
+      convert_to_f64(ctx, xd, is_f32, rows, d, ld, xf, d);
+      gemm_f64(ctx, false, true, rows, k, d, 1.0, xf, d, coef.get(), d, 0.0, z, k);
+      lda_epilogue_f64_kernel<<<static_cast<unsigned>(rows), 256, 0, ctx.stream>>>(z, rows, k, intercept.get(),
+                                                                                  log_proba, dst, ldo_dev);
+      PB_CUDA(cudaGetLastError());
+      ctx.count_launch();
+    } else {
+      split_rows(ctx, xd, is_f32, rows, d, ld, nullptr, nullptr, nullptr, ws_x);
+      GemmEpilogue epi;
+      epi.col_add = intercept_f32.get();
+      epi.col_ld = col_ld;
+      if (log_proba) {
+        // pass 1: online (max, sum exp) per row and column tile, nothing stored
+        const int n_tiles = static_cast<int>(ceil_div(k, k >= 256 ? 256 : round_up(k, 16)));
+        ws_lmax.reserve(static_cast<size_t>(rows) * n_tiles);
+        ws_lsum.reserve(static_cast<size_t>(rows) * n_tiles);
+        ws_neglse.reserve(rows);
+        GemmEpilogue e1 = epi;
+        e1.lse_max = ws_lmax.get();
+        e1.lse_sum = ws_lsum.get();
+        gemm_bf16x3(ctx, ws_x.view(), coef_split.view(), rows, k, d, e1);
+        lse_combine(ctx, ws_lmax.get(), ws_lsum.get(), rows, n_tiles, ws_neglse.get());
+        epi.row_add = ws_neglse.get();     // pass 2 recomputes the tile and stores z - lse
+      }
+      epi.out = dst;
+      epi.ldo = ldo_dev;
+      gemm_bf16x3(ctx, ws_x.view(), coef_split.view(), rows, k, d, epi);
+    }
+    if (out_loc == 0) {
+      PB_CUDA(cudaMemcpy2DAsync(out + r0 * ldo, ldo * sizeof(float), dst, ldo_dev * sizeof(float), k * sizeof(float),
+                                rows, cudaMemcpyDeviceToHost, ctx.stream));
+    }
+  }
+  ctx.sync();
+}
+
+}  // namespace pb

@@ -1,0 +1,109 @@
+// Launch wrappers of the SIMT (HBM-bound / latency-bound) kernels of the PLDA + LDA path.
+// Kernel numbering follows SURVEY.md section 8a (K1..K9).
+#pragma once
+
+#include "runtime.h"
+
+namespace pb {
+
+// ---- generic operand producers ------------------------------------------------ //
+// out(hi,lo)[r, c] = split( (in[r, c] - sub[c]) * col_scale[c] * row_scale[r] ), zero padded to ld.
+// in is fp64 (is_f32 = false) or fp32, row-major with pitch ld_in.  Null sub/col_scale/row_scale = identity.
+void split_rows(Context& ctx, const void* in, bool is_f32, int64_t rows, int64_t cols, int64_t ld_in,
+                const double* sub, const double* col_scale, const double* row_scale, SplitBuf& out);
+
+// out[r,c] = (double)in[r,c] - sub[c]   (sub may be null)
+void convert_to_f64(Context& ctx, const void* in, bool is_f32, int64_t rows, int64_t cols, int64_t ld_in, double* out,
+                    int64_t ld_out, const double* sub = nullptr);
+
+// ---- scoring (K6 operand prep; reference: Plda::LogLikelihoodRatio via src/pldamodule.cpp:235,266) ---- //
+// Enrol side: L = E * (a/v) (per-row n_e), row_term[e] = c(n_e) - 1/2 sum a^2/v e^2.
+// enrol is fp64/fp32 [ne x d]; counts int32 [ne] (device); psi fp64 [d] (device).
+// Writes the split operand (if l_out), the fp64 operand (if l_f64) and row terms (fp32 and/or fp64).
+void score_prep_enrol(Context& ctx, const void* enrol, bool is_f32, int64_t ne, int64_t d, int64_t ld,
+                      const int32_t* counts, const double* psi, SplitBuf* l_out, double* l_f64, float* row_term,
+                      double* row_term_f64);
+// Test side: R = T (split), col_term[g][t] = sum_i q_i(n_g) t_i^2 for each distinct enrol count n_g.
+// group_counts int32 [g] (device).  col_term pitch col_ld (floats, zero padded).
+void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, int64_t d, int64_t ld,
+                     const int32_t* group_counts, int ngroups, const double* psi, SplitBuf* r_out, float* col_term,
+                     int64_t col_ld, double* col_term_f64);
+// exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
+void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
+                        const double* col_term, int64_t col_ld, const int32_t* grp, const float* zmean,
+                        const float* zinv, float* out, int64_t ldo, double* rsum, double* rsq);
+// z-norm moments -> mean / population std (src/pldamodule.cpp:240-253)
+void znorm_finalize(Context& ctx, const double* rsum, const double* rsq, int64_t ne, int64_t m, float* zmean,
+                    float* zinv, double* mean_out, double* std_out);
+
+// ---- label segmentation (K1) + segmented sums (K2/K4) --------------------------- //
+struct Segments {
+  DevBuf<int32_t> order;       // [n] row index of sorted position p
+  DevBuf<int32_t> seg_of_pos;  // [n] segment id of sorted position p
+  DevBuf<uint64_t> seg_label;  // [nseg] label value (ascending)
+  DevBuf<int32_t> seg_start;   // [nseg+1] CSR offsets into the sorted order
+  int64_t n = 0;
+  int64_t nseg = 0;
+  // scratch
+  DevBuf<uint64_t> keys_in, keys_out;
+  DevBuf<int32_t> vals_in, flags;
+  DevBuf<uint8_t> cub_tmp;
+};
+// labels: uint64 [n] on device.  Synchronises once (to learn nseg).
+void build_segments(Context& ctx, const uint64_t* labels_dev, int64_t n, Segments& seg);
+// sums[seg, :] = sum of rows of that segment (fp64 accumulate); x fp64/fp32 [n x d]
+void segment_sums(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg, double* sums);
+// means = sums / count  (in place), counts_out int32 [nseg]
+void segment_finalize_means(Context& ctx, double* sums, int64_t d, const Segments& seg, int32_t* counts_out);
+
+// ---- transform (K5 epilogue; reference: Plda::TransformIvector, src/pldamodule.cpp:171,224) ---- //
+// y[r,:] *= sqrt(dim / sum_i y_i^2/(psi_i + 1/n_r)); y fp32 [rows x ld] from the tensor GEMM (or fp64 exact),
+// writes fp64 (and/or fp32) normalised rows.  dim = number of columns used (targetdim semantics: first `dim` rows of A).
+void length_normalise(Context& ctx, const void* y, bool y_is_f32, int64_t rows, int64_t dim, int64_t ld_y,
+                      const double* psi, const int32_t* counts, int32_t const_count, double* out64, int64_t ld64,
+                      float* out32, int64_t ld32);
+
+// ---- fit: stats (K3 operand) ------------------------------------------------------ //
+// Writes the centred, 1/sqrt(n_s)-scaled rows TRANSPOSED as a split operand [d x npad] (K-major in the
+// row index, which is the SYRK reduction axis): xt[c, p] = (x[order[p], c] - mean[seg(p), c]) / sqrt(n_seg).
+void center_scale_split_t(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
+                          const double* means, bool scale_by_count, SplitBuf& xt);
+// exact mode: same rows, fp64, not transposed [n x d]
+void center_scale_f64(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
+                      const double* means, bool scale_by_count, double* out);
+// sum_out[c] = sum_s w_s * means[s,c] with w_s = 1/n_s; class_weight = sum_s w_s  (PldaStats::AddSamples)
+void class_weighted_sum(Context& ctx, const double* means, const int32_t* counts, int64_t k, int64_t d,
+                        double* sum_out, double* class_weight_out);
+
+// ---- EM (K7) ----------------------------------------------------------------------- //
+// From U = (M - mu) A^T [k x d] build the two weighted SYRK operands (transposed, split) and diagonal terms:
+//   r = psi/(1+n psi), g = n r;  P = sqrt(w) g u;  Q = sqrt(w n) (1-g) u;  db = sum_s w r;  dw = sum_s w n r
+void em_posterior_t(Context& ctx, const float* u, int64_t ldu, int64_t k, int64_t d, const int32_t* counts,
+                    const double* psi, SplitBuf& pt, SplitBuf& qt, double* db, double* dw);
+void em_posterior_f64(Context& ctx, const double* u, int64_t k, int64_t d, const int32_t* counts, const double* psi,
+                      double* p, double* q, double* db, double* dw);
+// out = (base? base:0) + scale * x ; adds diag (if diag) before scaling:  out = base + scale*(x + diag(dg))
+void add_diag_scale(Context& ctx, double* x, const double* dg, int64_t d, double scale, const double* base);
+void set_identity(Context& ctx, double* a, int64_t d);
+
+// ---- d x d fp64 factorizations (K8) ------------------------------------------------- //
+// In-place lower Cholesky of a (row-major, ld = d); upper triangle zeroed.  *info (device int) = 0 or failing column+1.
+void cholesky_lower(Context& ctx, double* a, int64_t d, int* info_dev);
+// inv = L^-1 (lower triangular), row-major
+void tri_inverse_lower(Context& ctx, const double* l, double* inv, int64_t d);
+// Symmetric eigendecomposition by one-sided (Hestenes) Jacobi, cooperative grid kernel.
+//   in : b (d x d symmetric PSD-ish), v0_t = optional warm-start orthogonal basis (ROWS are the vectors), may be null
+//   out: evals (descending, floored at 0), evecs_t (d x d row-major, ROW p = eigenvector of the p-th largest value)
+struct EigWork {
+  DevBuf<double> g, v, lam, tmp;
+  DevBuf<int> flags;
+  DevBuf<int32_t> perm;
+};
+void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t, double* evals, double* evecs_t,
+                    EigWork& work, int* sweeps_out);
+
+// ---- LDA ----------------------------------------------------------------------------- //
+// log-softmax finalisation: lse[m] from per-tile (max,sum) partials
+void lse_combine(Context& ctx, const float* lmax, const float* lsum, int64_t m, int n_tiles, float* neg_lse);
+
+}  // namespace pb

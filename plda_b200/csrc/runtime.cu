@@ -1,0 +1,111 @@
+// Context lifetime + the small generic kernels every path shares (operand splitting,
+// fp64 SIMT GEMM used for d x d algebra and as the exact-precision mode).
+#include "runtime.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace pb {
+
+Context::Context(int dev) : device(dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    throw Error(kCudaError, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                "); plda_b200 has no CPU fallback");
+  }
+  PB_CHECK(dev >= 0 && dev < count, kInvalidArg, "device index out of range");
+  PB_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  PB_CHECK(prop.major == 10, kCudaError,
+           std::string("plda_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
+               std::to_string(prop.minor));
+  num_sms = prop.multiProcessorCount;
+  PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const char* epi = getenv("PLDA_B200_EPI");
+  epi_direct = (epi != nullptr && strcmp(epi, "direct") == 0);
+}
+
+Context::~Context() {
+  if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------- //
+// fp64 SIMT GEMM (64x64x16 tiles, 4x4 register micro-tile)
+// ------------------------------------------------------------------------- //
+namespace {
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_f64_kernel(int m, int n, int k, double alpha, const double* __restrict__ a, long long lda,
+                const double* __restrict__ b, long long ldb, double beta, double* __restrict__ c, long long ldc) {
+  __shared__ double sa[16][64 + 1];
+  __shared__ double sb[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += 16) {
+    // A tile: element (mm, kk) = TA ? a[kk*lda + mm] : a[mm*lda + kk]
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int mm, kk;
+      if (TA) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      double v = 0.0;
+      if (gm < m && gk < k) v = TA ? a[gk * lda + gm] : a[gm * lda + gk];
+      sa[kk][mm] = v;
+    }
+    // B tile: element (kk, nn) = TB ? b[nn*ldb + kk] : b[kk*ldb + nn]
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int nn, kk;
+      if (TB) { kk = i & 15; nn = i >> 4; } else { nn = i & 63; kk = i >> 6; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      double v = 0.0;
+      if (gn < n && gk < k) v = TB ? b[gn * ldb + gk] : b[gk * ldb + gn];
+      sb[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double ra[4], rb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ra[i] = sa[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = sb[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(ra[i], rb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty + 16 * i;
+    if (gm >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx + 16 * j;
+      if (gn >= n) continue;
+      double* p = c + gm * ldc + gn;
+      *p = beta == 0.0 ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*p);
+    }
+  }
+}
+
+}  // namespace
+
+void gemm_f64(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a,
+              int64_t lda, const double* b, int64_t ldb, double beta, double* c, int64_t ldc) {
+  PB_CHECK(m > 0 && n > 0 && k > 0, kInvalidArg, "gemm_f64: empty problem");
+  dim3 grid(static_cast<unsigned>(ceil_div(n, 64)), static_cast<unsigned>(ceil_div(m, 64)));
+  const int mi = static_cast<int>(m), ni = static_cast<int>(n), ki = static_cast<int>(k);
+  if (ta && tb) gemm_f64_kernel<true, true><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
+  else if (ta) gemm_f64_kernel<true, false><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
+  else if (tb) gemm_f64_kernel<false, true><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
+  else gemm_f64_kernel<false, false><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+}  // namespace pb

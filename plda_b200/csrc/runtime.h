@@ -1,0 +1,138 @@
+// Host-side runtime shared by all translation units: device buffers, the per-handle
+// context (device, stream, SM count, launch counter), TMA descriptor encoding and the
+// launch wrappers of every kernel family.  No torch types anywhere: the boundary above
+// this is the C ABI in include/plda_b200.h.
+#pragma once
+
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------- //
+// RAII device buffer
+// ------------------------------------------------------------------------- //
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) n = 1;
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T)));
+    n_ = n;
+  }
+  // grow-only (contents not preserved)
+  void reserve(size_t n) { if (n > n_) alloc(n); }
+  void release() { if (p_) { cudaFree(p_); p_ = nullptr; n_ = 0; } }
+  T* get() const { return p_; }
+  size_t size() const { return n_; }
+  void zero(cudaStream_t s) { PB_CUDA(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s)); }
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+// ------------------------------------------------------------------------- //
+// Context
+// ------------------------------------------------------------------------- //
+struct Context {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;     // launching stream (owned unless external)
+  bool owns_stream = true;
+  std::atomic<long long> launches{0};   // number of OUR kernels launched (bench "gpu_launches")
+  bool epi_direct = false;           // debug: epilogue stores straight from registers (env PLDA_B200_EPI=direct)
+  explicit Context(int dev);
+  ~Context();
+  void sync() { PB_CUDA(cudaStreamSynchronize(stream)); }
+  void count_launch(int n = 1) { launches.fetch_add(n, std::memory_order_relaxed); }
+};
+
+// Encode a 2-D row-major tensor map.  inner = contiguous dimension (elements).
+// swizzle128: box inner extent must be exactly 128 bytes.
+enum class TmaType { BF16, F32 };
+void encode_tmap_2d(CUtensorMap* out, TmaType type, const void* base, uint64_t inner, uint64_t outer,
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
+// ------------------------------------------------------------------------- //
+// Split-bf16 operand: a logical [rows x k] matrix stored K-major as two bf16
+// planes (hi, lo), each [rows x ld] with ld % 8 == 0 and columns k..ld-1 zero.
+// ------------------------------------------------------------------------- //
+struct SplitOperand {
+  const __nv_bfloat16* hi = nullptr;
+  const __nv_bfloat16* lo = nullptr;
+  int64_t rows = 0;
+  int64_t k = 0;      // logical reduction length
+  int64_t ld = 0;     // elements per row in memory (>= round_up(k,16))
+};
+
+struct SplitBuf {           // owning version
+  DevBuf<__nv_bfloat16> hi, lo;
+  int64_t rows = 0, k = 0, ld = 0;
+  void reserve(int64_t r, int64_t kk) {
+    rows = r; k = kk; ld = round_up(kk, 16);
+    size_t n = static_cast<size_t>(r > 0 ? r : 1) * ld;
+    hi.reserve(n); lo.reserve(n);
+  }
+  SplitOperand view() const { return SplitOperand{hi.get(), lo.get(), rows, k, ld}; }
+};
+
+// Epilogue of the tensor-core GEMM:  v = acc[m,n]
+//   + row_add[m]                      (if row_add)
+//   + col_add[grp[m]*col_ld + n]      (if col_add; grp==nullptr -> group 0)
+//   v = (v - zmean[m]) * zinv[m]      (if zmean)
+// then either stored to out[m*ldo+n] (fp32) and/or reduced per row into
+// rsum[m] += v, rsq[m] += v*v (fp64 atomics; for z-norm moments / log-sum-exp passes).
+struct GemmEpilogue {
+  float* out = nullptr;
+  int64_t ldo = 0;
+  const float* row_add = nullptr;
+  const float* col_add = nullptr;
+  const int32_t* grp = nullptr;
+  int64_t col_ld = 0;
+  const float* zmean = nullptr;
+  const float* zinv = nullptr;
+  double* rsum = nullptr;
+  double* rsq = nullptr;
+  // online log-sum-exp per row over the columns (LDA): rmax/rsumexp are [M x n_tiles]
+  float* lse_max = nullptr;
+  float* lse_sum = nullptr;
+};
+
+// C[M,N] = A[M,K] * B[N,K]^T with bf16x3 split operands on tcgen05 (fp32 TMEM accumulate).
+// ksplit > 1: reduction axis split into ksplit chunks, partial tiles written to
+// `partial` ([ksplit][Mpad][Npad] fp32, Mpad = round_up(M,128), Npad = round_up(N,4)) and
+// the caller reduces them (reduce_partials_f64).
+void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
+                 const GemmEpilogue& epi);
+void gemm_bf16x3_splitk(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
+                        int ksplit, float* partial);
+int choose_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k);
+// number of partial planes gemm_bf16x3_splitk actually writes for a requested ksplit
+int effective_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k, int ksplit);
+// out[m*ldo+n] = alpha * sum_s partial[s][m][n]  (+ beta * out) in fp64; optional symmetrise
+void reduce_partials_f64(Context& ctx, const float* partial, int ksplit, int64_t m, int64_t n, double* out,
+                         int64_t ldo, double alpha, bool symmetrise);
+
+// Exact-mode / cross-check fp64 SIMT GEMM:  C = alpha * op(A) * op(B) + beta * C, row-major.
+//   ta: A is [K x M] (read transposed) else [M x K];  tb: B is [N x K] (i.e. C = A*B^T) else [K x N].
+void gemm_f64(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a,
+              int64_t lda, const double* b, int64_t ldb, double beta, double* c, int64_t ldc);
+
+}  // namespace pb

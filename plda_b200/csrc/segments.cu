@@ -1,0 +1,294 @@
+// K1 (label segmentation) and K2/K4 (per-speaker segmented sums), plus the centred /
+// scaled operand producers of the scatter SYRK (K3's input).
+//
+// Reference behaviour replaced: the std::set / std::vector bucketing of
+// src/pldamodule.cpp:76-92 (fit) and the std::map accumulation of :147-156 (transform).
+// Labels are 8 bytes per row against d*8 bytes of features, so the label sort uses the
+// toolkit's cub::DeviceRadixSort; everything touching the feature rows is hand-written.
+#include <cub/cub.cuh>
+
+#include "kernels.h"
+
+namespace pb {
+namespace {
+
+__global__ void iota_kernel(int32_t* __restrict__ v, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) v[i] = static_cast<int32_t>(i);
+}
+
+__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, long long n, int32_t* __restrict__ flags) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// seg_of_pos = inclusive_scan(flags) - 1 (done in place by the caller via cub); this scatters the heads.
+__global__ void scatter_heads_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ seg_of_pos,
+                                     long long n, uint64_t* __restrict__ seg_label, int32_t* __restrict__ seg_start,
+                                     long long nseg) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int32_t s = seg_of_pos[i];
+  if (i == 0 || seg_of_pos[i - 1] != s) {
+    seg_label[s] = keys[i];
+    seg_start[s] = static_cast<int32_t>(i);
+  }
+  if (i == n - 1) seg_start[nseg] = static_cast<int32_t>(n);
+}
+
+__global__ void dec_kernel(int32_t* __restrict__ v, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) v[i] -= 1;
+}
+
+// Balanced segmented sum: each warp owns kRowsPerWarp consecutive SORTED positions, keeps a running
+// fp64 partial per column in registers and flushes it with atomicAdd at every segment change.
+// Work is independent of the segment-size distribution (2 speakers or 50k speakers).
+constexpr int kRowsPerWarp = 32;
+constexpr int kMaxColsPerLane = 32;   // d <= 1024
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_sums_kernel(const T* __restrict__ x, int d, long long ld, const int32_t* __restrict__ order,
+                    const int32_t* __restrict__ seg_of_pos, long long n, double* __restrict__ sums) {
+  const long long warp = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long p0 = warp * kRowsPerWarp;
+  if (p0 >= n) return;
+  const long long p1 = min(p0 + kRowsPerWarp, n);
+  const int ncol = (d + 31) >> 5;
+  double acc[kMaxColsPerLane];
+#pragma unroll
+  for (int j = 0; j < kMaxColsPerLane; ++j) acc[j] = 0.0;
+  int cur = seg_of_pos[p0];
+  for (long long p = p0; p < p1; ++p) {
+    const int s = seg_of_pos[p];
+    if (s != cur) {
+#pragma unroll
+      for (int j = 0; j < kMaxColsPerLane; ++j) {
+        if (j < ncol) {
+          const int c = lane + 32 * j;
+          if (c < d) atomicAdd(sums + static_cast<long long>(cur) * d + c, acc[j]);
+          acc[j] = 0.0;
+        }
+      }
+      cur = s;
+    }
+    const T* row = x + static_cast<long long>(order[p]) * ld;
+#pragma unroll
+    for (int j = 0; j < kMaxColsPerLane; ++j) {
+      if (j < ncol) {
+        const int c = lane + 32 * j;
+        if (c < d) acc[j] += static_cast<double>(row[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxColsPerLane; ++j) {
+    if (j < ncol) {
+      const int c = lane + 32 * j;
+      if (c < d) atomicAdd(sums + static_cast<long long>(cur) * d + c, acc[j]);
+    }
+  }
+}
+
+__global__ void finalize_means_kernel(double* __restrict__ sums, int d, const int32_t* __restrict__ seg_start,
+                                      long long nseg, int32_t* __restrict__ counts) {
+  const long long s = blockIdx.x;
+  const int cnt = seg_start[s + 1] - seg_start[s];
+  const double inv = 1.0 / static_cast<double>(cnt);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) sums[s * d + c] *= inv;
+  if (threadIdx.x == 0 && counts) counts[s] = cnt;
+}
+
+// Transposing producer: tile of 32 sorted positions x 32 columns through smem so that both the gathered
+// row reads (along d) and the transposed split-bf16 writes (along the position axis) are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+center_scale_split_t_kernel(const T* __restrict__ x, int d, long long ld, const int32_t* __restrict__ order,
+                            const int32_t* __restrict__ seg_of_pos, const int32_t* __restrict__ seg_start,
+                            long long n, const double* __restrict__ means, int scale_by_count,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ld_out) {
+  __shared__ float s_hi[32][33];
+  __shared__ float s_lo[32][33];
+  const long long p0 = blockIdx.x * 32ll;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const long long p = p0 + i;
+    const int c = c0 + tx;
+    double v = 0.0;
+    if (p < n && c < d) {
+      const int s = seg_of_pos[p];
+      const double sc = scale_by_count ? rsqrt(static_cast<double>(seg_start[s + 1] - seg_start[s])) : 1.0;
+      v = (static_cast<double>(x[static_cast<long long>(order[p]) * ld + c]) - means[static_cast<long long>(s) * d + c]) * sc;
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    s_hi[i][tx] = __bfloat162float(h);
+    s_lo[i][tx] = __bfloat162float(l);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long p = p0 + tx;
+    if (c < d && p < ld_out) {
+      hi[c * ld_out + p] = __float2bfloat16_rn(s_hi[tx][i]);
+      lo[c * ld_out + p] = __float2bfloat16_rn(s_lo[tx][i]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void center_scale_f64_kernel(const T* __restrict__ x, int d, long long ld, const int32_t* __restrict__ order,
+                                        const int32_t* __restrict__ seg_of_pos, const int32_t* __restrict__ seg_start,
+                                        long long n, const double* __restrict__ means, int scale_by_count,
+                                        double* __restrict__ out) {
+  const long long p = blockIdx.x;
+  const int s = seg_of_pos[p];
+  const double sc = scale_by_count ? rsqrt(static_cast<double>(seg_start[s + 1] - seg_start[s])) : 1.0;
+  const T* row = x + static_cast<long long>(order[p]) * ld;
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    out[p * d + c] = (static_cast<double>(row[c]) - means[static_cast<long long>(s) * d + c]) * sc;
+}
+
+// sum_out[c] = sum_s means[s,c]/n_s ; class_weight = sum_s 1/n_s.  One block per 32 columns, strided over classes.
+__global__ void __launch_bounds__(256)
+class_weighted_sum_kernel(const double* __restrict__ means, const int32_t* __restrict__ counts, long long k, int d,
+                          double* __restrict__ sum_out, double* __restrict__ class_weight_out) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double acc = 0.0, wacc = 0.0;
+  for (long long s = ty; s < k; s += 8) {
+    const double w = 1.0 / static_cast<double>(counts[s]);
+    if (c < d) acc += w * means[s * d + c];
+    wacc += w;
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    if (c < d) sum_out[c] = t;
+  }
+  if (blockIdx.x == 0 && class_weight_out) {
+    __syncthreads();
+    red[ty][tx] = wacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[i][0];
+      *class_weight_out = t;
+    }
+  }
+}
+
+inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(ceil_div(n, t)); }
+
+}  // namespace
+
+void build_segments(Context& ctx, const uint64_t* labels_dev, int64_t n, Segments& seg) {
+  PB_CHECK(n > 0 && n < (1ll << 31), kInvalidArg, "labels: need 1 <= n < 2^31 rows");
+  seg.n = n;
+  seg.keys_out.reserve(n);
+  seg.vals_in.reserve(n);
+  seg.order.reserve(n);
+  seg.seg_of_pos.reserve(n);
+  iota_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.vals_in.get(), n);
+  ctx.count_launch();
+  size_t tmp_bytes = 0, tmp2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, labels_dev, seg.keys_out.get(), seg.vals_in.get(),
+                                  seg.order.get(), static_cast<int>(n), 0, 64, ctx.stream);
+  cub::DeviceScan::InclusiveSum(nullptr, tmp2, seg.seg_of_pos.get(), seg.seg_of_pos.get(), static_cast<int>(n),
+                                ctx.stream);
+  seg.cub_tmp.reserve(std::max(tmp_bytes, tmp2));
+  size_t avail = seg.cub_tmp.size();
+  PB_CUDA(cub::DeviceRadixSort::SortPairs(seg.cub_tmp.get(), avail, labels_dev, seg.keys_out.get(), seg.vals_in.get(),
+                                          seg.order.get(), static_cast<int>(n), 0, 64, ctx.stream));
+  head_flags_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.keys_out.get(), n, seg.seg_of_pos.get());
+  ctx.count_launch();
+  avail = seg.cub_tmp.size();
+  PB_CUDA(cub::DeviceScan::InclusiveSum(seg.cub_tmp.get(), avail, seg.seg_of_pos.get(), seg.seg_of_pos.get(),
+                                        static_cast<int>(n), ctx.stream));
+  int32_t last = 0;
+  PB_CUDA(cudaMemcpyAsync(&last, seg.seg_of_pos.get() + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  seg.nseg = last;
+  dec_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.seg_of_pos.get(), n);
+  seg.seg_label.reserve(seg.nseg);
+  seg.seg_start.reserve(seg.nseg + 1);
+  scatter_heads_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.keys_out.get(), seg.seg_of_pos.get(), n,
+                                                                  seg.seg_label.get(), seg.seg_start.get(), seg.nseg);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch(2);
+}
+
+void segment_sums(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg, double* sums) {
+  PB_CHECK(d <= 32 * kMaxColsPerLane, kInvalidArg, "feature dimension above 1024 is not supported");
+  PB_CUDA(cudaMemsetAsync(sums, 0, seg.nseg * d * sizeof(double), ctx.stream));
+  const long long warps = ceil_div(seg.n, kRowsPerWarp);
+  const unsigned blocks = static_cast<unsigned>(ceil_div(warps, 8));
+  if (is_f32)
+    segment_sums_kernel<float><<<blocks, 256, 0, ctx.stream>>>(static_cast<const float*>(x), static_cast<int>(d), ld,
+                                                               seg.order.get(), seg.seg_of_pos.get(), seg.n, sums);
+  else
+    segment_sums_kernel<double><<<blocks, 256, 0, ctx.stream>>>(static_cast<const double*>(x), static_cast<int>(d), ld,
+                                                                seg.order.get(), seg.seg_of_pos.get(), seg.n, sums);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void segment_finalize_means(Context& ctx, double* sums, int64_t d, const Segments& seg, int32_t* counts_out) {
+  finalize_means_kernel<<<static_cast<unsigned>(seg.nseg), 128, 0, ctx.stream>>>(sums, static_cast<int>(d),
+                                                                                 seg.seg_start.get(), seg.nseg,
+                                                                                 counts_out);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void center_scale_split_t(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
+                          const double* means, bool scale_by_count, SplitBuf& xt) {
+  // operand [d rows x n cols]; pad the reduction axis to a multiple of 64 and zero the tail
+  const int64_t npad = round_up(seg.n, 64);
+  xt.rows = d;
+  xt.k = seg.n;
+  xt.ld = npad;
+  xt.hi.reserve(static_cast<size_t>(d) * npad);
+  xt.lo.reserve(static_cast<size_t>(d) * npad);
+  dim3 grid(static_cast<unsigned>(npad / 32), static_cast<unsigned>(ceil_div(d, 32)));
+  if (is_f32)
+    center_scale_split_t_kernel<float><<<grid, 256, 0, ctx.stream>>>(
+        static_cast<const float*>(x), static_cast<int>(d), ld, seg.order.get(), seg.seg_of_pos.get(),
+        seg.seg_start.get(), seg.n, means, scale_by_count ? 1 : 0, xt.hi.get(), xt.lo.get(), npad);
+  else
+    center_scale_split_t_kernel<double><<<grid, 256, 0, ctx.stream>>>(
+        static_cast<const double*>(x), static_cast<int>(d), ld, seg.order.get(), seg.seg_of_pos.get(),
+        seg.seg_start.get(), seg.n, means, scale_by_count ? 1 : 0, xt.hi.get(), xt.lo.get(), npad);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void center_scale_f64(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
+                      const double* means, bool scale_by_count, double* out) {
+  if (is_f32)
+    center_scale_f64_kernel<float><<<static_cast<unsigned>(seg.n), 128, 0, ctx.stream>>>(
+        static_cast<const float*>(x), static_cast<int>(d), ld, seg.order.get(), seg.seg_of_pos.get(),
+        seg.seg_start.get(), seg.n, means, scale_by_count ? 1 : 0, out);
+  else
+    center_scale_f64_kernel<double><<<static_cast<unsigned>(seg.n), 128, 0, ctx.stream>>>(
+        static_cast<const double*>(x), static_cast<int>(d), ld, seg.order.get(), seg.seg_of_pos.get(),
+        seg.seg_start.get(), seg.n, means, scale_by_count ? 1 : 0, out);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void class_weighted_sum(Context& ctx, const double* means, const int32_t* counts, int64_t k, int64_t d,
+                        double* sum_out, double* class_weight_out) {
+  class_weighted_sum_kernel<<<static_cast<unsigned>(ceil_div(d, 32)), 256, 0, ctx.stream>>>(
+      means, counts, k, static_cast<int>(d), sum_out, class_weight_out);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+}  // namespace pb

@@ -1,0 +1,141 @@
+"""``LDA`` -- host-side mirror of the reference's ``liblda.LDA``
+(``python/liblda/lda.py:88-349``) with the arithmetic on the device behind the C ABI
+(``lda_*`` entry points of ``include/plda_b200.h``).
+
+Hot-path rows of SURVEY.md section 8 implemented here: ``fit`` with the default ``svd``
+solver (``lda.py:178-221``), ``decision_function`` (``:253-279``) and
+``predict_log_proba`` (``:306-325``).  ``predict_proba`` (``:281-304``) and ``transform``
+(``:328-349``, evident intent -- the reference's svd branch is unreachable) are derived
+from device outputs.  The ``lsqr`` / ``eigen`` solvers are "next" rows (section 8f) and
+raise NotImplementedError until they have device kernels -- no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class LDA(object):
+    def __init__(self, solver="svd", priors=None, device: int = 0, precision: str = "bf16x3"):
+        self.priors = priors
+        self.solver = solver
+        self._lib = _ffi.lib()
+        h = C.c_void_p()
+        _ffi.check(self._lib.lda_create(int(device), C.byref(h)))
+        self._h = h
+        code = {"bf16x3": _ffi.PREC_BF16X3, "fp64": _ffi.PREC_FP64}.get(precision)
+        if code is None:
+            raise ValueError("precision must be 'bf16x3' or 'fp64'")
+        _ffi.check(self._lib.lda_set_precision(self._h, code))
+        self._coef = None
+        self._intercept = None
+        self._classes = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.lda_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _ffi.check(self._lib.lda_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, features, labels):
+        """``LDA.fit`` (``lda.py:106-138``).  Returns None."""
+        if self.solver != "svd":
+            raise NotImplementedError("solver %r has no device kernel yet (SURVEY section 8f 'next'); use 'svd'"
+                                      % (self.solver,))
+        x, dtype = _ffi.as_matrix(np.asarray(features, dtype=np.float64) if np.asarray(features).dtype.kind != "f"
+                                  else features, "features")
+        y = np.asarray(labels)
+        if y.dtype.kind not in "iub":
+            raise ValueError("labels must be integers")
+        y = np.ascontiguousarray(y.astype(np.int64).reshape(-1))
+        n, d = x.shape
+        if y.shape[0] != n:
+            raise ValueError("labels and features disagree on the number of samples")
+        pri = None
+        if self.priors is not None:
+            pri = np.ascontiguousarray(self.priors, dtype=np.float64)
+        _ffi.check(self._lib.lda_fit_svd(self._h, _ffi.ptr(x), n, d, d, dtype, _ffi.HOST, _ffi.ptr(y), _ffi.ptr(pri),
+                                         0 if pri is None else pri.shape[0]))
+        k = C.c_int64()
+        dd = C.c_int64()
+        _ffi.check(self._lib.lda_num_classes(self._h, C.byref(k), C.byref(dd)))
+        self._coef = np.empty((k.value, dd.value))
+        self._intercept = np.empty(k.value)
+        self._classes = np.empty(k.value, dtype=np.int64)
+        _ffi.check(self._lib.lda_get_coef(self._h, _ffi.ptr(self._coef), _ffi.ptr(self._intercept),
+                                          _ffi.ptr(self._classes)))
+        if self.priors is None:
+            _, cnt = np.unique(y, return_counts=True)
+            self.priors = cnt / float(n)
+        else:
+            p = np.asarray(self.priors, dtype=np.float64)
+            self.priors = p / p.sum() if p.sum() != 1 else p
+        return None
+
+    def set_coef(self, coef, intercept):
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        intercept = np.ascontiguousarray(intercept, dtype=np.float64)
+        _ffi.check(self._lib.lda_set_coef(self._h, coef.shape[0], coef.shape[1], _ffi.ptr(coef), _ffi.ptr(intercept)))
+        self._coef, self._intercept = coef, intercept
+        self._classes = np.arange(coef.shape[0])
+
+    # ------------------------------------------------------------------ predict
+    def _predict(self, x, log_proba):
+        if self._coef is None:
+            raise ValueError("This %(name)s instance is not fitted yet" % {"name": type(self).__name__})
+        if hasattr(x, "is_cuda") and x.is_cuda:
+            import torch
+            if x.dtype not in (torch.float32, torch.float64):
+                raise ValueError("features must be float tensors")
+            if x.stride(1) != 1:
+                x = x.contiguous()
+            nt, d = x.shape
+            k = self._coef.shape[0]
+            ldo = (k + 3) // 4 * 4
+            buf = torch.empty((nt, ldo), dtype=torch.float32, device=x.device)
+            _ffi.check(self._lib.lda_predict(self._h, C.c_void_p(x.data_ptr()), nt, d, x.stride(0),
+                                             _ffi.F32 if x.dtype == torch.float32 else _ffi.F64, _ffi.DEVICE,
+                                             int(log_proba), C.c_void_p(buf.data_ptr()), ldo, _ffi.DEVICE))
+            return buf[:, :k]
+        xa = np.asarray(x)
+        if xa.dtype.kind != "f":
+            xa = xa.astype(np.float64)
+        xa, dtype = _ffi.as_matrix(xa, "sample")
+        nt, d = xa.shape
+        k = self._coef.shape[0]
+        out = np.empty((nt, k), dtype=np.float32)
+        _ffi.check(self._lib.lda_predict(self._h, _ffi.ptr(xa), nt, d, d, dtype, _ffi.HOST, int(log_proba),
+                                         _ffi.ptr(out), k, _ffi.HOST))
+        return out
+
+    def decision_function(self, X):
+        """``decision_function`` (``lda.py:253-279``): ``X coef^T + intercept`` (float32 out)."""
+        scores = self._predict(X, 0)
+        return scores.ravel() if scores.shape[1] == 1 else scores
+
+    def predict_log_proba(self, sample):
+        """``predict_log_proba`` (``lda.py:306-325``): row log-softmax of the decision values."""
+        return self._predict(sample, 1)
+
+    def predict_proba(self, sample):
+        """``predict_proba`` (``lda.py:281-304``): OvR sigmoid of the decision values."""
+        prob = np.asarray(self.decision_function(sample), dtype=np.float64)
+        prob = 1.0 / (1.0 + np.exp(-prob))
+        if len(self._classes) == 2:
+            return np.column_stack([1 - prob, prob])
+        return prob / prob.sum(axis=1).reshape((prob.shape[0], -1))
+
+    def predict(self, sample):
+        return self._classes[np.asarray(self.decision_function(sample)).argmax(axis=1)]

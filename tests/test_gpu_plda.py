@@ -1,0 +1,299 @@
+"""GPU parity tests of the PLDA hot path: the CUDA path (through the C ABI / the PLDA
+class) against the CPU fp64 oracle (oracle/kaldi_plda.py) on identical seeded inputs, plus
+the committed regression fixture and the reference's own test call sequences
+(tests/pldatest.py) as API-conformance tests.
+
+Tolerances (stated by BASELINE.json north_star: scores <= 1e-3 rel, EER identical):
+  * scores:   |d| <= 1e-3 * max(|s|, 1)            (SURVEY hard part 2)
+  * psi:      rel 1e-3 for the default bf16x3 mode, 1e-8 for the exact fp64 mode
+  * EER:      +-0.01 % absolute
+Never compare transform_ element-wise (eigenvector signs) -- compare psi, invariants, scores.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import kaldi_plda as kp
+
+pytestmark = pytest.mark.gpu
+
+
+def score_tol_ok(got, ref, tol=1e-3):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) <= tol
+
+
+def oracle_fit(x, labels, iters):
+    m = kp.MPlda()
+    m.fit(x, labels, iters)
+    return m
+
+
+def synth(d, counts, seed):
+    a_b = kp.two_cov_generator(d, seed=1234)
+    return kp.synth_speakers(a_b, counts, seed)
+
+
+@pytest.fixture(scope="module")
+def small_problem():
+    d = 40
+    rng = np.random.RandomState(3)
+    counts = rng.randint(2, 12, size=120)
+    x, labels, _ = synth(d, counts, 1234)
+    xe, le, _ = synth(d, rng.randint(1, 5, size=37), 1235)
+    xt, lt, _ = synth(d, [1] * 53, 1236)
+    bkg, _, _ = synth(d, [1] * 64, 1237)
+    return dict(d=d, x=x, labels=labels, xe=xe, le=le, xt=xt, lt=lt, bkg=bkg, iters=6)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "bf16x3"])
+def test_fit_matches_oracle(small_problem, precision):
+    from plda_b200 import PLDA
+    p = small_problem
+    ref = oracle_fit(p["x"], p["labels"], p["iters"])
+    g = PLDA(precision=precision)
+    assert g.fit(p["x"], p["labels"], p["iters"]) is None
+    mean, a, psi = g.get_model()
+    w, b = g.get_covariances()
+    rtol = 1e-8 if precision == "fp64" else 2e-3
+    assert np.allclose(mean, ref.plda.mean, rtol=1e-12, atol=1e-12)
+    assert np.allclose(psi, ref.plda.psi, rtol=rtol, atol=rtol * 1e-3)
+    est = ref.estimator
+    assert np.allclose(w, est.within_var, rtol=rtol, atol=rtol * np.abs(est.within_var).max())
+    assert np.allclose(b, est.between_var, rtol=rtol, atol=rtol * np.abs(est.between_var).max())
+    # invariants of the joint diagonalisation on the device model
+    d = p["d"]
+    assert np.allclose(a @ w @ a.T, np.eye(d), atol=1e-8)
+    assert np.allclose(a @ b @ a.T, np.diag(psi), atol=1e-8)
+    assert np.all(np.diff(psi) <= 0) and psi.min() >= 0
+
+
+@pytest.mark.parametrize("precision", ["fp64", "bf16x3"])
+def test_transform_and_scores_match_oracle(small_problem, precision):
+    from plda_b200 import PLDA
+    p = small_problem
+    ref = oracle_fit(p["x"], p["labels"], p["iters"])
+    g = PLDA(precision=precision)
+    g.fit(p["x"], p["labels"], p["iters"])
+    te_ref, tt_ref = ref.transform(p["xe"], p["le"]), ref.transform(p["xt"], p["lt"])
+    te, tt = g.transform(p["xe"], p["le"]), g.transform(p["xt"], p["lt"])
+    assert sorted(te) == sorted(te_ref) and sorted(tt) == sorted(tt_ref)
+    assert list(te) == sorted(te)       # std::map order (src/pldamodule.cpp:164)
+    for k in te:
+        assert te[k][0] == te_ref[k][0]
+        assert te[k][1].dtype == np.float64 and te[k][1].shape == (p["d"],)
+        # length normalisation invariant (Plda::GetNormalizationFactor)
+        n, y = te[k]
+        _, _, psi = g.get_model()
+        assert np.sum(y * y / (psi + 1.0 / n)) == pytest.approx(p["d"], rel=1e-5)
+    # pair API == oracle pair API (scores are invariant to eigenvector signs)
+    ek, tk = sorted(te), sorted(tt)
+    got = np.array([[g.score(k, te[k], tt[j]) for j in tk[:7]] for k in ek[:9]])
+    want = np.array([[ref.score(k, te_ref[k], tt_ref[j]) for j in tk[:7]] for k in ek[:9]])
+    assert score_tol_ok(got, want, 1e-3 if precision == "bf16x3" else 1e-6)
+    # grid API == oracle grid
+    e = np.stack([te[k][1] for k in ek])
+    n = np.array([te[k][0] for k in ek])
+    t = np.stack([tt[k][1] for k in tk])
+    grid = g.score_grid(e, n, t)
+    assert grid.dtype == np.float32 and grid.shape == (len(ek), len(tk))
+    e_ref = np.stack([te_ref[k][1] for k in ek])
+    t_ref = np.stack([tt_ref[k][1] for k in tk])
+    want_grid = kp.score_grid(ref.plda, e_ref, n, t_ref)
+    assert score_tol_ok(grid, want_grid, 1e-3 if precision == "bf16x3" else 1e-5)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "bf16x3"])
+def test_znorm_matches_oracle(small_problem, precision):
+    from plda_b200 import PLDA
+    p = small_problem
+    ref = oracle_fit(p["x"], p["labels"], p["iters"])
+    g = PLDA(precision=precision)
+    g.fit(p["x"], p["labels"], p["iters"])
+    te_ref, tt_ref = ref.transform(p["xe"], p["le"]), ref.transform(p["xt"], p["lt"])
+    te, tt = g.transform(p["xe"], p["le"]), g.transform(p["xt"], p["lt"])
+    assert g.norm(p["bkg"], te) is None
+    ref.norm(p["bkg"], te_ref)
+    ids, zm, zs = g.znorm_tables()
+    assert list(ids) == sorted(te)
+    tol = 1e-3 if precision == "bf16x3" else 1e-7
+    assert np.allclose(zm, [ref.meanz[k] for k in ids], rtol=tol, atol=tol)
+    assert np.allclose(zs, [ref.stdvz[k] for k in ids], rtol=tol, atol=tol)
+    ek, tk = sorted(te), sorted(tt)
+    got = np.array([[g.score(k, te[k], tt[j]) for j in tk[:5]] for k in ek[:6]])
+    want = np.array([[ref.score(k, te_ref[k], tt_ref[j]) for j in tk[:5]] for k in ek[:6]])
+    assert score_tol_ok(got, want, 2e-3 if precision == "bf16x3" else 1e-5)
+    # z-normalised grid
+    e = np.stack([te[k][1] for k in ek])
+    n = np.array([te[k][0] for k in ek])
+    t = np.stack([tt[k][1] for k in tk])
+    zgrid = g.score_grid(e, n, t, enrol_ids=np.array(ek, dtype=np.uint64))
+    raw = kp.score_grid(ref.plda, np.stack([te_ref[k][1] for k in ek]), n, np.stack([tt_ref[k][1] for k in tk]))
+    want_z = (raw - np.array([ref.meanz[k] for k in ek])[:, None]) / np.array([ref.stdvz[k] for k in ek])[:, None]
+    assert score_tol_ok(zgrid, want_z, 2e-3 if precision == "bf16x3" else 1e-4)
+    # a second norm() never overwrites (insert semantics, src/pldamodule.cpp:245,250)
+    g.norm(p["bkg"][:10], te)
+    ids2, zm2, _ = g.znorm_tables()
+    assert np.array_equal(zm, zm2)
+
+
+def test_regression_fixture(golden_dir):
+    from plda_b200 import PLDA
+    f = np.load(os.path.join(golden_dir, "plda_small.npz"))
+    g = PLDA()
+    g.fit(f["x"], f["labels"], int(f["iters"]))
+    _, _, psi = g.get_model()
+    assert np.allclose(psi, f["psi"], rtol=2e-3, atol=1e-6)
+    te, tt = g.transform(f["xe"], f["le"]), g.transform(f["xt"], f["lt"])
+    e = np.stack([te[k][1] for k in sorted(te)])
+    t = np.stack([tt[k][1] for k in sorted(tt)])
+    grid = g.score_grid(e, f["enrol_counts"], t)
+    assert score_tol_ok(grid, f["scores"])
+    g.norm(f["bkg"], te)
+    z = g.score_grid(e, f["enrol_counts"], t, enrol_ids=np.array(sorted(te), dtype=np.uint64))
+    assert score_tol_ok(z, f["zscores"], 2e-3)
+
+
+def test_config1_readme_shape():
+    """BASELINE configs[0]: 500x200 rand, 2 speakers, fit + 500x500 scores (README.md:52-57,99-113)."""
+    from plda_b200 import PLDA
+    rng = np.random.RandomState(0)
+    x = rng.rand(500, 200)
+    y = rng.randint(0, 2, 500).astype("uint")
+    ref = oracle_fit(x, y, 10)
+    g = PLDA()
+    assert g.fit(x, y, 10) is None
+    _, _, psi = g.get_model()
+    assert np.allclose(psi, ref.plda.psi, rtol=5e-3, atol=1e-6)
+    xe = rng.rand(500, 200)
+    xt = rng.rand(500, 200)
+    ids = np.arange(500, dtype="uint")
+    te, tt = g.transform(xe, ids), g.transform(xt, ids)
+    te_r, tt_r = ref.transform(xe, ids), ref.transform(xt, ids)
+    e = np.stack([te[k][1] for k in range(500)])
+    t = np.stack([tt[k][1] for k in range(500)])
+    grid = g.score_grid(e, np.ones(500, dtype=np.int32), t)
+    want = kp.score_grid(ref.plda, np.stack([te_r[k][1] for k in range(500)]), np.ones(500, dtype=np.int64),
+                         np.stack([tt_r[k][1] for k in range(500)]))
+    assert score_tol_ok(grid, want)
+    assert np.all((grid >= -100) & (grid <= 100))     # the reference's only assertion (tests/pldatest.py:33)
+
+
+def test_eer_matches_oracle():
+    """EER on synthetic target / non-target trials: GPU vs oracle within 0.01 % absolute."""
+    from plda_b200 import PLDA
+    d, k_train, k_eval = 64, 300, 200
+    a_b = kp.two_cov_generator(d, seed=1234)
+    x, labels, _ = kp.synth_speakers(a_b, [8] * k_train, seed=1234)
+    xe, le, z = kp.synth_speakers(a_b, [3] * k_eval, seed=1235)
+    rng = np.random.RandomState(1236)
+    xt = 0.5 + z @ a_b.T + rng.randn(k_eval, d)
+    ref = oracle_fit(x, labels, 10)
+    g = PLDA()
+    g.fit(x, labels, 10)
+    ids = np.arange(k_eval, dtype=np.uint64)
+    te, tt = g.transform(xe, le), g.transform(xt, ids)
+    te_r, tt_r = ref.transform(xe, le), ref.transform(xt, ids)
+    grid = g.score_grid(np.stack([te[k][1] for k in range(k_eval)]), np.full(k_eval, 3, dtype=np.int32),
+                        np.stack([tt[k][1] for k in range(k_eval)])).astype(np.float64)
+    want = kp.score_grid(ref.plda, np.stack([te_r[k][1] for k in range(k_eval)]), np.full(k_eval, 3),
+                         np.stack([tt_r[k][1] for k in range(k_eval)]))
+    assert score_tol_ok(grid, want)
+    mask = np.eye(k_eval, dtype=bool)
+    eer_g = kp.eer_percent(grid[mask], grid[~mask])
+    eer_r = kp.eer_percent(want[mask], want[~mask])
+    assert abs(eer_g - eer_r) <= 0.01
+
+
+def test_reference_call_sequence_pldatest():
+    """tests/pldatest.py:13-33 ported to py3 / uint labels: fit 2000x10 (10 speakers), transform 100 rows
+    into 10 models and 100 single-utterance tests, norm on 100 background rows, 10x100 scores in [-100, 100]."""
+    from plda_b200 import PLDA
+    rng = np.random.RandomState(42)
+    m = PLDA()
+    data = rng.rand(2000, 10)
+    labels = np.array([i % 10 for i in range(2000)], dtype="uint")
+    assert m.fit(data, labels) is None
+    enrol = rng.rand(100, 10)
+    transformed = m.transform(enrol, np.array([i % 10 for i in range(100)], dtype="uint"))
+    transformedtest = m.transform(rng.rand(100, 10), np.arange(100, dtype="uint"))
+    assert len(transformedtest) == 100 and len(transformed) == 10
+    m.norm(rng.rand(100, 10), transformed)
+    for model, modelvec in transformed.items():
+        for _, testvec in list(transformedtest.items())[:20]:
+            s = m.score(model, modelvec, testvec)
+            assert isinstance(s, float) and -100 <= s <= 100
+
+
+def test_error_behaviour():
+    """The reference's three ValueErrors (src/pldamodule.cpp:55-62, 83-86, 128-136)."""
+    from plda_b200 import PLDA
+    m = PLDA()
+    x = np.random.RandomState(0).rand(20, 4)
+    with pytest.raises(ValueError):
+        m.fit(x.astype(np.int32), np.zeros(20, dtype="uint"))
+    with pytest.raises(ValueError):
+        m.fit(x, np.zeros(20, dtype="uint"))                 # a single speaker
+    with pytest.raises(ValueError):
+        m.fit(x, np.array(["a"] * 20))
+    with pytest.raises(ValueError):
+        m.fit(x, -np.ones(20, dtype=np.int64))
+    with pytest.raises(ValueError):
+        m.transform(x, np.zeros(20, dtype="uint"))           # not fitted
+    m.fit(x, (np.arange(20) % 2).astype("uint"), 2)
+    with pytest.raises(ValueError):
+        m.transform(np.random.rand(5, 3), np.zeros(5, dtype="uint"))   # wrong dimension
+
+
+def test_edge_cases():
+    from plda_b200 import PLDA
+    rng = np.random.RandomState(1)
+    m = PLDA()
+    x = rng.rand(64, 8)
+    m.fit(x, (np.arange(64) % 4).astype("uint"), 3)
+    # non-dense, huge label values survive (the reference truncates to uint32, App. B -- not replicated)
+    labs = np.array([2 ** 40 + 5, 7, 2 ** 40 + 5, 7, 123456789012], dtype=np.uint64)
+    out = m.transform(rng.rand(5, 8), labs)
+    assert sorted(out) == [7, 123456789012, 2 ** 40 + 5]
+    assert out[7][0] == 2 and out[123456789012][0] == 1
+    # empty grid
+    g = m.score_grid(np.zeros((0, 8)), np.zeros(0, dtype=np.int32), rng.rand(3, 8))
+    assert g.shape == (0, 3)
+    # float32 input is a supported superset
+    out32 = m.transform(rng.rand(6, 8).astype(np.float32), np.arange(6, dtype="uint"))
+    assert len(out32) == 6
+    # ragged enrol counts in one grid (several count groups)
+    e = rng.randn(9, 8)
+    t = rng.randn(11, 8)
+    cnt = np.array([1, 2, 3, 1, 2, 3, 5, 5, 1], dtype=np.int32)
+    grid = m.score_grid(e, cnt, t)
+    ref = kp.Plda()
+    ref.mean, ref.transform, ref.psi = m.get_model()
+    ref.compute_derived_vars()
+    assert score_tol_ok(grid, kp.score_grid(ref, e, cnt, t))
+    # targetdim keeps the leading directions and renormalises with dim = targetdim
+    y5 = m.transform_batch(x[:4], targetdim=5)
+    assert y5.shape == (4, 5)
+    _, a, psi = m.get_model()
+    assert np.allclose(np.sum(y5 * y5 / (psi[:5] + 1.0), axis=1), 5.0, rtol=1e-5)
+
+
+def test_smoothing_mutates_model_like_reference():
+    from plda_b200 import PLDA
+    rng = np.random.RandomState(2)
+    x = rng.rand(200, 6)
+    y = (np.arange(200) % 5).astype("uint")
+    g = PLDA(precision="fp64")
+    g.fit(x, y, 4)
+    ref = oracle_fit(x, y, 4)
+    q = rng.rand(10, 6)
+    ql = np.arange(10, dtype="uint")
+    a = g.transform(q, ql, smoothing=0.5)
+    b = ref.transform(q, ql, smoothfactor=0.5)
+    _, _, psi = g.get_model()
+    assert np.allclose(psi, ref.plda.psi, rtol=1e-8)
+    s_g = g.score(0, a[0], a[1])
+    s_r = ref.score(0, b[0], b[1])
+    assert s_g == pytest.approx(s_r, rel=1e-5, abs=1e-5)
