@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200 (BASELINE.json):
+
+    PLDA trial-scores/sec (enrol x test LLR)  [+ EM-iters/sec reported beside it]
+
+Workload (config.workload): BASELINE configs[1] = "100k x 200 d-vectors, 1k speakers, 10 EM
+iters + 10k x 10k scoring grid on 1 x B200", synthetic two-covariance d-vectors.
+A *step* is one pass of the scoring hot path over one batch: the all-pairs LLR grid of
+10 000 enrol models (3 utterances each) x 10 000 test vectors (1e8 trials) per GPU.
+
+  value        trials/s, whole job, inputs (transformed vectors) resident in HBM, fp32 score
+               matrix sink in HBM, CUDA-event timed per step with an L2 flush between steps
+  e2e          same metric through the public API with HOST (pinned) buffers: host->device
+               copy of both vector sets and device->host copy of the fp32 score matrix inside
+               the timed region
+  roofline     the tcgen05 Gram kernel: algorithmic 2*d flop per trial / its CUDA-event time
+               (measured on the launching stream), against MEASURED_PEAKS.json bf16 burst peak
+  cpu_baseline the C restatement of the reference's per-pair loop (oracle/plda_ref.c) on a
+               bounded sub-grid, all host threads (N=1, rank 0 only)
+  em           EM iterations/s of plda.fit on the same config (stats pass / GetOutput excluded)
+
+N > 1 (torchrun): weak scaling -- every rank owns 10 000 enrol models, the test vectors are
+sharded, each step does ONE NCCL all-gather of the transformed test vectors and the local grid.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 200
+N_TRAIN, K_TRAIN, EM_ITERS = 100_000, 1_000, 10
+NE, NT, ENROL_UTTS = 10_000, 10_000, 3
+METRIC = "plda_trial_scores_per_sec"
+UNIT = "trials/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return dict(bf16_tflops=j.get("bf16_tflops", 1590.0), hbm_gbs=j.get("hbm_gbs", 6650.0), source="measured")
+    return dict(bf16_tflops=1590.0, hbm_gbs=6650.0, source="fallback")
+
+
+# --------------------------------------------------------------------------- #
+# synthetic data (numpy, seeded): x = 0.5 + A_b z_spk + e    
+# --------------------------------------------------------------------------- #
+def two_cov(d, seed=1234):
+    rng = np.random.RandomState(seed)
+    q, _ = np.linalg.qr(rng.randn(d, d))
+    spec = 2.0 * np.exp(-np.arange(d) / (0.15 * d))
+    return q * np.sqrt(spec)[None, :]
+
+
+def speakers(a_b, k, per, seed):
+    rng = np.random.RandomState(seed)
+    d = a_b.shape[0]
+    z = rng.randn(k, d)
+    labels = np.repeat(np.arange(k), per)
+    x = 0.5 + (z @ a_b.T)[labels] + rng.randn(k * per, d)
+    return x, labels.astype(np.uint64), z
+
+
+# --------------------------------------------------------------------------- #
+# clocks sampler (NVML) -- runs during the timed regions
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self.index = index
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+            return self
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- #
+# CPU reference arm (oracle C port) -- also the cpu_baseline leg of the main arm
+# --------------------------------------------------------------------------- #
+def cpu_reference_model():
+    """Fit the C2 model with the C restatement, timing the EM iterations (single thread, like Kaldi)."""
+    from oracle import c_ref
+    a_b = two_cov(D)
+    x, labels, _ = speakers(a_b, K_TRAIN, N_TRAIN // K_TRAIN, 1234)
+    t0 = time.perf_counter()
+    ref = c_ref.RefPlda(x, labels)
+    t_stats = time.perf_counter() - t0
+    n_it = 3
+    t0 = time.perf_counter()
+    for _ in range(n_it):
+        ref.em_iter()
+    t_em = time.perf_counter() - t0
+    mean, tr, psi = ref.output()
+    return dict(mean=mean, transform=tr, psi=psi, em_iters_per_sec=n_it / t_em, stats_s=t_stats, a_b=a_b)
+
+
+def cpu_grid_sample(psi, sub_ne, sub_nt, steps, warmup, threads=0):
+    from oracle import c_ref
+    rng = np.random.RandomState(7)
+    e = rng.randn(sub_ne, D)
+    t = rng.randn(sub_nt, D)
+    cnt = np.full(sub_ne, ENROL_UTTS, dtype=np.int32)
+    used = 1
+    for _ in range(warmup):
+        _, used = c_ref.score_grid(psi, e[:256], cnt[:256], t[:256], threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, used = c_ref.score_grid(psi, e, cnt, t, threads)
+    dt = time.perf_counter() - t0
+    return steps * sub_ne * sub_nt / dt, used, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import c_ref
+    c_ref.build()
+    model = cpu_reference_model()
+    sub = 2000
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    v, used, spp = cpu_grid_sample(model["psi"], sub, sub, steps, warm)
+    sample = "%dx%d sub-grid of the %dx%d grid per step (per-pair LogLikelihoodRatio loop), %d steps" % (
+        sub, sub, NE, NT, steps)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: 100k x 200 d-vectors, 1k speakers, 10 EM iters + 10k x 10k scoring grid",
+                   "d": D, "enrol": NE, "test": NT, "enrol_utts": ENROL_UTTS},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "em": {"em_iters_per_sec": model["em_iters_per_sec"], "cores": 1, "stats_pass_s": model["stats_s"],
+               "note": "oracle/plda_ref.c EstimateOneIter, single thread like Kaldi+ATLAS"},
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# main arm
+# --------------------------------------------------------------------------- #
+def pinned_array(lib, shape, dtype):
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    from plda_b200 import _ffi
+    _ffi.check(lib.plda_host_malloc_pinned(nbytes, C.byref(p)))
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def run_main(args):
+    import torch
+    import torch.distributed as dist
+    from plda_b200 import PLDA, _ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _ffi.lib()
+
+    # ---- model: fit on C2 (also the EM-iters/s measurement) ----
+    a_b = two_cov(D)
+    x, labels, _ = speakers(a_b, K_TRAIN, N_TRAIN // K_TRAIN, 1234)
+    plda = PLDA(device=local)
+    if args.skip_em:
+        plda.fit(x, labels, 1)                        # profiling runs: keep the launch list short
+        em = None
+    else:
+        plda.fit(x, labels, EM_ITERS)                 # warm-up fit (first-touch allocations)
+        launches0 = plda.launch_count()
+        xd = torch.from_numpy(x).to(dev)
+        plda.fit(xd, labels, EM_ITERS)                # timed by the library's own CUDA events
+        ft = plda.fit_timings()
+        fit_launches = plda.launch_count() - launches0
+        em = {"em_iters_per_sec": ft["iters"] / (ft["em"] * 1e-3), "em_ms_per_iter": ft["em"] / ft["iters"],
+              "stats_pass_ms": ft["stats"], "stats_pass_gbs": N_TRAIN * D * 8 / (ft["stats"] * 1e-3) / 1e9,
+              "get_output_ms": ft["output"], "fit_total_ms": ft["total"], "iters": ft["iters"],
+              "launches_per_fit": fit_launches, "input": "fp64 rows resident in HBM"}
+        del xd
+
+    # ---- scoring inputs: enrol models (3 utts each) and test vectors, transformed on the device ----
+    ne_local, nt_total = NE, NT
+    xe, le, ze = speakers(a_b, ne_local, ENROL_UTTS, 1235 + 1000 * rank)
+    rng = np.random.RandomState(1236)
+    z_t = rng.randn(nt_total, D)
+    xt = 0.5 + z_t @ a_b.T + rng.randn(nt_total, D)
+    enrol_means = xe.reshape(ne_local, ENROL_UTTS, D).mean(axis=1)
+    enrol_t = plda.transform_batch(torch.from_numpy(enrol_means).to(dev), counts=ENROL_UTTS, out_dtype=np.float32)
+    counts = np.full(ne_local, ENROL_UTTS, dtype=np.int32)
+    # test vectors: each rank transforms its shard; the step all-gathers them (world > 1)
+    lo, hi = rank * nt_total // world, (rank + 1) * nt_total // world
+    test_shard = plda.transform_batch(torch.from_numpy(xt[lo:hi]).to(dev), counts=1, out_dtype=np.float32)
+    test_full = torch.empty((nt_total, D), dtype=torch.float32, device=dev) if world > 1 else test_shard
+    ldo = (nt_total + 3) // 4 * 4
+    outs = [torch.empty((ne_local, ldo), dtype=torch.float32, device=dev) for _ in range(2)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+
+    stream = torch.cuda.current_stream()
+    _ffi.check(lib.plda_set_stream(plda._h, C.c_void_p(stream.cuda_stream)))
+
+    def step(i):
+        if world > 1:
+            dist.all_gather_into_tensor(test_full, test_shard)
+        plda.score_grid(enrol_t, counts, test_full, out=outs[i & 1][:, :nt_total])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region: exactly K steps, device timed, L2 flushed between steps ----
+    sampler = ClockSampler(local).start()
+    _ffi.check(lib.plda_profile_gemm(plda._h, 1))
+    l0 = plda.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(stream)
+        step(i)
+        ev[i][1].record(stream)
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    gemm_ms, gemm_n = C.c_double(), C.c_int64()
+    _ffi.check(lib.plda_profile_collect(plda._h, C.byref(gemm_ms), C.byref(gemm_n)))
+    _ffi.check(lib.plda_profile_gemm(plda._h, 0))
+    launches = plda.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    trials_per_step = ne_local * nt_total * world
+    value = trials_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region ----
+    e_host, _p1 = pinned_array(lib, (ne_local, D), np.float64)
+    t_host, _p2 = pinned_array(lib, (nt_total, D), np.float64)
+    o_host, _p3 = pinned_array(lib, (ne_local, nt_total), np.float32)
+    e_host[:] = enrol_t.double().cpu().numpy()
+    t_host[:] = (test_full if world > 1 else test_shard).double().cpu().numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    plda.score_grid(e_host, counts, t_host, out=o_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plda.score_grid(e_host, counts, t_host, out=o_host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = trials_per_step * e2e_steps / e2e_s
+    clocks = sampler.stop()
+
+    # parity spot check of the timed output against the host result (same kernel, different path)
+    dev_out = outs[(args.steps - 1) & 1][:64, :64].cpu().numpy()
+    spot = float(np.max(np.abs(dev_out - o_host[:64, :64])))
+
+    pk = peaks()
+    gemm_ms_avg = gemm_ms.value / max(1, gemm_n.value)
+    algo_flops = 2.0 * D * ne_local * nt_total                       # per launch (2*d flop per trial)
+    achieved = algo_flops / (gemm_ms_avg * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " bf16 burst",
+                "kernel": "gemm_bf16x3_kernel", "kernel_ms": gemm_ms_avg, "launches_timed": int(gemm_n.value),
+                "issued_tflops": achieved * 3 * 208 / 200,
+                "issued_frac": achieved * 3 * 208 / 200 / pk["bf16_tflops"],
+                "hbm_write_gbs": 4.0 * ne_local * nt_total / (gemm_ms_avg * 1e-3) / 1e9,
+                "hbm_write_frac": 4.0 * ne_local * nt_total / (gemm_ms_avg * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "note": "algorithmic = 2*d flop/trial; issued = x3 (bf16 split) on K padded 200->208; "
+                        "co-bound by the 4 B/trial fp32 score write"}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate, fp32 scores)", "data": "synthetic",
+        "config": {"workload": "C2: 100k x 200 d-vectors, 1k speakers, 10 EM iters + 10k x 10k scoring grid",
+                   "d": D, "enrol_per_gpu": ne_local, "test": nt_total, "enrol_utts": ENROL_UTTS,
+                   "sink": "fp32 score matrix in HBM (400 MB per step per GPU)",
+                   "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events summed",
+                   "parallelism": "enrol-block shard per GPU, 1 NCCL all-gather of test vectors per step"
+                   if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((ne_local + nt_total) * D * 8),
+                "d2h_bytes_per_step": int(ne_local * nt_total * 4), "steps": e2e_steps,
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "host_buffers": "pinned fp64 in, pinned fp32 out"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "em": em,
+        "parity_spot_max_abs_diff": spot,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import c_ref
+            c_ref.build()
+            mean, tr, psi = plda.get_model()
+            sub = 4000
+            v, used, spp = cpu_grid_sample(psi, sub, sub, 1, 1)
+            ref = c_ref.RefPlda(x, labels)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ref.em_iter()
+            cpu_em = 2 / (time.perf_counter() - t0)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port",
+                                   "sample": "%dx%d sub-grid of the 10k x 10k grid, per-pair LLR loop "
+                                             "(oracle/plda_ref.c), %.1f s" % (sub, sub, spp),
+                                   "em_iters_per_sec": cpu_em, "em_cores": 1}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    for p in (_p1, _p2, _p3):
+        lib.plda_host_free_pinned(p)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-em", action="store_true", help="profiling aid: 1 EM iteration, no fit timing")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

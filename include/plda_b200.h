@@ -61,6 +61,11 @@ int plda_synchronize(plda_handle_t h);
 /* number of plda_b200 kernels launched through this handle so far (bench "gpu_launches") */
 int plda_launch_count(plda_handle_t h, int64_t* out);
 
+/* per-launch CUDA-event timing of the tensor-core GEMM kernel on the launching stream (bench roofline):
+ * enable/disable (resets the record); collect synchronises and returns the summed kernel ms + launch count */
+int plda_profile_gemm(plda_handle_t h, int enable);
+int plda_profile_collect(plda_handle_t h, double* total_ms, int64_t* count);
+
 /* ---- fit: replaces MPlda_fit (src/pldamodule.cpp:42-109) ------------------------------- *
  * x: [n x d]; labels: [n] uint64 (any values; the reference requires dense 0..K-1, :88-92 --
  * dense labels give identical results).  iters = EM iterations (default 10 in the reference).

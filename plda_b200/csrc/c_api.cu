@@ -96,6 +96,16 @@ int plda_launch_count(plda_handle_t h, int64_t* out) {
   return with_handle(h, [&](pb::PldaEngine& e) { *out = e.ctx.launches.load(); });
 }
 
+int plda_profile_gemm(plda_handle_t h, int enable) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.ctx.profile_reset();
+    e.ctx.profile_gemm = enable != 0;
+  });
+}
+int plda_profile_collect(plda_handle_t h, double* total_ms, int64_t* count) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.ctx.profile_collect(total_ms, count); });
+}
+
 int plda_fit(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
              const uint64_t* labels, int iters) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.fit(x, n, d, ldx, dtype, loc, labels, iters); });

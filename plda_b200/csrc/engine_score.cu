@@ -272,27 +272,41 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   if (ne == 0 || nt == 0) return;
   PB_CHECK(counts != nullptr, kInvalidArg, "score_grid: enrol counts are required");
 
-  // distinct enrol counts -> groups (host; ne ints)
-  std::vector<int32_t> gcounts(counts, counts + ne);
-  std::sort(gcounts.begin(), gcounts.end());
-  gcounts.erase(std::unique(gcounts.begin(), gcounts.end()), gcounts.end());
-  PB_CHECK(gcounts.front() > 0, kInvalidArg, "score_grid: enrol counts must be positive");
-  const int ng = static_cast<int>(gcounts.size());
-  std::vector<int32_t> grp(ne);
-  for (int64_t i = 0; i < ne; ++i)
-    grp[i] = static_cast<int32_t>(std::lower_bound(gcounts.begin(), gcounts.end(), counts[i]) - gcounts.begin());
+  // distinct enrol counts -> groups (host; ne ints).  Uniform counts (the common case) need no per-row
+  // tables on the device at all.
+  bool uniform = true;
+  for (int64_t i = 0; i < ne; ++i) {
+    PB_CHECK(counts[i] > 0, kInvalidArg, "score_grid: enrol counts must be positive");
+    uniform = uniform && counts[i] == counts[0];
+  }
+  const int32_t uniform_count = counts[0];
+  int ng = 1;
+  const int32_t* counts_dev = nullptr;
+  const int32_t* grp_dev = nullptr;
+  const int32_t* gcounts_dev = nullptr;
 
   Staged se, st;
   stage(enrol, ne, dim, ld_enrol, dtype, loc, se);
-  Staged* stp = &st;
-  stage(test, nt, dim, ld_test, dtype, loc, *stp);
+  stage(test, nt, dim, ld_test, dtype, loc, st);
 
-  ws_counts.reserve(ne);
-  ws_grp.reserve(ne);
-  ws_gcounts.reserve(ng);
-  PB_CUDA(cudaMemcpyAsync(ws_counts.get(), counts, ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(ws_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(ws_gcounts.get(), gcounts.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+  if (!uniform) {
+    std::vector<int32_t> gcounts(counts, counts + ne);
+    std::sort(gcounts.begin(), gcounts.end());
+    gcounts.erase(std::unique(gcounts.begin(), gcounts.end()), gcounts.end());
+    ng = static_cast<int>(gcounts.size());
+    std::vector<int32_t> grp(ne);
+    for (int64_t i = 0; i < ne; ++i)
+      grp[i] = static_cast<int32_t>(std::lower_bound(gcounts.begin(), gcounts.end(), counts[i]) - gcounts.begin());
+    ws_counts.reserve(ne);
+    ws_grp.reserve(ne);
+    ws_gcounts.reserve(ng);
+    PB_CUDA(cudaMemcpyAsync(ws_counts.get(), counts, ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(ws_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(ws_gcounts.get(), gcounts.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    counts_dev = ws_counts.get();
+    grp_dev = ws_grp.get();
+    gcounts_dev = ws_gcounts.get();
+  }
 
   // optional z-norm affine per enrol row
   const float* zmean = nullptr;
@@ -319,19 +333,19 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
     ws_f64a.reserve(ne * dim);                       // L (fp64)
     ws_row64.reserve(ne);
     ws_col64.reserve(static_cast<size_t>(ng) * col_ld);
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, ws_counts.get(), model.psi.get(), nullptr, ws_f64a.get(),
-                     nullptr, ws_row64.get());
-    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, ws_gcounts.get(), ng, model.psi.get(), nullptr, nullptr,
-                    col_ld, ws_col64.get());
+    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), nullptr,
+                     ws_f64a.get(), nullptr, ws_row64.get());
+    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), nullptr,
+                    nullptr, col_ld, ws_col64.get());
     ws_f64b.reserve(nt * dim);
     convert_to_f64(ctx, st.ptr, st.is_f32, nt, dim, st.ld, ws_f64b.get(), dim);
   } else {
     ws_row.reserve(ne);
     ws_col.reserve(static_cast<size_t>(ng) * col_ld);
     PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(ng) * col_ld * sizeof(float), ctx.stream));
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, ws_counts.get(), model.psi.get(), &ws_l, nullptr,
-                     ws_row.get(), nullptr);
-    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, ws_gcounts.get(), ng, model.psi.get(), &ws_r,
+    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), &ws_l,
+                     nullptr, ws_row.get(), nullptr);
+    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), &ws_r,
                     ws_col.get(), col_ld, nullptr);
   }
 
@@ -361,7 +375,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
       gemm_f64(ctx, false, true, rows, nt, dim, 1.0, ws_f64a.get() + r0 * dim, dim, ws_f64b.get(), dim, 0.0,
                ws_gram.get(), nt);
       score_epilogue_f64(ctx, ws_gram.get(), rows, nt, ws_row64.get() + r0, ws_col64.get(), col_ld,
-                         ws_grp.get() + r0, zmean ? zmean + r0 : nullptr, zinv ? zinv + r0 : nullptr, dst, ldo_dev,
+                         grp_dev ? grp_dev + r0 : nullptr, zmean ? zmean + r0 : nullptr, zinv ? zinv + r0 : nullptr, dst, ldo_dev,
                          nullptr, nullptr);
     } else {
       SplitOperand a = ws_l.view();
@@ -374,7 +388,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
       epi.row_add = ws_row.get() + r0;
       epi.col_add = ws_col.get();
       epi.col_ld = col_ld;
-      epi.grp = ng > 1 ? ws_grp.get() + r0 : nullptr;
+      epi.grp = grp_dev ? grp_dev + r0 : nullptr;
       epi.zmean = zmean ? zmean + r0 : nullptr;
       epi.zinv = zinv ? zinv + r0 : nullptr;
       gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, dim, epi);
@@ -391,7 +405,8 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   try {
     if (out_loc == 1) {
       for (int64_t r0 = 0; r0 < ne; r0 += chunk) launch_chunk(r0, 0);
-      ctx.sync();
+      // on a caller-provided stream the result is stream-ordered with the caller's work: no host sync
+      if (ctx.owns_stream) ctx.sync();
     } else {
       // software pipeline: the GEMM of chunk i+1 is in flight while chunk i drains over PCIe
       int b = 0;
@@ -464,11 +479,6 @@ void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dt
 
   // S[e, b] = LLR(train = bkg_b, n = 1, test = enrol_e): symmetric in (e,b) for n = 1, so enrol rows are the
   // M side (row reduction over the cohort happens in the GEMM epilogue; the grid is never materialised).
-  std::vector<int32_t> ones(ne, 1);
-  ws_counts.reserve(ne);
-  PB_CUDA(cudaMemcpyAsync(ws_counts.get(), ones.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-  ws_gcounts.reserve(1);
-  PB_CUDA(cudaMemcpyAsync(ws_gcounts.get(), ones.data(), sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
   ws_rsum.reserve(ne);
   ws_rsq.reserve(ne);
   PB_CUDA(cudaMemsetAsync(ws_rsum.get(), 0, ne * sizeof(double), ctx.stream));
@@ -478,9 +488,9 @@ void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dt
     ws_f64a.reserve(ne * dim);
     ws_row64.reserve(ne);
     ws_col64.reserve(col_ld);
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, ws_counts.get(), model.psi.get(), nullptr, ws_f64a.get(),
+    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, nullptr, 1, model.psi.get(), nullptr, ws_f64a.get(),
                      nullptr, ws_row64.get());
-    score_prep_test(ctx, bt.get(), false, numutts, dim, dim, ws_gcounts.get(), 1, model.psi.get(), nullptr, nullptr,
+    score_prep_test(ctx, bt.get(), false, numutts, dim, dim, nullptr, 1, 1, model.psi.get(), nullptr, nullptr,
                     col_ld, ws_col64.get());
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ne, (512ll << 20) / 8 / numutts));
     ws_gram.reserve(static_cast<size_t>(chunk) * numutts);
@@ -495,9 +505,9 @@ void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dt
     ws_row.reserve(ne);
     ws_col.reserve(col_ld);
     PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, col_ld * sizeof(float), ctx.stream));
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, ws_counts.get(), model.psi.get(), &ws_l, nullptr,
+    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, nullptr, 1, model.psi.get(), &ws_l, nullptr,
                      ws_row.get(), nullptr);
-    score_prep_test(ctx, bt.get(), false, numutts, dim, dim, ws_gcounts.get(), 1, model.psi.get(), &ws_r, ws_col.get(),
+    score_prep_test(ctx, bt.get(), false, numutts, dim, dim, nullptr, 1, 1, model.psi.get(), &ws_r, ws_col.get(),
                     col_ld, nullptr);
     GemmEpilogue epi;
     epi.row_add = ws_row.get();

@@ -400,8 +400,18 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx.profile_gemm) {
+    PB_CUDA(cudaEventCreate(&e0));
+    PB_CUDA(cudaEventCreate(&e1));
+    PB_CUDA(cudaEventRecord(e0, ctx.stream));
+  }
   gemm_bf16x3_kernel<<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, tout, p);
   PB_CUDA(cudaGetLastError());
+  if (ctx.profile_gemm) {
+    PB_CUDA(cudaEventRecord(e1, ctx.stream));
+    ctx.gemm_events.emplace_back(e0, e1);
+  }
   ctx.count_launch();
 }
 

@@ -21,12 +21,12 @@ void convert_to_f64(Context& ctx, const void* in, bool is_f32, int64_t rows, int
 // enrol is fp64/fp32 [ne x d]; counts int32 [ne] (device); psi fp64 [d] (device).
 // Writes the split operand (if l_out), the fp64 operand (if l_f64) and row terms (fp32 and/or fp64).
 void score_prep_enrol(Context& ctx, const void* enrol, bool is_f32, int64_t ne, int64_t d, int64_t ld,
-                      const int32_t* counts, const double* psi, SplitBuf* l_out, double* l_f64, float* row_term,
+                      const int32_t* counts, int const_count, const double* psi, SplitBuf* l_out, double* l_f64, float* row_term,
                       double* row_term_f64);
 // Test side: R = T (split), col_term[g][t] = sum_i q_i(n_g) t_i^2 for each distinct enrol count n_g.
 // group_counts int32 [g] (device).  col_term pitch col_ld (floats, zero padded).
 void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, int64_t d, int64_t ld,
-                     const int32_t* group_counts, int ngroups, const double* psi, SplitBuf* r_out, float* col_term,
+                     const int32_t* group_counts, int ngroups, int const_count, const double* psi, SplitBuf* r_out, float* col_term,
                      int64_t col_ld, double* col_term_f64);
 // exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,

@@ -58,14 +58,14 @@ __global__ void convert_kernel(const T* __restrict__ in, long long rows, int col
 //   L[e,i] = e_i a_i / v_i ;  row[e] = 1/2 sum_i [log(1+psi_i) - log v_i - a_i^2 e_i^2 / v_i]
 template <typename T>
 __global__ void score_prep_enrol_kernel(const T* __restrict__ enrol, long long ne, int d, long long ld,
-                                        const int32_t* __restrict__ counts, const double* __restrict__ psi,
+                                        const int32_t* __restrict__ counts, int const_count, const double* __restrict__ psi,
                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out,
                                         double* __restrict__ l_f64, float* __restrict__ row_term,
                                         double* __restrict__ row_term_f64) {
   const long long r = blockIdx.x * static_cast<long long>(kWarpsPerBlock) + (threadIdx.x >> 5);
   if (r >= ne) return;
   const int lane = threadIdx.x & 31;
-  const double n = static_cast<double>(counts[r]);
+  const double n = static_cast<double>(counts ? counts[r] : const_count);
   const T* src = enrol + r * ld;
   double acc = 0.0;
   const int cmax = hi ? ld_out : d;
@@ -93,7 +93,7 @@ __global__ void score_prep_enrol_kernel(const T* __restrict__ enrol, long long n
 // test-side: R = T ; col[g][t] = sum_i q_i(n_g) t_i^2,  q_i(n) = 1/2 (1/(1+psi_i) - 1/v_i(n))
 template <typename T>
 __global__ void score_prep_test_kernel(const T* __restrict__ test, long long nt, int d, long long ld,
-                                       const int32_t* __restrict__ group_counts, int ngroups,
+                                       const int32_t* __restrict__ group_counts, int ngroups, int const_count,
                                        const double* __restrict__ psi, __nv_bfloat16* __restrict__ hi,
                                        __nv_bfloat16* __restrict__ lo, int ld_out, float* __restrict__ col_term,
                                        long long col_ld, double* __restrict__ col_term_f64) {
@@ -108,7 +108,7 @@ __global__ void score_prep_test_kernel(const T* __restrict__ test, long long nt,
     }
   }
   for (int g = 0; g < ngroups; ++g) {
-    const double n = static_cast<double>(group_counts[g]);
+    const double n = static_cast<double>(group_counts ? group_counts[g] : const_count);
     double acc = 0.0;
     for (int c = lane; c < d; c += 32) {
       const double p = psi[c];
@@ -229,7 +229,7 @@ void convert_to_f64(Context& ctx, const void* in, bool is_f32, int64_t rows, int
 }
 
 void score_prep_enrol(Context& ctx, const void* enrol, bool is_f32, int64_t ne, int64_t d, int64_t ld,
-                      const int32_t* counts, const double* psi, SplitBuf* l_out, double* l_f64, float* row_term,
+                      const int32_t* counts, int const_count, const double* psi, SplitBuf* l_out, double* l_f64, float* row_term,
                       double* row_term_f64) {
   if (l_out) l_out->reserve(ne, d);
   __nv_bfloat16* hi = l_out ? l_out->hi.get() : nullptr;
@@ -237,18 +237,18 @@ void score_prep_enrol(Context& ctx, const void* enrol, bool is_f32, int64_t ne, 
   const int ldo = l_out ? static_cast<int>(l_out->ld) : 0;
   if (is_f32)
     score_prep_enrol_kernel<float><<<row_blocks(ne), kWarpsPerBlock * 32, 0, ctx.stream>>>(
-        static_cast<const float*>(enrol), ne, static_cast<int>(d), ld, counts, psi, hi, lo, ldo, l_f64, row_term,
+        static_cast<const float*>(enrol), ne, static_cast<int>(d), ld, counts, const_count, psi, hi, lo, ldo, l_f64, row_term,
         row_term_f64);
   else
     score_prep_enrol_kernel<double><<<row_blocks(ne), kWarpsPerBlock * 32, 0, ctx.stream>>>(
-        static_cast<const double*>(enrol), ne, static_cast<int>(d), ld, counts, psi, hi, lo, ldo, l_f64, row_term,
+        static_cast<const double*>(enrol), ne, static_cast<int>(d), ld, counts, const_count, psi, hi, lo, ldo, l_f64, row_term,
         row_term_f64);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }
 
 void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, int64_t d, int64_t ld,
-                     const int32_t* group_counts, int ngroups, const double* psi, SplitBuf* r_out, float* col_term,
+                     const int32_t* group_counts, int ngroups, int const_count, const double* psi, SplitBuf* r_out, float* col_term,
                      int64_t col_ld, double* col_term_f64) {
   if (r_out) r_out->reserve(nt, d);
   __nv_bfloat16* hi = r_out ? r_out->hi.get() : nullptr;
@@ -256,11 +256,11 @@ void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, in
   const int ldo = r_out ? static_cast<int>(r_out->ld) : 0;
   if (is_f32)
     score_prep_test_kernel<float><<<row_blocks(nt), kWarpsPerBlock * 32, 0, ctx.stream>>>(
-        static_cast<const float*>(test), nt, static_cast<int>(d), ld, group_counts, ngroups, psi, hi, lo, ldo,
+        static_cast<const float*>(test), nt, static_cast<int>(d), ld, group_counts, ngroups, const_count, psi, hi, lo, ldo,
         col_term, col_ld, col_term_f64);
   else
     score_prep_test_kernel<double><<<row_blocks(nt), kWarpsPerBlock * 32, 0, ctx.stream>>>(
-        static_cast<const double*>(test), nt, static_cast<int>(d), ld, group_counts, ngroups, psi, hi, lo, ldo,
+        static_cast<const double*>(test), nt, static_cast<int>(d), ld, group_counts, ngroups, const_count, psi, hi, lo, ldo,
         col_term, col_ld, col_term_f64);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();

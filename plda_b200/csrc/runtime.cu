@@ -28,7 +28,28 @@ Context::Context(int dev) : device(dev) {
 }
 
 Context::~Context() {
+  profile_reset();
   if (owns_stream && stream) cudaStreamDestroy(stream);
+}
+
+void Context::profile_reset() {
+  for (auto& pr : gemm_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  gemm_events.clear();
+}
+
+void Context::profile_collect(double* total_ms, int64_t* count) {
+  sync();
+  double tot = 0.0;
+  for (auto& pr : gemm_events) {
+    float ms = 0.f;
+    PB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *count = static_cast<int64_t>(gemm_events.size());
 }
 
 // ------------------------------------------------------------------------- //

@@ -58,6 +58,12 @@ struct Context {
   bool owns_stream = true;
   std::atomic<long long> launches{0};   // number of OUR kernels launched (bench "gpu_launches")
   bool epi_direct = false;           // debug: epilogue stores straight from registers (env PLDA_B200_EPI=direct)
+  // optional per-launch timing of the tensor-core GEMM (CUDA events on the launching stream); bench roofline
+  bool profile_gemm = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+  void profile_reset();
+  // synchronises; returns total ms and number of launches recorded since the last reset
+  void profile_collect(double* total_ms, int64_t* count);
   explicit Context(int dev);
   ~Context();
   void sync() { PB_CUDA(cudaStreamSynchronize(stream)); }

@@ -273,6 +273,8 @@ class PLDA(object):
             raise ValueError("score_grid: enrol_counts length mismatch")
         if out is None:
             out = np.empty((ne, nt), dtype=np.float32)
+        if ne == 0 or nt == 0:
+            return out
         _ffi.check(self._lib.plda_score_grid(self._h, _ffi.ptr(ea), ne, dim, _ffi.ptr(cnt), _ffi.ptr(ids), _ffi.ptr(ta),
                                              nt, dim, dim, dtype, _ffi.HOST, _ffi.ptr(out), out.strides[0] // 4,
                                              _ffi.HOST))
