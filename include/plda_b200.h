@@ -155,6 +155,10 @@ int plda_memcpy(void* dst, const void* src, size_t bytes, int kind /* 0 h2d, 1 d
  *      HOST fp32 out) through the tensor-core kernel (ksplit <= 1: fused-store path; > 1: split-K) */
 int plda_test_gemm(plda_handle_t h, const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit,
                    float* out);
+/* stall counters (clock cycles) of CTA 0 and 1 of the last tensor GEMM launch; needs env PLDA_B200_DBG=1.
+ * per CTA 16 slots: 0 producer wait-empty, 1 producer total, 2 mma wait-full, 3 mma wait-tmem-empty, 4 mma total,
+ * 5 tiles, 6/7/8 epilogue warp 0 wait-tmem-full / wait-store / total, 9/10/11 same for epilogue warp 7 */
+int plda_debug_counters(plda_handle_t h, int64_t* out, int n);
 /* fp64 d x d helpers exposed for tests: op 0 = cholesky (lower), 1 = lower-triangular inverse,
  * 2 = symmetric eig (out = eigenvectors as columns, out2 = eigenvalues descending) */
 int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2);

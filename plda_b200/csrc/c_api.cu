@@ -260,6 +260,13 @@ int plda_test_gemm(plda_handle_t h, const double* a, const double* b, int64_t m,
                    float* out) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.test_gemm(a, b, m, n, k, ksplit, out); });
 }
+int plda_debug_counters(plda_handle_t h, int64_t* out, int n) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.ctx.sync();
+    PB_CHECK(e.ctx.gemm_dbg.size() >= 32 && n <= 32, pb::kInvalidArg, "debug counters need PLDA_B200_DBG=1");
+    PB_CUDA(cudaMemcpy(out, e.ctx.gemm_dbg.get(), n * sizeof(long long), cudaMemcpyDeviceToHost));
+  });
+}
 int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.test_linalg(op, a, d, out, out2); });
 }

@@ -189,19 +189,86 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cluster / cta_group::2 (CTA pair) variants ------------------------------------------ //
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// NOTE: no .release.cluster here -- that form compiles to MEMBAR.ALL.GPU (it must publish every prior global
+// write of the thread, TMA stores included) and stalled the epilogue warps for ~10% of the kernel.  The arrive only
+// hands TMEM columns back (ordered by tcgen05.wait::ld + tcgen05.fence), no memory needs publishing.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are signalled on the mbarrier at `mbar_cluster_addr`
+// (a shared::cluster address, normally the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs, 256 x N] (+)= A[256 x 16 (128 rows per CTA)] * B[N x 16 (N/2 rows per CTA)]^T; leader CTA only
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at the same smem offset in every CTA of `cta_mask` once the issued MMAs retire
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // ---- UMMA descriptors (bit layouts: PTX ISA "tcgen05 matrix / instruction descriptor") ---- //
 // K-major operand tile, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.
 //   [0,14)  start address >> 4      [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1)
 //   [32,46) stride byte offset >> 4 (1024 B between 8-row groups)
 //   [46,48) descriptor version = 1 (sm_100)      [61,64) layout type: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+// Narrower swizzles (used for a short K tail): rows are `swizzle_bytes` apart, 8-row groups 8*swizzle_bytes
+// apart; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t swizzle_bytes) {
+  const uint64_t layout = swizzle_bytes == 128 ? 2 : (swizzle_bytes == 64 ? 4 : 6);
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>((8 * swizzle_bytes) >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= layout << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  return umma_desc_kmajor(smem_addr, 128);
 }
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major.
 //   [4,6) D format 1=F32   [7,10) A format 1=BF16   [10,13) B format 1=BF16

@@ -15,10 +15,15 @@ __global__ void lse_combine_kernel(const float* __restrict__ lmax, const float* 
                                    int n_tiles, float* __restrict__ neg_lse) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= m) return;
+  // two partials per (row, column tile): one per epilogue warp half; an unused half holds (-inf, 0)
+  const int np = 2 * n_tiles;
   float mx = -INFINITY;
-  for (int t = 0; t < n_tiles; ++t) mx = fmaxf(mx, lmax[i * n_tiles + t]);
+  for (int t = 0; t < np; ++t) mx = fmaxf(mx, lmax[i * np + t]);
   float s = 0.f;
-  for (int t = 0; t < n_tiles; ++t) s += lsum[i * n_tiles + t] * __expf(lmax[i * n_tiles + t] - mx);
+  for (int t = 0; t < np; ++t) {
+    const float lm = lmax[i * np + t];
+    if (lm > -INFINITY) s += lsum[i * np + t] * __expf(lm - mx);
+  }
   neg_lse[i] = -(mx + __logf(s));
 }
 
@@ -289,8 +294,8 @@ void LdaEngine::predict(const void* x, int64_t nt, int64_t d_, int64_t ldx, int 
       if (log_proba) {
         // pass 1: online (max, sum exp) per row and column tile, nothing stored
         const int n_tiles = static_cast<int>(ceil_div(k, k >= 256 ? 256 : round_up(k, 16)));
-        ws_lmax.reserve(static_cast<size_t>(rows) * n_tiles);
-        ws_lsum.reserve(static_cast<size_t>(rows) * n_tiles);
+        ws_lmax.reserve(static_cast<size_t>(rows) * n_tiles * 2);
+        ws_lsum.reserve(static_cast<size_t>(rows) * n_tiles * 2);
         ws_neglse.reserve(rows);
         GemmEpilogue e1 = epi;
         e1.lse_max = ws_lmax.get();

@@ -14,16 +14,19 @@
 //   * EM projection + 2 SYRKs    (PldaEstimator::GetStatsFromClassMeans, src/pldamodule.cpp:106)
 //   * LDA decision values        (python/liblda/lda.py:278)
 //
-// Kernel anatomy (persistent, warp-specialised, one CTA per SM, 192 threads):
+// Kernel anatomy (persistent, warp-specialised, one CTA per SM, 384 threads = 3 warpgroups):
 //   warp 0      TMA producer: 4 tile loads per k-block (A_hi, A_lo, B_hi, B_lo), 128B swizzle,
 //               2-stage smem ring (96 KB/stage) guarded by full/empty mbarriers
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases smem
 //               stages and publishes finished accumulators
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> fused row/col/z-norm terms ->
-//               swizzled smem staging -> TMA store (or fused row reductions, no store)
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks, TMEM loads
+//               software-pipelined): tcgen05.ld -> fused row/col/z-norm terms -> swizzled smem staging
+//               -> TMA store (or fused row reductions, no store)
 //   TMEM        2 accumulator stages x 256 fp32 columns (all 512 columns): the epilogue of tile i
 //               overlaps the MMAs of tile i+1.
 // Tile = 128 x BN (BN <= 256, multiple of 16) x 64.
+#include <algorithm>
+
 #include "runtime.h"
 
 namespace pb {
@@ -37,12 +40,17 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;                           // 16 KB
 constexpr int B_TILE_BYTES = BN_MAX * BK * 2;                       // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;    // 96 KB
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF_BYTES = 32 * 32 * 4;                          // one 32x32 fp32 box
-constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;            // 32 KB
+constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES;                // 32 KB (one staging box per warp)
+constexpr int COLC_BYTES = 2 * BN_MAX * 4;                          // column-term cache, one slot per accumulator stage
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + COLC_BYTES + BAR_BYTES;
+// warpgroup 0 = {TMA warp, MMA warp, 2 idle warps} gives its registers away (setmaxnreg.dec), warpgroups 1-2 =
+// 8 epilogue warps take them (setmaxnreg.inc) so a whole 128-column accumulator slice fits in registers
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
+constexpr int CTRL_REGS = 56;
+constexpr int EPI_REGS = 224;
 constexpr int TMEM_COLS = 512;
 
 struct GemmParams {
@@ -54,7 +62,9 @@ struct GemmParams {
   int last_ksteps;    // UMMA_K steps in the very last k-block (1..4)
   int group_m;
   int mpad;           // split-K: row pitch between partial planes
-  int direct_store;
+  int direct_store;   // 3 TMA store via swizzled smem staging (default), 0 coalesced LSU stores, 1 register stores, 2 none
+  int tail_cols;      // K columns of the last k-block when it uses a narrow box (16 -> 32B swizzle, 32 -> 64B), else 0
+  long long* dbg;     // optional stall counters of CTA 0/1 (env PLDA_B200_DBG=1): see plda_debug_counters
   GemmEpilogue epi;
 };
 
@@ -62,137 +72,248 @@ struct Work {
   int m_blk, n_blk, ks;
 };
 
-__device__ __forceinline__ Work decode(const GemmParams& p, int item) {
+template <bool TWO>
+struct Cfg {
+  // cta_group::2: each CTA of the pair stages its own 128 rows of A and HALF of the B tile -> 64 KB per stage,
+  // three stages; cta_group::1: full B tile per CTA -> 96 KB per stage, two stages.
+  static constexpr int kStages = TWO ? 3 : 2;
+  static constexpr int kBBytes = TWO ? B_TILE_BYTES / 2 : B_TILE_BYTES;
+  static constexpr int kStageBytes = 2 * A_TILE_BYTES + 2 * kBBytes;
+};
+static_assert(Cfg<true>::kStages * Cfg<true>::kStageBytes == STAGES * STAGE_BYTES, "smem budget");
+
+template <bool TWO>
+__device__ __forceinline__ Work decode(const GemmParams& p, int item, uint32_t rank) {
+  // TWO: the unit of work is a PAIR of vertically adjacent 128-row tiles (one per CTA of the pair)
+  const int m_units = TWO ? (p.m_tiles + 1) / 2 : p.m_tiles;
   Work w;
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = m_units * p.n_tiles;
   w.ks = item / tiles;
   const int t = item - w.ks * tiles;
   const int per_group = p.group_m * p.n_tiles;
   const int g = t / per_group;
   const int first_m = g * p.group_m;
-  const int gsz = min(p.group_m, p.m_tiles - first_m);
+  const int gsz = min(p.group_m, m_units - first_m);
   const int r = t - g * per_group;
-  w.m_blk = first_m + r % gsz;
+  const int unit = first_m + r % gsz;
+  w.m_blk = TWO ? unit * 2 + static_cast<int>(rank) : unit;
   w.n_blk = r / gsz;
   return w;
 }
 
+// FAST: the score-grid hot path only (TMA store; row term, uniform column term, z-norm affine) -- keeps the
+// unrolled epilogue small enough for the instruction cache.  !FAST: every epilogue feature (per-row column
+// groups, row moments, log-sum-exp partials, all store modes).
+template <bool TWO, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const __grid_constant__ CUtensorMap tt_a_hi, const __grid_constant__ CUtensorMap tt_a_lo,
+                   const __grid_constant__ CUtensorMap tt_b_hi, const __grid_constant__ CUtensorMap tt_b_lo,
                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_base = smem + STAGES * STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_base + EPI_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  constexpr int kStages = Cfg<TWO>::kStages;
+  constexpr int kStageBytes = Cfg<TWO>::kStageBytes;
+  constexpr int kBBytes = Cfg<TWO>::kBBytes;
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("plda_b200: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* epi_base = smem + kStages * kStageBytes;
+  float* colc = reinterpret_cast<float*>(epi_base + EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_base + EPI_BYTES + COLC_BYTES);
+  uint64_t* empty = full + 3;
+  uint64_t* tfull = empty + 3;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = p.m_tiles * p.n_tiles * p.ksplit;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;     // 0 = leader CTA of the pair (issues the MMAs)
+  const int m_units = TWO ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total_items = m_units * p.n_tiles * p.ksplit;
+  const int first_item = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_stride = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int bn_cta = TWO ? p.bn / 2 : p.bn;              // B rows staged by this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_b_hi);
     tma_prefetch_desc(&tm_b_lo);
-    tma_prefetch_desc(&tm_out);
+    if (p.tail_cols) {
+      tma_prefetch_desc(&tt_a_hi);
+      tma_prefetch_desc(&tt_a_lo);
+      tma_prefetch_desc(&tt_b_hi);
+      tma_prefetch_desc(&tt_b_lo);
+    }
+    if (p.direct_store == 3) tma_prefetch_desc(&tm_out);
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < kStages; ++s) {
+        // TWO: only the leader arms its full barrier (expect_tx covers the bytes of both CTAs); the peer's TMA
+        // loads complete_tx on it remotely.  The peer cannot run a phase ahead: it refills a stage only after the
+        // leader's multicast commit on empty[s], i.e. after the leader consumed the previous phase of full[s].
+        // empty / tfull are signalled in both CTAs by the leader's multicast commits.
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], EPI_WARPS);
+        mbar_init(&tempty[a], TWO ? 2 * EPI_WARPS : EPI_WARPS);
       }
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (TWO) {
+      tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
   if (warp == 0) {
-    // ===================== TMA producer ===================== //
+    // ===================== TMA producer (both CTAs of a pair) ===================== //
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = 2 * A_TILE_BYTES + 2 * (p.bn * BK * 2);
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Work w = decode(p, item);
+      const uint32_t tx_cta = 2 * A_TILE_BYTES + 2 * (bn_cta * BK * 2);
+      // a short K tail (16 or 32 columns) is fetched with a narrow box: 1/4 or 1/2 of the bytes of a full k-block
+      const uint32_t tx_tail_cta = 2 * (BM + bn_cta) * p.tail_cols * 2;
+      long long dbg_prod_wait = 0;
+      const long long t_start = clock64();
+      uint32_t lead_full_addr[3] = {0, 0, 0};
+      if (TWO) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) lead_full_addr[i] = mapa_shared(smem_u32(&full[i]), 0);
+      }
+      for (int item = first_item; item < total_items; item += item_stride) {
+        const Work w = decode<TWO>(p, item, rank);
         const int kb0 = w.ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.nkb_total);
+        const int brow = w.n_blk * p.bn + (TWO ? static_cast<int>(rank) * bn_cta : 0);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long t_w0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          uint8_t* s = smem + stage * STAGE_BYTES;
-          tma_load_2d(s, &tm_a_hi, &full[stage], kb * BK, w.m_blk * BM);
-          tma_load_2d(s + A_TILE_BYTES, &tm_a_lo, &full[stage], kb * BK, w.m_blk * BM);
-          tma_load_2d(s + 2 * A_TILE_BYTES, &tm_b_hi, &full[stage], kb * BK, w.n_blk * p.bn);
-          tma_load_2d(s + 2 * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, &full[stage], kb * BK, w.n_blk * p.bn);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          dbg_prod_wait += clock64() - t_w0;
+          uint8_t* s = smem + stage * kStageBytes;
+          const bool tail = p.tail_cols != 0 && kb == p.nkb_total - 1;
+          const uint32_t tx = tail ? tx_tail_cta : tx_cta;
+          const CUtensorMap* ma_hi = tail ? &tt_a_hi : &tm_a_hi;
+          const CUtensorMap* ma_lo = tail ? &tt_a_lo : &tm_a_lo;
+          const CUtensorMap* mb_hi = tail ? &tt_b_hi : &tm_b_hi;
+          const CUtensorMap* mb_lo = tail ? &tt_b_lo : &tm_b_lo;
+          if (TWO) {
+            const uint32_t lead_full = stage == 0 ? lead_full_addr[0] : (stage == 1 ? lead_full_addr[1] : lead_full_addr[2]);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * tx);
+            tma_load_2d_2sm(s, ma_hi, lead_full, kb * BK, w.m_blk * BM);
+            tma_load_2d_2sm(s + A_TILE_BYTES, ma_lo, lead_full, kb * BK, w.m_blk * BM);
+            tma_load_2d_2sm(s + 2 * A_TILE_BYTES, mb_hi, lead_full, kb * BK, brow);
+            tma_load_2d_2sm(s + 2 * A_TILE_BYTES + kBBytes, mb_lo, lead_full, kb * BK, brow);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], tx);
+            tma_load_2d(s, ma_hi, &full[stage], kb * BK, w.m_blk * BM);
+            tma_load_2d(s + A_TILE_BYTES, ma_lo, &full[stage], kb * BK, w.m_blk * BM);
+            tma_load_2d(s + 2 * A_TILE_BYTES, mb_hi, &full[stage], kb * BK, brow);
+            tma_load_2d(s + 2 * A_TILE_BYTES + kBBytes, mb_lo, &full[stage], kb * BK, brow);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (p.dbg != nullptr && blockIdx.x < 2) {
+        p.dbg[blockIdx.x * 16 + 0] = dbg_prod_wait;
+        p.dbg[blockIdx.x * 16 + 1] = clock64() - t_start;
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer ===================== //
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only when paired) ===================== //
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn);
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const Work w = decode(p, item);
+      const uint32_t idesc = umma_idesc_bf16_f32(TWO ? 2 * BM : BM, p.bn);
+      long long dbg_full = 0, dbg_tempty = 0, dbg_tiles = 0;
+      const long long t_start = clock64();
+      for (int item = first_item; item < total_items; item += item_stride) {
+        const Work w = decode<TWO>(p, item, rank);
         const int kb0 = w.ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.nkb_total);
+        long long t_w0 = clock64();
         mbar_wait(&tempty[acc], acc_phase ^ 1);
+        dbg_tempty += clock64() - t_w0;
+        ++dbg_tiles;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN_MAX;
         for (int kb = kb0; kb < kb1; ++kb) {
+          t_w0 = clock64();
           mbar_wait(&full[stage], phase);
+          dbg_full += clock64() - t_w0;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = umma_desc_kmajor_sw128(sa);
-          const uint64_t a_lo = umma_desc_kmajor_sw128(sa + A_TILE_BYTES);
-          const uint64_t b_hi = umma_desc_kmajor_sw128(sa + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = umma_desc_kmajor_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
-          const int nks = (kb == p.nkb_total - 1) ? p.last_ksteps : (BK / UMMA_K);
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const bool last_kb = kb == p.nkb_total - 1;
+          // tile rows are (2 * tail_cols) bytes apart when the narrow tail box was used, 128 B otherwise
+          const uint32_t swz = (last_kb && p.tail_cols != 0) ? 2u * p.tail_cols : 128u;
+          const uint64_t a_hi = umma_desc_kmajor(sa, swz);
+          const uint64_t a_lo = umma_desc_kmajor(sa + A_TILE_BYTES, swz);
+          const uint64_t b_hi = umma_desc_kmajor(sa + 2 * A_TILE_BYTES, swz);
+          const uint64_t b_lo = umma_desc_kmajor(sa + 2 * A_TILE_BYTES + kBBytes, swz);
+          const int nks = last_kb ? p.last_ksteps : (BK / UMMA_K);
           for (int ks = 0; ks < nks; ++ks) {
-            // advance 32 B (= UMMA_K bf16) inside the 128 B swizzle atom: +2 in the >>4 address field
+            // advance 32 B (= UMMA_K bf16) inside the swizzle atom: +2 in the >>4 address field
             const uint64_t off = static_cast<uint64_t>(ks * 2);
             const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
-            umma_bf16_ss(d_tmem, a_hi + off, b_hi + off, idesc, first);
-            umma_bf16_ss(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
-            umma_bf16_ss(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
+            if (TWO) {
+              umma_bf16_ss_2cta(d_tmem, a_hi + off, b_hi + off, idesc, first);
+              umma_bf16_ss_2cta(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+              umma_bf16_ss_2cta(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
+            } else {
+              umma_bf16_ss(d_tmem, a_hi + off, b_hi + off, idesc, first);
+              umma_bf16_ss(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+              umma_bf16_ss(d_tmem, a_lo + off, b_hi + off, idesc, 1u);
+            }
           }
-          umma_commit(&empty[stage]);          // smem stage reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // smem stage reusable (in both CTAs) once these MMAs retire
+          if (TWO) umma_commit_2cta(&empty[stage], 3); else umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);              // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (TWO) umma_commit_2cta(&tfull[acc], 3); else umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (p.dbg != nullptr && blockIdx.x < 2) {
+        p.dbg[blockIdx.x * 16 + 2] = dbg_full;
+        p.dbg[blockIdx.x * 16 + 3] = dbg_tempty;
+        p.dbg[blockIdx.x * 16 + 4] = clock64() - t_start;
+        p.dbg[blockIdx.x * 16 + 5] = dbg_tiles;
+      }
     }
+  }
   } else {
-    // ===================== epilogue (warps 2..5) ===================== //
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    // ===================== epilogue (warps 4..11) ===================== //
+    // Two warps per TMEM lane quarter: warp handles the 32-column chunks c with c % 2 == h.
+    const int ew = warp - 4;
     const int q = warp & 3;   // TMEM lane quarter this warp is allowed to read
-    uint8_t* my_epi = epi_base + (warp - 2) * 2 * EPI_BUF_BYTES;
+    const int h = ew >> 2;
+    uint8_t* sb = epi_base + ew * EPI_BUF_BYTES;
+    const uint32_t sb_row = smem_u32(sb) + lane * 128;
     const GemmEpilogue& e = p.epi;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int buf = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const Work w = decode(p, item);
+    long long dbg_tfull = 0, dbg_store = 0, dbg_load = 0;
+    const long long t_start = clock64();
+    for (int item = first_item; item < total_items; item += item_stride) {
+      const Work w = decode<TWO>(p, item, rank);
       const int m0 = w.m_blk * BM;
       const int n0 = w.n_blk * p.bn;
       const int m = m0 + q * 32 + lane;
@@ -205,25 +326,41 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (e.grp) g = __ldg(e.grp + m);
         if (e.zmean) { zm = __ldg(e.zmean + m); zi = __ldg(e.zinv + m); }
       }
+      const float radd = ra - zm;
       float rs = 0.f, rq = 0.f;
       float lmax = -INFINITY, lsum = 0.f;
       const int ncols = min(p.bn, p.n - n0);
       const int nchunks = (ncols + 31) >> 5;
       const long long out_row = static_cast<long long>(w.ks) * p.mpad + m;
+      const float* colp = e.col_add ? e.col_add + static_cast<long long>(g) * e.col_ld + n0 : nullptr;
+      // uniform column terms (no per-row groups): fetch this warp's chunks now (4 coalesced loads in flight
+      // while the MMAs finish), park them in the per-stage smem cache once the accumulator is ready
+      const bool col_cached = e.col_add != nullptr && e.grp == nullptr;
+      float cpre[4] = {0.f, 0.f, 0.f, 0.f};
+      if (col_cached) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc < nchunks) cpre[i] = __ldg(e.col_add + n0 + cc * 32 + lane);
+        }
+      }
+      float* colslot = colc + acc * BN_MAX;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN_MAX;
 
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN_MAX + c * 32;
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
+      auto process = [&](uint32_t (&r)[32], int c) {
+        const int nbase = n0 + c * 32;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int nbase = n0 + c * 32;
-        if (e.col_add != nullptr && mvalid) {
-          const float4* cp = reinterpret_cast<const float4*>(e.col_add + static_cast<long long>(g) * e.col_ld + nbase);
+        if (col_cached) {
+          const float4* cp = reinterpret_cast<const float4*>(colslot + c * 32);   // smem broadcast reads
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = cp[j4];
+            v[4 * j4 + 0] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+          }
+        } else if (!FAST && colp != nullptr && mvalid) {
+          const float4* cp = reinterpret_cast<const float4*>(colp + c * 32);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 t = __ldg(cp + j4);
@@ -231,14 +368,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (v[j] + ra - zm) * zi;
-        if (e.rsum != nullptr) {
+        for (int j = 0; j < 32; ++j) v[j] = (v[j] + radd) * zi;
+        if (!FAST && e.rsum != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (nbase + j < p.n) { rs += v[j]; rq += v[j] * v[j]; }
           }
         }
-        if (e.lse_max != nullptr) {
+        if (!FAST && e.lse_max != nullptr) {
           float cmax = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (nbase + j < p.n) cmax = fmaxf(cmax, v[j]);
@@ -249,21 +386,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           lsum = lsum * __expf(lmax - nmax) + add;
           lmax = nmax;
         }
-        if (e.out != nullptr) {
-          if (p.direct_store) {
-            if (mvalid) {
-              float* op = e.out + out_row * e.ldo + nbase;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (nbase + j < p.n) op[j] = v[j];
-            }
-          } else if (warp_rows_valid) {
-            uint8_t* sb = my_epi + buf * EPI_BUF_BYTES;
-            if (lane == 0) tma_store_wait_read<1>();   // the store that last used this buffer has drained
+        if (FAST) {
+          if (warp_rows_valid) {
+            if (lane == 0) tma_store_wait_read<0>();   // the previous TMA store of this warp has drained the buffer
             __syncwarp();
-            const uint32_t row_addr = smem_u32(sb) + lane * 128;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const uint32_t addr = row_addr + ((j4 ^ (lane & 7)) << 4);   // 128B-swizzle: chunk ^= row%8
+              const uint32_t addr = sb_row + ((j4 ^ (lane & 7)) << 4);   // 16-byte chunk ^= row % 8 (128B swizzle)
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j4 + 0]),
                            "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3])
                            : "memory");
@@ -274,36 +403,134 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               tma_store_2d(&tm_out, sb, nbase, w.ks * p.mpad + m0 + q * 32);
               tma_store_commit();
             }
-            buf ^= 1;
+          }
+        } else if (e.out != nullptr) {
+          if (p.direct_store == 2) {
+            // debug (PLDA_B200_EPI=skip): no store at all -> isolates the TMA/MMA main loop
+          } else if (p.direct_store == 1) {
+            if (mvalid) {
+              float* op = e.out + out_row * e.ldo + nbase;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nbase + j < p.n) op[j] = v[j];
+            }
+          } else if (warp_rows_valid) {
+            if (p.direct_store == 3) {
+              const long long t_s0 = clock64();
+              if (lane == 0) tma_store_wait_read<0>();   // the previous TMA store of this warp has drained the buffer
+              dbg_store += clock64() - t_s0;
+            }
+            __syncwarp();
+            // transpose through a 128B-swizzled 32x32 staging box: thread = row on the way in ...
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const uint32_t addr = sb_row + ((j4 ^ (lane & 7)) << 4);   // 16-byte chunk ^= row % 8
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j4 + 0]),
+                           "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3])
+                           : "memory");
+            }
+            if (p.direct_store == 3) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tm_out, sb, nbase, w.ks * p.mpad + m0 + q * 32);
+                tma_store_commit();
+              }
+            } else {
+              // ... and 8 lanes per row on the way out: every warp store writes four full 128-byte rows
+              __syncwarp();
+              const int ch = lane & 7;
+              const int col = nbase + ch * 4;
+              const long long row_base = static_cast<long long>(w.ks) * p.mpad + m0 + q * 32;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3);
+                float4 t;
+                const uint32_t addr = smem_u32(sb) + rr * 128 + ((ch ^ (rr & 7)) << 4);
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                             : "r"(addr));
+                if (m0 + q * 32 + rr < p.m) {
+                  float* op = e.out + (row_base + rr) * e.ldo + col;
+                  if (col + 3 < p.n) {
+                    *reinterpret_cast<float4*>(op) = t;
+                  } else {
+                    if (col < p.n) op[0] = t.x;
+                    if (col + 1 < p.n) op[1] = t.y;
+                    if (col + 2 < p.n) op[2] = t.z;
+                  }
+                }
+              }
+            }
           }
         }
+      };
+
+      const long long t_w0 = clock64();
+      mbar_wait(&tfull[acc], acc_phase);
+      dbg_tfull += clock64() - t_w0;
+      tc_fence_after();
+      if (col_cached) {
+        // every reader of this slot for the tile two steps back has arrived on tempty before this tile's
+        // MMAs could start, so the slot is free; warps sharing chunks write identical values
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc < nchunks) colslot[cc * 32 + lane] = cpre[i];
+        }
+        __syncwarp();
       }
-      // accumulator stage drained -> hand it back to the MMA warp
+      // all of this warp's chunks are fetched with the TMEM loads in flight together (one ~1k-cycle latency per
+      // tile instead of one per chunk), then the accumulator stage is handed back BEFORE the post-processing
+      // and the stores, so the MMA warp never waits for the store path
+      uint32_t r[4][32];
+      const long long t_l0 = clock64();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int cc = h + 2 * i;
+        if (cc < nchunks) tmem_ld_32x32b_x32(tbase + cc * 32, r[i]);
+      }
+      tmem_ld_wait();
+      dbg_load += clock64() - t_l0;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // the leader CTA's MMA warp waits for both
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int cc = h + 2 * i;
+        if (cc < nchunks) process(r[i], cc);
+      }
 
-      if (mvalid) {
+      if (!FAST && mvalid) {
         if (e.rsum != nullptr) {
           atomicAdd(e.rsum + m, static_cast<double>(rs));
           atomicAdd(e.rsq + m, static_cast<double>(rq));
         }
         if (e.lse_max != nullptr) {
-          e.lse_max[static_cast<long long>(m) * p.n_tiles + w.n_blk] = lmax;
-          e.lse_sum[static_cast<long long>(m) * p.n_tiles + w.n_blk] = lsum;
+          const long long slot = (static_cast<long long>(m) * p.n_tiles + w.n_blk) * 2 + h;
+          e.lse_max[slot] = lmax;
+          e.lse_sum[slot] = lsum;
         }
       }
     }
-    if (lane == 0) tma_store_wait<0>();
+    if ((FAST || p.direct_store == 3) && lane == 0) tma_store_wait<0>();
+    if (p.dbg != nullptr && blockIdx.x < 2 && lane == 0 && (ew == 0 || ew == 7)) {
+      const int o = blockIdx.x * 16 + (ew == 0 ? 6 : 9);
+      p.dbg[o + 0] = dbg_tfull;
+      p.dbg[o + 1] = dbg_store;
+      p.dbg[o + 2] = clock64() - t_start;
+      if (ew == 0) p.dbg[blockIdx.x * 16 + 12] = dbg_load;
+    }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -347,6 +574,7 @@ EncodeTiledFn get_encode_fn() {
 struct Plan {
   GemmParams p;
   int grid;
+  bool two_cta;
 };
 
 Plan make_plan(const Context& ctx, int64_t m, int64_t n, int64_t k, int ksplit) {
@@ -371,6 +599,13 @@ Plan make_plan(const Context& ctx, int64_t m, int64_t n, int64_t k, int ksplit) 
   const long long items = static_cast<long long>(p.m_tiles) * p.n_tiles * p.ksplit;
   PB_CHECK(items < (1ll << 31), kInvalidArg, "gemm: too many tiles");
   pl.grid = static_cast<int>(items < ctx.num_sms ? items : ctx.num_sms);
+  // CTA pairs (cta_group::2): worth it once there are at least two row tiles to pair up
+  pl.two_cta = ctx.gemm_two_cta && p.m_tiles >= 2;
+  if (pl.two_cta) {
+    const long long pair_items = static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles * p.ksplit;
+    const long long clusters = std::min<long long>(pair_items, ctx.num_sms / 2);
+    pl.grid = static_cast<int>(2 * clusters);
+  }
   return pl;
 }
 
@@ -384,21 +619,42 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
   const uint64_t kext = static_cast<uint64_t>(p.nkb_total - 1) * BK + static_cast<uint64_t>(p.last_ksteps) * UMMA_K;
   PB_CHECK(static_cast<int64_t>(kext) <= a.ld && static_cast<int64_t>(kext) <= b.ld, kInvalidArg,
            "gemm: operand pitch smaller than round_up(k,16)");
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tout;
-  encode_tmap_2d(&ta_hi, TmaType::BF16, a.hi, kext, a.rows, a.ld * 2, BK, BM);
-  encode_tmap_2d(&ta_lo, TmaType::BF16, a.lo, kext, a.rows, a.ld * 2, BK, BM);
-  encode_tmap_2d(&tb_hi, TmaType::BF16, b.hi, kext, b.rows, b.ld * 2, BK, p.bn);
-  encode_tmap_2d(&tb_lo, TmaType::BF16, b.lo, kext, b.rows, b.ld * 2, BK, p.bn);
-  const bool can_tma_store = out != nullptr && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  p.direct_store = (ctx.epi_direct || !can_tma_store) ? 1 : 0;
-  if (out != nullptr && !p.direct_store) {
-    encode_tmap_2d(&tout, TmaType::F32, out, p.n, out_rows, ldo * 4, 32, 32);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout;
+  encode_tmap_2d(&ta_hi, TmaType::BF16, a.hi, kext, a.rows, a.ld * 2, BK, BM, 128);
+  encode_tmap_2d(&ta_lo, TmaType::BF16, a.lo, kext, a.rows, a.ld * 2, BK, BM, 128);
+  const uint32_t b_box = pl.two_cta ? p.bn / 2 : p.bn;      // a CTA pair stages half of the B tile per CTA
+  encode_tmap_2d(&tb_hi, TmaType::BF16, b.hi, kext, b.rows, b.ld * 2, BK, b_box, 128);
+  encode_tmap_2d(&tb_lo, TmaType::BF16, b.lo, kext, b.rows, b.ld * 2, BK, b_box, 128);
+  // K tail of 16 / 32 columns: narrow boxes (32 B / 64 B swizzle) instead of a zero-padded 64-column block
+  const int tail = p.last_ksteps * UMMA_K;
+  p.tail_cols = (p.nkb_total > 1 && (tail == 16 || tail == 32) && ctx.k_tail_boxes) ? tail : 0;
+  if (p.tail_cols) {
+    encode_tmap_2d(&tta_hi, TmaType::BF16, a.hi, kext, a.rows, a.ld * 2, tail, BM, tail * 2);
+    encode_tmap_2d(&tta_lo, TmaType::BF16, a.lo, kext, a.rows, a.ld * 2, tail, BM, tail * 2);
+    encode_tmap_2d(&ttb_hi, TmaType::BF16, b.hi, kext, b.rows, b.ld * 2, tail, b_box, tail * 2);
+    encode_tmap_2d(&ttb_lo, TmaType::BF16, b.lo, kext, b.rows, b.ld * 2, tail, b_box, tail * 2);
+  } else {
+    tta_hi = ta_hi; tta_lo = ta_lo; ttb_hi = tb_hi; ttb_lo = tb_lo;
+  }
+  const bool aligned_out = out != nullptr && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  // 3: TMA store from the swizzled staging box (default); 0: coalesced LSU stores from the same box
+  // (PLDA_B200_EPI=lsu); 1: register stores (unaligned outputs / PLDA_B200_EPI=direct); 2: no store (debug)
+  p.direct_store = ctx.epi_mode == 2 ? 2 : ((ctx.epi_mode == 1 || !aligned_out) ? 1 : (ctx.epi_mode == 3 ? 0 : 3));
+  if (out != nullptr && p.direct_store == 3) {
+    encode_tmap_2d(&tout, TmaType::F32, out, p.n, out_rows, ldo * 4, 32, 32, 128);
   } else {
     tout = ta_hi;  // never dereferenced
   }
+  p.dbg = ctx.gemm_dbg.size() >= 32 ? ctx.gemm_dbg.get() : nullptr;
+  const GemmEpilogue& ep = p.epi;
+  const bool fast = out != nullptr && p.direct_store == 3 && ep.rsum == nullptr && ep.lse_max == nullptr &&
+                    ep.grp == nullptr;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx.profile_gemm) {
@@ -406,7 +662,32 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     PB_CUDA(cudaEventCreate(&e1));
     PB_CUDA(cudaEventRecord(e0, ctx.stream));
   }
-  gemm_bf16x3_kernel<<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, tout, p);
+  if (pl.two_cta) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (fast)
+      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, true>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo,
+                                 ttb_hi, ttb_lo, tout, p));
+    else
+      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, false>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo,
+                                 ttb_hi, ttb_lo, tout, p));
+  } else if (fast) {
+    gemm_bf16x3_kernel<false, true><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
+        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
+  } else {
+    gemm_bf16x3_kernel<false, false><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
+        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
+  }
   PB_CUDA(cudaGetLastError());
   if (ctx.profile_gemm) {
     PB_CUDA(cudaEventRecord(e1, ctx.stream));
@@ -418,15 +699,17 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
 }  // namespace
 
 void encode_tmap_2d(CUtensorMap* out, TmaType type, const void* base, uint64_t inner, uint64_t outer,
-                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, uint32_t swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstride[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = type == TmaType::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     throw Error(kCudaError, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) +
                                 " (inner=" + std::to_string(inner) + " outer=" + std::to_string(outer) +

@@ -24,7 +24,17 @@ Context::Context(int dev) : device(dev) {
   num_sms = prop.multiProcessorCount;
   PB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const char* epi = getenv("PLDA_B200_EPI");
-  epi_direct = (epi != nullptr && strcmp(epi, "direct") == 0);
+  epi_mode = epi == nullptr ? 0
+             : (strcmp(epi, "direct") == 0 ? 1 : (strcmp(epi, "skip") == 0 ? 2 : (strcmp(epi, "lsu") == 0 ? 3 : 0)));
+  const char* kt = getenv("PLDA_B200_KTAIL");
+  k_tail_boxes = !(kt != nullptr && strcmp(kt, "0") == 0);
+  const char* dbg = getenv("PLDA_B200_DBG");
+  if (dbg != nullptr && strcmp(dbg, "1") == 0) {
+    gemm_dbg.alloc(32);
+    PB_CUDA(cudaMemset(gemm_dbg.get(), 0, 32 * sizeof(long long)));
+  }
+  const char* gm = getenv("PLDA_B200_GEMM");
+  gemm_two_cta = !(gm != nullptr && strcmp(gm, "1cta") == 0);
 }
 
 Context::~Context() {

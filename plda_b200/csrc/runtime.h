@@ -57,7 +57,10 @@ struct Context {
   cudaStream_t stream = nullptr;     // launching stream (owned unless external)
   bool owns_stream = true;
   std::atomic<long long> launches{0};   // number of OUR kernels launched (bench "gpu_launches")
-  bool epi_direct = false;           // debug: epilogue stores straight from registers (env PLDA_B200_EPI=direct)
+  int epi_mode = 0;                  // debug (env PLDA_B200_EPI): 0 default (TMA store), 1 "direct" register stores, 2 "skip", 3 "lsu"
+  bool k_tail_boxes = true;          // env PLDA_B200_KTAIL=0 disables the narrow K-tail boxes
+  DevBuf<long long> gemm_dbg;        // env PLDA_B200_DBG=1: stall counters written by CTA 0/1 of the last GEMM launch
+  bool gemm_two_cta = true;          // env PLDA_B200_GEMM=1cta forces the single-CTA (cta_group::1) kernel
   // optional per-launch timing of the tensor-core GEMM (CUDA events on the launching stream); bench roofline
   bool profile_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
@@ -71,10 +74,10 @@ struct Context {
 };
 
 // Encode a 2-D row-major tensor map.  inner = contiguous dimension (elements).
-// swizzle128: box inner extent must be exactly 128 bytes.
+// swizzle_bytes (128 / 64 / 32) must equal the box inner extent in bytes.
 enum class TmaType { BF16, F32 };
 void encode_tmap_2d(CUtensorMap* out, TmaType type, const void* base, uint64_t inner, uint64_t outer,
-                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, uint32_t swizzle_bytes);
 
 // ------------------------------------------------------------------------- //
 // Split-bf16 operand: a logical [rows x k] matrix stored K-major as two bf16

@@ -1,0 +1,50 @@
+"""Micro-benchmark of the score-grid GEMM kernel (CUDA-event timed inside the library).
+usage: python scripts/bench_gemm.py [ne nt d reps]   (env PLDA_B200_EPI = tma|direct|skip)"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from plda_b200 import PLDA, _ffi  # noqa: E402
+
+ne, nt, d, reps = (int(a) for a in (sys.argv[1:5] + ["10000", "10000", "200", "20"][len(sys.argv) - 1:]))
+rng = np.random.RandomState(0)
+p = PLDA()
+q, _ = np.linalg.qr(rng.randn(d, d))
+p.set_model(rng.randn(d), q, np.sort(2.0 * np.exp(-np.arange(d) / (0.15 * d)))[::-1].copy())
+dev = torch.device("cuda", 0)
+e = torch.randn(ne, d, device=dev)
+t = torch.randn(nt, d, device=dev)
+cnt = np.full(ne, 3, dtype=np.int32)
+ldo = (nt + 3) // 4 * 4
+out = torch.empty((ne, ldo), device=dev)
+lib = _ffi.lib()
+for _ in range(3):
+    p.score_grid(e, cnt, t, out=out[:, :nt])
+torch.cuda.synchronize()
+_ffi.check(lib.plda_profile_gemm(p._h, 1))
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+_ffi.check(lib.plda_set_stream(p._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+ev0.record()
+for _ in range(reps):
+    p.score_grid(e, cnt, t, out=out[:, :nt])
+ev1.record()
+torch.cuda.synchronize()
+ms, n = C.c_double(), C.c_int64()
+_ffi.check(lib.plda_profile_collect(p._h, C.byref(ms), C.byref(n)))
+k_ms = ms.value / n.value
+k16 = (d + 15) // 16 * 16
+print("mode=%s ne=%d nt=%d d=%d  gemm %.4f ms  step %.4f ms  %.3e trials/s (kernel)  issued %.0f TFLOP/s  write %.0f GB/s"
+      % (os.environ.get("PLDA_B200_EPI", "default") + "/" + os.environ.get("PLDA_B200_GEMM", "2cta"), ne, nt, d, k_ms, ev0.elapsed_time(ev1) / reps, ne * nt / k_ms * 1e3,
+         3 * 2 * k16 * ne * nt / k_ms / 1e9, 4.0 * ne * nt / k_ms / 1e6))
+
+if os.environ.get("PLDA_B200_DBG") == "1":
+    c = np.zeros(32, dtype=np.int64)
+    _ffi.check(lib.plda_debug_counters(p._h, _ffi.ptr(c), 32))
+    names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tempty", "mma_total", "tiles",
+             "epi0_wait_tfull", "epi0_wait_store", "epi0_total", "epi7_wait_tfull", "epi7_wait_store", "epi7_total", "epi0_tmem_load"]
+    for b in range(2):
+        print("  cta%d: " % b + "  ".join("%s=%d" % (n, c[b * 16 + i]) for i, n in enumerate(names)))

@@ -1,0 +1,123 @@
+"""CPU emulation of the DEVICE arithmetic (split-bf16 x3 operands, fp32 accumulate, the diagonalised
+EM, centre-before-split) against the fp64 oracle: shows on the authoring box, without a GPU, that the
+precision design meets the parity bar (scores <= 1e-3*max(|s|,1), psi rel << 1e-3).  The GPU tests
+check the real kernels; this pins the *design* so a precision regression is caught before GPU time
+is spent."""
+import numpy as np
+import pytest
+
+from oracle import kaldi_plda as kp
+
+
+def bf16(x):
+    f = np.asarray(x, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def split(x):
+    hi = bf16(x)
+    return hi, bf16(np.asarray(x, dtype=np.float64) - hi)
+
+
+def mm3(a, b):
+    """a[M,K] @ b[N,K]^T the way gemm_bf16x3_kernel computes it."""
+    ah, al = split(a)
+    bh, bl = split(b)
+    return (ah @ bh.T + ah @ bl.T + al @ bh.T).astype(np.float32).astype(np.float64)
+
+
+def device_fit(x, labels, iters):
+    lab = labels.astype(np.int64)
+    uniq, inv, cnt = np.unique(lab, return_inverse=True, return_counts=True)
+    k, d = len(uniq), x.shape[1]
+    sums = np.zeros((k, d))
+    np.add.at(sums, inv, x)
+    means = sums / cnt[:, None]
+    xc = (x - means[inv]) / np.sqrt(cnt[inv])[:, None]
+    s = mm3(xc.T.copy(), xc.T.copy())
+    s = 0.5 * (s + s.T)
+    w = 1.0 / cnt
+    cw = w.sum()
+    mu = (w[:, None] * means).sum(0) / cw
+    mc = means - mu
+    within, between = np.eye(d), np.eye(d)
+    for _ in range(iters):
+        a, psi, ainv = kp.joint_diag(within, between)
+        u = mm3(mc, a)
+        n = cnt[:, None].astype(float)
+        r = psi[None, :] / (1 + n * psi[None, :])
+        g = n * r
+        p = np.sqrt(w)[:, None] * g * u
+        q = (1 - g) * u
+        bs = mm3(p.T.copy(), p.T.copy())
+        ws = mm3(q.T.copy(), q.T.copy())
+        bs = 0.5 * (bs + bs.T) + np.diag((w[:, None] * r).sum(0))
+        ws = 0.5 * (ws + ws.T) + np.diag(r.sum(0))
+        between = ainv @ bs @ ainv.T / cw
+        within = (s + ainv @ ws @ ainv.T) / k
+        between, within = 0.5 * (between + between.T), 0.5 * (within + within.T)
+    a, psi, _ = kp.joint_diag(within, between)
+    m = kp.Plda()
+    m.mean, m.transform, m.psi = mu, a, psi
+    m.compute_derived_vars()
+    return m
+
+
+def device_transform(m, means, counts):
+    y = mm3(means - m.mean, m.transform)
+    f = np.sqrt(m.dim() / np.sum(y * y / (m.psi[None, :] + 1.0 / counts[:, None]), axis=1))
+    return y * f[:, None]
+
+
+def device_grid(m, e, n, t):
+    psi = m.psi
+    nn = n[:, None].astype(float)
+    a = nn * psi / (nn * psi + 1)
+    v = 1 + psi / (nn * psi + 1)
+    lmat = e * a / v
+    row = (0.5 * np.sum(np.log1p(psi) - np.log(v) - a * a * e * e / v, axis=1)).astype(np.float32)
+    g = mm3(lmat, t)
+    out = np.empty_like(g)
+    for i in range(e.shape[0]):
+        vv = 1 + psi / (n[i] * psi + 1)
+        q = 0.5 * (1 / (1 + psi) - 1 / vv)
+        out[i] = (g[i].astype(np.float32) + row[i] + (t * t @ q).astype(np.float32)).astype(np.float64)
+    return out
+
+
+CASES = {
+    "ragged_d40": dict(d=40, counts="ragged", iters=6),
+    "config1_rand_500x200": dict(d=200, counts="c1", iters=10),
+    "d200_structured": dict(d=200, counts="uniform", iters=10),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_device_arithmetic_meets_parity_bar(name):
+    c = CASES[name]
+    d = c["d"]
+    if c["counts"] == "c1":
+        rng = np.random.RandomState(0)
+        x = rng.rand(500, 200)
+        labels = rng.randint(0, 2, 500).astype("uint")
+        xe, xt = rng.rand(120, 200), rng.rand(150, 200)
+        le, lt = np.arange(120, dtype="uint"), np.arange(150, dtype="uint")
+    else:
+        a_b = kp.two_cov_generator(d, 1234)
+        rng = np.random.RandomState(3)
+        cnt = rng.randint(2, 12, size=120) if c["counts"] == "ragged" else [20] * 150
+        x, labels, _ = kp.synth_speakers(a_b, cnt, 1234)
+        xe, le, _ = kp.synth_speakers(a_b, rng.randint(1, 5, size=37), 1235)
+        xt, lt, _ = kp.synth_speakers(a_b, [1] * 53, 1236)
+    ref = kp.MPlda()
+    ref.fit(x, labels, c["iters"])
+    dev = device_fit(x, labels, c["iters"])
+    assert np.max(np.abs(dev.psi - ref.plda.psi) / np.maximum(ref.plda.psi, 1e-12)) < 1e-4
+    _, ce, me = kp.group_means(xe, le)
+    _, ct, mt = kp.group_means(xt, lt)
+    want = kp.score_grid(ref.plda, kp.transform_batch(ref.plda, me, ce), ce, kp.transform_batch(ref.plda, mt, ct))
+    got = device_grid(dev, device_transform(dev, me, ce), ce, device_transform(dev, mt, ct))
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+    assert err.max() < 5e-4, err.max()      # bar is 1e-3

@@ -43,6 +43,11 @@ SHAPES = [
     (257, 513, 512),    # tile edges + 8 k-blocks
     (5, 3, 7),          # tiny
     (2048, 4096, 256),  # many tiles per CTA (accumulator double-buffer wrap)
+    (260, 300, 150),    # K16 = 160 = 64 + 64 + 32 -> 64-byte-swizzle tail box (C3 targetdim=150)
+    (130, 258, 80),     # 64 + 16 -> 32-byte-swizzle tail box
+    (64, 64, 96),       # 64 + 32
+    (1000, 1000, 600),  # 9 full k-blocks + 32 tail
+    (129, 33, 1),       # K = 1
 ]
 
 
