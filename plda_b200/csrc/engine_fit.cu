@@ -5,6 +5,8 @@
 //     -> PldaStats::AddSamples per speaker with weight 1/n_s (:94-98), Sort (:100)
 //     -> PldaEstimator::Estimate (:102-106): EstimateOneIter x iters, GetOutput
 #include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "engine.h"
 
@@ -50,8 +52,12 @@ void PldaEngine::joint_diagonalise(int64_t d, bool warm) {
   symmetrise_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(em_bp.get(), static_cast<int>(d));
   ctx.count_launch();
   // eigenvectors as ROWS of em_u (= U^T), eigenvalues descending, floored at 0
+  int sweeps = 0;
+  const bool dbg = getenv("PLDA_B200_DBG") != nullptr;
   eig_sym_jacobi(ctx, em_bp.get(), d, (warm && em_have_basis) ? em_u.get() : nullptr, em_psi.get(), em_tmp.get(), eig,
-                 nullptr);
+                 dbg ? &sweeps : nullptr);
+  if (dbg) fprintf(stderr, "plda_b200: joint_diagonalise d=%lld warm=%d sweeps=%d\n", static_cast<long long>(d),
+                   static_cast<int>(warm && em_have_basis), sweeps);
   PB_CUDA(cudaMemcpyAsync(em_u.get(), em_tmp.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
   em_have_basis = true;
   gemm_f64(ctx, false, false, d, d, d, 1.0, em_u.get(), d, em_t1.get(), d, 0.0, em_a.get(), d);     // A = U^T T1
@@ -219,6 +225,8 @@ void PldaEngine::test_linalg(int op, const double* a, int64_t d, double* out, do
   } else if (op == 2) {
     int sweeps = 0;
     eig_sym_jacobi(ctx, da.get(), d, nullptr, dv.get(), db.get(), eig, &sweeps);
+    if (getenv("PLDA_B200_DBG")) fprintf(stderr, "plda_b200: jacobi d=%lld converged after %d sweeps\n",
+                                         static_cast<long long>(d), sweeps);
     // return eigenvectors as columns
     std::vector<double> vt(dd);
     PB_CUDA(cudaMemcpyAsync(vt.data(), db.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));

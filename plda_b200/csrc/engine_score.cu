@@ -342,11 +342,16 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   } else {
     ws_row.reserve(ne);
     ws_col.reserve(static_cast<size_t>(ng) * col_ld);
-    PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(ng) * col_ld * sizeof(float), ctx.stream));
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), &ws_l,
-                     nullptr, ws_row.get(), nullptr);
-    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), &ws_r,
-                    ws_col.get(), col_ld, nullptr);
+    if (uniform) {
+      score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, uniform_count, model.psi.get(), ws_l,
+                         ws_r, ws_row.get(), ws_col.get(), col_ld);
+    } else {
+      PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(ng) * col_ld * sizeof(float), ctx.stream));
+      score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), &ws_l,
+                       nullptr, ws_row.get(), nullptr);
+      score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), &ws_r,
+                      ws_col.get(), col_ld, nullptr);
+    }
   }
 
   // enrol-row chunks: bounded staging when the result goes back to the host, one chunk otherwise

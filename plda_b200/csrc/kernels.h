@@ -28,6 +28,11 @@ void score_prep_enrol(Context& ctx, const void* enrol, bool is_f32, int64_t ne, 
 void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, int64_t d, int64_t ld,
                      const int32_t* group_counts, int ngroups, int const_count, const double* psi, SplitBuf* r_out, float* col_term,
                      int64_t col_ld, double* col_term_f64);
+// Fused enrol + test operand producer for a single enrol count (one launch, per-column constants computed once per
+// block, writes the zero padding of col_term itself).  enrol and test share dtype.
+void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const void* test, int64_t nt,
+                        int64_t ld_t, bool is_f32, int64_t d, int count, const double* psi, SplitBuf& l_out,
+                        SplitBuf& r_out, float* row_term, float* col_term, int64_t col_ld);
 // exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
                         const double* col_term, int64_t col_ld, const int32_t* grp, const float* zmean,

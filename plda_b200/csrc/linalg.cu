@@ -214,6 +214,256 @@ __global__ void frob2_kernel(const double* __restrict__ a, long long n, double* 
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+
+// ------------------------------------------------------------------------- //
+// Block one-sided Jacobi (the production eigensolver).
+//   gt[p,:] = column p of G = B V (rows contiguous).  Columns are grouped in blocks of `bw`; a CTA owns one
+//   PAIR of blocks per global round (round-robin tournament over blocks), keeps its 2*bw columns in shared
+//   memory and orthogonalises ALL pairs among them with a local tournament (one warp per pair,
+//   __syncthreads between local rounds).  Device-wide barriers: (#blocks - 1) per sweep instead of (d - 1).
+//   V is not tracked: at convergence G = V diag(lambda), so v_p = g_p / |g_p| and lambda_p = |g_p|.
+// ------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(1024, 1)
+block_jacobi_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, double abs_tol, int max_sweeps,
+                    unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated,
+                    int* __restrict__ sweeps_done) {
+  extern __shared__ double cols[];            // [2*bw][d]
+  __shared__ int s_rot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nthreads = blockDim.x;
+  const int m2 = 2 * bw;                      // column slots held by this CTA
+  unsigned int target = 0;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    for (int r = 0; r < nblk_pad - 1; ++r) {
+      // block pair of this CTA in global round r (circle method over nblk_pad blocks)
+      int bi, bj;
+      const int k = blockIdx.x;
+      if (k == 0) { bi = nblk_pad - 1; bj = r; }
+      else { bi = (r + k) % (nblk_pad - 1); bj = (r - k + (nblk_pad - 1)) % (nblk_pad - 1); }
+      // load the 2*bw columns (global column index of slot s: blk*bw + s%bw); slots beyond d stay unused
+      for (int idx = threadIdx.x; idx < m2 * d; idx += nthreads) {
+        const int slot = idx / d, i = idx - slot * d;
+        const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+        cols[idx] = col < d ? __ldcg(gt + static_cast<long long>(col) * d + i) : 0.0;
+      }
+      if (threadIdx.x == 0) s_rot = 0;
+      __syncthreads();
+      // local tournament over m2 slots: m2 - 1 rounds, warp w owns one pair per round
+      for (int lr = 0; lr < m2 - 1; ++lr) {
+        if (warp < bw) {
+          int x, y;
+          if (warp == 0) { x = m2 - 1; y = lr; }
+          else { x = (lr + warp) % (m2 - 1); y = (lr - warp + (m2 - 1)) % (m2 - 1); }
+          const int cx = (x < bw ? bi : bj) * bw + (x < bw ? x : x - bw);
+          const int cy = (y < bw ? bi : bj) * bw + (y < bw ? y : y - bw);
+          if (cx < d && cy < d) {
+            double* px = cols + x * d;
+            double* py = cols + y * d;
+            double alpha = 0.0, beta = 0.0, gamma = 0.0;
+            for (int i = lane; i < d; i += 32) {
+              const double a = px[i], b = py[i];
+              alpha += a * a;
+              beta += b * b;
+              gamma += a * b;
+            }
+            alpha = warp_sum(alpha);
+            beta = warp_sum(beta);
+            gamma = warp_sum(gamma);
+            if (fabs(gamma) > tol * sqrt(alpha * beta) && fabs(gamma) > abs_tol) {
+              const double zeta = (beta - alpha) / (2.0 * gamma);
+              const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+              const double c = 1.0 / sqrt(1.0 + t * t);
+              const double sn = c * t;
+              for (int i = lane; i < d; i += 32) {
+                const double a = px[i], b = py[i];
+                px[i] = c * a - sn * b;
+                py[i] = sn * a + c * b;
+              }
+              if (lane == 0) s_rot = 1;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // write back
+      for (int idx = threadIdx.x; idx < m2 * d; idx += nthreads) {
+        const int slot = idx / d, i = idx - slot * d;
+        const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+        if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, cols[idx]);
+      }
+      if (threadIdx.x == 0 && s_rot) atomicOr(rotated + sweep, 1);
+      grid_barrier(barrier_counter, target, gridDim.x);
+    }
+    const int any = *reinterpret_cast<volatile int*>(rotated + sweep);
+    if (!any) { ++sweep; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
+}
+
+// ------------------------------------------------------------------------- //
+// Block Jacobi, Gram formulation (production path).  Same block tournament as above, but inside a CTA the
+// 2*bw columns are orthogonalised through their small Gram matrix:
+//   1. Gl = C^T C            (m2 x m2, register-tiled dot products out of shared memory)
+//   2. one two-sided Jacobi tournament on Gl (m2 - 1 rounds of m2/2 disjoint rotations, rows then columns),
+//      accumulating the rotations in Q -- rotation angles come from 3 Gram entries, no d-length reductions
+//   3. C <- C Q              (written straight back to global memory)
+// Steps 1 and 3 are GEMM-shaped and use every thread; only step 2 is sequential, on a 32x32 / 64x64 matrix.
+// ------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(1024, 1)
+block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, int max_sweeps,
+                         unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated,
+                         int* __restrict__ sweeps_done) {
+  extern __shared__ double sm[];
+  const int m2 = 2 * bw;
+  const int dp = d | 1;                       // odd pitch: strided column reads are bank-conflict free
+  const int gp = m2 + 1;
+  double* cols = sm;                          // [m2][dp]
+  double* gl = cols + m2 * dp;                // [m2][gp]
+  double* qm = gl + m2 * gp;                  // [m2][gp]
+  __shared__ int s_rot;
+  __shared__ double s_abs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nthreads = blockDim.x;
+  const int half = m2 >> 1;
+  unsigned int target = 0;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    for (int r = 0; r < nblk_pad - 1; ++r) {
+      int bi, bj;
+      const int k = blockIdx.x;
+      if (k == 0) { bi = nblk_pad - 1; bj = r; }
+      else { bi = (r + k) % (nblk_pad - 1); bj = (r - k + (nblk_pad - 1)) % (nblk_pad - 1); }
+      for (int idx = threadIdx.x; idx < m2 * d; idx += nthreads) {
+        const int slot = idx / d, i = idx - slot * d;
+        const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+        cols[slot * dp + i] = col < d ? __ldcg(gt + static_cast<long long>(col) * d + i) : 0.0;
+      }
+      for (int idx = threadIdx.x; idx < m2 * m2; idx += nthreads) {
+        const int i = idx / m2, j = idx - i * m2;
+        qm[i * gp + j] = i == j ? 1.0 : 0.0;
+      }
+      if (threadIdx.x == 0) s_rot = 0;
+      __syncthreads();
+      // ---- 1. Gram: thread owns the strided 2x2 tile {ti, ti+half} x {tj, tj+half}
+      for (int t = threadIdx.x; t < half * half; t += nthreads) {
+        const int ti = t / half, tj = t - ti * half;
+        const double* a0 = cols + ti * dp;
+        const double* a1 = cols + (ti + half) * dp;
+        const double* b0 = cols + tj * dp;
+        const double* b1 = cols + (tj + half) * dp;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        for (int i = 0; i < d; ++i) {
+          const double x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
+          c00 = fma(x0, y0, c00);
+          c01 = fma(x0, y1, c01);
+          c10 = fma(x1, y0, c10);
+          c11 = fma(x1, y1, c11);
+        }
+        gl[ti * gp + tj] = c00;
+        gl[ti * gp + tj + half] = c01;
+        gl[(ti + half) * gp + tj] = c10;
+        gl[(ti + half) * gp + tj + half] = c11;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int i = 0; i < m2; ++i) mx = fmax(mx, gl[i * gp + i]);
+        // rounding noise of a Gram entry is relative to |g_x||g_y| (covered by `tol`); the absolute floor only
+        // guards columns that vanished entirely
+        s_abs = 1e-290 * mx;
+      }
+      __syncthreads();
+      const double abs_tol = s_abs;
+      // ---- 2. two-sided Jacobi tournament on the Gram matrix
+      for (int lr = 0; lr < m2 - 1; ++lr) {
+        int x = 0, y = 0;
+        double c = 1.0, sn = 0.0;
+        bool rot = false;
+        if (warp < half) {
+          if (warp == 0) { x = m2 - 1; y = lr; }
+          else { x = (lr + warp) % (m2 - 1); y = (lr - warp + (m2 - 1)) % (m2 - 1); }
+          const double alpha = gl[x * gp + x], beta = gl[y * gp + y], gamma = gl[x * gp + y];
+          if (fabs(gamma) > tol * sqrt(alpha * beta) && fabs(gamma) > abs_tol) {
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            c = 1.0 / sqrt(1.0 + t * t);
+            sn = c * t;
+            rot = true;
+          }
+        }
+        __syncthreads();                       // every pair has read its three entries
+        if (rot) {
+          for (int j = lane; j < m2; j += 32) {   // rows x, y  (J^T G)
+            const double gx = gl[x * gp + j], gy = gl[y * gp + j];
+            gl[x * gp + j] = c * gx - sn * gy;
+            gl[y * gp + j] = sn * gx + c * gy;
+          }
+          if (lane == 0) s_rot = 1;
+        }
+        __syncthreads();
+        if (rot) {
+          for (int i = lane; i < m2; i += 32) {   // columns x, y  (G J) and Q <- Q J
+            const double gx = gl[i * gp + x], gy = gl[i * gp + y];
+            gl[i * gp + x] = c * gx - sn * gy;
+            gl[i * gp + y] = sn * gx + c * gy;
+            const double qx = qm[i * gp + x], qy = qm[i * gp + y];
+            qm[i * gp + x] = c * qx - sn * qy;
+            qm[i * gp + y] = sn * qx + c * qy;
+          }
+        }
+        __syncthreads();
+      }
+      // ---- 3. C <- C Q, written back to global: new column x' = sum_x Q[x][x'] * old column x
+      if (s_rot) {
+        const int groups = m2 >> 2;
+        for (int idx = threadIdx.x; idx < groups * d; idx += nthreads) {
+          const int xg = idx / d, i = idx - xg * d;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          const double* qrow = qm + xg * 4;
+          for (int x = 0; x < m2; ++x) {
+            const double v = cols[x * dp + i];
+            a0 = fma(v, qrow[x * gp + 0], a0);
+            a1 = fma(v, qrow[x * gp + 1], a1);
+            a2 = fma(v, qrow[x * gp + 2], a2);
+            a3 = fma(v, qrow[x * gp + 3], a3);
+          }
+          const double out[4] = {a0, a1, a2, a3};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int slot = xg * 4 + j;
+            const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+            if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, out[j]);
+          }
+        }
+        if (threadIdx.x == 0) atomicOr(rotated + sweep, 1);
+      }
+      grid_barrier(barrier_counter, target, gridDim.x);
+    }
+    const int any = *reinterpret_cast<volatile int*>(rotated + sweep);
+    if (!any) { ++sweep; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
+}
+
+// lambda_p = |g_p| ; v_p = g_p / |g_p|  (zero vector if the column vanished)
+__global__ void __launch_bounds__(256)
+eig_normalise_kernel(const double* __restrict__ gt, int d, double* __restrict__ lam, double* __restrict__ vt) {
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= d) return;
+  double acc = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const double g = gt[static_cast<long long>(p) * d + i];
+    acc += g * g;
+  }
+  acc = warp_sum(acc);
+  const double nrm = sqrt(acc);
+  const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+  for (int i = lane; i < d; i += 32) vt[static_cast<long long>(p) * d + i] = gt[static_cast<long long>(p) * d + i] * inv;
+  if (lane == 0) lam[p] = nrm;
+}
+
 }  // namespace
 
 void cholesky_lower(Context& ctx, double* a, int64_t d, int* info_dev) {
@@ -246,40 +496,40 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   w.flags.reserve(max_sweeps + 4);   // [0] barrier counter, [1] sweeps_done, [2..] rotated flags
   PB_CUDA(cudaMemsetAsync(w.flags.get(), 0, (max_sweeps + 4) * sizeof(int), ctx.stream));
   if (v0_t != nullptr) {
-    // warm start: V = V0, G^T = V0^T B  (B symmetric)
-    PB_CUDA(cudaMemcpyAsync(w.v.get(), v0_t, d * d * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    // warm start from an orthogonal basis V0 (rows): G^T = V0^T B  (B symmetric)
     gemm_f64(ctx, false, false, d, d, d, 1.0, v0_t, d, b, d, 0.0, w.g.get(), d);
   } else {
     PB_CUDA(cudaMemcpyAsync(w.g.get(), b, d * d * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
-    set_identity(ctx, w.v.get(), d);
   }
-  // absolute floor on |g_p . g_q| relative to ||B||_F^2 (noise level of near-null directions)
-  PB_CUDA(cudaMemsetAsync(w.tmp.get(), 0, sizeof(double), ctx.stream));
-  frob2_kernel<<<32, 256, 0, ctx.stream>>>(b, d * d, w.tmp.get());
-  ctx.count_launch();
-  double frob2 = 0.0;
-  PB_CUDA(cudaMemcpyAsync(&frob2, w.tmp.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  ctx.sync();
-  double tol = 1e-14, abs_tol = 1e-26 * frob2;
+  // |g_p.g_q| / (|g_p||g_q|) cannot be driven below ~d*eps in fp64 (rounding of the d-term dot products);
+  // a tighter threshold makes every sweep "rotate" forever (measured: 40 sweeps instead of ~8)
+  double tol = 4.0 * static_cast<double>(d) * 2.220446049250313e-16;
   int di = static_cast<int>(d);
-  const int m = di + (di & 1);
-  const int npairs = m / 2;
-  int blocks = static_cast<int>(ceil_div(npairs, 8));
+  // block width: 16 columns per block up to d = 512 (32 x 32 Gram per CTA), 8 above
+  int bw = d <= 512 ? 16 : 8;
+  int nblk = static_cast<int>(ceil_div(d, bw));
+  if (nblk < 2) nblk = 2;
+  int nblk_pad = nblk + (nblk & 1);
+  const int blocks = nblk_pad / 2;
+  const int m2 = 2 * bw;
+  const size_t smem = (static_cast<size_t>(m2) * (d | 1) + 2 * static_cast<size_t>(m2) * (m2 + 1)) * sizeof(double);
+  PB_CHECK(smem <= 200 * 1024, kInvalidArg, "eig: dimension too large");
   PB_CHECK(blocks <= ctx.num_sms, kInvalidArg, "eig: too many blocks for a cooperative launch");
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(block_jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
   double* gp = w.g.get();
-  double* vp = w.v.get();
   unsigned int* counter = reinterpret_cast<unsigned int*>(w.flags.get());
   int* sweeps_done = w.flags.get() + 1;
   int* rotated = w.flags.get() + 2;
   int ms = max_sweeps;
-  void* args[] = {&gp, &vp, &di, &tol, &abs_tol, &ms, &counter, &rotated, &sweeps_done};
-  const void* fn = d <= 256 ? reinterpret_cast<const void*>(jacobi_kernel<8>)
-                 : d <= 512 ? reinterpret_cast<const void*>(jacobi_kernel<16>)
-                            : reinterpret_cast<const void*>(jacobi_kernel<32>);
-  PB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, ctx.stream));
+  void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &ms, &counter, &rotated, &sweeps_done};
+  PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(block_jacobi_gram_kernel), dim3(blocks),
+                                      dim3(512), args, smem, ctx.stream));
   ctx.count_launch();
-  eig_lambda_kernel<<<static_cast<unsigned>(ceil_div(d, 8)), 256, 0, ctx.stream>>>(w.g.get(), w.v.get(), di,
-                                                                                  w.lam.get());
+  eig_normalise_kernel<<<static_cast<unsigned>(ceil_div(d, 8)), 256, 0, ctx.stream>>>(w.g.get(), di, w.lam.get(),
+                                                                                     w.v.get());
   eig_sort_kernel<<<static_cast<unsigned>(d), 128, 0, ctx.stream>>>(w.lam.get(), w.v.get(), di, evals, evecs_t);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch(2);

@@ -124,6 +124,83 @@ __global__ void score_prep_test_kernel(const T* __restrict__ test, long long nt,
   }
 }
 
+// Fused operand producer of the score grid for the common case of ONE enrol count n (tensor path):
+// blocks [0, eb) handle 32 enrol rows each, blocks [eb, eb+tb) 32 test rows each.  The per-column constants
+// (a/v, a^2/v, q and the log-determinant term) depend only on (n, psi) and are computed once per block in smem
+// instead of once per element; the zero padding of the column-term row is written here too (no memset).
+template <typename T>
+__global__ void __launch_bounds__(256)
+score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const T* __restrict__ test,
+                          long long nt, long long ld_t, int d, int count, const double* __restrict__ psi,
+                          __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo,
+                          __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo, int ld_out,
+                          float* __restrict__ row_term, float* __restrict__ col_term, long long col_ld,
+                          unsigned enrol_blocks) {
+  __shared__ double s_s[1024], s_w[1024], s_q[1024];
+  __shared__ double s_red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_enrol = blockIdx.x < enrol_blocks;
+  const double n = static_cast<double>(count);
+  double cpart = 0.0;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    const double p = psi[c];
+    const double den = n * p + 1.0;
+    const double a = n * p / den;
+    const double v = 1.0 + p / den;
+    s_s[c] = a / v;
+    s_w[c] = a * a / v;
+    s_q[c] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
+    if (is_enrol) cpart += log1p(p) - log(v);
+  }
+  cpart = warp_sum(cpart);
+  if (lane == 0) s_red[warp] = cpart;
+  __syncthreads();
+  double cst = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cst += s_red[i];
+  if (is_enrol) {
+    const long long r0 = static_cast<long long>(blockIdx.x) * 32;
+    for (int i = warp; i < 32; i += 8) {
+      const long long r = r0 + i;
+      if (r >= ne) break;
+      const T* src = enrol + r * ld_e;
+      double acc = 0.0;
+      for (int c = lane; c < ld_out; c += 32) {
+        double lv = 0.0;
+        if (c < d) {
+          const double e = static_cast<double>(src[c]);
+          lv = e * s_s[c];
+          acc += s_w[c] * e * e;
+        }
+        store_split(l_hi, l_lo, r * ld_out + c, lv);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) row_term[r] = static_cast<float>(0.5 * (cst - acc));
+    }
+  } else {
+    const long long r0 = static_cast<long long>(blockIdx.x - enrol_blocks) * 32;
+    for (int i = warp; i < 32; i += 8) {
+      const long long r = r0 + i;
+      if (r >= nt) {
+        if (lane == 0 && r < col_ld) col_term[r] = 0.f;   // padding read (never stored) by the GEMM epilogue
+        continue;
+      }
+      const T* src = test + r * ld_t;
+      double acc = 0.0;
+      for (int c = lane; c < ld_out; c += 32) {
+        double tv = 0.0;
+        if (c < d) {
+          tv = static_cast<double>(src[c]);
+          acc += s_q[c] * tv * tv;
+        }
+        store_split(r_hi, r_lo, r * ld_out + c, tv);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) col_term[r] = static_cast<float>(acc);
+    }
+  }
+}
+
 __global__ void score_epilogue_f64_kernel(const double* __restrict__ gram, long long ne, long long nt,
                                           const double* __restrict__ row_term, const double* __restrict__ col_term,
                                           long long col_ld, const int32_t* __restrict__ grp,
@@ -262,6 +339,28 @@ void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, in
     score_prep_test_kernel<double><<<row_blocks(nt), kWarpsPerBlock * 32, 0, ctx.stream>>>(
         static_cast<const double*>(test), nt, static_cast<int>(d), ld, group_counts, ngroups, const_count, psi, hi, lo, ldo,
         col_term, col_ld, col_term_f64);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const void* test, int64_t nt,
+                        int64_t ld_t, bool is_f32, int64_t d, int count, const double* psi, SplitBuf& l_out,
+                        SplitBuf& r_out, float* row_term, float* col_term, int64_t col_ld) {
+  PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
+  l_out.reserve(ne, d);
+  r_out.reserve(nt, d);
+  const unsigned eb = static_cast<unsigned>(ceil_div(ne, 32));
+  const unsigned tb = static_cast<unsigned>(ceil_div(col_ld, 32));
+  if (is_f32)
+    score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
+        static_cast<const float*>(enrol), ne, ld_e, static_cast<const float*>(test), nt, ld_t, static_cast<int>(d),
+        count, psi, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(), static_cast<int>(l_out.ld),
+        row_term, col_term, col_ld, eb);
+  else
+    score_prep_uniform_kernel<double><<<eb + tb, 256, 0, ctx.stream>>>(
+        static_cast<const double*>(enrol), ne, ld_e, static_cast<const double*>(test), nt, ld_t, static_cast<int>(d),
+        count, psi, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(), static_cast<int>(l_out.ld),
+        row_term, col_term, col_ld, eb);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }
