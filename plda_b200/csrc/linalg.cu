@@ -6,6 +6,8 @@
 // fixed number of device-wide synchronisations, all matrices L2-resident.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace pb {
@@ -50,6 +52,67 @@ cholesky_kernel(double* __restrict__ a, int d, int* __restrict__ info) {
     const int i = static_cast<int>(idx / d), k = static_cast<int>(idx % d);
     if (k > i) a[idx] = 0.0;
   }
+}
+
+// ------------------------------------------------------------------------- //
+// Blocked (left-looking) Cholesky, panel width 32: per panel
+//   (1) gemm_f64:  A[k0:, panel] -= L[k0:, :k0] L[panel, :k0]^T          (all SMs)
+//   (2) chol_diag_kernel:  factor the 32 x 32 diagonal block in shared memory (one CTA, 1024 threads)
+//   (3) chol_solve_kernel: rows below, X Lkk^T = A[rows, panel]            (32 rows per CTA)
+// ------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(1024)
+chol_diag_kernel(double* __restrict__ a, int d, int k0, int nb, int* __restrict__ info) {
+  __shared__ double s[32][33];
+  __shared__ int s_fail;
+  const int i = threadIdx.x >> 5, k = threadIdx.x & 31;   // thread (i, k) owns s[i][k]
+  if (threadIdx.x == 0) s_fail = 0;
+  s[i][k] = (i < nb && k < nb) ? a[static_cast<long long>(k0 + i) * d + k0 + k] : 0.0;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    const double ajj = s[j][j];
+    if (!(ajj > 0.0)) {
+      if (threadIdx.x == 0) { *info = k0 + j + 1; }
+      return;                       // uniform: every thread read the same pivot
+    }
+    const double inv = rsqrt(ajj);
+    __syncthreads();
+    if (k == j && i >= j) s[i][j] = (i == j) ? sqrt(ajj) : s[i][j] * inv;
+    __syncthreads();
+    if (k > j && i >= k) s[i][k] -= s[i][j] * s[k][j];
+    __syncthreads();
+  }
+  if (i < nb && k < nb) a[static_cast<long long>(k0 + i) * d + k0 + k] = k <= i ? s[i][k] : 0.0;
+}
+
+__global__ void __launch_bounds__(32)
+chol_solve_kernel(double* __restrict__ a, int d, int k0, int nb) {
+  __shared__ double lkk[32][33];
+  const int t = threadIdx.x;
+  for (int j = 0; j < nb; ++j) lkk[j][t] = t < nb ? a[static_cast<long long>(k0 + j) * d + k0 + t] : 0.0;
+  __syncwarp();
+  const int r = k0 + nb + blockIdx.x * 32 + t;
+  if (r >= d) return;
+  double* row = a + static_cast<long long>(r) * d + k0;
+  double x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < nb) {
+      double v = row[j];
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (q < j) v -= x[q] * lkk[j][q];
+      x[j] = v / lkk[j][j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < nb) row[j] = x[j];
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ a, int d) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(d) * d) return;
+  if (idx % d > idx / d) a[idx] = 0.0;
 }
 
 // ------------------------------------------------------------------------- //
@@ -322,6 +385,7 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
   double* gl = cols + m2 * dp;                // [m2][gp]
   double* qm = gl + m2 * gp;                  // [m2][gp]
   __shared__ int s_rot;
+  __shared__ int s_big;                       // a pair with |gamma|/sqrt(alpha beta) >= 1e-7 was seen
   __shared__ double s_abs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nthreads = blockDim.x;
@@ -343,7 +407,7 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
         const int i = idx / m2, j = idx - i * m2;
         qm[i * gp + j] = i == j ? 1.0 : 0.0;
       }
-      if (threadIdx.x == 0) s_rot = 0;
+      if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
       __syncthreads();
       // ---- 1. Gram: thread owns the strided 2x2 tile {ti, ti+half} x {tj, tj+half}
       for (int t = threadIdx.x; t < half * half; t += nthreads) {
@@ -353,6 +417,7 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
         const double* b0 = cols + tj * dp;
         const double* b1 = cols + (tj + half) * dp;
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 4
         for (int i = 0; i < d; ++i) {
           const double x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
           c00 = fma(x0, y0, c00);
@@ -384,15 +449,22 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
           if (warp == 0) { x = m2 - 1; y = lr; }
           else { x = (lr + warp) % (m2 - 1); y = (lr - warp + (m2 - 1)) % (m2 - 1); }
           const double alpha = gl[x * gp + x], beta = gl[y * gp + y], gamma = gl[x * gp + y];
-          if (fabs(gamma) > tol * sqrt(alpha * beta) && fabs(gamma) > abs_tol) {
-            const double zeta = (beta - alpha) / (2.0 * gamma);
-            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            c = 1.0 / sqrt(1.0 + t * t);
+          if (lane == 0 && gamma * gamma > 1e-14 * alpha * beta) s_big = 1;
+          if (gamma * gamma > tol * tol * alpha * beta && fabs(gamma) > abs_tol) {
+            // rotation angle in fp32 (a 1e-7 relative error in the angle only leaves a 1e-7 * gamma residual),
+            // but (c, s) exactly orthonormal in fp64: c = rsqrt(1 + t^2) by two Newton steps, s = c t
+            const float zf = static_cast<float>(beta - alpha) / (2.0f * static_cast<float>(gamma));
+            const float tf = copysignf(1.0f, zf) / (fabsf(zf) + sqrtf(1.0f + zf * zf));
+            const double t = static_cast<double>(tf);
+            const double xx = fma(t, t, 1.0);
+            double c0 = static_cast<double>(rsqrtf(static_cast<float>(xx)));
+            c0 = c0 * fma(-0.5 * xx, c0 * c0, 1.5);
+            c0 = c0 * fma(-0.5 * xx, c0 * c0, 1.5);
+            c = c0;
             sn = c * t;
-            rot = true;
+            rot = tf != 0.0f;
           }
         }
-        __syncthreads();                       // every pair has read its three entries
         if (rot) {
           for (int j = lane; j < m2; j += 32) {   // rows x, y  (J^T G)
             const double gx = gl[x * gp + j], gy = gl[y * gp + j];
@@ -421,6 +493,7 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
           const int xg = idx / d, i = idx - xg * d;
           double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
           const double* qrow = qm + xg * 4;
+#pragma unroll 4
           for (int x = 0; x < m2; ++x) {
             const double v = cols[x * dp + i];
             a0 = fma(v, qrow[x * gp + 0], a0);
@@ -436,12 +509,15 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
             if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, out[j]);
           }
         }
-        if (threadIdx.x == 0) atomicOr(rotated + sweep, 1);
+        // bit 0: something rotated; bit 1: a rotation larger than 1e-7 (relative) happened.  Jacobi converges
+        // quadratically, so a sweep whose largest rotation was < 1e-7 leaves every pair below ~1e-14: converged
+        // without paying for a verification sweep.
+        if (threadIdx.x == 0) atomicOr(rotated + sweep, s_big ? 3 : 1);
       }
       grid_barrier(barrier_counter, target, gridDim.x);
     }
-    const int any = *reinterpret_cast<volatile int*>(rotated + sweep);
-    if (!any) { ++sweep; break; }
+    const int flags = *reinterpret_cast<volatile int*>(rotated + sweep);
+    if ((flags & 2) == 0) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
 }
@@ -468,7 +544,19 @@ eig_normalise_kernel(const double* __restrict__ gt, int d, double* __restrict__ 
 
 void cholesky_lower(Context& ctx, double* a, int64_t d, int* info_dev) {
   PB_CHECK(d > 0 && d <= 4096, kInvalidArg, "cholesky: dimension out of range");
-  cholesky_kernel<<<1, 1024, d * sizeof(double), ctx.stream>>>(a, static_cast<int>(d), info_dev);
+  PB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx.stream));
+  const int di = static_cast<int>(d);
+  for (int k0 = 0; k0 < di; k0 += 32) {
+    const int nb = std::min(32, di - k0);
+    if (k0 > 0)   // A[k0:, k0:k0+nb] -= L[k0:, :k0] L[k0:k0+nb, :k0]^T
+      gemm_f64(ctx, false, true, di - k0, nb, k0, -1.0, a + static_cast<int64_t>(k0) * d, d,
+               a + static_cast<int64_t>(k0) * d, d, 1.0, a + static_cast<int64_t>(k0) * d + k0, d);
+    chol_diag_kernel<<<1, 1024, 0, ctx.stream>>>(a, di, k0, nb, info_dev);
+    const int below = di - k0 - nb;
+    if (below > 0) chol_solve_kernel<<<static_cast<unsigned>(ceil_div(below, 32)), 32, 0, ctx.stream>>>(a, di, k0, nb);
+    ctx.count_launch(below > 0 ? 2 : 1);
+  }
+  zero_upper_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(a, di);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

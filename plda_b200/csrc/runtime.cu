@@ -67,29 +67,30 @@ void Context::profile_collect(double* total_ms, int64_t* count) {
 // ------------------------------------------------------------------------- //
 namespace {
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, int TILE>   // TILE = 64 (4x4 per thread) or 32 (2x2 per thread: more CTAs for d x d work)
 __global__ void __launch_bounds__(256)
 gemm_f64_kernel(int m, int n, int k, double alpha, const double* __restrict__ a, long long lda,
                 const double* __restrict__ b, long long ldb, double beta, double* __restrict__ c, long long ldc) {
-  __shared__ double sa[16][64 + 1];
-  __shared__ double sb[16][64 + 1];
+  constexpr int MT = TILE / 16;
+  __shared__ double sa[16][TILE + 1];
+  __shared__ double sb[16][TILE + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  double acc[4][4] = {};
+  const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+  double acc[MT][MT] = {};
   for (int k0 = 0; k0 < k; k0 += 16) {
     // A tile: element (mm, kk) = TA ? a[kk*lda + mm] : a[mm*lda + kk]
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    for (int i = threadIdx.x; i < TILE * 16; i += 256) {
       int mm, kk;
-      if (TA) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+      if (TA) { mm = i % TILE; kk = i / TILE; } else { kk = i & 15; mm = i >> 4; }
       const int gm = m0 + mm, gk = k0 + kk;
       double v = 0.0;
       if (gm < m && gk < k) v = TA ? a[gk * lda + gm] : a[gm * lda + gk];
       sa[kk][mm] = v;
     }
     // B tile: element (kk, nn) = TB ? b[nn*ldb + kk] : b[kk*ldb + nn]
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    for (int i = threadIdx.x; i < TILE * 16; i += 256) {
       int nn, kk;
-      if (TB) { kk = i & 15; nn = i >> 4; } else { nn = i & 63; kk = i >> 6; }
+      if (TB) { kk = i & 15; nn = i >> 4; } else { nn = i % TILE; kk = i / TILE; }
       const int gn = n0 + nn, gk = k0 + kk;
       double v = 0.0;
       if (gn < n && gk < k) v = TB ? b[gn * ldb + gk] : b[gk * ldb + gn];
@@ -98,24 +99,24 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double* __restrict__ a,
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      double ra[4], rb[4];
+      double ra[MT], rb[MT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ra[i] = sa[kk][ty + 16 * i];
+      for (int i = 0; i < MT; ++i) ra[i] = sa[kk][ty + 16 * i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rb[j] = sb[kk][tx + 16 * j];
+      for (int j = 0; j < MT; ++j) rb[j] = sb[kk][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(ra[i], rb[j], acc[i][j]);
+        for (int j = 0; j < MT; ++j) acc[i][j] = fma(ra[i], rb[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MT; ++i) {
     const int gm = m0 + ty + 16 * i;
     if (gm >= m) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < MT; ++j) {
       const int gn = n0 + tx + 16 * j;
       if (gn >= n) continue;
       double* p = c + gm * ldc + gn;
@@ -124,17 +125,27 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double* __restrict__ a,
   }
 }
 
+template <int TILE>
+void launch_gemm_f64(Context& ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* a, int64_t lda,
+                     const double* b, int64_t ldb, double beta, double* c, int64_t ldc) {
+  dim3 grid(static_cast<unsigned>(ceil_div(n, TILE)), static_cast<unsigned>(ceil_div(m, TILE)));
+  if (ta && tb) gemm_f64_kernel<true, true, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+  else if (ta) gemm_f64_kernel<true, false, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+  else if (tb) gemm_f64_kernel<false, true, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+  else gemm_f64_kernel<false, false, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+
 }  // namespace
 
 void gemm_f64(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a,
               int64_t lda, const double* b, int64_t ldb, double beta, double* c, int64_t ldc) {
   PB_CHECK(m > 0 && n > 0 && k > 0, kInvalidArg, "gemm_f64: empty problem");
-  dim3 grid(static_cast<unsigned>(ceil_div(n, 64)), static_cast<unsigned>(ceil_div(m, 64)));
   const int mi = static_cast<int>(m), ni = static_cast<int>(n), ki = static_cast<int>(k);
-  if (ta && tb) gemm_f64_kernel<true, true><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
-  else if (ta) gemm_f64_kernel<true, false><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
-  else if (tb) gemm_f64_kernel<false, true><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
-  else gemm_f64_kernel<false, false><<<grid, 256, 0, ctx.stream>>>(mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
+  // d x d algebra (a handful of 64x64 tiles) is latency bound: use 32x32 tiles to spread over more SMs
+  if (ceil_div(m, 64) * ceil_div(n, 64) < 2 * ctx.num_sms)
+    launch_gemm_f64<32>(ctx, ta, tb, mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
+  else
+    launch_gemm_f64<64>(ctx, ta, tb, mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }
