@@ -155,6 +155,9 @@ def cpu_reference_model():
 
 def cpu_grid_sample(psi, sub_ne, sub_nt, steps, warmup, threads=0):
     from oracle import c_ref
+    if threads <= 0:
+        # explicit: torchrun exports OMP_NUM_THREADS=1, the reference arm may use every host core
+        threads = len(os.sched_getaffinity(0))
     rng = np.random.RandomState(7)
     e = rng.randn(sub_ne, D)
     t = rng.randn(sub_nt, D)

@@ -14,17 +14,20 @@
 //   * EM projection + 2 SYRKs    (PldaEstimator::GetStatsFromClassMeans, src/pldamodule.cpp:106)
 //   * LDA decision values        (python/liblda/lda.py:278)
 //
-// Kernel anatomy (persistent, warp-specialised, one CTA per SM, 384 threads = 3 warpgroups):
-//   warp 0      TMA producer: 4 tile loads per k-block (A_hi, A_lo, B_hi, B_lo), 128B swizzle,
-//               2-stage smem ring (96 KB/stage) guarded by full/empty mbarriers
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases smem
-//               stages and publishes finished accumulators
-//   warps 2..9  epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks, TMEM loads
-//               software-pipelined): tcgen05.ld -> fused row/col/z-norm terms -> swizzled smem staging
-//               -> TMA store (or fused row reductions, no store)
+// Kernel anatomy (persistent, warp-specialised, one CTA per SM, 384 threads = 3 warpgroups; CTA PAIRS with
+// tcgen05 cta_group::2 -- pair tile 256 x BN x 64, each CTA owns 128 rows):
+//   warp 0      TMA producer (both CTAs): 4 tile loads per k-block (own A_hi, A_lo; HALF of B_hi, B_lo), 128B
+//               swizzle, 3-stage smem ring (64 KB/stage) guarded by full/empty mbarriers; the leader CTA's full
+//               barrier collects the bytes of both CTAs; narrow boxes for a 16/32-column K tail
+//   warp 1      TMEM allocator; in the leader CTA a single thread issues tcgen05.mma.cta_group::2 (M = 256);
+//               multicast tcgen05.commit releases smem stages and publishes accumulators in both CTAs
+//   warps 2-3   idle (they complete warpgroup 0, which donates registers via setmaxnreg)
+//   warps 4..11 epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks): all tcgen05.ld of a
+//               tile in flight together -> accumulator stage released -> fused row/col/z-norm terms -> swizzled
+//               smem staging -> TMA store (or fused row reductions, no store)
 //   TMEM        2 accumulator stages x 256 fp32 columns (all 512 columns): the epilogue of tile i
 //               overlaps the MMAs of tile i+1.
-// Tile = 128 x BN (BN <= 256, multiple of 16) x 64.
+// A cta_group::1 instantiation (tile 128 x BN x 64, 2 x 96 KB stages) serves single-row-tile problems.
 #include <algorithm>
 
 #include "runtime.h"

@@ -4,55 +4,12 @@
 // (reached from src/pldamodule.cpp:106) and are also what lets the EM iteration run in the jointly
 // diagonalising basis.  They are latency-bound (no meaningful roofline); the design goal is a small,
 // fixed number of device-wide synchronisations, all matrices L2-resident.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 
 #include "kernels.h"
 
 namespace pb {
 namespace {
-
-// ------------------------------------------------------------------------- //
-// Cholesky: one CTA, right-looking, column j staged in smem, trailing rows updated warp-per-row.
-// ------------------------------------------------------------------------- //
-__global__ void __launch_bounds__(1024)
-cholesky_kernel(double* __restrict__ a, int d, int* __restrict__ info) {
-  extern __shared__ double col[];   // d doubles
-  __shared__ double s_piv;
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  if (tid == 0) *info = 0;
-  for (int j = 0; j < d; ++j) {
-    if (tid == 0) s_piv = a[static_cast<long long>(j) * d + j];
-    __syncthreads();
-    const double ajj = s_piv;
-    if (!(ajj > 0.0)) {
-      if (tid == 0) *info = j + 1;
-      return;
-    }
-    const double ljj = sqrt(ajj);
-    const double inv = 1.0 / ljj;
-    for (int i = j + tid; i < d; i += nthreads) {
-      const double v = (i == j) ? ljj : a[static_cast<long long>(i) * d + j] * inv;
-      a[static_cast<long long>(i) * d + j] = v;
-      col[i] = v;
-    }
-    __syncthreads();
-    // a[i][k] -= l[i] * l[k]  for j < k <= i
-    for (int i = j + 1 + warp; i < d; i += nwarps) {
-      const double li = col[i];
-      double* row = a + static_cast<long long>(i) * d;
-      for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= li * col[k];
-    }
-    __syncthreads();
-  }
-  // zero the strict upper triangle
-  for (long long idx = tid; idx < static_cast<long long>(d) * d; idx += nthreads) {
-    const int i = static_cast<int>(idx / d), k = static_cast<int>(idx % d);
-    if (k > i) a[idx] = 0.0;
-  }
-}
 
 // ------------------------------------------------------------------------- //
 // Blocked (left-looking) Cholesky, panel width 32: per panel
@@ -139,10 +96,7 @@ tri_inverse_kernel(const double* __restrict__ l, double* __restrict__ inv, int d
 }
 
 // ------------------------------------------------------------------------- //
-// One-sided (Hestenes) Jacobi on a symmetric matrix.
-//   gt[p,:] = column p of G = B V ;  vt[p,:] = column p of V   (rows are contiguous)
-// Each round pairs rows by the round-robin tournament; a warp owns one pair.  Rounds are
-// separated by a device-wide barrier (cooperative launch guarantees co-residency).
+// Device-wide barrier used by the eigensolver (cooperative launch guarantees co-residency).
 // ------------------------------------------------------------------------- //
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblocks) {
   __syncthreads();
@@ -161,90 +115,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __threadfence();
   }
   __syncthreads();
-}
-
-template <int EPL>   // elements per lane: d <= 32*EPL
-__global__ void __launch_bounds__(256)
-jacobi_kernel(double* __restrict__ gt, double* __restrict__ vt, int d, double tol, double abs_tol, int max_sweeps,
-              unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated, int* __restrict__ sweeps_done) {
-  const int warp_in_grid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int m = d + (d & 1);
-  const int npairs = m >> 1;
-  unsigned int target = 0;
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    for (int r = 0; r < m - 1; ++r) {
-      if (warp_in_grid < npairs) {
-        int p, q;
-        if (warp_in_grid == 0) { p = m - 1; q = r; }
-        else { p = (r + warp_in_grid) % (m - 1); q = (r - warp_in_grid + (m - 1)) % (m - 1); }
-        if (p > q) { const int t = p; p = q; q = t; }
-        if (q < d) {   // (odd d: the padded index sits out)
-          double gp[EPL], gq[EPL];
-          double alpha = 0.0, beta = 0.0, gamma = 0.0;
-          double* rp = gt + static_cast<long long>(p) * d;
-          double* rq = gt + static_cast<long long>(q) * d;
-#pragma unroll
-          for (int j = 0; j < EPL; ++j) {
-            const int i = lane + 32 * j;
-            gp[j] = i < d ? __ldcg(rp + i) : 0.0;
-            gq[j] = i < d ? __ldcg(rq + i) : 0.0;
-            alpha += gp[j] * gp[j];
-            beta += gq[j] * gq[j];
-            gamma += gp[j] * gq[j];
-          }
-          alpha = warp_sum(alpha);
-          beta = warp_sum(beta);
-          gamma = warp_sum(gamma);
-          const double lim = tol * sqrt(alpha * beta);
-          if (fabs(gamma) > lim && fabs(gamma) > abs_tol) {
-            const double zeta = (beta - alpha) / (2.0 * gamma);
-            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double c = 1.0 / sqrt(1.0 + t * t);
-            const double s = c * t;
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-              const int i = lane + 32 * j;
-              if (i < d) {
-                __stcg(rp + i, c * gp[j] - s * gq[j]);
-                __stcg(rq + i, s * gp[j] + c * gq[j]);
-              }
-            }
-            double* vp = vt + static_cast<long long>(p) * d;
-            double* vq = vt + static_cast<long long>(q) * d;
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-              const int i = lane + 32 * j;
-              if (i < d) {
-                const double a = __ldcg(vp + i), b = __ldcg(vq + i);
-                __stcg(vp + i, c * a - s * b);
-                __stcg(vq + i, s * a + c * b);
-              }
-            }
-            if (lane == 0) atomicOr(rotated + sweep, 1);
-          }
-        }
-      }
-      grid_barrier(barrier_counter, target, gridDim.x);
-    }
-    // every block reads the flag after the barrier that closed the sweep
-    const int any = *reinterpret_cast<volatile int*>(rotated + sweep);
-    if (!any) { ++sweep; break; }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
-}
-
-// lam[p] = v_p . g_p (Rayleigh quotient), rank by descending value, write sorted rows.
-__global__ void __launch_bounds__(256)
-eig_lambda_kernel(const double* __restrict__ gt, const double* __restrict__ vt, int d, double* __restrict__ lam) {
-  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (p >= d) return;
-  double acc = 0.0;
-  for (int i = lane; i < d; i += 32) acc += gt[static_cast<long long>(p) * d + i] * vt[static_cast<long long>(p) * d + i];
-  acc = warp_sum(acc);
-  if (lane == 0) lam[p] = acc;
 }
 
 __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __restrict__ vt, int d,
@@ -268,105 +138,11 @@ __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __
     evecs_t[static_cast<long long>(rk) * d + i] = vt[static_cast<long long>(p) * d + i];
 }
 
-__global__ void frob2_kernel(const double* __restrict__ a, long long n, double* __restrict__ out) {
-  double acc = 0.0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    acc += a[i] * a[i];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
-}
-
-
 // ------------------------------------------------------------------------- //
-// Block one-sided Jacobi (the production eigensolver).
+// Block one-sided (Hestenes) Jacobi on a symmetric matrix, Gram formulation.
 //   gt[p,:] = column p of G = B V (rows contiguous).  Columns are grouped in blocks of `bw`; a CTA owns one
-//   PAIR of blocks per global round (round-robin tournament over blocks), keeps its 2*bw columns in shared
-//   memory and orthogonalises ALL pairs among them with a local tournament (one warp per pair,
-//   __syncthreads between local rounds).  Device-wide barriers: (#blocks - 1) per sweep instead of (d - 1).
-//   V is not tracked: at convergence G = V diag(lambda), so v_p = g_p / |g_p| and lambda_p = |g_p|.
-// ------------------------------------------------------------------------- //
-__global__ void __launch_bounds__(1024, 1)
-block_jacobi_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, double abs_tol, int max_sweeps,
-                    unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated,
-                    int* __restrict__ sweeps_done) {
-  extern __shared__ double cols[];            // [2*bw][d]
-  __shared__ int s_rot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nthreads = blockDim.x;
-  const int m2 = 2 * bw;                      // column slots held by this CTA
-  unsigned int target = 0;
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    for (int r = 0; r < nblk_pad - 1; ++r) {
-      // block pair of this CTA in global round r (circle method over nblk_pad blocks)
-      int bi, bj;
-      const int k = blockIdx.x;
-      if (k == 0) { bi = nblk_pad - 1; bj = r; }
-      else { bi = (r + k) % (nblk_pad - 1); bj = (r - k + (nblk_pad - 1)) % (nblk_pad - 1); }
-      // load the 2*bw columns (global column index of slot s: blk*bw + s%bw); slots beyond d stay unused
-      for (int idx = threadIdx.x; idx < m2 * d; idx += nthreads) {
-        const int slot = idx / d, i = idx - slot * d;
-        const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
-        cols[idx] = col < d ? __ldcg(gt + static_cast<long long>(col) * d + i) : 0.0;
-      }
-      if (threadIdx.x == 0) s_rot = 0;
-      __syncthreads();
-      // local tournament over m2 slots: m2 - 1 rounds, warp w owns one pair per round
-      for (int lr = 0; lr < m2 - 1; ++lr) {
-        if (warp < bw) {
-          int x, y;
-          if (warp == 0) { x = m2 - 1; y = lr; }
-          else { x = (lr + warp) % (m2 - 1); y = (lr - warp + (m2 - 1)) % (m2 - 1); }
-          const int cx = (x < bw ? bi : bj) * bw + (x < bw ? x : x - bw);
-          const int cy = (y < bw ? bi : bj) * bw + (y < bw ? y : y - bw);
-          if (cx < d && cy < d) {
-            double* px = cols + x * d;
-            double* py = cols + y * d;
-            double alpha = 0.0, beta = 0.0, gamma = 0.0;
-            for (int i = lane; i < d; i += 32) {
-              const double a = px[i], b = py[i];
-              alpha += a * a;
-              beta += b * b;
-              gamma += a * b;
-            }
-            alpha = warp_sum(alpha);
-            beta = warp_sum(beta);
-            gamma = warp_sum(gamma);
-            if (fabs(gamma) > tol * sqrt(alpha * beta) && fabs(gamma) > abs_tol) {
-              const double zeta = (beta - alpha) / (2.0 * gamma);
-              const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-              const double c = 1.0 / sqrt(1.0 + t * t);
-              const double sn = c * t;
-              for (int i = lane; i < d; i += 32) {
-                const double a = px[i], b = py[i];
-                px[i] = c * a - sn * b;
-                py[i] = sn * a + c * b;
-              }
-              if (lane == 0) s_rot = 1;
-            }
-          }
-        }
-        __syncthreads();
-      }
-      // write back
-      for (int idx = threadIdx.x; idx < m2 * d; idx += nthreads) {
-        const int slot = idx / d, i = idx - slot * d;
-        const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
-        if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, cols[idx]);
-      }
-      if (threadIdx.x == 0 && s_rot) atomicOr(rotated + sweep, 1);
-      grid_barrier(barrier_counter, target, gridDim.x);
-    }
-    const int any = *reinterpret_cast<volatile int*>(rotated + sweep);
-    if (!any) { ++sweep; break; }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
-}
-
-// ------------------------------------------------------------------------- //
-// Block Jacobi, Gram formulation (production path).  Same block tournament as above, but inside a CTA the
-// 2*bw columns are orthogonalised through their small Gram matrix:
+//   PAIR of blocks per global round (round-robin tournament over blocks, one device-wide barrier per round)
+//   and orthogonalises its 2*bw columns through their small Gram matrix:
 //   1. Gl = C^T C            (m2 x m2, register-tiled dot products out of shared memory)
 //   2. one two-sided Jacobi tournament on Gl (m2 - 1 rounds of m2/2 disjoint rotations, rows then columns),
 //      accumulating the rotations in Q -- rotation angles come from 3 Gram entries, no d-length reductions
