@@ -289,7 +289,12 @@ def run_main(args):
     outs = [torch.empty((ne_local, ldo), dtype=torch.float32, device=dev) for _ in range(2)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
 
-    stream = torch.cuda.current_stream()
+    # everything below (NCCL all-gather, L2 flush, the library's kernels, the timing events) is ordered on ONE
+    # dedicated stream: the library launches on it (plda_set_stream) and does not host-synchronise
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     _ffi.check(lib.plda_set_stream(plda._h, C.c_void_p(stream.cuda_stream)))
 
     def step(i):
@@ -351,6 +356,9 @@ def run_main(args):
         e2e_s = float(t.item())
     e2e_value = trials_per_step * e2e_steps / e2e_s
     clocks = sampler.stop()
+    torch.cuda.synchronize()
+    _ffi.check(lib.plda_set_stream(plda._h, C.c_void_p(None)))
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
 
     # parity spot check of the timed output against the host result (same kernel, different path)
     dev_out = outs[(args.steps - 1) & 1][:64, :64].cpu().numpy()

@@ -66,6 +66,14 @@ int plda_launch_count(plda_handle_t h, int64_t* out);
 int plda_profile_gemm(plda_handle_t h, int enable);
 int plda_profile_collect(plda_handle_t h, double* total_ms, int64_t* count);
 
+/* Sharded fit (one process per GPU, whole speakers per rank): the library calls `fn(user, count)` whenever the
+ * first `count` fp64 values of `scratch_dev` (a device buffer of `capacity` >= 2*d*d + d + 2 doubles owned by the
+ * caller) must be SUM-all-reduced in place across ranks, stream-ordered on the handle's stream (plda_set_stream).
+ * Calls per fit: one after the stats pass (scatter, weighted mean sum, class weight, class count) and one per EM
+ * iteration (the two d x d statistics).  fn == NULL disables it.  Returns 0 on success from fn. */
+typedef int (*plda_allreduce_fn)(void* user, int64_t count);
+int plda_set_allreduce(plda_handle_t h, plda_allreduce_fn fn, void* user, double* scratch_dev, int64_t capacity);
+
 /* ---- fit: replaces MPlda_fit (src/pldamodule.cpp:42-109) ------------------------------- *
  * x: [n x d]; labels: [n] uint64 (any values; the reference requires dense 0..K-1, :88-92 --
  * dense labels give identical results).  iters = EM iterations (default 10 in the reference).

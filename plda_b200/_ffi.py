@@ -35,6 +35,7 @@ SIGNATURES = {
     "plda_launch_count": [_vp, C.POINTER(_i64)],
     "plda_profile_gemm": [_vp, _int],
     "plda_profile_collect": [_vp, C.POINTER(C.c_double), C.POINTER(_i64)],
+    "plda_set_allreduce": [_vp, _vp, _vp, _vp, _i64],
     "plda_fit": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _int],
     "plda_fit_timings": [_vp, C.POINTER(C.c_double)],
     "plda_dim": [_vp, C.POINTER(_i64)],

@@ -106,6 +106,17 @@ int plda_profile_collect(plda_handle_t h, double* total_ms, int64_t* count) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.ctx.profile_collect(total_ms, count); });
 }
 
+int plda_set_allreduce(plda_handle_t h, plda_allreduce_fn fn, void* user, double* scratch_dev, int64_t capacity) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(fn == nullptr || (scratch_dev != nullptr && capacity > 0), pb::kInvalidArg,
+             "set_allreduce: a device scratch buffer is required");
+    e.reduce_fn = fn;
+    e.reduce_user = user;
+    e.reduce_scratch = scratch_dev;
+    e.reduce_capacity = capacity;
+  });
+}
+
 int plda_fit(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
              const uint64_t* labels, int iters) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.fit(x, n, d, ldx, dtype, loc, labels, iters); });

@@ -25,9 +25,19 @@ struct PldaModel {
   std::vector<double> h_psi;     // host mirror for cheap validation
 };
 
+// Sum-all-reduce hook for the sharded fit (stats pass + EM iteration): the engine packs the fp64
+// quantities to reduce into the caller's device scratch buffer and calls `fn(user, count)`; the callee all-reduces
+// the first `count` doubles of the scratch in place, stream-ordered on the handle's stream (NCCL via torch).
+typedef int (*AllReduceFn)(void* user, int64_t count);
+
 class PldaEngine {
  public:
   explicit PldaEngine(int device) : ctx(device) {}
+  AllReduceFn reduce_fn = nullptr;
+  void* reduce_user = nullptr;
+  double* reduce_scratch = nullptr;
+  int64_t reduce_capacity = 0;
+  void allreduce_parts(const std::vector<std::pair<double*, int64_t>>& parts);
   Context ctx;
   std::mutex mu;
   int precision = 0;

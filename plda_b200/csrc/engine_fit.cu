@@ -37,6 +37,26 @@ double ms_between(cudaEvent_t a, cudaEvent_t b) {
 
 }  // namespace
 
+void PldaEngine::allreduce_parts(const std::vector<std::pair<double*, int64_t>>& parts) {
+  if (reduce_fn == nullptr) return;
+  int64_t total = 0;
+  for (const auto& pr : parts) total += pr.second;
+  PB_CHECK(total <= reduce_capacity, kInvalidArg, "all-reduce scratch buffer too small (need 2*d*d + d + 2 doubles)");
+  int64_t off = 0;
+  for (const auto& pr : parts) {
+    PB_CUDA(cudaMemcpyAsync(reduce_scratch + off, pr.first, pr.second * sizeof(double), cudaMemcpyDeviceToDevice,
+                            ctx.stream));
+    off += pr.second;
+  }
+  PB_CHECK(reduce_fn(reduce_user, total) == 0, kInternal, "all-reduce callback failed");
+  off = 0;
+  for (const auto& pr : parts) {
+    PB_CUDA(cudaMemcpyAsync(pr.first, reduce_scratch + off, pr.second * sizeof(double), cudaMemcpyDeviceToDevice,
+                            ctx.stream));
+    off += pr.second;
+  }
+}
+
 // C = chol(W); T1 = C^-1; B' = T1 B T1^T; B' = U diag(psi) U^T; A = U^T T1; A^-1 = C U
 // (PldaEstimator::GetOutput / ComputeNormalizingTransform).  Leaves A in em_a, A^-1 in em_ainv, psi in em_psi.
 void PldaEngine::joint_diagonalise(int64_t d, bool warm) {
@@ -104,6 +124,9 @@ void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const
   // add the diagonal terms (no scaling yet)
   add_diag_scale(ctx, em_bs.get(), em_db.get(), d, 1.0, nullptr);
   add_diag_scale(ctx, em_ws.get(), em_dw.get(), d, 1.0, nullptr);
+  // sharded fit: every rank holds a shard of the classes and the same (A, psi); the two d x d statistics are
+  // the only per-iteration exchange
+  allreduce_parts({{em_bs.get(), static_cast<int64_t>(dd)}, {em_ws.get(), static_cast<int64_t>(dd)}});
   // back to the original basis:  X -> A^-1 X A^-T
   gemm_f64(ctx, false, false, d, d, d, 1.0, em_ainv.get(), d, em_bs.get(), d, 0.0, em_tmp2.get(), d);
   gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp2.get(), d, em_ainv.get(), d, 0.0, model.between.get(), d);
@@ -137,7 +160,7 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   PB_CUDA(cudaMemcpyAsync(lab.get(), labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
   build_segments(ctx, lab.get(), n, segs);                                  // K1
   const int64_t k = segs.nseg;
-  if (k < 2) {
+  if (k < 2 && reduce_fn == nullptr) {
     for (auto& e : ev) cudaEventDestroy(e);
     throw Error(kValueError,
                 "Number of speakers is 1. Aborting PLDA esimation, at least two speakers are required!");
@@ -165,11 +188,19 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   model.d = d;
   model.mean.reserve(d);
   class_weighted_sum(ctx, means.get(), counts.get(), k, d, model.mean.get(), class_weight.get());
+  // sharded fit (whole speakers per rank): S, sum_, class_weight and the class count are the only quantities
+  // exchanged by the stats pass
+  DevBuf<double> k_dev(1);
+  const double k_local = static_cast<double>(k);
+  PB_CUDA(cudaMemcpyAsync(k_dev.get(), &k_local, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  allreduce_parts({{scatter.get(), static_cast<int64_t>(dd)}, {model.mean.get(), d}, {class_weight.get(), 1},
+                   {k_dev.get(), 1}});
   scale_vec_kernel<<<static_cast<unsigned>(ceil_div(d, 128)), 128, 0, ctx.stream>>>(model.mean.get(), static_cast<int>(d),
                                                                                   class_weight.get());
   ctx.count_launch();
-  double h_cw = 0.0;
+  double h_cw = 0.0, h_k = 0.0;
   PB_CUDA(cudaMemcpyAsync(&h_cw, class_weight.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(&h_k, k_dev.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   // centred class means (constant across iterations)
   DevBuf<double> mc(static_cast<size_t>(k) * d);
   convert_to_f64(ctx, means.get(), false, k, d, d, mc.get(), d, model.mean.get());
@@ -177,7 +208,12 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   PB_CUDA(cudaEventRecord(ev[1], ctx.stream));
   ctx.sync();
   // example_weight = sum w_s n_s = K;  W_count = (K - class_weight) + class_weight = K;  B_count = class_weight
-  const double w_count = static_cast<double>(k);
+  if (h_k < 2.0) {
+    for (auto& e : ev) cudaEventDestroy(e);
+    throw Error(kValueError,
+                "Number of speakers is 1. Aborting PLDA esimation, at least two speakers are required!");
+  }
+  const double w_count = h_k;          // global number of classes
   const double b_count = h_cw;
 
   // ---- EM (InitParameters: W = B = I) ----

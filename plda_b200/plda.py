@@ -79,6 +79,46 @@ class PLDA(object):
         _ffi.check(self._lib.plda_fit(self._h, _ffi.ptr(xa), n, d, d, dtype, _ffi.HOST, _ffi.ptr(lab), iters))
         return None
 
+    def fit_distributed(self, x, y, iters=10, group=None):
+        """Sharded fit: every rank passes ITS rows (whole speakers per rank -- a speaker must
+        not be split across ranks; label values only need to be unique within a rank).  The stats pass exchanges
+        one all-reduce (scatter, weighted mean sum, class weight, class count), every EM iteration one all-reduce of
+        the two d x d statistics; the d x d factorizations are replicated.  Requires an initialised NCCL process
+        group; without one this is `fit`."""
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return self.fit(x, y, iters)
+        d = int(x.shape[1])
+        dev = torch.device("cuda", self.device)
+        scratch = torch.zeros(2 * d * d + d + 2, dtype=torch.float64, device=dev)
+        stream = torch.cuda.Stream(device=dev)
+        failure = []
+
+        def _cb(_user, count):
+            try:
+                dist.all_reduce(scratch[:count], group=group)
+                return 0
+            except Exception as e:  # surfaced as PLDA_E_INTERNAL by the library
+                failure.append(e)
+                return 1
+
+        cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64)(_cb)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(stream):
+            _ffi.check(self._lib.plda_set_stream(self._h, C.c_void_p(stream.cuda_stream)))
+            _ffi.check(self._lib.plda_set_allreduce(self._h, C.cast(cb, C.c_void_p), None,
+                                                    C.c_void_p(scratch.data_ptr()), scratch.numel()))
+            try:
+                self.fit(x, y, iters)
+            finally:
+                self._lib.plda_set_allreduce(self._h, None, None, None, 0)
+                self._lib.plda_set_stream(self._h, C.c_void_p(None))
+        stream.synchronize()
+        if failure:
+            raise failure[0]
+        return None
+
     def fit_timings(self):
         """ms: dict(stats=, em=, output=, total=, iters=) of the last fit."""
         out = (C.c_double * 5)()

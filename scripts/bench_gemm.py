@@ -27,7 +27,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 _ffi.check(lib.plda_profile_gemm(p._h, 1))
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-_ffi.check(lib.plda_set_stream(p._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+_st = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(_st)
+_ffi.check(lib.plda_set_stream(p._h, C.c_void_p(_st.cuda_stream)))
 ev0.record()
 for _ in range(reps):
     p.score_grid(e, cnt, t, out=out[:, :nt])
