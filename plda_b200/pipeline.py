@@ -1,0 +1,90 @@
+"""Trial-list scoring pipeline -- py3 port of the CALLER of the hot path, ``scoring/scorePLDA.py``.
+
+The reference parses a trial list, enumerates string labels to ``uint`` (``scorePLDA.py:243-255``), runs
+``fit -> transform x2 -> [norm]`` (``:258-298``) and then scores every listed trial with one ``plda.score`` call in a
+Python double loop (``:302-318``).  Here the same flow ends in ONE ``score_grid`` on the device followed by a gather of
+the listed trials; the output lines keep the reference's format ``"{model} {target}-{utt} {score:.3f}\\n"`` (``:317-318``).
+File formats beyond the two trial-list formats (HTK features, marshalled d-vector dumps) stay out of scope.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def parse_test_ref(path: str) -> Dict[str, List[List[str]]]:
+    """``test_ref`` (``scoring/scorePLDA.py:40-50``): lines ``<targetmodel> <enrolmodel>-<testutt> ...``."""
+    tests = defaultdict(list)
+    with open(path, "r") as fh:
+        for line in fh:
+            line = line.rstrip("\n")
+            if not line.strip():
+                continue
+            targetmdl, enrol_testutt = line.split()[:2]
+            parts = enrol_testutt.split("-")
+            tests[targetmdl].append(["-".join(parts[1:]), parts[0]])
+    return tests
+
+
+def parse_mlf(path: str) -> Dict[str, List[List[str]]]:
+    """``mlffile`` (``scoring/scorePLDA.py:55-73``): HTK master label file, ``"*/<enrol>-<utt>.lab"`` then the target."""
+    tests = defaultdict(list)
+    with open(path, "r") as fh:
+        next(fh)                                   # "#!MLF!#"
+        for line in fh:
+            line = line.rstrip("\n")
+            if line.startswith('"'):
+                without_lab = line.split(".")[0]
+                without_slashes = without_lab.split("/")[1]
+                parts = without_slashes.split("-")
+                targetmdl = next(fh).rstrip("\n")
+                tests[targetmdl].append(["-".join(parts[1:]), parts[0]])
+    return tests
+
+
+def enumerate_labels(labels: Sequence[str]) -> Tuple[Dict[str, int], np.ndarray]:
+    """String labels -> dense uint ids in ``np.unique`` order (``scorePLDA.py:243-255``)."""
+    uniq = np.unique(np.asarray(labels))
+    table = {str(s): i for i, s in enumerate(uniq)}
+    return table, np.array([table[str(s)] for s in labels], dtype="uint")
+
+
+def score_trials(plda, bkg_vectors, bkg_labels: Sequence[str], enrol_vectors, enrol_labels: Sequence[str],
+                 test_vectors, test_labels: Sequence[str], trials: Dict[str, Iterable[Sequence[str]]],
+                 iters: int = 10, znorm_vectors=None, zutt: int = 0, fit: bool = True) -> Tuple[List[str], int]:
+    """The body of ``scorePLDA.main`` (``:258-318``).  Returns (output lines, number of skipped trials).
+
+    ``trials``: ``{enrolmodel: [[testutt, targetmodel], ...]}`` as produced by ``parse_test_ref`` / ``parse_mlf``.
+    """
+    enrol_tab, enrol_ids = enumerate_labels(enrol_labels)
+    test_tab, test_ids = enumerate_labels(test_labels)
+    if fit:
+        _, bkg_ids = enumerate_labels(bkg_labels)
+        plda.fit(np.asarray(bkg_vectors), bkg_ids, iters)
+    enrol_t = plda.transform(np.asarray(enrol_vectors), enrol_ids)
+    test_t = plda.transform(np.asarray(test_vectors), test_ids)
+    if znorm_vectors is not None:
+        plda.norm(np.asarray(znorm_vectors), enrol_t, zutt)
+    ek, tk = sorted(enrol_t), sorted(test_t)
+    e = np.stack([enrol_t[k][1] for k in ek])
+    n = np.array([enrol_t[k][0] for k in ek], dtype=np.int32)
+    t = np.stack([test_t[k][1] for k in tk])
+    # the reference scores test vectors as transformed with their own utterance count; LLR uses n of the enrol side
+    grid = plda.score_grid(e, n, t, enrol_ids=np.array(ek, dtype=np.uint64) if znorm_vectors is not None else None)
+    e_pos = {k: i for i, k in enumerate(ek)}
+    t_pos = {k: i for i, k in enumerate(tk)}
+    lines, errors = [], 0
+    for enrolmodel, vals in trials.items():
+        if enrolmodel not in enrol_tab:
+            errors += 1
+            continue
+        ei = e_pos[enrol_tab[enrolmodel]]
+        for testutt, targetmdl in vals:
+            if testutt not in test_tab:
+                errors += 1
+                continue
+            score = float(grid[ei, t_pos[test_tab[testutt]]])
+            lines.append("{} {}-{} {:.3f}\n".format(enrolmodel, targetmdl, testutt, score))
+    return lines, errors

@@ -1,0 +1,63 @@
+"""Trial-list pipeline (plda_b200/pipeline.py, port of scoring/scorePLDA.py): parsers on CPU; the scoring flow on GPU
+against the per-trial loop the reference runs (scorePLDA.py:302-318) driven through the oracle."""
+import numpy as np
+import pytest
+
+from plda_b200 import pipeline
+
+
+def test_parse_test_ref(tmp_path):
+    p = tmp_path / "trials.txt"
+    p.write_text("F001 F001-F001_s1_utt1 extra\nF001 F002-F002_s2-utt-3\n\nM007 M007-M007_x\n")
+    t = pipeline.parse_test_ref(str(p))
+    assert t["F001"] == [["F001_s1_utt1", "F001"], ["F002_s2-utt-3", "F002"]]       # scorePLDA.py:45-49
+    assert t["M007"] == [["M007_x", "M007"]]
+
+
+def test_parse_mlf(tmp_path):
+    p = tmp_path / "test.mlf"
+    p.write_text('#!MLF!#\n"*/F001-F001_s1_utt1.lab"\nF001\n.\n"*/F002-F002_s2-utt-3.lab"\nF001\n.\n')
+    t = pipeline.parse_mlf(str(p))
+    assert t["F001"] == [["F001_s1_utt1", "F001"], ["F002_s2-utt-3", "F002"]]       # scorePLDA.py:61-72
+
+
+def test_enumerate_labels_matches_reference_order():
+    tab, ids = pipeline.enumerate_labels(["spk_b", "spk_a", "spk_b", "spk_c"])
+    assert tab == {"spk_a": 0, "spk_b": 1, "spk_c": 2} and ids.dtype.kind == "u"   # np.unique order, :243-246
+    assert list(ids) == [1, 0, 1, 2]
+
+
+@pytest.mark.gpu
+def test_pipeline_equals_per_trial_loop():
+    from oracle import kaldi_plda as kp
+    from plda_b200 import PLDA
+    d = 24
+    a_b = kp.two_cov_generator(d, seed=1234)
+    xb, lb, _ = kp.synth_speakers(a_b, [6] * 30, seed=1234)
+    xe, le, z = kp.synth_speakers(a_b, [3] * 8, seed=1235)
+    rng = np.random.RandomState(1236)
+    xt = 0.5 + z @ a_b.T + rng.randn(8, d)
+    zn, _, _ = kp.synth_speakers(a_b, [1] * 20, seed=1237)
+    bkg_labels = ["b%03d" % i for i in lb]
+    enrol_labels = ["m%02d" % i for i in le]
+    test_labels = ["m%02d_utt" % i for i in range(8)]
+    trials = {"m%02d" % e: [["m%02d_utt" % t, "m%02d" % t] for t in range(8)] for e in range(8)}
+    trials["ghost"] = [["m00_utt", "m00"]]                                  # unknown model -> counted as error
+    trials["m01"].append(["nope", "m01"])                                   # unknown utterance -> error
+    g = PLDA()
+    lines, errors = pipeline.score_trials(g, xb, bkg_labels, xe, enrol_labels, xt, test_labels, trials, iters=4,
+                                          znorm_vectors=zn)
+    assert errors == 2 and len(lines) == 64
+    # the reference flow, per trial, through the oracle
+    ref = kp.MPlda()
+    _, bi = pipeline.enumerate_labels(bkg_labels)
+    etab, ei = pipeline.enumerate_labels(enrol_labels)
+    ttab, ti = pipeline.enumerate_labels(test_labels)
+    ref.fit(xb, bi, 4)
+    te, tt = ref.transform(xe, ei), ref.transform(xt, ti)
+    ref.norm(zn, te)
+    for line in lines:
+        model, rest, score = line.split()
+        target, utt = rest.split("-", 1)
+        want = ref.score(etab[model], te[etab[model]], tt[ttab[utt]])
+        assert abs(float(score) - want) <= 2e-3 * max(1.0, abs(want)) + 5e-4     # "{:.3f}" rounding
