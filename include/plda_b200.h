@@ -145,10 +145,19 @@ int lda_synchronize(lda_handle_t h);
 /* labels: HOST int64 [n] (any values; classes = sorted unique, lda.py:118); priors NULL = empirical */
 int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                 const int64_t* labels, const double* priors, int64_t n_priors);
+/* lsqr solver (lda.py:223-251): coef = means cov^-1, cov = pooled class covariance; empirical priors only */
+int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                 const int64_t* labels, const double* priors, int64_t n_priors);
+/* svd solver state: rank (0 for other solvers), xbar[d], scalings[d*rank] row-major (any pointer may be NULL) */
+int lda_get_svd(lda_handle_t h, int64_t* rank, double* xbar, double* scalings);
+/* LDA.transform for the svd solver (lda.py:328-349, evident intent): out[nt x n_components] = (X - xbar) scalings */
+int lda_transform(lda_handle_t h, const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc,
+                  int64_t n_components, float* out, int64_t ldo, int out_loc);
 int lda_num_classes(lda_handle_t h, int64_t* k, int64_t* d);
 int lda_get_coef(lda_handle_t h, double* coef /* [k*d] */, double* intercept /* [k] */, int64_t* classes /* [k] */);
 int lda_set_coef(lda_handle_t h, int64_t k, int64_t d, const double* coef, const double* intercept);
-/* out[nt x k] fp32: decision values (log_proba = 0) or row log-softmax of them (log_proba = 1) */
+/* out[nt x k] fp32: decision values (log_proba = 0), row log-softmax of them (1: predict_log_proba) or
+ * OvR sigmoid probabilities (2: predict_proba, lda.py:281-304; not row-normalised when k == 2) */
 int lda_predict(lda_handle_t h, const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int log_proba,
                 float* out, int64_t ldo, int out_loc);
 

@@ -58,6 +58,9 @@ SIGNATURES = {
     "lda_launch_count": [_vp, C.POINTER(_i64)],
     "lda_synchronize": [_vp],
     "lda_fit_svd": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
+    "lda_fit_lsqr": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
+    "lda_get_svd": [_vp, C.POINTER(_i64), _vp, _vp],
+    "lda_transform": [_vp, _vp, _i64, _i64, _i64, _int, _int, _i64, _vp, _i64, _int],
     "lda_num_classes": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "lda_get_coef": [_vp, _vp, _vp, _vp],
     "lda_set_coef": [_vp, _i64, _i64, _vp, _vp],

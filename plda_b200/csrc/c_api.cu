@@ -225,6 +225,22 @@ int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx
                 const int64_t* labels, const double* priors, int64_t n_priors) {
   return with_handle(h, [&](pb::LdaEngine& e) { e.fit_svd(x, n, d, ldx, dtype, loc, labels, priors, n_priors); });
 }
+int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                 const int64_t* labels, const double* priors, int64_t n_priors) {
+  return with_handle(h, [&](pb::LdaEngine& e) { e.fit_lsqr(x, n, d, ldx, dtype, loc, labels, priors, n_priors); });
+}
+int lda_get_svd(lda_handle_t h, int64_t* rank, double* xbar, double* scalings) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    PB_CHECK(e.ready, pb::kNotFitted, "This LDA instance is not fitted yet");
+    if (rank) *rank = e.rank;
+    if (xbar && e.rank > 0) memcpy(xbar, e.h_xbar.data(), e.h_xbar.size() * sizeof(double));
+    if (scalings && e.rank > 0) memcpy(scalings, e.h_scalings.data(), e.h_scalings.size() * sizeof(double));
+  });
+}
+int lda_transform(lda_handle_t h, const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc,
+                  int64_t n_components, float* out, int64_t ldo, int out_loc) {
+  return with_handle(h, [&](pb::LdaEngine& e) { e.transform(x, nt, d, ldx, dtype, loc, n_components, out, ldo, out_loc); });
+}
 int lda_num_classes(lda_handle_t h, int64_t* k, int64_t* d) {
   return with_handle(h, [&](pb::LdaEngine& e) { *k = e.ready ? e.k : 0; *d = e.ready ? e.d : 0; });
 }

@@ -106,12 +106,31 @@ class LdaEngine {
 
   void fit_svd(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
                const double* priors, int64_t n_priors);
+  // lda.py:223-251 (_solve_lsqr): coef = means cov^-1 with cov = sum_k priors_k cov_k
+  void fit_lsqr(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                const double* priors, int64_t n_priors);
+  // lda.py:328-349 (transform, svd solver): (X - xbar) scalings[:, :n_components]
+  void transform(const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int64_t n_components,
+                 float* out, int64_t ldo, int out_loc);
+  std::vector<double> h_xbar, h_scalings;   // svd solver: xbar [d], scalings [d x rank]
+  int64_t rank = 0;
+  SplitBuf scal_split;                      // scalings^T as the B operand [rank x d]
+  DevBuf<double> xbar_dev;
   void set_coef(int64_t k, int64_t d, const double* coef, const double* intercept);
   void predict(const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int log_proba, float* out,
                int64_t ldo, int out_loc);
 
  private:
   void refresh_operands();
+  // shared front end of the solvers: stage rows, segment by class, class means / counts, unscaled within scatter
+  struct ClassStats {
+    int64_t k = 0;
+    std::vector<double> sw, means, priors;
+    std::vector<int32_t> counts;
+    std::vector<int64_t> classes;
+  };
+  void class_stats(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                   const double* priors, int64_t n_priors, ClassStats& out);
   SplitBuf ws_x;
   DevBuf<float> ws_out[2], ws_lmax, ws_lsum, ws_neglse;
   DevBuf<double> ws_gram;

@@ -59,6 +59,29 @@ lda_epilogue_f64_kernel(const double* __restrict__ z, long long nt, long long k,
 
 }  // namespace
 
+// predict_proba (lda.py:281-304): p = 1 / (1 + exp(-z)) then OvR normalisation by the row sum, in place on fp32 rows
+__global__ void __launch_bounds__(256)
+proba_rows_kernel(float* __restrict__ z, long long nt, long long k, long long ld, int normalise) {
+  __shared__ float red[256];
+  const long long r = blockIdx.x;
+  float* row = z + r * ld;
+  float sum = 0.f;
+  for (long long c = threadIdx.x; c < k; c += blockDim.x) {
+    const float p = 1.0f / (1.0f + __expf(-row[c]));
+    row[c] = p;
+    sum += p;
+  }
+  if (!normalise) return;
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float inv = 1.0f / red[0];
+  for (long long c = threadIdx.x; c < k; c += blockDim.x) row[c] *= inv;
+}
+
 void lse_combine(Context& ctx, const float* lmax, const float* lsum, int64_t m, int n_tiles, float* neg_lse) {
   lse_combine_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, ctx.stream>>>(lmax, lsum, m, n_tiles, neg_lse);
   PB_CUDA(cudaGetLastError());
@@ -91,15 +114,13 @@ void LdaEngine::set_coef(int64_t k_, int64_t d_, const double* c, const double* 
   refresh_operands();
 }
 
-void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
-                        const double* priors_in, int64_t n_priors) {
+void LdaEngine::class_stats(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc,
+                            const int64_t* labels, const double* priors_in, int64_t n_priors, ClassStats& out) {
   PB_CHECK(n > 1 && d_ > 0 && d_ <= 1024, kInvalidArg, "lda_fit: need n > 1 and 0 < d <= 1024");
   PB_CHECK(labels != nullptr && x != nullptr, kInvalidArg, "lda_fit: null input");
   PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
-  const double tol = 1e-4;
   const bool is_f32 = dtype == 1;
   const size_t es = is_f32 ? 4 : 8;
-  // stage rows
   const void* xd = x;
   int64_t ld = ldx;
   if (loc == 0) {
@@ -138,27 +159,41 @@ void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int d
     gemm_bf16x3_splitk(ctx, xt.view(), xt.view(), d_, d_, n, ks, partial.get());
     reduce_partials_f64(ctx, partial.get(), eff, d_, d_, sw.get(), d_, 1.0, true);
   }
-  // The remaining algebra is K x d and d x d: bring the small pieces to the host-visible side only for the
-  // rank decisions (two scalar thresholds); the matrices themselves stay on the device.
-  std::vector<double> h_sw(dd), h_means(static_cast<size_t>(kk) * d_);
-  std::vector<int32_t> h_counts(kk);
+  out.k = kk;
+  out.sw.resize(dd);
+  out.means.resize(static_cast<size_t>(kk) * d_);
+  out.counts.resize(kk);
   std::vector<uint64_t> h_keys(kk);
-  PB_CUDA(cudaMemcpyAsync(h_sw.data(), sw.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(h_means.data(), means.get(), kk * d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(h_counts.data(), counts.get(), kk * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(out.sw.data(), sw.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(out.means.data(), means.get(), kk * d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(out.counts.data(), counts.get(), kk * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
   PB_CUDA(cudaMemcpyAsync(h_keys.data(), segs.seg_label.get(), kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
+  out.classes.resize(kk);
+  for (int64_t c = 0; c < kk; ++c) out.classes[c] = static_cast<int64_t>(h_keys[c] ^ (1ull << 63));
   // priors (lda.py:119-127)
-  std::vector<double> pri(kk);
+  out.priors.resize(kk);
   if (priors_in != nullptr) {
     PB_CHECK(n_priors == kk, kInvalidArg, "lda_fit: priors length does not match the number of classes");
-    for (int64_t i = 0; i < kk; ++i) pri[i] = priors_in[i];
+    for (int64_t i = 0; i < kk; ++i) out.priors[i] = priors_in[i];
   } else {
-    for (int64_t i = 0; i < kk; ++i) pri[i] = static_cast<double>(h_counts[i]) / static_cast<double>(n);
+    for (int64_t i = 0; i < kk; ++i) out.priors[i] = static_cast<double>(out.counts[i]) / static_cast<double>(n);
   }
   double psum = 0.0;
-  for (double v : pri) psum += v;
-  if (psum != 1.0) for (double& v : pri) v /= psum;
+  for (double v : out.priors) psum += v;
+  if (psum != 1.0) for (double& v : out.priors) v /= psum;
+}
+
+void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                        const double* priors_in, int64_t n_priors) {
+  const double tol = 1e-4;
+  ClassStats cs;
+  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs);
+  const int64_t kk = cs.k;
+  const size_t dd = static_cast<size_t>(d_) * d_;
+  const std::vector<double>& h_sw = cs.sw;
+  const std::vector<double>& h_means = cs.means;
+  const std::vector<double>& pri = cs.priors;
   // xbar = priors . means ; std_j = sqrt(Sw_jj / n)  (xc has zero column mean) ; fac = 1/(n - K)
   std::vector<double> xbar(d_, 0.0), stdv(d_);
   for (int64_t c = 0; c < kk; ++c)
@@ -232,11 +267,116 @@ void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int d
     double dot = 0.0;
     for (int64_t j = 0; j < d_; ++j) dot += xbar[j] * h_coef[c * d_ + j];
     h_intercept[c] = -0.5 * s + std::log(pri[c]) - dot;
-    h_classes[c] = static_cast<int64_t>(h_keys[c] ^ (1ull << 63));
+    h_classes[c] = cs.classes[c];
   }
   k = kk;
   d = d_;
+  // keep xbar / scalings for transform()
+  this->rank = rank2;   // (a local `rank` holds the first SVD rank above)
+  h_xbar = xbar;
+  h_scalings.resize(static_cast<size_t>(d_) * rank2);
+  PB_CUDA(cudaMemcpyAsync(h_scalings.data(), dscal2.get(), d_ * rank2 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  // B operand of the projection GEMM: scalings^T [rank x d]
+  std::vector<double> st(static_cast<size_t>(rank2) * d_);
+  for (int64_t j = 0; j < d_; ++j)
+    for (int64_t r = 0; r < rank2; ++r) st[r * d_ + j] = h_scalings[j * rank2 + r];
+  DevBuf<double> dst(rank2 * d_);
+  PB_CUDA(cudaMemcpyAsync(dst.get(), st.data(), rank2 * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  split_rows(ctx, dst.get(), false, rank2, d_, d_, nullptr, nullptr, nullptr, scal_split);
+  xbar_dev.reserve(d_);
+  PB_CUDA(cudaMemcpyAsync(xbar_dev.get(), h_xbar.data(), d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  ctx.sync();
   refresh_operands();
+}
+
+void LdaEngine::fit_lsqr(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                         const double* priors_in, int64_t n_priors) {
+  ClassStats cs;
+  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs);
+  const int64_t kk = cs.k;
+  const size_t dd = static_cast<size_t>(d_) * d_;
+  // cov = sum_k priors_k * cov_k,  cov_k = (1/n_k) sum_{i in k} (x - m_k)(x - m_k)^T   (_class_cov, lda.py:10-16).
+  // With empirical priors n_k/n this is Sw/n exactly; general priors need the per-class scatters, which the fused
+  // scatter pass does not keep -> only the empirical case runs on the fused path.
+  bool empirical = true;
+  for (int64_t c = 0; c < kk; ++c)
+    if (std::fabs(cs.priors[c] - static_cast<double>(cs.counts[c]) / static_cast<double>(n)) > 1e-12) empirical = false;
+  PB_CHECK(empirical, kInvalidArg, "lda lsqr: only empirical priors (priors=None) are supported on the device path");
+  std::vector<double> cov(dd);
+  for (size_t i = 0; i < dd; ++i) cov[i] = cs.sw[i] / static_cast<double>(n);
+  // coef = means cov^-1 via Cholesky: cov = L L^T, T1 = L^-1, cov^-1 = T1^T T1
+  DevBuf<double> dcov(dd), dt1(dd), dmeans(kk * d_), dtmp(kk * d_), dcoef(kk * d_);
+  DevBuf<int> info(1);
+  PB_CUDA(cudaMemcpyAsync(dcov.get(), cov.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(dmeans.get(), cs.means.data(), kk * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  cholesky_lower(ctx, dcov.get(), d_, info.get());
+  tri_inverse_lower(ctx, dcov.get(), dt1.get(), d_);
+  gemm_f64(ctx, false, true, kk, d_, d_, 1.0, dmeans.get(), d_, dt1.get(), d_, 0.0, dtmp.get(), d_);    // means T1^T
+  gemm_f64(ctx, false, false, kk, d_, d_, 1.0, dtmp.get(), d_, dt1.get(), d_, 0.0, dcoef.get(), d_);    // (.) T1
+  int h_info = 0;
+  h_coef.resize(static_cast<size_t>(kk) * d_);
+  PB_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(h_coef.data(), dcoef.get(), kk * d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  PB_CHECK(h_info == 0, kValueError, "lda lsqr: the pooled class covariance is singular (need more samples than dims)");
+  h_intercept.resize(kk);
+  h_classes = cs.classes;
+  for (int64_t c = 0; c < kk; ++c) {
+    double dot = 0.0;
+    for (int64_t j = 0; j < d_; ++j) dot += cs.means[c * d_ + j] * h_coef[c * d_ + j];
+    h_intercept[c] = -0.5 * dot + std::log(cs.priors[c]);
+  }
+  k = kk;
+  d = d_;
+  rank = 0;
+  refresh_operands();
+}
+
+void LdaEngine::transform(const void* x, int64_t nt, int64_t d_, int64_t ldx, int dtype, int loc, int64_t n_components,
+                          float* out, int64_t ldo, int out_loc) {
+  PB_CHECK(ready && rank > 0, kNotFitted, "transform needs a model fitted with the 'svd' solver");
+  PB_CHECK(d_ == d, kValueError, "X has a different number of features than the model");
+  PB_CHECK(n_components > 0 && n_components <= rank && ldo >= n_components, kInvalidArg, "transform: bad n_components");
+  if (nt == 0) return;
+  const bool is_f32 = dtype == 1;
+  const size_t es = is_f32 ? 4 : 8;
+  const void* xd = x;
+  int64_t ld = ldx;
+  if (loc == 0) {
+    ws_in.reserve(static_cast<size_t>(nt) * d * es);
+    PB_CUDA(cudaMemcpy2DAsync(ws_in.get(), d * es, x, ldx * es, d * es, nt, cudaMemcpyHostToDevice, ctx.stream));
+    xd = ws_in.get();
+    ld = d;
+  }
+  const int64_t ldo_dev = out_loc == 1 ? ldo : round_up(n_components, 4);
+  float* dst = out;
+  if (out_loc == 0) {
+    ws_out[0].reserve(static_cast<size_t>(nt) * ldo_dev);
+    dst = ws_out[0].get();
+  }
+  if (precision == 1) {
+    ws_gram.reserve(static_cast<size_t>(nt) * (d + n_components) + static_cast<size_t>(d) * rank);
+    double* xf = ws_gram.get();
+    double* z = xf + nt * d;
+    double* sc = z + nt * n_components;
+    convert_to_f64(ctx, xd, is_f32, nt, d, ld, xf, d, xbar_dev.get());
+    PB_CUDA(cudaMemcpyAsync(sc, h_scalings.data(), d * rank * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+    gemm_f64(ctx, false, false, nt, n_components, d, 1.0, xf, d, sc, rank, 0.0, z, n_components);
+    convert_f64_to_f32(ctx, z, nt, n_components, n_components, dst, ldo_dev);
+  } else {
+    split_rows(ctx, xd, is_f32, nt, d, ld, xbar_dev.get(), nullptr, nullptr, ws_x);
+    SplitOperand b = scal_split.view();
+    b.rows = n_components;
+    GemmEpilogue epi;
+    epi.out = dst;
+    epi.ldo = ldo_dev;
+    gemm_bf16x3(ctx, ws_x.view(), b, nt, n_components, d, epi);
+  }
+  if (out_loc == 0)
+    PB_CUDA(cudaMemcpy2DAsync(out, ldo * sizeof(float), dst, ldo_dev * sizeof(float), n_components * sizeof(float), nt,
+                              cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
 }
 
 void LdaEngine::predict(const void* x, int64_t nt, int64_t d_, int64_t ldx, int dtype, int loc, int log_proba,
@@ -283,7 +423,7 @@ void LdaEngine::predict(const void* x, int64_t nt, int64_t d_, int64_t ldx, int 
       convert_to_f64(ctx, xd, is_f32, rows, d, ld, xf, d);
       gemm_f64(ctx, false, true, rows, k, d, 1.0, xf, d, coef.get(), d, 0.0, z, k);
       lda_epilogue_f64_kernel<<<static_cast<unsigned>(rows), 256, 0, ctx.stream>>>(z, rows, k, intercept.get(),
-                                                                                  log_proba, dst, ldo_dev);
+                                                                                  log_proba == 1 ? 1 : 0, dst, ldo_dev);
       PB_CUDA(cudaGetLastError());
       ctx.count_launch();
     } else {
@@ -291,7 +431,7 @@ void LdaEngine::predict(const void* x, int64_t nt, int64_t d_, int64_t ldx, int 
       GemmEpilogue epi;
       epi.col_add = intercept_f32.get();
       epi.col_ld = col_ld;
-      if (log_proba) {
+      if (log_proba == 1) {
         // pass 1: online (max, sum exp) per row and column tile, nothing stored
         const int n_tiles = static_cast<int>(ceil_div(k, k >= 256 ? 256 : round_up(k, 16)));
         ws_lmax.reserve(static_cast<size_t>(rows) * n_tiles * 2);
@@ -307,6 +447,11 @@ void LdaEngine::predict(const void* x, int64_t nt, int64_t d_, int64_t ldx, int 
       epi.out = dst;
       epi.ldo = ldo_dev;
       gemm_bf16x3(ctx, ws_x.view(), coef_split.view(), rows, k, d, epi);
+    }
+    if (log_proba == 2) {     // OvR sigmoid probabilities from the decision values
+      proba_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, ctx.stream>>>(dst, rows, k, ldo_dev, k == 2 ? 0 : 1);
+      PB_CUDA(cudaGetLastError());
+      ctx.count_launch();
     }
     if (out_loc == 0) {
       PB_CUDA(cudaMemcpy2DAsync(out + r0 * ldo, ldo * sizeof(float), dst, ldo_dev * sizeof(float), k * sizeof(float),

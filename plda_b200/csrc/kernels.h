@@ -16,6 +16,9 @@ void split_rows(Context& ctx, const void* in, bool is_f32, int64_t rows, int64_t
 void convert_to_f64(Context& ctx, const void* in, bool is_f32, int64_t rows, int64_t cols, int64_t ld_in, double* out,
                     int64_t ld_out, const double* sub = nullptr);
 
+void convert_f64_to_f32(Context& ctx, const double* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                        int64_t ld_out);
+
 // ---- scoring (K6 operand prep; reference: Plda::LogLikelihoodRatio via src/pldamodule.cpp:235,266) ---- //
 // Enrol side: L = E * (a/v) (per-row n_e), row_term[e] = c(n_e) - 1/2 sum a^2/v e^2.
 // enrol is fp64/fp32 [ne x d]; counts int32 [ne] (device); psi fp64 [d] (device).

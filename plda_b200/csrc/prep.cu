@@ -53,6 +53,15 @@ __global__ void convert_kernel(const T* __restrict__ in, long long rows, int col
   out[r * ld_out + c] = v;
 }
 
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, long long rows, int cols, long long ld_in,
+                                  float* __restrict__ out, long long ld_out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols;
+  const int c = static_cast<int>(idx - r * cols);
+  out[r * ld_out + c] = static_cast<float>(in[r * ld_in + c]);
+}
+
 // ------------------------------------------------------------------------- //
 // enrol-side LLR operand:  a = n psi/(n psi+1), v = 1 + psi/(n psi+1)
 //   L[e,i] = e_i a_i / v_i ;  row[e] = 1/2 sum_i [log(1+psi_i) - log v_i - a_i^2 e_i^2 / v_i]
@@ -301,6 +310,15 @@ void convert_to_f64(Context& ctx, const void* in, bool is_f32, int64_t rows, int
   else
     convert_kernel<double><<<blocks, 256, 0, ctx.stream>>>(static_cast<const double*>(in), rows,
                                                            static_cast<int>(cols), ld_in, sub, out, ld_out);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void convert_f64_to_f32(Context& ctx, const double* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                        int64_t ld_out) {
+  if (rows == 0) return;
+  f64_to_f32_kernel<<<static_cast<unsigned>(ceil_div(rows * cols, 256)), 256, 0, ctx.stream>>>(
+      in, rows, static_cast<int>(cols), ld_in, out, ld_out);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

@@ -4,10 +4,11 @@
 
 Hot-path rows of SURVEY.md section 8 implemented here: ``fit`` with the default ``svd``
 solver (``lda.py:178-221``), ``decision_function`` (``:253-279``) and
-``predict_log_proba`` (``:306-325``).  ``predict_proba`` (``:281-304``) and ``transform``
-(``:328-349``, evident intent -- the reference's svd branch is unreachable) are derived
-from device outputs.  The ``lsqr`` / ``eigen`` solvers are "next" rows (section 8f) and
-raise NotImplementedError until they have device kernels -- no CPU fallback.
+``predict_log_proba`` (``:306-325``).  Section 8f "next" rows built on the same kernels: the
+``lsqr`` solver (``:223-251``), ``predict_proba`` (``:281-304``) and ``transform`` (``:328-349``,
+evident intent -- the reference's svd branch is unreachable).  The ``eigen`` solver is not
+offered (its result depends on LAPACK's arbitrary null-space basis whenever K - 1 < d) and
+raises NotImplementedError -- there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -51,8 +52,11 @@ class LDA(object):
     # ------------------------------------------------------------------ fit
     def fit(self, features, labels):
         """``LDA.fit`` (``lda.py:106-138``).  Returns None."""
-        if self.solver != "svd":
-            raise NotImplementedError("solver %r has no device kernel yet (SURVEY section 8f 'next'); use 'svd'"
+        if self.solver not in ("svd", "lsqr"):
+            # 'eigen' (lda.py:140-176) normalises generalised eigenvectors column-wise, which makes coef depend on
+            # the arbitrary basis LAPACK picks inside the (d - K + 1)-dimensional null space of Sb whenever
+            # K - 1 < d: the reference's own result is not reproducible by construction, so it is not offered.
+            raise NotImplementedError("solver %r is not available on the device path; use 'svd' or 'lsqr'"
                                       % (self.solver,))
         x, dtype = _ffi.as_matrix(np.asarray(features, dtype=np.float64) if np.asarray(features).dtype.kind != "f"
                                   else features, "features")
@@ -66,8 +70,9 @@ class LDA(object):
         pri = None
         if self.priors is not None:
             pri = np.ascontiguousarray(self.priors, dtype=np.float64)
-        _ffi.check(self._lib.lda_fit_svd(self._h, _ffi.ptr(x), n, d, d, dtype, _ffi.HOST, _ffi.ptr(y), _ffi.ptr(pri),
-                                         0 if pri is None else pri.shape[0]))
+        fit_fn = self._lib.lda_fit_svd if self.solver == "svd" else self._lib.lda_fit_lsqr
+        _ffi.check(fit_fn(self._h, _ffi.ptr(x), n, d, d, dtype, _ffi.HOST, _ffi.ptr(y), _ffi.ptr(pri),
+                          0 if pri is None else pri.shape[0]))
         k = C.c_int64()
         dd = C.c_int64()
         _ffi.check(self._lib.lda_num_classes(self._h, C.byref(k), C.byref(dd)))
@@ -76,6 +81,13 @@ class LDA(object):
         self._classes = np.empty(k.value, dtype=np.int64)
         _ffi.check(self._lib.lda_get_coef(self._h, _ffi.ptr(self._coef), _ffi.ptr(self._intercept),
                                           _ffi.ptr(self._classes)))
+        self._xbar = self._scalings = None
+        if self.solver == "svd":
+            rank = C.c_int64()
+            _ffi.check(self._lib.lda_get_svd(self._h, C.byref(rank), None, None))
+            self._xbar = np.empty(dd.value)
+            self._scalings = np.empty((dd.value, rank.value))
+            _ffi.check(self._lib.lda_get_svd(self._h, C.byref(rank), _ffi.ptr(self._xbar), _ffi.ptr(self._scalings)))
         if self.priors is None:
             _, cnt = np.unique(y, return_counts=True)
             self.priors = cnt / float(n)
@@ -130,12 +142,35 @@ class LDA(object):
         return self._predict(sample, 1)
 
     def predict_proba(self, sample):
-        """``predict_proba`` (``lda.py:281-304``): OvR sigmoid of the decision values."""
-        prob = np.asarray(self.decision_function(sample), dtype=np.float64)
-        prob = 1.0 / (1.0 + np.exp(-prob))
+        """``predict_proba`` (``lda.py:281-304``): OvR sigmoid of the decision values, row-normalised for more than
+        two classes; computed on the device.  Two classes: ``column_stack([1 - p, p])`` like the reference."""
+        prob = self._predict(sample, 2)
         if len(self._classes) == 2:
+            if hasattr(prob, "is_cuda"):
+                import torch
+                return torch.cat([1 - prob, prob], dim=1)
             return np.column_stack([1 - prob, prob])
-        return prob / prob.sum(axis=1).reshape((prob.shape[0], -1))
+        return prob
+
+    def transform(self, X, n_components=None):
+        """``transform`` (``lda.py:328-349``) for the svd solver: ``(X - xbar) @ scalings[:, :n_components]``
+        (the reference's svd branch is unreachable -- SURVEY App. B -- this is its evident intent)."""
+        if self.solver == "lsqr":
+            raise NotImplementedError("transform not implemented for 'lsqr' solver (use 'svd' or 'eigen').")
+        if self._coef is None:
+            raise ValueError("This %(name)s instance is not fitted yet" % {"name": type(self).__name__})
+        xa = np.asarray(X)
+        if xa.dtype.kind != "f":
+            xa = xa.astype(np.float64)
+        xa, dtype = _ffi.as_matrix(xa, "X")
+        nt, d = xa.shape
+        rank = self._scalings.shape[1]
+        # the reference slices X_new[:, :n_components] with n_components defaulting to X.shape[1]
+        n_comp = min(rank, d if n_components is None else int(n_components))
+        out = np.empty((nt, n_comp), dtype=np.float32)
+        _ffi.check(self._lib.lda_transform(self._h, _ffi.ptr(xa), nt, d, d, dtype, _ffi.HOST, n_comp, _ffi.ptr(out),
+                                           n_comp, _ffi.HOST))
+        return out
 
     def predict(self, sample):
         return self._classes[np.asarray(self.decision_function(sample)).argmax(axis=1)]
