@@ -107,13 +107,16 @@ __device__ __forceinline__ Work decode(const GemmParams& p, int item, uint32_t r
 // FAST: the score-grid hot path only (TMA store; row term, uniform column term, z-norm affine) -- keeps the
 // unrolled epilogue small enough for the instruction cache.  !FAST: every epilogue feature (per-row column
 // groups, row moments, log-sum-exp partials, all store modes).
-template <bool TWO, bool FAST>
+// LSE (EPI == 2): nothing stored, only the per-row online (max, sum exp) partials of the LDA log-softmax pass 1.
+template <bool TWO, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tt_a_hi, const __grid_constant__ CUtensorMap tt_a_lo,
                    const __grid_constant__ CUtensorMap tt_b_hi, const __grid_constant__ CUtensorMap tt_b_lo,
                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
+  constexpr bool FAST = EPI == 1;
+  constexpr bool LSE = EPI == 2;
   constexpr int kStages = Cfg<TWO>::kStages;
   constexpr int kStageBytes = Cfg<TWO>::kStageBytes;
   constexpr int kBBytes = Cfg<TWO>::kBBytes;
@@ -348,6 +351,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
       float* colslot = colc + acc * BN_MAX;
+      // The accumulator stage is handed back BEFORE process() reads the column cache, so tfull of tile i+2 alone
+      // does not prove that the three sibling warps (same chunk parity h, other lane quarters) are done reading
+      // this slot for tile i: the four warps that share a slot half meet here once per tile (after this point
+      // every one of them has finished tile i-1, hence its reads of tile i-2's slot).
+      if (col_cached) asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN_MAX;
 
       auto process = [&](uint32_t (&r)[32], int c) {
@@ -362,7 +370,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             const float4 t = cp[j4];
             v[4 * j4 + 0] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
           }
-        } else if (!FAST && colp != nullptr && mvalid) {
+        } else if (!FAST && !LSE && colp != nullptr && mvalid) {
           const float4* cp = reinterpret_cast<const float4*>(colp + c * 32);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -372,13 +380,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (v[j] + radd) * zi;
-        if (!FAST && e.rsum != nullptr) {
+        if (!FAST && !LSE && e.rsum != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (nbase + j < p.n) { rs += v[j]; rq += v[j] * v[j]; }
           }
         }
-        if (!FAST && e.lse_max != nullptr) {
+        if (LSE || (!FAST && e.lse_max != nullptr)) {
           float cmax = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (nbase + j < p.n) cmax = fmaxf(cmax, v[j]);
@@ -407,7 +415,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               tma_store_commit();
             }
           }
-        } else if (e.out != nullptr) {
+        } else if (!LSE && e.out != nullptr) {
           if (p.direct_store == 2) {
             // debug (PLDA_B200_EPI=skip): no store at all -> isolates the TMA/MMA main loop
           } else if (p.direct_store == 1) {
@@ -472,8 +480,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       dbg_tfull += clock64() - t_w0;
       tc_fence_after();
       if (col_cached) {
-        // every reader of this slot for the tile two steps back has arrived on tempty before this tile's
-        // MMAs could start, so the slot is free; warps sharing chunks write identical values
+        // slot free (named barrier above); warps sharing chunks write identical values
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int cc = h + 2 * i;
@@ -507,7 +514,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
 
       if (!FAST && mvalid) {
-        if (e.rsum != nullptr) {
+        if (!LSE && e.rsum != nullptr) {
           atomicAdd(e.rsum + m, static_cast<double>(rs));
           atomicAdd(e.rsq + m, static_cast<double>(rq));
         }
@@ -650,14 +657,18 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
   }
   p.dbg = ctx.gemm_dbg.size() >= 32 ? ctx.gemm_dbg.get() : nullptr;
   const GemmEpilogue& ep = p.epi;
-  const bool fast = out != nullptr && p.direct_store == 3 && ep.rsum == nullptr && ep.lse_max == nullptr &&
-                    ep.grp == nullptr;
+  // 1: score-grid hot path, 2: LDA log-sum-exp pass (nothing stored), 0: everything else
+  int epi = 0;
+  if (out != nullptr && p.direct_store == 3 && ep.rsum == nullptr && ep.lse_max == nullptr && ep.grp == nullptr) epi = 1;
+  else if (out == nullptr && ep.lse_max != nullptr && ep.rsum == nullptr && ep.grp == nullptr) epi = 2;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx.profile_gemm) {
@@ -678,17 +689,23 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (fast)
-      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, true>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo,
-                                 ttb_hi, ttb_lo, tout, p));
+    if (epi == 1)
+      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 1>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
+                                 ttb_lo, tout, p));
+    else if (epi == 2)
+      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 2>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
+                                 ttb_lo, tout, p));
     else
-      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, false>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo,
-                                 ttb_hi, ttb_lo, tout, p));
-  } else if (fast) {
-    gemm_bf16x3_kernel<false, true><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
+      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 0>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
+                                 ttb_lo, tout, p));
+  } else if (epi == 1) {
+    gemm_bf16x3_kernel<false, 1><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
+        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
+  } else if (epi == 2) {
+    gemm_bf16x3_kernel<false, 2><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
         ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
   } else {
-    gemm_bf16x3_kernel<false, false><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
+    gemm_bf16x3_kernel<false, 0><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
         ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
   }
   PB_CUDA(cudaGetLastError());

@@ -5,6 +5,8 @@
 // src/pldamodule.cpp:76-92 (fit) and the std::map accumulation of :147-156 (transform).
 // Labels are 8 bytes per row against d*8 bytes of features, so the label sort uses the
 // toolkit's cub::DeviceRadixSort; everything touching the feature rows is hand-written.
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "kernels.h"
@@ -92,6 +94,60 @@ segment_sums_kernel(const T* __restrict__ x, int d, long long ld, const int32_t*
   }
 }
 
+// 16-byte vectorised variant (float4 / double2 loads): used when d, the row pitch and the base address allow it.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+segment_sums_vec_kernel(const T* __restrict__ x, int d, long long ld, const int32_t* __restrict__ order,
+                        const int32_t* __restrict__ seg_of_pos, long long n, double* __restrict__ sums) {
+  constexpr int kMaxVec = 1024 / (32 * VEC);      // vector slots per lane for d <= 1024
+  struct alignas(16) Vec { T v[VEC]; };
+  const long long warp = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long p0 = warp * kRowsPerWarp;
+  if (p0 >= n) return;
+  const long long p1 = min(p0 + kRowsPerWarp, n);
+  const int nvec = d / VEC;                        // vectors per row
+  double acc[kMaxVec][VEC];
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0;
+  auto flush = [&](int seg) {
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int vi = lane + 32 * j;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          atomicAdd(sums + static_cast<long long>(seg) * d + vi * VEC + e, acc[j][e]);
+          acc[j][e] = 0.0;
+        }
+      }
+    }
+  };
+  int cur = seg_of_pos[p0];
+  for (long long p = p0; p < p1; ++p) {
+    const int sg = seg_of_pos[p];
+    if (sg != cur) { flush(cur); cur = sg; }
+    const Vec* row = reinterpret_cast<const Vec*>(x + static_cast<long long>(order[p]) * ld);
+    Vec tmp[kMaxVec];
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {            // all loads of the row first (memory-level parallelism)
+      const int vi = lane + 32 * j;
+      if (vi < nvec) tmp[j] = row[vi];
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int vi = lane + 32 * j;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[j][e] += static_cast<double>(tmp[j].v[e]);
+      }
+    }
+  }
+  flush(cur);
+}
+
 __global__ void finalize_means_kernel(double* __restrict__ sums, int d, const int32_t* __restrict__ seg_start,
                                       long long nseg, int32_t* __restrict__ counts) {
   const long long s = blockIdx.x;
@@ -152,7 +208,8 @@ __global__ void center_scale_f64_kernel(const T* __restrict__ x, int d, long lon
     out[p * d + c] = (static_cast<double>(row[c]) - means[static_cast<long long>(s) * d + c]) * sc;
 }
 
-// sum_out[c] = sum_s means[s,c]/n_s ; class_weight = sum_s 1/n_s.  One block per 32 columns, strided over classes.
+// sum_out[c] += sum_s means[s,c]/n_s ; class_weight += sum_s 1/n_s.  Grid: 32 columns x a slice of the classes
+// per block (fp64 atomics across slices); outputs are zeroed by the launcher.
 __global__ void __launch_bounds__(256)
 class_weighted_sum_kernel(const double* __restrict__ means, const int32_t* __restrict__ counts, long long k, int d,
                           double* __restrict__ sum_out, double* __restrict__ class_weight_out) {
@@ -160,7 +217,7 @@ class_weighted_sum_kernel(const double* __restrict__ means, const int32_t* __res
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   double acc = 0.0, wacc = 0.0;
-  for (long long s = ty; s < k; s += 8) {
+  for (long long s = static_cast<long long>(blockIdx.y) * 8 + ty; s < k; s += 8ll * gridDim.y) {
     const double w = 1.0 / static_cast<double>(counts[s]);
     if (c < d) acc += w * means[s * d + c];
     wacc += w;
@@ -170,7 +227,7 @@ class_weighted_sum_kernel(const double* __restrict__ means, const int32_t* __res
   if (ty == 0) {
     double t = 0.0;
     for (int i = 0; i < 8; ++i) t += red[i][tx];
-    if (c < d) sum_out[c] = t;
+    if (c < d) atomicAdd(sum_out + c, t);
   }
   if (blockIdx.x == 0 && class_weight_out) {
     __syncthreads();
@@ -179,7 +236,7 @@ class_weighted_sum_kernel(const double* __restrict__ means, const int32_t* __res
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int i = 0; i < 8; ++i) t += red[i][0];
-      *class_weight_out = t;
+      atomicAdd(class_weight_out, t);
     }
   }
 }
@@ -229,7 +286,17 @@ void segment_sums(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t l
   PB_CUDA(cudaMemsetAsync(sums, 0, seg.nseg * d * sizeof(double), ctx.stream));
   const long long warps = ceil_div(seg.n, kRowsPerWarp);
   const unsigned blocks = static_cast<unsigned>(ceil_div(warps, 8));
-  if (is_f32)
+  const int vec = is_f32 ? 4 : 2;
+  const bool can_vec = d % vec == 0 && ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (can_vec && is_f32)
+    segment_sums_vec_kernel<float, 4><<<blocks, 256, 0, ctx.stream>>>(static_cast<const float*>(x), static_cast<int>(d),
+                                                                      ld, seg.order.get(), seg.seg_of_pos.get(), seg.n,
+                                                                      sums);
+  else if (can_vec)
+    segment_sums_vec_kernel<double, 2><<<blocks, 256, 0, ctx.stream>>>(static_cast<const double*>(x),
+                                                                       static_cast<int>(d), ld, seg.order.get(),
+                                                                       seg.seg_of_pos.get(), seg.n, sums);
+  else if (is_f32)
     segment_sums_kernel<float><<<blocks, 256, 0, ctx.stream>>>(static_cast<const float*>(x), static_cast<int>(d), ld,
                                                                seg.order.get(), seg.seg_of_pos.get(), seg.n, sums);
   else
@@ -285,7 +352,10 @@ void center_scale_f64(Context& ctx, const void* x, bool is_f32, int64_t d, int64
 
 void class_weighted_sum(Context& ctx, const double* means, const int32_t* counts, int64_t k, int64_t d,
                         double* sum_out, double* class_weight_out) {
-  class_weighted_sum_kernel<<<static_cast<unsigned>(ceil_div(d, 32)), 256, 0, ctx.stream>>>(
+  PB_CUDA(cudaMemsetAsync(sum_out, 0, d * sizeof(double), ctx.stream));
+  if (class_weight_out) PB_CUDA(cudaMemsetAsync(class_weight_out, 0, sizeof(double), ctx.stream));
+  const unsigned slices = static_cast<unsigned>(std::min<int64_t>(64, std::max<int64_t>(1, k / 64)));
+  class_weighted_sum_kernel<<<dim3(static_cast<unsigned>(ceil_div(d, 32)), slices), 256, 0, ctx.stream>>>(
       means, counts, k, static_cast<int>(d), sum_out, class_weight_out);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();

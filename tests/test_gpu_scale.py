@@ -153,3 +153,21 @@ def test_lda_c5_shape_scaled_down():
     ref = o.predict_log_proba(t)
     assert np.max(np.abs(lp - ref) / np.maximum(1.0, np.abs(ref))) <= 2e-3
     assert (lp.argmax(1) == ref.argmax(1)).mean() > 0.9999
+
+
+def test_grid_is_bitwise_repeatable(model200):
+    """Regression: the epilogue's shared column-term cache used to be rewritten while a slow sibling warp was still
+    reading it (32 x 32 blocks of wrong scores in ~1 of 5 launches).  Same inputs -> the same bits, every launch."""
+    import torch
+    from plda_b200 import PLDA
+    ref, a_b = model200
+    g = PLDA()
+    g.set_model(ref.plda.mean, ref.plda.transform, ref.plda.psi)
+    x, _, _ = kp.synth_speakers(a_b, [1] * 16000, seed=99)
+    v = torch.as_tensor(g.transform_batch(x, counts=1), device="cuda", dtype=torch.float32)
+    e, t = v[:8000], v[8000:]
+    n = np.full(8000, 3, dtype=np.int32)
+    first = g.score_grid(e, n, t).clone()
+    for _ in range(60):
+        again = g.score_grid(e, n, t)
+        assert torch.equal(again, first)
