@@ -148,6 +148,18 @@ int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx
 /* lsqr solver (lda.py:223-251): coef = means cov^-1, cov = pooled class covariance; empirical priors only */
 int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                  const int64_t* labels, const double* priors, int64_t n_priors);
+/* Sharded fit (SURVEY 8e "LDA fit": rows sharded by class, one d x d all-reduce + one all-gather of class rows).
+ * lda_class_stats: statistics of THIS rank's rows -- k local classes, their means / counts / labels (ascending) and the
+ * unscaled within-class scatter sum_i (x_i - m_class(i))(x_i - m_class(i))^T; read them with lda_get_class_stats
+ * (sw[d*d], means[k*d], counts[k], classes[k]; any pointer may be NULL).  After the caller has summed `sw` over ranks
+ * and concatenated the per-class rows (classes strictly increasing, every class on exactly one rank),
+ * lda_fit_from_stats runs the solver (0 = svd, lda.py:178-221; 1 = lsqr, lda.py:223-251) on every rank. */
+int lda_class_stats(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                    const int64_t* labels, int64_t* k);
+int lda_get_class_stats(lda_handle_t h, double* sw, double* means, int64_t* counts, int64_t* classes);
+int lda_fit_from_stats(lda_handle_t h, int solver, int64_t n, int64_t k, int64_t d, const double* sw,
+                       const double* means, const int64_t* counts, const int64_t* classes, const double* priors,
+                       int64_t n_priors);
 /* svd solver state: rank (0 for other solvers), xbar[d], scalings[d*rank] row-major (any pointer may be NULL) */
 int lda_get_svd(lda_handle_t h, int64_t* rank, double* xbar, double* scalings);
 /* LDA.transform for the svd solver (lda.py:328-349, evident intent): out[nt x n_components] = (X - xbar) scalings */

@@ -229,6 +229,31 @@ int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ld
                  const int64_t* labels, const double* priors, int64_t n_priors) {
   return with_handle(h, [&](pb::LdaEngine& e) { e.fit_lsqr(x, n, d, ldx, dtype, loc, labels, priors, n_priors); });
 }
+int lda_class_stats(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                    const int64_t* labels, int64_t* k) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    e.local_class_stats(x, n, d, ldx, dtype, loc, labels);
+    if (k) *k = e.shard_stats.k;
+  });
+}
+int lda_get_class_stats(lda_handle_t h, double* sw, double* means, int64_t* counts, int64_t* classes) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    const auto& cs = e.shard_stats;
+    PB_CHECK(cs.k > 0, pb::kNotFitted, "lda_get_class_stats: call lda_class_stats first");
+    if (sw) memcpy(sw, cs.sw.data(), cs.sw.size() * sizeof(double));
+    if (means) memcpy(means, cs.means.data(), cs.means.size() * sizeof(double));
+    if (counts) for (int64_t c = 0; c < cs.k; ++c) counts[c] = cs.counts[c];
+    if (classes) memcpy(classes, cs.classes.data(), cs.k * sizeof(int64_t));
+  });
+}
+int lda_fit_from_stats(lda_handle_t h, int solver, int64_t n, int64_t k, int64_t d, const double* sw,
+                       const double* means, const int64_t* counts, const int64_t* classes, const double* priors,
+                       int64_t n_priors) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    PB_CHECK(solver == 0 || solver == 1, pb::kInvalidArg, "lda_fit_from_stats: solver must be 0 (svd) or 1 (lsqr)");
+    e.fit_from_stats(solver, n, k, d, sw, means, counts, classes, priors, n_priors);
+  });
+}
 int lda_get_svd(lda_handle_t h, int64_t* rank, double* xbar, double* scalings) {
   return with_handle(h, [&](pb::LdaEngine& e) {
     PB_CHECK(e.ready, pb::kNotFitted, "This LDA instance is not fitted yet");

@@ -119,18 +119,27 @@ class LdaEngine {
   void set_coef(int64_t k, int64_t d, const double* coef, const double* intercept);
   void predict(const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int log_proba, float* out,
                int64_t ldo, int out_loc);
+  // sharded fit: statistics of this rank's rows, then the solver on the merged statistics
+  void local_class_stats(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels);
+  void fit_from_stats(int solver, int64_t n, int64_t k, int64_t d, const double* sw, const double* means,
+                      const int64_t* counts, const int64_t* classes, const double* priors, int64_t n_priors);
 
- private:
-  void refresh_operands();
   // shared front end of the solvers: stage rows, segment by class, class means / counts, unscaled within scatter
   struct ClassStats {
-    int64_t k = 0;
+    int64_t k = 0, n = 0, d = 0;
     std::vector<double> sw, means, priors;
     std::vector<int32_t> counts;
     std::vector<int64_t> classes;
   };
+  ClassStats shard_stats;
+
+ private:
+  void refresh_operands();
   void class_stats(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
-                   const double* priors, int64_t n_priors, ClassStats& out);
+                   const double* priors, int64_t n_priors, ClassStats& out, bool allow_single_class);
+  void finish_priors(ClassStats& out, const double* priors, int64_t n_priors);
+  void solve_svd(const ClassStats& cs);
+  void solve_lsqr(const ClassStats& cs);
   SplitBuf ws_x;
   DevBuf<float> ws_out[2], ws_lmax, ws_lsum, ws_neglse;
   DevBuf<double> ws_gram;

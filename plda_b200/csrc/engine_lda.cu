@@ -115,8 +115,9 @@ void LdaEngine::set_coef(int64_t k_, int64_t d_, const double* c, const double* 
 }
 
 void LdaEngine::class_stats(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc,
-                            const int64_t* labels, const double* priors_in, int64_t n_priors, ClassStats& out) {
-  PB_CHECK(n > 1 && d_ > 0 && d_ <= 1024, kInvalidArg, "lda_fit: need n > 1 and 0 < d <= 1024");
+                            const int64_t* labels, const double* priors_in, int64_t n_priors, ClassStats& out,
+                            bool allow_single_class) {
+  PB_CHECK((n > 1 || allow_single_class) && n > 0 && d_ > 0 && d_ <= 1024, kInvalidArg, "lda_fit: need n > 1 and 0 < d <= 1024");
   PB_CHECK(labels != nullptr && x != nullptr, kInvalidArg, "lda_fit: null input");
   PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
   const bool is_f32 = dtype == 1;
@@ -137,8 +138,10 @@ void LdaEngine::class_stats(const void* x, int64_t n, int64_t d_, int64_t ldx, i
   Segments segs;
   build_segments(ctx, dkeys.get(), n, segs);
   const int64_t kk = segs.nseg;
-  PB_CHECK(kk >= 2, kValueError, "lda_fit: at least two classes are required");
-  PB_CHECK(n > kk, kValueError, "lda_fit: need more samples than classes");
+  if (!allow_single_class) {
+    PB_CHECK(kk >= 2, kValueError, "lda_fit: at least two classes are required");
+    PB_CHECK(n > kk, kValueError, "lda_fit: need more samples than classes");
+  }
   DevBuf<double> means(static_cast<size_t>(kk) * d_);
   DevBuf<int32_t> counts(kk);
   segment_sums(ctx, xd, is_f32, d_, ld, segs, means.get());
@@ -171,25 +174,71 @@ void LdaEngine::class_stats(const void* x, int64_t n, int64_t d_, int64_t ldx, i
   ctx.sync();
   out.classes.resize(kk);
   for (int64_t c = 0; c < kk; ++c) out.classes[c] = static_cast<int64_t>(h_keys[c] ^ (1ull << 63));
-  // priors (lda.py:119-127)
+  out.n = n;
+  out.d = d_;
+  finish_priors(out, priors_in, n_priors);
+}
+
+// priors (lda.py:119-127): given or empirical n_k / n, renormalised when they do not sum to one
+void LdaEngine::finish_priors(ClassStats& out, const double* priors_in, int64_t n_priors) {
+  const int64_t kk = out.k;
   out.priors.resize(kk);
   if (priors_in != nullptr) {
     PB_CHECK(n_priors == kk, kInvalidArg, "lda_fit: priors length does not match the number of classes");
     for (int64_t i = 0; i < kk; ++i) out.priors[i] = priors_in[i];
   } else {
-    for (int64_t i = 0; i < kk; ++i) out.priors[i] = static_cast<double>(out.counts[i]) / static_cast<double>(n);
+    for (int64_t i = 0; i < kk; ++i) out.priors[i] = static_cast<double>(out.counts[i]) / static_cast<double>(out.n);
   }
   double psum = 0.0;
   for (double v : out.priors) psum += v;
   if (psum != 1.0) for (double& v : out.priors) v /= psum;
 }
 
+// Stats of this rank's rows only (sharded fit, SURVEY 8e "LDA fit"): the caller all-reduces the scatter and
+// all-gathers the per-class rows, then calls fit_from_stats on every rank.
+void LdaEngine::local_class_stats(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc,
+                                  const int64_t* labels) {
+  class_stats(x, n, d_, ldx, dtype, loc, labels, nullptr, 0, shard_stats, /*allow_single_class=*/true);
+}
+
+void LdaEngine::fit_from_stats(int solver, int64_t n, int64_t kk, int64_t d_, const double* sw, const double* means,
+                               const int64_t* counts, const int64_t* classes, const double* priors_in,
+                               int64_t n_priors) {
+  PB_CHECK(kk >= 2, kValueError, "lda_fit: at least two classes are required");
+  PB_CHECK(n > kk, kValueError, "lda_fit: need more samples than classes");
+  PB_CHECK(d_ > 0 && d_ <= 1024, kInvalidArg, "lda_fit: need 0 < d <= 1024");
+  PB_CHECK(sw && means && counts && classes, kInvalidArg, "lda_fit_from_stats: null input");
+  ClassStats cs;
+  cs.k = kk;
+  cs.n = n;
+  cs.d = d_;
+  cs.sw.assign(sw, sw + static_cast<size_t>(d_) * d_);
+  cs.means.assign(means, means + static_cast<size_t>(kk) * d_);
+  cs.counts.resize(kk);
+  cs.classes.assign(classes, classes + kk);
+  int64_t total = 0;
+  for (int64_t c = 0; c < kk; ++c) {
+    PB_CHECK(counts[c] > 0, kInvalidArg, "lda_fit_from_stats: class counts must be positive");
+    PB_CHECK(c == 0 || classes[c] > classes[c - 1], kInvalidArg, "lda_fit_from_stats: classes must be strictly increasing");
+    cs.counts[c] = static_cast<int32_t>(counts[c]);
+    total += counts[c];
+  }
+  PB_CHECK(total == n, kInvalidArg, "lda_fit_from_stats: class counts do not add up to n");
+  finish_priors(cs, priors_in, n_priors);
+  if (solver == 0) solve_svd(cs); else solve_lsqr(cs);
+}
+
 void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
                         const double* priors_in, int64_t n_priors) {
-  const double tol = 1e-4;
   ClassStats cs;
-  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs);
-  const int64_t kk = cs.k;
+  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs, false);
+  solve_svd(cs);
+}
+
+// lda.py:178-221 (_solve_svd) from the class statistics: both SVDs as symmetric eigenproblems of Gram matrices
+void LdaEngine::solve_svd(const ClassStats& cs) {
+  const double tol = 1e-4;
+  const int64_t kk = cs.k, n = cs.n, d_ = cs.d;
   const size_t dd = static_cast<size_t>(d_) * d_;
   const std::vector<double>& h_sw = cs.sw;
   const std::vector<double>& h_means = cs.means;
@@ -293,8 +342,12 @@ void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int d
 void LdaEngine::fit_lsqr(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
                          const double* priors_in, int64_t n_priors) {
   ClassStats cs;
-  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs);
-  const int64_t kk = cs.k;
+  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs, false);
+  solve_lsqr(cs);
+}
+
+void LdaEngine::solve_lsqr(const ClassStats& cs) {
+  const int64_t kk = cs.k, n = cs.n, d_ = cs.d;
   const size_t dd = static_cast<size_t>(d_) * d_;
   // cov = sum_k priors_k * cov_k,  cov_k = (1/n_k) sum_{i in k} (x - m_k)(x - m_k)^T   (_class_cov, lda.py:10-16).
   // With empirical priors n_k/n this is Sw/n exactly; general priors need the per-class scatters, which the fused

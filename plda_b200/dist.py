@@ -79,3 +79,87 @@ class ShardedScorer:
         if rank != 0:
             return None
         return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
+def _coll_device(group=None):
+    """NCCL moves CUDA tensors only; gloo (CPU tests) moves host tensors."""
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def merge_class_stats(sw, means, counts, classes, group=None):
+    """Merge per-rank LDA class statistics (SURVEY 8e "LDA fit"): ONE sum-all-reduce of the ``d x d`` within scatter
+    and ONE all-gather of the packed per-class rows ``[class, count, mean...]`` (ragged -> padded to the largest
+    rank).  Returns ``(sw, means, counts, classes)`` with classes ascending; a class seen on two ranks is an error
+    (its scatter would be centred on two different means)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sw = np.ascontiguousarray(sw, dtype=np.float64)
+    means = np.ascontiguousarray(means, dtype=np.float64)
+    k, d = means.shape
+    if world > 1:
+        dev = _coll_device(group)
+        t_sw = torch.from_numpy(sw.copy()).to(dev)
+        dist.all_reduce(t_sw, group=group)
+        sw = t_sw.cpu().numpy()
+        t_k = torch.tensor([k], dtype=torch.int64, device=dev)
+        ks = [torch.zeros_like(t_k) for _ in range(world)]
+        dist.all_gather(ks, t_k, group=group)
+        ks = [int(v.item()) for v in ks]
+        mx = max(ks)
+        # class ids and counts travel as int64 next to the fp64 means (bit-exact for any label value)
+        ids = torch.zeros((mx, 2), dtype=torch.int64, device=dev)
+        ids[:k, 0] = torch.from_numpy(np.asarray(classes, dtype=np.int64)).to(dev)
+        ids[:k, 1] = torch.from_numpy(np.asarray(counts, dtype=np.int64)).to(dev)
+        mm = torch.zeros((mx, d), dtype=torch.float64, device=dev)
+        mm[:k] = torch.from_numpy(means).to(dev)
+        g_ids = torch.empty((world * mx, 2), dtype=torch.int64, device=dev)
+        g_mm = torch.empty((world * mx, d), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g_ids, ids, group=group)
+        dist.all_gather_into_tensor(g_mm, mm, group=group)
+        keep = np.concatenate([np.arange(r * mx, r * mx + kr) for r, kr in enumerate(ks)])
+        g_ids = g_ids.cpu().numpy()[keep]
+        means = g_mm.cpu().numpy()[keep]
+        classes, counts = g_ids[:, 0], g_ids[:, 1]
+    classes = np.asarray(classes, dtype=np.int64)
+    counts = np.asarray(counts, dtype=np.int64)
+    order = np.argsort(classes, kind="stable")
+    classes, counts, means = classes[order], counts[order], means[order]
+    if np.any(classes[1:] == classes[:-1]):
+        raise ValueError("sharded LDA fit: every class must live on exactly one rank")
+    return sw, np.ascontiguousarray(means), counts, classes
+
+
+def broadcast_lda(lda, src: int = 0, group=None):
+    """Replicate a fitted LDA's ``coef`` / ``intercept`` from rank ``src`` (SURVEY 8e "LDA predict": test rows are
+    sharded, the K x d coefficients are broadcast once after the fit)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    dev = _coll_device(group)
+    shape = torch.zeros(2, dtype=torch.int64, device=dev)
+    if rank == src:
+        shape[0], shape[1] = lda._coef.shape
+    dist.broadcast(shape, src=src, group=group)
+    k, d = int(shape[0].item()), int(shape[1].item())
+    buf = torch.empty((k, d + 1), dtype=torch.float64, device=dev)
+    if rank == src:
+        buf[:, :d] = torch.from_numpy(np.asarray(lda._coef, dtype=np.float64)).to(dev)
+        buf[:, d] = torch.from_numpy(np.asarray(lda._intercept, dtype=np.float64)).to(dev)
+    dist.broadcast(buf, src=src, group=group)
+    if rank != src:
+        h = buf.cpu().numpy()
+        lda.set_coef(np.ascontiguousarray(h[:, :d]), np.ascontiguousarray(h[:, d]))
+    return lda
+
+
+def sharded_norm(plda, cohort_shard, n_cohort_total: int, enrol_block: dict, numutts: int = 0, seed: int = 0,
+                 group=None):
+    """z-norm with enrol-block ownership (SURVEY 8e "z-norm"): the cohort rows are all-gathered (one small
+    collective), the moments of this rank's enrol models stay local to it."""
+    import torch
+    t = torch.as_tensor(np.ascontiguousarray(cohort_shard, dtype=np.float64)).to(_coll_device(group))
+    cohort = all_gather_rows(t, n_cohort_total, group).cpu().numpy()
+    return plda.norm(cohort, enrol_block, numutts, seed)

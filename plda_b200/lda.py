@@ -58,21 +58,32 @@ class LDA(object):
             # K - 1 < d: the reference's own result is not reproducible by construction, so it is not offered.
             raise NotImplementedError("solver %r is not available on the device path; use 'svd' or 'lsqr'"
                                       % (self.solver,))
-        x, dtype = _ffi.as_matrix(np.asarray(features, dtype=np.float64) if np.asarray(features).dtype.kind != "f"
-                                  else features, "features")
-        y = np.asarray(labels)
-        if y.dtype.kind not in "iub":
-            raise ValueError("labels must be integers")
-        y = np.ascontiguousarray(y.astype(np.int64).reshape(-1))
+        x, dtype, y = self._check_xy(features, labels)
         n, d = x.shape
-        if y.shape[0] != n:
-            raise ValueError("labels and features disagree on the number of samples")
         pri = None
         if self.priors is not None:
             pri = np.ascontiguousarray(self.priors, dtype=np.float64)
         fit_fn = self._lib.lda_fit_svd if self.solver == "svd" else self._lib.lda_fit_lsqr
         _ffi.check(fit_fn(self._h, _ffi.ptr(x), n, d, d, dtype, _ffi.HOST, _ffi.ptr(y), _ffi.ptr(pri),
                           0 if pri is None else pri.shape[0]))
+        _, cnt = np.unique(y, return_counts=True)
+        self._read_back(cnt, n)
+        return None
+
+    @staticmethod
+    def _check_xy(features, labels):
+        x, dtype = _ffi.as_matrix(np.asarray(features, dtype=np.float64) if np.asarray(features).dtype.kind != "f"
+                                  else features, "features")
+        y = np.asarray(labels)
+        if y.dtype.kind not in "iub":
+            raise ValueError("labels must be integers")
+        y = np.ascontiguousarray(y.astype(np.int64).reshape(-1))
+        if y.shape[0] != x.shape[0]:
+            raise ValueError("labels and features disagree on the number of samples")
+        return x, dtype, y
+
+    def _read_back(self, class_counts, n):
+        """coef / intercept / classes (and the svd state) from the handle; priors as the reference leaves them."""
         k = C.c_int64()
         dd = C.c_int64()
         _ffi.check(self._lib.lda_num_classes(self._h, C.byref(k), C.byref(dd)))
@@ -89,12 +100,56 @@ class LDA(object):
             self._scalings = np.empty((dd.value, rank.value))
             _ffi.check(self._lib.lda_get_svd(self._h, C.byref(rank), _ffi.ptr(self._xbar), _ffi.ptr(self._scalings)))
         if self.priors is None:
-            _, cnt = np.unique(y, return_counts=True)
-            self.priors = cnt / float(n)
+            self.priors = np.asarray(class_counts) / float(n)
         else:
             p = np.asarray(self.priors, dtype=np.float64)
             self.priors = p / p.sum() if p.sum() != 1 else p
+
+    def fit_distributed(self, features, labels, group=None):
+        """Sharded ``fit``: every rank passes ITS rows; all rows of a class must live on one rank.
+
+        Per rank one pass over its rows (class means + within scatter on the device), then ONE sum-all-reduce of the
+        ``d x d`` scatter and ONE all-gather of the per-class rows (``plda_b200.dist.merge_class_stats``); the small
+        solver runs replicated on every rank, so all ranks end with identical coefficients."""
+        from . import dist as _dist
+        if self.solver not in ("svd", "lsqr"):
+            raise NotImplementedError("solver %r is not available on the device path; use 'svd' or 'lsqr'"
+                                      % (self.solver,))
+        sw, means, counts, classes = self.local_class_stats(features, labels)
+        sw, means, counts, classes = _dist.merge_class_stats(sw, means, counts, classes, group)
+        self.fit_from_stats(sw, means, counts, classes)
         return None
+
+    def local_class_stats(self, features, labels):
+        """Device pass over THIS rank's rows: ``(sw [d,d], means [k,d], counts [k], classes [k])``."""
+        x, dtype, y = self._check_xy(features, labels)
+        n_loc, d = x.shape
+        k = C.c_int64()
+        _ffi.check(self._lib.lda_class_stats(self._h, _ffi.ptr(x), n_loc, d, d, dtype, _ffi.HOST, _ffi.ptr(y),
+                                             C.byref(k)))
+        sw = np.empty((d, d))
+        means = np.empty((k.value, d))
+        counts = np.empty(k.value, dtype=np.int64)
+        classes = np.empty(k.value, dtype=np.int64)
+        _ffi.check(self._lib.lda_get_class_stats(self._h, _ffi.ptr(sw), _ffi.ptr(means), _ffi.ptr(counts),
+                                                 _ffi.ptr(classes)))
+        return sw, means, counts, classes
+
+    def fit_from_stats(self, sw, means, counts, classes):
+        """Solver stage on merged class statistics (see ``fit_distributed``)."""
+        sw = np.ascontiguousarray(sw, dtype=np.float64)
+        means = np.ascontiguousarray(means, dtype=np.float64)
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        classes = np.ascontiguousarray(classes, dtype=np.int64)
+        kk, d = means.shape
+        n = int(counts.sum())
+        pri = None
+        if self.priors is not None:
+            pri = np.ascontiguousarray(self.priors, dtype=np.float64)
+        _ffi.check(self._lib.lda_fit_from_stats(self._h, 0 if self.solver == "svd" else 1, n, kk, d, _ffi.ptr(sw),
+                                                _ffi.ptr(means), _ffi.ptr(counts), _ffi.ptr(classes), _ffi.ptr(pri),
+                                                0 if pri is None else pri.shape[0]))
+        self._read_back(counts, n)
 
     def set_coef(self, coef, intercept):
         coef = np.ascontiguousarray(coef, dtype=np.float64)

@@ -5,8 +5,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from plda_b200 import PLDA
-from plda_b200.dist import block_bounds
+from plda_b200 import LDA, PLDA
+from plda_b200.dist import block_bounds, broadcast_lda
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -44,5 +44,31 @@ dist.all_gather(gathered, psi_t)
 same = all(torch.equal(gathered[0], g) for g in gathered)     # replicas stay bit-identical
 if rank == 0:
     print("replica psi bit-identical across ranks:", same)
+
+# ---- LDA: rows sharded by class (fit), test rows sharded + coefficients broadcast (predict) ----
+kc, dl = 40, 24
+yl = rng.randint(0, kc, 4000)
+xl = rng.randn(4000, dl) + rng.randn(kc, dl)[yl]
+tl = rng.randn(300, dl)
+clo, chi = block_bounds(kc, world, rank)
+mine = (yl >= clo) & (yl < chi)
+ld = LDA(device=local, precision="fp64")
+ld.fit_distributed(xl[mine], yl[mine])
+lda_ok = True
+coef_t = torch.from_numpy(ld._coef).cuda()
+gath = [torch.empty_like(coef_t) for _ in range(world)]
+dist.all_gather(gath, coef_t)
+lda_same = all(torch.equal(gath[0], g) for g in gath)
+one = LDA(device=local, precision="fp64")
+if rank == 0:
+    one.fit(xl, yl)
+    e4 = np.max(np.abs(ld._coef - one._coef)) + np.max(np.abs(ld._intercept - one._intercept))
+    print("sharded LDA fit vs single fit: coef+intercept abs %.2e  identical across ranks: %s" % (e4, lda_same))
+    lda_ok = e4 < 1e-8
+broadcast_lda(one, src=0)
+rlo, rhi = block_bounds(300, world, rank)
+part = torch.from_numpy(np.asarray(one.predict_log_proba(tl[rlo:rhi]), dtype=np.float64)).cuda()
+want = torch.from_numpy(np.asarray(ld.predict_log_proba(tl[rlo:rhi]), dtype=np.float64)).cuda()
+lda_ok = lda_ok and bool(torch.allclose(part, want, atol=1e-4))
 dist.destroy_process_group()
-sys.exit(0 if (ok and same) else 1)
+sys.exit(0 if (ok and same and lda_ok and lda_same) else 1)

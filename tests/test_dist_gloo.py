@@ -74,3 +74,72 @@ def test_sharded_scoring_gloo(tmp_path, world, ne, nt):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, ne, nt, 6, str(tmp_path)), nprocs=world, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "ok_%d" % world))
+
+
+class _FakeLda:
+    """Stand-in with the attributes broadcast_lda touches (the real LDA needs a GPU)."""
+    def __init__(self):
+        self._coef = self._intercept = None
+
+    def set_coef(self, coef, intercept):
+        self._coef, self._intercept = coef, intercept
+
+
+class _FakePlda:
+    def norm(self, cohort, enrol, numutts, seed):
+        return cohort.copy(), sorted(enrol), numutts, seed
+
+
+def _lda_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.lda_port import LDAOracle
+        from plda_b200.dist import broadcast_lda, merge_class_stats, sharded_norm
+        rng = np.random.RandomState(3)           # same global problem on every rank
+        k, d, n = 7, 5, 210
+        y = rng.randint(0, k, n) * 3 - 4         # sparse, partly negative labels
+        x = rng.randn(n, d) + y[:, None] * 0.1
+        classes = np.unique(y)
+        # whole classes per rank, ragged (4 + 3 for world 2), interleaved so the merge has to sort
+        mine = classes[rank::world]
+        rows = np.isin(y, mine)
+        xl, yl = x[rows], y[rows]
+        means = np.stack([xl[yl == c].mean(0) for c in mine])
+        counts = np.array([(yl == c).sum() for c in mine])
+        sw = sum((xl[yl == c] - xl[yl == c].mean(0)).T @ (xl[yl == c] - xl[yl == c].mean(0)) for c in mine)
+        g_sw, g_means, g_counts, g_classes = merge_class_stats(sw, means, counts, mine)
+        assert np.array_equal(g_classes, classes)
+        assert np.array_equal(g_counts, np.array([(y == c).sum() for c in classes]))
+        assert np.allclose(g_means, np.stack([x[y == c].mean(0) for c in classes]), atol=1e-13)
+        want_sw = sum((x[y == c] - x[y == c].mean(0)).T @ (x[y == c] - x[y == c].mean(0)) for c in classes)
+        assert np.allclose(g_sw, want_sw, atol=1e-10)
+        # a class present on two ranks is refused
+        with pytest.raises(ValueError):
+            merge_class_stats(sw, means[:1], counts[:1], classes[:1])
+        # coefficient broadcast
+        lda = _FakeLda()
+        if rank == 0:
+            o = LDAOracle("svd")
+            o.fit(x, y)
+            lda.set_coef(np.asarray(o._coef), np.asarray(o._intercept))
+        broadcast_lda(lda, src=0)
+        o = LDAOracle("svd")
+        o.fit(x, y)
+        assert np.array_equal(lda._coef, o._coef) and np.array_equal(lda._intercept, o._intercept)
+        # cohort all-gather in front of norm
+        cohort = rng.randn(9, d)
+        lo, hi = block_bounds(9, world, rank)
+        got = sharded_norm(_FakePlda(), cohort[lo:hi], 9, {5: None, 2: None}, numutts=4, seed=11)
+        assert np.array_equal(got[0], cohort) and got[1:] == ([2, 5], 4, 11)
+        open(os.path.join(result_dir, "lda_ok_%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lda_and_norm_plumbing_gloo(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_lda_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "lda_ok_%d" % r)) for r in range(world))

@@ -25,3 +25,4 @@ def test_sharded_fit_matches_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "bit-identical across ranks: True" in r.stdout
+    assert "identical across ranks: True" in r.stdout.split("sharded LDA fit")[1]
