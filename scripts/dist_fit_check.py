@@ -47,6 +47,7 @@ if rank == 0:
 
 # ---- LDA: rows sharded by class (fit), test rows sharded + coefficients broadcast (predict) ----
 kc, dl = 40, 24
+rng = np.random.RandomState(1)                            # fresh stream: rank 0 drew extra numbers above
 yl = rng.randint(0, kc, 4000)
 xl = rng.randn(4000, dl) + rng.randn(kc, dl)[yl]
 tl = rng.randn(300, dl)
