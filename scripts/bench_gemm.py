@@ -50,3 +50,40 @@ if os.environ.get("PLDA_B200_DBG") == "1":
              "epi0_wait_tfull", "epi0_wait_store", "epi0_total", "epi7_wait_tfull", "epi7_wait_store", "epi7_total", "epi0_tmem_load"]
     for b in range(2):
         print("  cta%d: " % b + "  ".join("%s=%d" % (n, c[b * 16 + i]) for i, n in enumerate(names)))
+
+if os.environ.get("PLDA_B200_CUBLAS", "1") == "1":
+    # Library yardstick at EQUAL ISSUED WORK: one cuBLAS bf16 GEMM with K = 3 * K16 (the three split products laid end
+    # to end), no fused score terms.  bf16 output halves its store traffic; fp32 output where torch exposes it.
+    kk = 3 * k16
+    a = torch.randn(ne, kk, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(nt, kk, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            fn()
+            s1.record()
+            torch.cuda.synchronize()
+            tot += s0.elapsed_time(s1)
+        return tot / reps
+    ms16 = timed(lambda: torch.mm(a, b.t()))
+    print("cuBLAS bf16 [%d x %d x %d] -> bf16 out: %.4f ms  %.0f TFLOP/s" % (ne, nt, kk, ms16, 2.0 * kk * ne * nt / ms16 / 1e9))
+    try:
+        o32 = torch.empty((ne, nt), device=dev, dtype=torch.float32)
+        ms32 = timed(lambda: torch.mm(a, b.t(), out_dtype=torch.float32, out=o32))
+        print("cuBLAS bf16 [%d x %d x %d] -> fp32 out: %.4f ms  %.0f TFLOP/s" % (ne, nt, kk, ms32, 2.0 * kk * ne * nt / ms32 / 1e9))
+    except Exception as exc:  # noqa: BLE001
+        print("cuBLAS fp32-out variant not available in this torch:", type(exc).__name__, str(exc)[:100])
+    # fp32 (TF32 off) and TF32 GEMMs on the unsplit operands, for the precision / speed trade-off table
+    a32, b32 = torch.randn(ne, d, device=dev), torch.randn(nt, d, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ms_f32 = timed(lambda: torch.mm(a32, b32.t()))
+    torch.backends.cuda.matmul.allow_tf32 = True
+    ms_tf32 = timed(lambda: torch.mm(a32, b32.t()))
+    print("cuBLAS fp32 (no TF32) [K=%d] -> fp32: %.4f ms ; TF32 -> fp32: %.4f ms" % (d, ms_f32, ms_tf32))
