@@ -20,7 +20,10 @@ A *step* is one pass of the scoring hot path over one batch: the all-pairs LLR g
   em           EM iterations/s of plda.fit on the same config (stats pass / GetOutput excluded)
 
 N > 1 (torchrun): weak scaling -- every rank owns 10 000 enrol models, the test vectors are
-sharded, each step does ONE NCCL all-gather of the transformed test vectors and the local grid.
+sharded.  Each step exchanges the transformed test vectors and scores the local slab: the operand
+producer kernel of every rank writes its rows into the operand buffers of ALL ranks over NVLink
+peer memory and the GEMM waits per column tile for the owner's flag (no collective on the data
+path; `--nccl-allgather` or a failed CUDA-IPC setup selects ONE NCCL all-gather per step instead).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
@@ -297,7 +300,30 @@ def run_main(args):
     assert stream.cuda_stream != 0
     _ffi.check(lib.plda_set_stream(plda._h, C.c_void_p(stream.cuda_stream)))
 
+    # N > 1: the operand producer pushes this rank's test rows into every rank's operand buffer over NVLink peer
+    # memory and the GEMM waits per column tile for the owner's flag (plda_b200.dist.PeerShardedScorer); if the
+    # CUDA-IPC wiring is unavailable on any rank, every rank falls back to ONE NCCL all-gather per step
+    peer = None
+    if world > 1 and not args.nccl_allgather:
+        from plda_b200.dist import PeerShardedScorer
+        try:
+            peer = PeerShardedScorer(plda, nt_total, D)
+            okf = 1
+        except Exception as e:  # pragma: no cover
+            log("rank %d: peer-memory scorer unavailable (%r)" % (rank, e))
+            okf = 0
+        t_ok = torch.tensor([okf], device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer = None
+        torch.cuda.current_stream().synchronize()
+
     def step(i):
+        if peer is not None:
+            peer.score(enrol_t, ENROL_UTTS, test_shard, out=outs[i & 1][:, :nt_total], sync=False)
+            return
         if world > 1:
             dist.all_gather_into_tensor(test_full, test_shard)
         plda.score_grid(enrol_t, counts, test_full, out=outs[i & 1][:, :nt_total])
@@ -335,6 +361,17 @@ def run_main(args):
         total_ms = float(t.item())
     trials_per_step = ne_local * nt_total * world
     value = trials_per_step * args.steps / (total_ms * 1e-3)
+    shard_timeouts = None
+    peer_used = peer is not None
+    if peer is not None:
+        # cross-check of the last timed slab against the all-gather path, then release the regions
+        shard_timeouts = peer.status()[1]
+        dist.all_gather_into_tensor(test_full, test_shard)
+        chk = plda.score_grid(enrol_t, counts, test_full)
+        torch.cuda.current_stream().synchronize()
+        if not torch.equal(chk, outs[(args.steps - 1) & 1][:, :nt_total]) or shard_timeouts:
+            raise RuntimeError("peer-memory sharded grid disagrees with the all-gather grid (timeouts=%r)" % shard_timeouts)
+        peer.close()
 
     # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region ----
     e_host, _p1 = pinned_array(lib, (ne_local, D), np.float64)
@@ -400,8 +437,11 @@ def run_main(args):
                    "d": D, "enrol_per_gpu": ne_local, "test": nt_total, "enrol_utts": ENROL_UTTS,
                    "sink": "fp32 score matrix in HBM (400 MB per step per GPU)",
                    "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events summed",
-                   "parallelism": "enrol-block shard per GPU, 1 NCCL all-gather of test vectors per step"
-                   if world > 1 else "single GPU"},
+                   "parallelism": ("single GPU" if world == 1 else
+                                   "enrol-block shard per GPU; each rank's producer kernel pushes its test rows into "
+                                   "every rank's operand buffer over NVLink peer memory (CUDA IPC), the GEMM waits per "
+                                   "column tile on the owner's flag; no NCCL on the data path" if peer_used else
+                                   "enrol-block shard per GPU, 1 NCCL all-gather of test vectors per step")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((ne_local + nt_total) * D * 8),
                 "d2h_bytes_per_step": int(ne_local * nt_total * 4), "steps": e2e_steps,
                 "ms_per_step": e2e_s / e2e_steps * 1e3, "host_buffers": "pinned fp64 in, pinned fp32 out"},
@@ -446,6 +486,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-allgather", action="store_true",
+                    help="N > 1: exchange the test vectors with one NCCL all-gather per step instead of peer memory")
     ap.add_argument("--skip-em", action="store_true", help="profiling aid: 1 EM iteration, no fit timing")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

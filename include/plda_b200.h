@@ -135,6 +135,32 @@ int plda_znorm_clear(plda_handle_t h);
 /* restore tables saved with plda_znorm_get (first insert wins, like plda_norm) */
 int plda_znorm_set(plda_handle_t h, const uint64_t* ids, const double* mean, const double* stdv, int64_t n);
 
+/* ---- sharded score grid over NVLink peer memory (multi-GPU form of plda_score_grid) --------- *
+ * Replaces, for one process per GPU, the all-pairs loop over MPlda_score (src/pldamodule.cpp:258-277)
+ * when the grid is sharded by ENROL BLOCK and the test vectors by row block (`bounds`, [world+1]).
+ * Instead of an all-gather collective, plda_shard_push writes this rank's test rows (split operand +
+ * column terms for `enrol_count`) into the operand buffer of EVERY rank through peer mappings and
+ * raises a ready flag; plda_shard_score runs the grid of this rank's enrol block against all test
+ * rows, waiting per column tile for the rank that owns the rows.  Uniform enrol count only (ragged
+ * counts: all-gather + plda_score_grid).  All pointers are DEVICE pointers; both calls are
+ * stream-ordered on the handle's stream and do NOT synchronise (plda_synchronize does).
+ *   open     allocates the region; ipc_handle_out (64 bytes, cudaIpcMemHandle_t) is what the peers
+ *            need, region_out the raw pointer for peers living in the same process
+ *   connect  once per peer, with that peer's IPC handle (other process) or region pointer (same
+ *            process); all ranks must have connected (barrier) before the first push
+ *   push / score must be called the same number of times, in the same order, on every rank
+ *   status   epoch = pushes so far; timeouts = waits that gave up after 5 s (results invalid if > 0) */
+#define PLDA_IPC_HANDLE_BYTES 64
+int plda_shard_open(plda_handle_t h, int world, int rank, const int64_t* bounds, int64_t dim,
+                    unsigned char* ipc_handle_out, void** region_out);
+int plda_shard_connect(plda_handle_t h, int peer_rank, const unsigned char* ipc_handle, void* same_process_region);
+int plda_shard_push(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, int dtype,
+                    int enrol_count);
+int plda_shard_score(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count,
+                     const uint64_t* enrol_ids, int dtype, float* out, int64_t ldo);
+int plda_shard_status(plda_handle_t h, int64_t* epoch, int64_t* timeouts);
+int plda_shard_close(plda_handle_t h);
+
 /* ---- LDA: replaces python/liblda/lda.py (LDA.fit svd :178-221, decision_function :253-279,
  *      predict_log_proba :306-325) ---------------------------------------------------------- */
 int lda_create(int device, lda_handle_t* out);

@@ -52,6 +52,12 @@ SIGNATURES = {
     "plda_znorm_get": [_vp, _vp, _vp, _vp, _i64, C.POINTER(_i64)],
     "plda_znorm_clear": [_vp],
     "plda_znorm_set": [_vp, _vp, _vp, _vp, _i64],
+    "plda_shard_open": [_vp, _int, _int, _vp, _i64, _vp, C.POINTER(_vp)],
+    "plda_shard_connect": [_vp, _int, _vp, _vp],
+    "plda_shard_push": [_vp, _vp, _i64, _i64, _int, _int],
+    "plda_shard_score": [_vp, _vp, _i64, _i64, _int, _vp, _int, _vp, _i64],
+    "plda_shard_status": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "plda_shard_close": [_vp],
     "lda_create": [_int, C.POINTER(_vp)],
     "lda_destroy": [_vp],
     "lda_set_precision": [_vp, _int],

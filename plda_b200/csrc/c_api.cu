@@ -202,6 +202,30 @@ int plda_znorm_set(plda_handle_t h, const uint64_t* ids, const double* mean, con
 }
 int plda_znorm_clear(plda_handle_t h) { return with_handle(h, [&](pb::PldaEngine& e) { e.znorm.clear(); }); }
 
+int plda_shard_open(plda_handle_t h, int world, int rank, const int64_t* bounds, int64_t dim,
+                    unsigned char* ipc_handle_out, void** region_out) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.shard_open(world, rank, bounds, dim, ipc_handle_out, region_out); });
+}
+int plda_shard_connect(plda_handle_t h, int peer_rank, const unsigned char* ipc_handle, void* same_process_region) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.shard_connect(peer_rank, ipc_handle, same_process_region); });
+}
+int plda_shard_push(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, int dtype,
+                    int enrol_count) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.shard_push(test_shard, nt_local, ld_test, dtype, enrol_count); });
+}
+int plda_shard_score(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count,
+                     const uint64_t* enrol_ids, int dtype, float* out, int64_t ldo) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.shard_score(enrol, ne, ld_enrol, enrol_count, enrol_ids, dtype, out, ldo);
+  });
+}
+int plda_shard_status(plda_handle_t h, int64_t* epoch, int64_t* timeouts) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.shard_status(epoch, timeouts); });
+}
+int plda_shard_close(plda_handle_t h) {
+  return with_handle(h, [&](pb::PldaEngine& e) { e.shard_close(); });
+}
+
 int lda_create(int device, lda_handle_t* out) {
   if (out == nullptr) { g_last_error = "null output pointer"; return PLDA_E_INVALID; }
   *out = nullptr;

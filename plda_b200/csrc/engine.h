@@ -30,6 +30,25 @@ struct PldaModel {
 // the first `count` doubles of the scratch in place, stream-ordered on the handle's stream (NCCL via torch).
 typedef int (*AllReduceFn)(void* user, int64_t count);
 
+// Sharded score grid over NVLink peer memory (SURVEY 8e "scoring grid"): every rank owns one REGION holding
+// ready flags and two generations of the full test operand (split planes + column terms).  A rank's push kernel
+// writes ITS test rows into every region (its own and, through CUDA-IPC mappings, the peers'); the score GEMM reads
+// the local region, waiting per column tile for the owner's flag.  Two generations + monotonic epochs make the
+// exchange safe without any host-side barrier per step (a rank can be at most one step ahead of a peer).
+struct ShardSession {
+  bool open = false;
+  int world = 0, rank = 0;
+  int64_t nt_total = 0, dim = 0, ldk = 0, col_ld = 0;
+  std::vector<int64_t> bounds;          // [world+1] row partition of the test set
+  uint8_t* region = nullptr;            // own region (cudaMalloc)
+  size_t bytes = 0;
+  size_t off_gen[2] = {0, 0}, off_lo = 0, off_col = 0;   // generation base; lo plane / column terms inside it
+  std::vector<uint8_t*> peer;           // [world] region base of every rank as mapped in THIS process
+  std::vector<bool> peer_ipc;           // mapped with cudaIpcOpenMemHandle (to be closed)
+  unsigned epoch = 0;                   // number of pushes so far (same on every rank)
+  int push_count = 0;                   // enrol count the column terms of the current generation were built for
+};
+
 class PldaEngine {
  public:
   explicit PldaEngine(int device) : ctx(device) {}
@@ -62,6 +81,17 @@ class PldaEngine {
   void norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc, const uint64_t* enrol_ids,
             const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype, int enrol_loc,
             int64_t numutts, uint64_t seed);
+  // sharded score grid (engine_shard.cu)
+  ShardSession shard;
+  void shard_open(int world, int rank, const int64_t* bounds, int64_t dim, unsigned char* ipc_handle_out,
+                  void** region_out);
+  void shard_connect(int peer_rank, const unsigned char* ipc_handle, void* same_process_region);
+  void shard_push(const void* test_shard, int64_t nt_local, int64_t ld, int dtype, int enrol_count);
+  void shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids, int dtype,
+                   float* out, int64_t ldo);
+  void shard_status(int64_t* epoch, int64_t* timeouts);
+  void shard_close();
+  ~PldaEngine();
   void test_gemm(const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit, float* out);
   void test_linalg(int op, const double* a, int64_t d, double* out, double* out2);
 

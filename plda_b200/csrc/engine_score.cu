@@ -79,7 +79,9 @@ void PldaEngine::stage(const void* p, int64_t rows, int64_t cols, int64_t ld, in
   }
   const size_t es = elem_size(dtype);
   s.own.reserve(static_cast<size_t>(rows > 0 ? rows : 1) * cols * es);
-  if (rows > 0)
+  if (rows > 0 && ld == cols)
+    PB_CUDA(cudaMemcpyAsync(s.own.get(), p, static_cast<size_t>(rows) * cols * es, cudaMemcpyHostToDevice, ctx.stream));
+  else if (rows > 0)
     PB_CUDA(cudaMemcpy2DAsync(s.own.get(), cols * es, p, ld * es, cols * es, rows, cudaMemcpyHostToDevice, ctx.stream));
   s.ptr = s.own.get();
   s.ld = cols;
@@ -403,8 +405,12 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   auto copy_chunk = [&](int64_t r0, int b) {
     const int64_t rows = std::min(chunk, ne - r0);
     PB_CUDA(cudaStreamWaitEvent(copy_stream, ev_done[b], 0));
-    PB_CUDA(cudaMemcpy2DAsync(out + r0 * ldo, ldo * sizeof(float), ws_out[b].get(), ldo_dev * sizeof(float),
-                              nt * sizeof(float), rows, cudaMemcpyDeviceToHost, copy_stream));
+    if (ldo == nt && ldo_dev == nt)   // contiguous on both sides: one linear copy (full-rate DMA)
+      PB_CUDA(cudaMemcpyAsync(out + r0 * ldo, ws_out[b].get(), static_cast<size_t>(rows) * nt * sizeof(float),
+                              cudaMemcpyDeviceToHost, copy_stream));
+    else
+      PB_CUDA(cudaMemcpy2DAsync(out + r0 * ldo, ldo * sizeof(float), ws_out[b].get(), ldo_dev * sizeof(float),
+                                nt * sizeof(float), rows, cudaMemcpyDeviceToHost, copy_stream));
     PB_CUDA(cudaEventRecord(ev_free[b], copy_stream));
   };
   try {

@@ -1,0 +1,200 @@
+// Sharded enrol x test score grid over NVLink peer memory (SURVEY 8e "scoring grid").
+//
+// The reference scores one pair per call (Plda::LogLikelihoodRatio via src/pldamodule.cpp:258-277); the grid
+// shards by ENROL BLOCK across GPUs and needs the transformed test vectors of every rank.  Instead of an NCCL
+// all-gather followed by the operand producer, the producer kernel itself writes each rank's test rows (split
+// bf16 planes + column terms) into the operand buffer of EVERY rank through peer mappings and raises a ready flag;
+// the tcgen05 GEMM consumes the local buffer and waits per column tile for the flag of the rank that owns the
+// rows (gemm_tc.cu, GemmShard), starting with its own rows.  No NCCL, no host synchronisation per step.
+#include <string.h>
+
+#include "engine.h"
+
+namespace pb {
+namespace {
+
+constexpr size_t kFlagsOff = 0;       // unsigned[64]: ready epoch per source rank
+constexpr size_t kErrOff = 256;       // unsigned: number of timed-out waits
+constexpr size_t kCounterOff = 512;   // unsigned: block counter of the local push kernel
+constexpr size_t kHeaderBytes = 1024;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+PldaEngine::~PldaEngine() {
+  try {
+    cudaSetDevice(ctx.device);
+    shard_close();
+  } catch (...) {
+  }
+}
+
+void PldaEngine::shard_open(int world, int rank, const int64_t* bounds, int64_t dim, unsigned char* ipc_handle_out,
+                            void** region_out) {
+  require_model();
+  PB_CHECK(!shard.open, kInvalidArg, "shard_open: a session is already open on this handle");
+  PB_CHECK(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, kInvalidArg, "shard_open: bad world/rank");
+  PB_CHECK(bounds != nullptr && bounds[0] == 0, kInvalidArg, "shard_open: bounds must start at 0");
+  for (int r = 0; r < world; ++r) PB_CHECK(bounds[r + 1] >= bounds[r], kInvalidArg, "shard_open: bounds must ascend");
+  PB_CHECK(bounds[world] > 0 && bounds[world] < (1ll << 31), kInvalidArg, "shard_open: bad number of test rows");
+  PB_CHECK(dim > 0 && dim <= model.d && dim <= 1024, kInvalidArg, "shard_open: dimension does not match the model");
+  PB_CHECK(precision == 0, kInvalidArg, "shard_open: the sharded grid runs on the tensor path (precision bf16x3)");
+  ShardSession s;
+  s.world = world;
+  s.rank = rank;
+  s.bounds.assign(bounds, bounds + world + 1);
+  s.nt_total = bounds[world];
+  s.dim = dim;
+  s.ldk = round_up(dim, 16);
+  s.col_ld = round_up(s.nt_total, 32);
+  const size_t plane = align_up(static_cast<size_t>(s.nt_total) * s.ldk * sizeof(__nv_bfloat16), 1024);
+  const size_t colb = align_up(static_cast<size_t>(s.col_ld) * sizeof(float), 1024);
+  s.off_lo = plane;
+  s.off_col = 2 * plane;
+  const size_t gen = 2 * plane + colb;
+  s.off_gen[0] = kHeaderBytes;
+  s.off_gen[1] = kHeaderBytes + gen;
+  s.bytes = kHeaderBytes + 2 * gen;
+  PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.region), s.bytes));
+  cudaError_t e = cudaMemsetAsync(s.region, 0, s.bytes, ctx.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx.stream);
+  if (e == cudaSuccess && ipc_handle_out != nullptr) {
+    cudaIpcMemHandle_t hnd;
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    e = cudaIpcGetMemHandle(&hnd, s.region);
+    if (e == cudaSuccess) memcpy(ipc_handle_out, &hnd, sizeof(hnd));
+  }
+  if (e != cudaSuccess) {
+    cudaFree(s.region);
+    throw Error(kCudaError, std::string("shard_open failed: ") + cudaGetErrorString(e));
+  }
+  s.peer.assign(world, nullptr);
+  s.peer_ipc.assign(world, false);
+  s.peer[rank] = s.region;
+  s.open = true;
+  shard = std::move(s);
+  if (region_out) *region_out = shard.region;
+}
+
+void PldaEngine::shard_connect(int peer_rank, const unsigned char* ipc_handle, void* same_process_region) {
+  PB_CHECK(shard.open, kInvalidArg, "shard_connect: no open session");
+  PB_CHECK(peer_rank >= 0 && peer_rank < shard.world, kInvalidArg, "shard_connect: bad peer rank");
+  if (peer_rank == shard.rank) return;
+  PB_CHECK(shard.peer[peer_rank] == nullptr, kInvalidArg, "shard_connect: peer already connected");
+  if (same_process_region != nullptr) {
+    // a peer handle of the same process (tests: several ranks on one GPU; multi-GPU single process)
+    shard.peer[peer_rank] = static_cast<uint8_t*>(same_process_region);
+    return;
+  }
+  PB_CHECK(ipc_handle != nullptr, kInvalidArg, "shard_connect: an IPC handle or a region pointer is required");
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, ipc_handle, sizeof(hnd));
+  void* p = nullptr;
+  PB_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+  shard.peer[peer_rank] = static_cast<uint8_t*>(p);
+  shard.peer_ipc[peer_rank] = true;
+}
+
+void PldaEngine::shard_push(const void* test_shard, int64_t nt_local, int64_t ld, int dtype, int enrol_count) {
+  require_model();
+  PB_CHECK(shard.open, kInvalidArg, "shard_push: no open session");
+  for (int r = 0; r < shard.world; ++r) PB_CHECK(shard.peer[r] != nullptr, kInvalidArg, "shard_push: a peer is not connected");
+  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+  const int64_t row0 = shard.bounds[shard.rank];
+  PB_CHECK(nt_local == shard.bounds[shard.rank + 1] - row0, kInvalidArg, "shard_push: shard size does not match the bounds");
+  PB_CHECK(nt_local == 0 || (test_shard != nullptr && ld >= shard.dim), kInvalidArg, "shard_push: bad test rows");
+  PB_CHECK(enrol_count > 0, kInvalidArg, "shard_push: enrol count must be positive");
+  shard.epoch += 1;
+  shard.push_count = enrol_count;
+  const size_t gen = shard.off_gen[shard.epoch & 1u];
+  PrepDst dst;
+  PrepSignal sig;
+  dst.n = sig.n = shard.world;
+  for (int r = 0; r < shard.world; ++r) {
+    uint8_t* base = shard.peer[r];
+    dst.hi[r] = reinterpret_cast<__nv_bfloat16*>(base + gen);
+    dst.lo[r] = reinterpret_cast<__nv_bfloat16*>(base + gen + shard.off_lo);
+    dst.term[r] = reinterpret_cast<float*>(base + gen + shard.off_col);
+    sig.flag[r] = reinterpret_cast<unsigned*>(base + kFlagsOff) + shard.rank;
+  }
+  sig.counter = reinterpret_cast<unsigned*>(shard.region + kCounterOff);
+  sig.epoch = shard.epoch;
+  score_prep_uniform_multi(ctx, nullptr, 0, 0, nullptr, nullptr, test_shard, nt_local, ld, row0, row0 + nt_local, dst,
+                           shard.ldk, dtype == 1, shard.dim, enrol_count, model.psi.get(), sig);
+}
+
+void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids,
+                             int dtype, float* out, int64_t ldo) {
+  require_model();
+  PB_CHECK(shard.open, kInvalidArg, "shard_score: no open session");
+  PB_CHECK(shard.epoch > 0, kInvalidArg, "shard_score: nothing pushed yet");
+  PB_CHECK(enrol_count == shard.push_count, kInvalidArg,
+           "shard_score: the column terms were pushed for a different enrol count");
+  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+  PB_CHECK(ne >= 0 && (ne == 0 || (enrol != nullptr && out != nullptr)), kInvalidArg, "shard_score: null pointer");
+  PB_CHECK(ld_enrol >= shard.dim && ldo >= shard.nt_total, kInvalidArg, "shard_score: pitch too small");
+  if (ne == 0) return;
+  const float* zmean = nullptr;
+  const float* zinv = nullptr;
+  if (ids != nullptr && !znorm.empty()) {
+    std::vector<float> hz(2 * ne);
+    for (int64_t i = 0; i < ne; ++i) {
+      auto it = znorm.find(ids[i]);
+      hz[i] = it == znorm.end() ? 0.f : static_cast<float>(it->second.first);
+      hz[ne + i] = it == znorm.end() ? 1.f : static_cast<float>(1.0 / it->second.second);
+    }
+    ws_zmean.reserve(2 * ne);
+    PB_CUDA(cudaMemcpyAsync(ws_zmean.get(), hz.data(), 2 * ne * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+    PB_CUDA(cudaStreamSynchronize(ctx.stream));   // hz is a stack-lifetime staging buffer
+    zmean = ws_zmean.get();
+    zinv = ws_zmean.get() + ne;
+  }
+  ws_row.reserve(ne);
+  PrepDst none;
+  score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, &ws_l, ws_row.get(), nullptr, 0, 0, 0, 0, none, shard.ldk,
+                           dtype == 1, shard.dim, enrol_count, model.psi.get(), PrepSignal{});
+  const size_t gen = shard.off_gen[shard.epoch & 1u];
+  SplitOperand b;
+  b.hi = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen);
+  b.lo = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen + shard.off_lo);
+  b.rows = shard.nt_total;
+  b.k = shard.dim;
+  b.ld = shard.ldk;
+  GemmEpilogue epi;
+  epi.out = out;
+  epi.ldo = ldo;
+  epi.row_add = ws_row.get();
+  epi.col_add = reinterpret_cast<const float*>(shard.region + gen + shard.off_col);
+  epi.col_ld = shard.col_ld;
+  epi.zmean = zmean;
+  epi.zinv = zinv;
+  GemmShard gs;
+  gs.flags = reinterpret_cast<const unsigned*>(shard.region + kFlagsOff);
+  gs.err = reinterpret_cast<unsigned*>(shard.region + kErrOff);
+  gs.epoch = shard.epoch;
+  gs.world = shard.world;
+  gs.rank = shard.rank;
+  for (int r = 0; r <= shard.world; ++r) gs.bounds[r] = static_cast<int>(shard.bounds[r]);
+  gemm_bf16x3(ctx, ws_l.view(), b, ne, shard.nt_total, shard.dim, epi, &gs);
+}
+
+void PldaEngine::shard_status(int64_t* epoch, int64_t* timeouts) {
+  PB_CHECK(shard.open, kInvalidArg, "shard_status: no open session");
+  unsigned err = 0;
+  PB_CUDA(cudaMemcpyAsync(&err, shard.region + kErrOff, sizeof(err), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  if (epoch) *epoch = shard.epoch;
+  if (timeouts) *timeouts = err;
+}
+
+void PldaEngine::shard_close() {
+  if (!shard.open) return;
+  cudaStreamSynchronize(ctx.stream);
+  for (int r = 0; r < shard.world; ++r)
+    if (shard.peer_ipc[r] && shard.peer[r] != nullptr) cudaIpcCloseMemHandle(shard.peer[r]);
+  cudaFree(shard.region);
+  shard = ShardSession{};
+}
+
+}  // namespace pb

@@ -68,7 +68,9 @@ struct GemmParams {
   int direct_store;   // 3 TMA store via swizzled smem staging (default), 0 coalesced LSU stores, 1 register stores, 2 none
   int tail_cols;      // K columns of the last k-block when it uses a narrow box (16 -> 32B swizzle, 32 -> 64B), else 0
   long long* dbg;     // optional stall counters of CTA 0/1 (env PLDA_B200_DBG=1): see plda_debug_counters
+  int n_rot;          // column tiles are visited starting at this one (sharded B: the rank's own rows first)
   GemmEpilogue epi;
+  GemmShard shard;    // flags == nullptr: B is complete before the launch
 };
 
 struct Work {
@@ -85,6 +87,24 @@ struct Cfg {
 };
 static_assert(Cfg<true>::kStages * Cfg<true>::kStageBytes == STAGES * STAGE_BYTES, "smem budget");
 
+// Bounded poll of a peer's ready flag: a rank that never arrives is counted in shard.err (the host reports it)
+// instead of hanging the GPU.
+__device__ __noinline__ void shard_wait(const unsigned* f, unsigned epoch, unsigned* err) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  if (static_cast<int>(v - epoch) >= 0) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (static_cast<int>(v - epoch) >= 0) return;
+    if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 5000000000ull) {
+      atomicAdd(err, 1u);
+      return;
+    }
+  }
+}
+
 template <bool TWO>
 __device__ __forceinline__ Work decode(const GemmParams& p, int item, uint32_t rank) {
   // TWO: the unit of work is a PAIR of vertically adjacent 128-row tiles (one per CTA of the pair)
@@ -100,7 +120,8 @@ __device__ __forceinline__ Work decode(const GemmParams& p, int item, uint32_t r
   const int r = t - g * per_group;
   const int unit = first_m + r % gsz;
   w.m_blk = TWO ? unit * 2 + static_cast<int>(rank) : unit;
-  w.n_blk = r / gsz;
+  w.n_blk = r / gsz + p.n_rot;
+  if (w.n_blk >= p.n_tiles) w.n_blk -= p.n_tiles;
   return w;
 }
 
@@ -197,6 +218,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const uint32_t tx_tail_cta = 2 * (BM + bn_cta) * p.tail_cols * 2;
       long long dbg_prod_wait = 0;
       const long long t_start = clock64();
+      uint32_t shard_ready = 0;
       uint32_t lead_full_addr[3] = {0, 0, 0};
       if (TWO) {
 #pragma unroll
@@ -207,6 +229,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int kb0 = w.ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.nkb_total);
         const int brow = w.n_blk * p.bn + (TWO ? static_cast<int>(rank) * bn_cta : 0);
+        if (p.shard.flags != nullptr) {
+          // sharded B: rows of rank r are valid once flags[r] reaches this step's epoch
+          const int b_lo = brow, b_hi = min(brow + bn_cta, p.n);
+          bool waited = false;
+          for (int r = 0; r < p.shard.world; ++r) {
+            if ((shard_ready >> r) & 1u) continue;
+            if (p.shard.bounds[r] >= b_hi || p.shard.bounds[r + 1] <= b_lo) continue;
+            shard_wait(p.shard.flags + r, p.shard.epoch, p.shard.err);
+            shard_ready |= 1u << r;
+            waited = true;
+          }
+          // the peers wrote through the generic proxy; the TMA loads below read through the async proxy
+          if (waited) asm volatile("fence.proxy.async;" ::: "memory");
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const long long t_w0 = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
@@ -342,8 +378,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       // uniform column terms (no per-row groups): fetch this warp's chunks now (4 coalesced loads in flight
       // while the MMAs finish), park them in the per-stage smem cache once the accumulator is ready
       const bool col_cached = e.col_add != nullptr && e.grp == nullptr;
+      // sharded B: the column terms travel with the operand rows, so they are only valid once the accumulator is
+      // (producer saw the owner's flag -> TMA -> MMA -> tfull): fetched after the tfull wait, L1 bypassed
+      const bool col_late = p.shard.flags != nullptr;
       float cpre[4] = {0.f, 0.f, 0.f, 0.f};
-      if (col_cached) {
+      if (col_cached && !col_late) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int cc = h + 2 * i;
@@ -479,6 +518,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       mbar_wait(&tfull[acc], acc_phase);
       dbg_tfull += clock64() - t_w0;
       tc_fence_after();
+      if (col_cached && col_late) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc < nchunks) cpre[i] = __ldcg(e.col_add + n0 + cc * 32 + lane);
+        }
+      }
       if (col_cached) {
         // slot free (named barrier above); warps sharing chunks write identical values
 #pragma unroll
@@ -739,9 +785,19 @@ void encode_tmap_2d(CUtensorMap* out, TmaType type, const void* base, uint64_t i
 }
 
 void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
-                 const GemmEpilogue& epi) {
+                 const GemmEpilogue& epi, const GemmShard* shard) {
   Plan pl = make_plan(ctx, m, n, k, 1);
   pl.p.epi = epi;
+  if (shard != nullptr && shard->flags != nullptr) {
+    PB_CHECK(shard->world >= 1 && shard->world <= 16 && shard->rank >= 0 && shard->rank < shard->world &&
+                 shard->err != nullptr && shard->bounds[0] == 0 && shard->bounds[shard->world] == n,
+             kInvalidArg, "gemm: bad shard description");
+    PB_CHECK(epi.grp == nullptr, kInvalidArg, "gemm: sharded B needs uniform column terms");
+    pl.p.shard = *shard;
+    // start with the column tile that holds this rank's first row (empty shard: tile 0)
+    const int first = shard->bounds[shard->rank] < n ? shard->bounds[shard->rank] : 0;
+    pl.p.n_rot = first / pl.p.bn;
+  }
   if (epi.col_add != nullptr) {
     PB_CHECK(epi.col_ld % 4 == 0 && epi.col_ld >= round_up(n, 32) &&
                  (reinterpret_cast<uintptr_t>(epi.col_add) & 15) == 0,

@@ -1,6 +1,8 @@
 // HBM-bound operand producers and row-wise epilogues of the scoring / transform path.
 // All are one-warp-per-row kernels with coalesced loads along the feature axis, fp64
 // arithmetic on the way in (inputs are the caller's fp64/fp32 rows), split-bf16 or fp32 out.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace pb {
@@ -137,14 +139,61 @@ __global__ void score_prep_test_kernel(const T* __restrict__ test, long long nt,
 // blocks [0, eb) handle 32 enrol rows each, blocks [eb, eb+tb) 32 test rows each.  The per-column constants
 // (a/v, a^2/v, q and the log-determinant term) depend only on (n, psi) and are computed once per block in smem
 // instead of once per element; the zero padding of the column-term row is written here too (no memset).
+//
+// A lane owns groups of 8 consecutive columns: two 16-byte loads in (fp32 rows), one 16-byte store per bf16 plane
+// out.  Every output (both planes and the row / column term) is written to `ndst` destinations: 1 on a single GPU;
+// on a sharded grid the test-side destinations are the operand buffers of EVERY rank, mapped over
+// NVLink peer memory, so this kernel is the producer AND the all-gather of the transformed test operand.  The
+// last block to finish then publishes `epoch` in each rank's ready flag (release at system scope); the consuming
+// GEMM polls those flags tile by tile (gemm_tc.cu, GemmShard).
+template <typename T>
+__device__ __forceinline__ void load8(const T* __restrict__ src, int c, int d, bool vec, double (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* __restrict__ src, int c, int d, bool vec, double (&v)[8]) {
+  if (vec && c + 8 <= d) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + c + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c + j < d ? static_cast<double>(__ldg(src + c + j)) : 0.0;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<double>(const double* __restrict__ src, int c, int d, bool vec, double (&v)[8]) {
+  if (vec && c + 8 <= d) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(src + c + 2 * j));
+      v[2 * j] = t.x; v[2 * j + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c + j < d ? __ldg(src + c + j) : 0.0;
+  }
+}
+
+__device__ __forceinline__ void split8(const double (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * j], h0, l0);
+    split_bf16(v[2 * j + 1], h1, l1);
+    h[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    l[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const T* __restrict__ test,
-                          long long nt, long long ld_t, int d, int count, const double* __restrict__ psi,
-                          __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo,
-                          __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo, int ld_out,
-                          float* __restrict__ row_term, float* __restrict__ col_term, long long col_ld,
-                          unsigned enrol_blocks) {
+                          long long nt, long long ld_t, long long test_row0, long long test_pad_end, int d, int count,
+                          const double* __restrict__ psi, __nv_bfloat16* __restrict__ l_hi,
+                          __nv_bfloat16* __restrict__ l_lo, float* __restrict__ row_term, const PrepDst tdst,
+                          int ld_out, unsigned enrol_blocks, int vec_e, int vec_t, const PrepSignal sig) {
   __shared__ double s_s[1024], s_w[1024], s_q[1024];
   __shared__ double s_red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,14 +223,21 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
       if (r >= ne) break;
       const T* src = enrol + r * ld_e;
       double acc = 0.0;
-      for (int c = lane; c < ld_out; c += 32) {
-        double lv = 0.0;
-        if (c < d) {
-          const double e = static_cast<double>(src[c]);
-          lv = e * s_s[c];
-          acc += s_w[c] * e * e;
+      for (int c = lane * 8; c < ld_out; c += 256) {
+        double v[8];
+        load8<T>(src, c, d, vec_e != 0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c + j < d) {
+            const double e = v[j];
+            acc += s_w[c + j] * e * e;
+            v[j] = e * s_s[c + j];
+          }
         }
-        store_split(l_hi, l_lo, r * ld_out + c, lv);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(l_hi + r * ld_out + c) = hi;
+        *reinterpret_cast<uint4*>(l_lo + r * ld_out + c) = lo;
       }
       acc = warp_sum(acc);
       if (lane == 0) row_term[r] = static_cast<float>(0.5 * (cst - acc));
@@ -190,22 +246,47 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
     const long long r0 = static_cast<long long>(blockIdx.x - enrol_blocks) * 32;
     for (int i = warp; i < 32; i += 8) {
       const long long r = r0 + i;
+      const long long gr = test_row0 + r;          // row in the (global) operand
       if (r >= nt) {
-        if (lane == 0 && r < col_ld) col_term[r] = 0.f;   // padding read (never stored) by the GEMM epilogue
+        // padding of the column-term row: read (never stored) by the GEMM epilogue
+        if (lane == 0 && gr < test_pad_end)
+          for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = 0.f;
         continue;
       }
       const T* src = test + r * ld_t;
       double acc = 0.0;
-      for (int c = lane; c < ld_out; c += 32) {
-        double tv = 0.0;
-        if (c < d) {
-          tv = static_cast<double>(src[c]);
-          acc += s_q[c] * tv * tv;
+      for (int c = lane * 8; c < ld_out; c += 256) {
+        double v[8];
+        load8<T>(src, c, d, vec_t != 0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < d) acc += s_q[c + j] * v[j] * v[j];
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const long long o = gr * ld_out + c;
+        for (int w = 0; w < tdst.n; ++w) {
+          *reinterpret_cast<uint4*>(tdst.hi[w] + o) = hi;
+          *reinterpret_cast<uint4*>(tdst.lo[w] + o) = lo;
         }
-        store_split(r_hi, r_lo, r * ld_out + c, tv);
       }
       acc = warp_sum(acc);
-      if (lane == 0) col_term[r] = static_cast<float>(acc);
+      if (lane == 0)
+        for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = static_cast<float>(acc);
+    }
+  }
+  if (sig.counter != nullptr) {
+    // publish: every thread's peer stores are performed system-wide, then the LAST block raises the ready flag of
+    // this source rank in every destination region
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(sig.counter, 1u);
+      if (prev == gridDim.x - 1) {
+        atomicExch(sig.counter, 0u);
+        __threadfence_system();
+        for (int w = 0; w < sig.n; ++w)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sig.flag[w]), "r"(sig.epoch) : "memory");
+      }
     }
   }
 }
@@ -361,26 +442,54 @@ void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, in
   ctx.count_launch();
 }
 
+namespace {
+inline bool rows_vectorisable(const void* p, int64_t ld, bool is_f32) {
+  // 8-column groups start 16-byte aligned: fp32 rows need ld % 4 == 0, fp64 rows ld % 2 == 0
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % (is_f32 ? 4 : 2) == 0;
+}
+}  // namespace
+
+void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, SplitBuf* l_out,
+                              float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,
+                              int64_t test_pad_end, const PrepDst& tdst, int64_t ld_out, bool is_f32, int64_t d,
+                              int count, const double* psi, const PrepSignal& sig) {
+  PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
+  PB_CHECK(ld_out % 16 == 0 && ld_out >= d, kInvalidArg, "score prep: operand pitch must be a multiple of 16");
+  PB_CHECK(tdst.n >= 0 && tdst.n <= kMaxPeers && sig.n <= kMaxPeers, kInvalidArg, "score prep: too many destinations");
+  if (l_out) l_out->reserve(ne, d);
+  PB_CHECK(l_out == nullptr || l_out->ld == ld_out || nt == 0, kInvalidArg, "score prep: operand pitches differ");
+  const int ldo = static_cast<int>(l_out ? l_out->ld : ld_out);
+  const unsigned eb = l_out ? static_cast<unsigned>(ceil_div(ne, 32)) : 0u;
+  unsigned tb = tdst.n > 0 ? static_cast<unsigned>(ceil_div(std::max<int64_t>(test_pad_end - test_row0, nt), 32)) : 0u;
+  if (sig.counter != nullptr && tb == 0) tb = 1;   // an empty shard still has to raise its ready flag
+  if (eb + tb == 0) return;
+  const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
+  const int vec_t = test && rows_vectorisable(test, ld_t, is_f32) ? 1 : 0;
+  __nv_bfloat16* lhi = l_out ? l_out->hi.get() : nullptr;
+  __nv_bfloat16* llo = l_out ? l_out->lo.get() : nullptr;
+  if (is_f32)
+    score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
+        static_cast<const float*>(enrol), l_out ? ne : 0, ld_e, static_cast<const float*>(test), nt, ld_t, test_row0,
+        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
+  else
+    score_prep_uniform_kernel<double><<<eb + tb, 256, 0, ctx.stream>>>(
+        static_cast<const double*>(enrol), l_out ? ne : 0, ld_e, static_cast<const double*>(test), nt, ld_t, test_row0,
+        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
 void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const void* test, int64_t nt,
                         int64_t ld_t, bool is_f32, int64_t d, int count, const double* psi, SplitBuf& l_out,
                         SplitBuf& r_out, float* row_term, float* col_term, int64_t col_ld) {
-  PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
-  l_out.reserve(ne, d);
   r_out.reserve(nt, d);
-  const unsigned eb = static_cast<unsigned>(ceil_div(ne, 32));
-  const unsigned tb = static_cast<unsigned>(ceil_div(col_ld, 32));
-  if (is_f32)
-    score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
-        static_cast<const float*>(enrol), ne, ld_e, static_cast<const float*>(test), nt, ld_t, static_cast<int>(d),
-        count, psi, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(), static_cast<int>(l_out.ld),
-        row_term, col_term, col_ld, eb);
-  else
-    score_prep_uniform_kernel<double><<<eb + tb, 256, 0, ctx.stream>>>(
-        static_cast<const double*>(enrol), ne, ld_e, static_cast<const double*>(test), nt, ld_t, static_cast<int>(d),
-        count, psi, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(), static_cast<int>(l_out.ld),
-        row_term, col_term, col_ld, eb);
-  PB_CUDA(cudaGetLastError());
-  ctx.count_launch();
+  PrepDst tdst;
+  tdst.n = 1;
+  tdst.hi[0] = r_out.hi.get();
+  tdst.lo[0] = r_out.lo.get();
+  tdst.term[0] = col_term;
+  score_prep_uniform_multi(ctx, enrol, ne, ld_e, &l_out, row_term, test, nt, ld_t, 0, col_ld, tdst, r_out.ld, is_f32, d,
+                           count, psi, PrepSignal{});
 }
 
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,

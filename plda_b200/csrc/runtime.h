@@ -124,12 +124,25 @@ struct GemmEpilogue {
   float* lse_sum = nullptr;
 };
 
+// Sharded B operand (scoring grid): rows [bounds[r], bounds[r+1]) of B (and of the column-term row)
+// are produced by rank r and pushed into this GPU's buffer over NVLink peer memory.  The GEMM does not wait for
+// the whole exchange: its TMA producer polls `flags[r] >= epoch` (acquire, system scope) only before the first
+// tile that touches rows of rank r, and the column tiles are visited starting with this rank's own rows.
+struct GemmShard {
+  const unsigned* flags = nullptr;   // [world] ready epochs in the LOCAL region (written by the peers)
+  unsigned* err = nullptr;           // timeouts are counted here instead of hanging the GPU
+  unsigned epoch = 0;
+  int world = 0;
+  int rank = 0;
+  int bounds[17] = {0};
+};
+
 // C[M,N] = A[M,K] * B[N,K]^T with bf16x3 split operands on tcgen05 (fp32 TMEM accumulate).
 // ksplit > 1: reduction axis split into ksplit chunks, partial tiles written to
 // `partial` ([ksplit][Mpad][Npad] fp32, Mpad = round_up(M,128), Npad = round_up(N,4)) and
 // the caller reduces them (reduce_partials_f64).
 void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
-                 const GemmEpilogue& epi);
+                 const GemmEpilogue& epi, const GemmShard* shard = nullptr);
 void gemm_bf16x3_splitk(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
                         int ksplit, float* partial);
 int choose_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k);

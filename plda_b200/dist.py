@@ -81,6 +81,127 @@ class ShardedScorer:
         return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
 
 
+class PeerShardedScorer:
+    """Enrol-block sharded scoring WITHOUT a collective: the operand producer of every rank writes its test rows
+    straight into the operand buffer of every other rank over NVLink peer memory and the tcgen05 GEMM waits, per
+    column tile, for the rank that owns the rows (C ABI ``plda_shard_*``, ``csrc/engine_shard.cu``).
+
+    One instance per process (rank); ``torch.distributed`` is used once, at construction, to exchange the 64-byte
+    CUDA-IPC handles of the regions -- no collective runs on the data path.  ``score`` must be called the same
+    number of times on every rank.  Uniform enrol counts only (ragged counts: ``ShardedScorer``).
+
+    ``peers``: same-process alternative to ``torch.distributed`` (tests, several handles in one process): a list of
+    all ranks' ``PeerShardedScorer`` objects is connected with ``PeerShardedScorer.connect_local``.
+    """
+
+    def __init__(self, plda, n_test_total: int, dim: int, group=None, world: Optional[int] = None,
+                 rank: Optional[int] = None):
+        import ctypes as C
+        from . import _ffi
+        self._ffi, self._C = _ffi, C
+        self._lib = _ffi.lib()
+        self.plda = plda
+        self.group = group
+        self._local_only = world is not None
+        if world is None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.world, self.rank = int(world), int(rank)
+        self.n_test_total, self.dim = int(n_test_total), int(dim)
+        self.bounds = np.array([block_bounds(self.n_test_total, self.world, r)[0] for r in range(self.world)]
+                               + [self.n_test_total], dtype=np.int64)
+        self._handle = (C.c_ubyte * 64)()
+        self._region = C.c_void_p()
+        self._open = False
+        _ffi.check(self._lib.plda_shard_open(plda._h, self.world, self.rank, _ffi.ptr(self.bounds), self.dim,
+                                             C.cast(self._handle, C.c_void_p), C.byref(self._region)))
+        self._open = True
+        if not self._local_only:
+            self._exchange()
+
+    # -- wiring ---------------------------------------------------------------------------------
+    def _exchange(self):
+        import torch
+        import torch.distributed as dist
+        dev = _coll_device(self.group)
+        mine = torch.tensor(list(bytes(self._handle)), dtype=torch.uint8, device=dev)
+        allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        allh = allh.cpu().numpy()
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            buf = (self._C.c_ubyte * 64)(*allh[r].tolist())
+            self._ffi.check(self._lib.plda_shard_connect(self.plda._h, r, self._C.cast(buf, self._C.c_void_p), None))
+        dist.barrier(group=self.group)         # every region is mapped everywhere before the first push
+
+    @staticmethod
+    def connect_local(scorers):
+        """Wire scorers that live in ONE process (their regions are plain device pointers to each other)."""
+        for a in scorers:
+            for b in scorers:
+                if a is not b:
+                    a._ffi.check(a._lib.plda_shard_connect(a.plda._h, b.rank, None, b._region))
+
+    # -- data path --------------------------------------------------------------------------------
+    def push(self, test_shard, enrol_count: int):
+        """Producer + exchange: this rank's transformed test rows (CUDA tensor ``[bounds[rank+1]-bounds[rank], dim]``,
+        fp32 or fp64) -> every rank's operand buffer.  Stream-ordered, does not synchronise."""
+        tt, dtype = _cuda_matrix(test_shard)
+        self._ffi.check(self._lib.plda_shard_push(self.plda._h, self._C.c_void_p(tt.data_ptr()), tt.shape[0],
+                                                  tt.stride(0) if tt.shape[0] else self.dim, dtype, int(enrol_count)))
+
+    def grid(self, enrol_block, enrol_count: int, out=None, enrol_ids=None):
+        """This rank's ``[block, n_test_total]`` slab of the grid (fp32 CUDA tensor); stream-ordered."""
+        import torch
+        et, dtype = _cuda_matrix(enrol_block)
+        ne = et.shape[0]
+        if out is None:
+            ldo = (self.n_test_total + 3) // 4 * 4
+            out = torch.empty((ne, ldo), dtype=torch.float32, device=et.device)[:, : self.n_test_total]
+        ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
+        self._ffi.check(self._lib.plda_shard_score(self.plda._h, self._C.c_void_p(et.data_ptr()), ne,
+                                                   et.stride(0) if ne else self.dim, int(enrol_count),
+                                                   self._ffi.ptr(ids), dtype, self._C.c_void_p(out.data_ptr()),
+                                                   out.stride(0)))
+        return out
+
+    def score(self, enrol_block, enrol_count: int, test_shard, out=None, enrol_ids=None, sync: bool = True):
+        """One sharded scoring step: push + grid (+ a stream synchronisation unless ``sync=False``)."""
+        self.push(test_shard, enrol_count)
+        out = self.grid(enrol_block, enrol_count, out=out, enrol_ids=enrol_ids)
+        if sync:
+            self._ffi.check(self._lib.plda_synchronize(self.plda._h))
+        return out
+
+    def status(self):
+        """``(pushes so far, waits that timed out)`` -- a non-zero second value invalidates the results."""
+        e, t = self._C.c_int64(), self._C.c_int64()
+        self._ffi.check(self._lib.plda_shard_status(self.plda._h, self._C.byref(e), self._C.byref(t)))
+        return int(e.value), int(t.value)
+
+    def close(self):
+        if not self._open:
+            return
+        self._open = False
+        if not self._local_only:
+            import torch.distributed as dist
+            self._ffi.check(self._lib.plda_synchronize(self.plda._h))
+            dist.barrier(group=self.group)     # nobody writes into a region that is about to be freed
+        self._ffi.check(self._lib.plda_shard_close(self.plda._h))
+
+
+def _cuda_matrix(x):
+    import torch
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise ValueError("the sharded scorer works on CUDA tensors (resident operands)")
+    if x.dim() != 2 or x.dtype not in (torch.float32, torch.float64):
+        raise ValueError("expected a 2-D float32/float64 CUDA tensor")
+    if x.shape[0] and x.stride(1) != 1:
+        x = x.contiguous()
+    return x, (1 if x.dtype == torch.float32 else 0)
+
+
 def _coll_device(group=None):
     """NCCL moves CUDA tensors only; gloo (CPU tests) moves host tensors."""
     import torch

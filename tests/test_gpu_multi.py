@@ -26,3 +26,13 @@ def test_sharded_fit_matches_single_gpu():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "bit-identical across ranks: True" in r.stdout
     assert "identical across ranks: True" in r.stdout.split("sharded LDA fit")[1]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+def test_peer_sharded_grid_over_ipc_matches_allgather():
+    """CUDA-IPC regions + NVLink pushes + in-GEMM flag waits across two processes == NCCL all-gather + score_grid."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "scripts", "dist_shard_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "on every rank: True" in r.stdout
