@@ -98,7 +98,9 @@ class PldaEngine {
  private:
   void require_model() const { PB_CHECK(model.ready, kNotFitted, "PLDA model is not fitted (call fit or set_model)"); }
   void refresh_model_operands();
-  void stage(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype, int loc, Staged& s);
+  // `keep`: grow-only staging buffer owned by the engine (hot host paths must not cudaMalloc/cudaFree per call)
+  void stage(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype, int loc, Staged& s,
+             DevBuf<uint8_t>* keep = nullptr);
   // device rows [n x d] (centred by the model mean) -> transformed + length-normalised rows
   void transform_device_rows(const void* x, bool is_f32, int64_t n, int64_t d, int64_t ld, const double* sub,
                              const int32_t* counts_dev, int32_t const_count, int64_t dim, double* out64, int64_t ld64,
@@ -112,6 +114,11 @@ class PldaEngine {
   DevBuf<float> ws_row, ws_col, ws_out[2], ws_y, ws_zmean, ws_zinv, ws_partial, ws_u;
   DevBuf<double> ws_rsum, ws_rsq, ws_f64a, ws_f64b, ws_f64c, ws_gram, ws_row64, ws_col64;
   DevBuf<int32_t> ws_counts, ws_grp, ws_gcounts;
+  DevBuf<uint8_t> ws_stage[2];
+  // device->host drain of the score grid: second stream + events, created on first use
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  void ensure_copy_stream();
   Segments segs;
   EigWork eig;
   // EM state (d x d, fp64)

@@ -1,5 +1,8 @@
 // PldaEngine: model state, transform, pair / grid scoring, z-norm.
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <random>
 
@@ -66,7 +69,17 @@ inline size_t elem_size(int dtype) { return dtype == 1 ? 4 : 8; }
 }  // namespace
 
 // ------------------------------------------------------------------------- //
-void PldaEngine::stage(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype, int loc, Staged& s) {
+void PldaEngine::ensure_copy_stream() {
+  if (copy_stream != nullptr) return;
+  PB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    PB_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+  }
+}
+
+void PldaEngine::stage(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype, int loc, Staged& s,
+                       DevBuf<uint8_t>* keep) {
   PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
   PB_CHECK(loc == 0 || loc == 1, kInvalidArg, "loc must be PLDA_HOST or PLDA_DEVICE");
   PB_CHECK(p != nullptr || rows == 0, kInvalidArg, "null matrix pointer");
@@ -78,12 +91,13 @@ void PldaEngine::stage(const void* p, int64_t rows, int64_t cols, int64_t ld, in
     return;
   }
   const size_t es = elem_size(dtype);
-  s.own.reserve(static_cast<size_t>(rows > 0 ? rows : 1) * cols * es);
+  DevBuf<uint8_t>& buf = keep ? *keep : s.own;
+  buf.reserve(static_cast<size_t>(rows > 0 ? rows : 1) * cols * es);
   if (rows > 0 && ld == cols)
-    PB_CUDA(cudaMemcpyAsync(s.own.get(), p, static_cast<size_t>(rows) * cols * es, cudaMemcpyHostToDevice, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(buf.get(), p, static_cast<size_t>(rows) * cols * es, cudaMemcpyHostToDevice, ctx.stream));
   else if (rows > 0)
-    PB_CUDA(cudaMemcpy2DAsync(s.own.get(), cols * es, p, ld * es, cols * es, rows, cudaMemcpyHostToDevice, ctx.stream));
-  s.ptr = s.own.get();
+    PB_CUDA(cudaMemcpy2DAsync(buf.get(), cols * es, p, ld * es, cols * es, rows, cudaMemcpyHostToDevice, ctx.stream));
+  s.ptr = buf.get();
   s.ld = cols;
 }
 
@@ -287,9 +301,17 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   const int32_t* grp_dev = nullptr;
   const int32_t* gcounts_dev = nullptr;
 
+  const bool trace = getenv("PLDA_B200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    fprintf(stderr, "plda_b200 score_grid: %-28s +%.3f ms\n", what, ms);
+  };
   Staged se, st;
-  stage(enrol, ne, dim, ld_enrol, dtype, loc, se);
-  stage(test, nt, dim, ld_test, dtype, loc, st);
+  stage(enrol, ne, dim, ld_enrol, dtype, loc, se, &ws_stage[0]);
+  stage(test, nt, dim, ld_test, dtype, loc, st, &ws_stage[1]);
+  lap("inputs staged (enqueued)");
 
   if (!uniform) {
     std::vector<int32_t> gcounts(counts, counts + ne);
@@ -363,16 +385,14 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
     chunk = std::max<int64_t>(128, (budget / std::max<int64_t>(ldo_dev, 1)) / 128 * 128);
     chunk = std::min(chunk, ne);
   }
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   if (out_loc == 0) {
-    PB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      PB_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-      PB_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
-      ws_out[i].reserve(static_cast<size_t>(chunk) * ldo_dev);
-    }
+    ensure_copy_stream();
+    const int nbuf = chunk < ne ? 2 : 1;   // the second staging buffer is only needed when the grid is chunked
+    for (int i = 0; i < nbuf; ++i) ws_out[i].reserve(static_cast<size_t>(chunk) * ldo_dev);
+    // the events may still carry a record of an earlier call: this call's chain starts clean
+    for (int i = 0; i < 2; ++i) PB_CUDA(cudaEventRecord(ev_free[i], copy_stream));
   }
+  lap("workspaces ready");
   auto launch_chunk = [&](int64_t r0, int b) {
     const int64_t rows = std::min(chunk, ne - r0);
     float* dst = out_loc == 1 ? out + r0 * ldo : ws_out[b].get();
@@ -413,33 +433,24 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
                                 nt * sizeof(float), rows, cudaMemcpyDeviceToHost, copy_stream));
     PB_CUDA(cudaEventRecord(ev_free[b], copy_stream));
   };
-  try {
-    if (out_loc == 1) {
-      for (int64_t r0 = 0; r0 < ne; r0 += chunk) launch_chunk(r0, 0);
-      // on a caller-provided stream the result is stream-ordered with the caller's work: no host sync
-      if (ctx.owns_stream) ctx.sync();
-    } else {
-      // software pipeline: the GEMM of chunk i+1 is in flight while chunk i drains over PCIe
-      int b = 0;
-      launch_chunk(0, 0);
-      for (int64_t r0 = 0; r0 < ne; r0 += chunk) {
-        if (r0 + chunk < ne) launch_chunk(r0 + chunk, b ^ 1);
-        copy_chunk(r0, b);
-        b ^= 1;
-      }
-      PB_CUDA(cudaStreamSynchronize(copy_stream));
-      ctx.sync();
+  if (out_loc == 1) {
+    for (int64_t r0 = 0; r0 < ne; r0 += chunk) launch_chunk(r0, 0);
+    // on a caller-provided stream the result is stream-ordered with the caller's work: no host sync
+    if (ctx.owns_stream) ctx.sync();
+  } else {
+    // software pipeline: the GEMM of chunk i+1 is in flight while chunk i drains over PCIe
+    int b = 0;
+    launch_chunk(0, 0);
+    for (int64_t r0 = 0; r0 < ne; r0 += chunk) {
+      if (r0 + chunk < ne) launch_chunk(r0 + chunk, b ^ 1);
+      copy_chunk(r0, b);
+      b ^= 1;
     }
-  } catch (...) {
-    if (copy_stream) {
-      cudaStreamDestroy(copy_stream);
-      for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_free[i]); }
-    }
-    throw;
-  }
-  if (copy_stream) {
-    cudaStreamDestroy(copy_stream);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_free[i]); }
+    lap("all work enqueued");
+    if (trace) { ctx.sync(); lap("compute stream drained"); }
+    PB_CUDA(cudaStreamSynchronize(copy_stream));
+    ctx.sync();
+    lap("device->host drained");
   }
 }
 

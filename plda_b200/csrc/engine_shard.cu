@@ -26,6 +26,10 @@ PldaEngine::~PldaEngine() {
   try {
     cudaSetDevice(ctx.device);
     shard_close();
+    if (copy_stream) {
+      cudaStreamDestroy(copy_stream);
+      for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_free[i]); }
+    }
   } catch (...) {
   }
 }

@@ -146,17 +146,18 @@ __global__ void score_prep_test_kernel(const T* __restrict__ test, long long nt,
 // NVLink peer memory, so this kernel is the producer AND the all-gather of the transformed test operand.  The
 // last block to finish then publishes `epoch` in each rank's ready flag (release at system scope); the consuming
 // GEMM polls those flags tile by tile (gemm_tc.cu, GemmShard).
+// Raw 8-column group of a row: two 16-byte loads when the row allows it, guarded scalar loads otherwise.
 template <typename T>
-__device__ __forceinline__ void load8(const T* __restrict__ src, int c, int d, bool vec, double (&v)[8]);
+__device__ __forceinline__ void load8(const T* __restrict__ src, int c, int d, bool vec, T (&v)[8]);
 template <>
-__device__ __forceinline__ void load8<float>(const float* __restrict__ src, int c, int d, bool vec, double (&v)[8]) {
+__device__ __forceinline__ void load8<float>(const float* __restrict__ src, int c, int d, bool vec, float (&v)[8]) {
   if (vec && c + 8 <= d) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
     const float4 b = __ldg(reinterpret_cast<const float4*>(src + c + 4));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = c + j < d ? static_cast<double>(__ldg(src + c + j)) : 0.0;
+    for (int j = 0; j < 8; ++j) v[j] = c + j < d ? __ldg(src + c + j) : 0.f;
   }
 }
 template <>
@@ -173,7 +174,8 @@ __device__ __forceinline__ void load8<double>(const double* __restrict__ src, in
   }
 }
 
-__device__ __forceinline__ void split8(const double (&v)[8], uint4& hi, uint4& lo) {
+template <typename T>
+__device__ __forceinline__ void split8(const T (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -187,14 +189,20 @@ __device__ __forceinline__ void split8(const double (&v)[8], uint4& hi, uint4& l
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// fp64 rows are scaled and split in fp64 (reference contract).  fp32 rows (the resident hot path) carry 24 bits:
+// the operand value is formed and split in fp32 (the split of an fp32 value is exact: x - hi is representable),
+// only the row / column terms -- sums of d products -- are accumulated in fp64.  This keeps the per-element work
+// off the fp64 conversion path (4 conversions per element -> 1).
 template <typename T>
 __global__ void __launch_bounds__(256)
 score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const T* __restrict__ test,
                           long long nt, long long ld_t, long long test_row0, long long test_pad_end, int d, int count,
                           const double* __restrict__ psi, __nv_bfloat16* __restrict__ l_hi,
                           __nv_bfloat16* __restrict__ l_lo, float* __restrict__ row_term, const PrepDst tdst,
-                          int ld_out, unsigned enrol_blocks, int vec_e, int vec_t, const PrepSignal sig) {
-  __shared__ double s_s[1024], s_w[1024], s_q[1024];
+                          int ld_out, unsigned enrol_blocks, int passes, int vec_e, int vec_t,
+                          const PrepSignal sig) {
+  __shared__ double s_s[1024];   // enrol: a/v (operand scale)
+  __shared__ double s_k[1024];   // enrol: a^2/v ; test: q   (weights of the squared terms)
   __shared__ double s_red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_enrol = blockIdx.x < enrol_blocks;
@@ -205,10 +213,13 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
     const double den = n * p + 1.0;
     const double a = n * p / den;
     const double v = 1.0 + p / den;
-    s_s[c] = a / v;
-    s_w[c] = a * a / v;
-    s_q[c] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
-    if (is_enrol) cpart += log1p(p) - log(v);
+    if (is_enrol) {
+      s_s[c] = a / v;
+      s_k[c] = a * a / v;
+      cpart += log1p(p) - log(v);
+    } else {
+      s_k[c] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
+    }
   }
   cpart = warp_sum(cpart);
   if (lane == 0) s_red[warp] = cpart;
@@ -216,64 +227,67 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
   double cst = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) cst += s_red[i];
-  if (is_enrol) {
-    const long long r0 = static_cast<long long>(blockIdx.x) * 32;
-    for (int i = warp; i < 32; i += 8) {
-      const long long r = r0 + i;
-      if (r >= ne) break;
-      const T* src = enrol + r * ld_e;
-      double acc = 0.0;
-      for (int c = lane * 8; c < ld_out; c += 256) {
-        double v[8];
-        load8<T>(src, c, d, vec_e != 0, v);
+
+  // a block owns 32 * passes rows; per pass a warp owns rows {warp, warp+8, warp+16, warp+24}; a lane owns
+  // 8-column groups
+  const long long nrows = is_enrol ? ne : nt;
+  const T* base = is_enrol ? enrol : test;
+  const long long ld_in = is_enrol ? ld_e : ld_t;
+  const bool vec = (is_enrol ? vec_e : vec_t) != 0;
+  for (int pass = 0; pass < passes; ++pass) {
+  const long long r0 = (static_cast<long long>(is_enrol ? blockIdx.x : blockIdx.x - enrol_blocks) * passes + pass) * 32;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int c = lane * 8; c < ld_out; c += 256) {
+    double kk[8];
+    T ks[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c + j < d) {
-            const double e = v[j];
-            acc += s_w[c + j] * e * e;
-            v[j] = e * s_s[c + j];
-          }
-        }
-        uint4 hi, lo;
-        split8(v, hi, lo);
+    for (int j = 0; j < 8; ++j) {
+      const bool in = c + j < d;
+      kk[j] = in ? s_k[c + j] : 0.0;
+      ks[j] = (in && is_enrol) ? static_cast<T>(s_s[c + j]) : static_cast<T>(in ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = r0 + warp + 8 * i;
+      if (r >= nrows) continue;
+      T v[8];
+      load8<T>(base + r * ld_in, c, d, vec, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (sizeof(T) == 4) acc[i] += kk[j] * static_cast<double>(v[j] * v[j]);
+        else acc[i] += kk[j] * v[j] * v[j];
+        v[j] = v[j] * ks[j];          // test side: x 1 (exact); padding columns: x 0
+      }
+      uint4 hi, lo;
+      split8<T>(v, hi, lo);
+      if (is_enrol) {
         *reinterpret_cast<uint4*>(l_hi + r * ld_out + c) = hi;
         *reinterpret_cast<uint4*>(l_lo + r * ld_out + c) = lo;
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) row_term[r] = static_cast<float>(0.5 * (cst - acc));
-    }
-  } else {
-    const long long r0 = static_cast<long long>(blockIdx.x - enrol_blocks) * 32;
-    for (int i = warp; i < 32; i += 8) {
-      const long long r = r0 + i;
-      const long long gr = test_row0 + r;          // row in the (global) operand
-      if (r >= nt) {
-        // padding of the column-term row: read (never stored) by the GEMM epilogue
-        if (lane == 0 && gr < test_pad_end)
-          for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = 0.f;
-        continue;
-      }
-      const T* src = test + r * ld_t;
-      double acc = 0.0;
-      for (int c = lane * 8; c < ld_out; c += 256) {
-        double v[8];
-        load8<T>(src, c, d, vec_t != 0, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c + j < d) acc += s_q[c + j] * v[j] * v[j];
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        const long long o = gr * ld_out + c;
+      } else {
+        const long long o = (test_row0 + r) * ld_out + c;
         for (int w = 0; w < tdst.n; ++w) {
           *reinterpret_cast<uint4*>(tdst.hi[w] + o) = hi;
           *reinterpret_cast<uint4*>(tdst.lo[w] + o) = lo;
         }
       }
-      acc = warp_sum(acc);
-      if (lane == 0)
-        for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = static_cast<float>(acc);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long r = r0 + warp + 8 * i;
+    const double a = warp_sum(acc[i]);
+    if (lane != 0) continue;
+    if (is_enrol) {
+      if (r < ne) row_term[r] = static_cast<float>(0.5 * (cst - a));
+    } else {
+      const long long gr = test_row0 + r;          // row in the (global) operand
+      // rows past nt: zero padding of the column-term row, read (never stored) by the GEMM epilogue
+      const float t = r < nt ? static_cast<float>(a) : 0.f;
+      if (r < nt || gr < test_pad_end)
+        for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = t;
+    }
+  }
+  }  // pass
   if (sig.counter != nullptr) {
     // publish: every thread's peer stores are performed system-wide, then the LAST block raises the ready flag of
     // this source rank in every destination region
@@ -459,8 +473,13 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   if (l_out) l_out->reserve(ne, d);
   PB_CHECK(l_out == nullptr || l_out->ld == ld_out || nt == 0, kInvalidArg, "score prep: operand pitches differ");
   const int ldo = static_cast<int>(l_out ? l_out->ld : ld_out);
-  const unsigned eb = l_out ? static_cast<unsigned>(ceil_div(ne, 32)) : 0u;
-  unsigned tb = tdst.n > 0 ? static_cast<unsigned>(ceil_div(std::max<int64_t>(test_pad_end - test_row0, nt), 32)) : 0u;
+  // 32 rows per block pass; enough passes per block that the grid is ONE wave (3 resident blocks per SM at 80 registers)
+  const int64_t e_rows = l_out ? ne : 0;
+  const int64_t t_rows = tdst.n > 0 ? std::max<int64_t>(test_pad_end - test_row0, nt) : 0;
+  const int64_t b32 = ceil_div(e_rows, 32) + ceil_div(t_rows, 32);
+  const int passes = static_cast<int>(std::max<int64_t>(1, ceil_div(b32, 3ll * ctx.num_sms)));
+  const unsigned eb = static_cast<unsigned>(ceil_div(e_rows, 32ll * passes));
+  unsigned tb = static_cast<unsigned>(ceil_div(t_rows, 32ll * passes));
   if (sig.counter != nullptr && tb == 0) tb = 1;   // an empty shard still has to raise its ready flag
   if (eb + tb == 0) return;
   const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
@@ -470,11 +489,11 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   if (is_f32)
     score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const float*>(enrol), l_out ? ne : 0, ld_e, static_cast<const float*>(test), nt, ld_t, test_row0,
-        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
+        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, passes, vec_e, vec_t, sig);
   else
     score_prep_uniform_kernel<double><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const double*>(enrol), l_out ? ne : 0, ld_e, static_cast<const double*>(test), nt, ld_t, test_row0,
-        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
+        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, passes, vec_e, vec_t, sig);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }
