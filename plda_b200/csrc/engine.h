@@ -115,6 +115,11 @@ class PldaEngine {
   DevBuf<double> ws_rsum, ws_rsq, ws_f64a, ws_f64b, ws_f64c, ws_gram, ws_row64, ws_col64;
   DevBuf<int32_t> ws_counts, ws_grp, ws_gcounts;
   DevBuf<uint8_t> ws_stage[2];
+  // per-column LLR constants (a/v, a^2/v, q, log-determinant term) for one (enrol count, dim): computed on the host
+  // from the psi mirror once and kept on the device until the model changes
+  struct ScoreConsts { int count = 0; int64_t dim = 0; DevBuf<double> dev; };
+  std::vector<ScoreConsts> score_consts;
+  const double* score_consts_for(int count, int64_t dim);
   // device->host drain of the score grid: second stream + events, created on first use
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};

@@ -1,4 +1,5 @@
 // PldaEngine: model state, transform, pair / grid scoring, z-norm.
+#include <math.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -101,7 +102,39 @@ void PldaEngine::stage(const void* p, int64_t rows, int64_t cols, int64_t ld, in
   s.ld = cols;
 }
 
+const double* PldaEngine::score_consts_for(int count, int64_t dim) {
+  for (auto& c : score_consts)
+    if (c.count == count && c.dim == dim) return c.dev.get();
+  PB_CHECK(dim > 0 && dim <= 1024 && dim <= static_cast<int64_t>(model.h_psi.size()), kInvalidArg,
+           "score: dimension above 1024 is not supported");
+  // SURVEY App. A.7:  a = n psi/(n psi+1), v = 1 + psi/(n psi+1), q = 1/2 (1/(1+psi) - 1/v)
+  std::vector<double> h(kScoreConstsSize, 0.0);
+  const double n = static_cast<double>(count);
+  double logdet = 0.0;
+  for (int64_t i = 0; i < dim; ++i) {
+    const double p = model.h_psi[i];
+    const double den = n * p + 1.0;
+    const double a = n * p / den;
+    const double v = 1.0 + p / den;
+    h[kScoreConstsScale + i] = a / v;
+    h[kScoreConstsEnrolSq + i] = a * a / v;
+    h[kScoreConstsTestSq + i] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
+    logdet += log1p(p) - log(v);
+  }
+  h[kScoreConstsLogdet] = logdet;
+  if (score_consts.size() >= 16) score_consts.erase(score_consts.begin());
+  score_consts.emplace_back();
+  ScoreConsts& c = score_consts.back();
+  c.count = count;
+  c.dim = dim;
+  c.dev.alloc(kScoreConstsSize);
+  PB_CUDA(cudaMemcpyAsync(c.dev.get(), h.data(), kScoreConstsSize * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaStreamSynchronize(ctx.stream));   // h is stack-lifetime
+  return c.dev.get();
+}
+
 void PldaEngine::refresh_model_operands() {
+  score_consts.clear();
   const int64_t d = model.d;
   split_rows(ctx, model.transform.get(), false, d, d, d, nullptr, nullptr, nullptr, model.a_split);
   model.h_psi.resize(d);
@@ -367,7 +400,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
     ws_row.reserve(ne);
     ws_col.reserve(static_cast<size_t>(ng) * col_ld);
     if (uniform) {
-      score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, uniform_count, model.psi.get(), ws_l,
+      score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, score_consts_for(uniform_count, dim), ws_l,
                          ws_r, ws_row.get(), ws_col.get(), col_ld);
     } else {
       PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(ng) * col_ld * sizeof(float), ctx.stream));

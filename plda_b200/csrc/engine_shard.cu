@@ -125,7 +125,7 @@ void PldaEngine::shard_push(const void* test_shard, int64_t nt_local, int64_t ld
   sig.counter = reinterpret_cast<unsigned*>(shard.region + kCounterOff);
   sig.epoch = shard.epoch;
   score_prep_uniform_multi(ctx, nullptr, 0, 0, nullptr, nullptr, test_shard, nt_local, ld, row0, row0 + nt_local, dst,
-                           shard.ldk, dtype == 1, shard.dim, enrol_count, model.psi.get(), sig);
+                           shard.ldk, dtype == 1, shard.dim, score_consts_for(enrol_count, shard.dim), sig);
 }
 
 void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids,
@@ -157,7 +157,7 @@ void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, in
   ws_row.reserve(ne);
   PrepDst none;
   score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, &ws_l, ws_row.get(), nullptr, 0, 0, 0, 0, none, shard.ldk,
-                           dtype == 1, shard.dim, enrol_count, model.psi.get(), PrepSignal{});
+                           dtype == 1, shard.dim, score_consts_for(enrol_count, shard.dim), PrepSignal{});
   const size_t gen = shard.off_gen[shard.epoch & 1u];
   SplitOperand b;
   b.hi = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen);

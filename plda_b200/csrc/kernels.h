@@ -33,8 +33,11 @@ void score_prep_test(Context& ctx, const void* test, bool is_f32, int64_t nt, in
                      int64_t col_ld, double* col_term_f64);
 // Fused enrol + test operand producer for a single enrol count (one launch, per-column constants computed once per
 // block, writes the zero padding of col_term itself).  enrol and test share dtype.
+// `consts`: device table of the per-column LLR constants for one (model, enrol count), layout kScoreConsts*.
+constexpr int kScoreConstsScale = 0, kScoreConstsEnrolSq = 1024, kScoreConstsTestSq = 2048, kScoreConstsLogdet = 3072,
+              kScoreConstsSize = 3073;
 void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const void* test, int64_t nt,
-                        int64_t ld_t, bool is_f32, int64_t d, int count, const double* psi, SplitBuf& l_out,
+                        int64_t ld_t, bool is_f32, int64_t d, const double* consts, SplitBuf& l_out,
                         SplitBuf& r_out, float* row_term, float* col_term, int64_t col_ld);
 // The same producer with the test-side outputs written to up to kMaxPeers destinations (operand planes with pitch
 // ld_out and a column-term row each) at global row offset test_row0, and an optional completion signal: the last
@@ -57,7 +60,7 @@ struct PrepSignal {
 void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, SplitBuf* l_out,
                               float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,
                               int64_t test_pad_end, const PrepDst& tdst, int64_t ld_out, bool is_f32, int64_t d,
-                              int count, const double* psi, const PrepSignal& sig);
+                              const double* consts, const PrepSignal& sig);
 // exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
                         const double* col_term, int64_t col_ld, const int32_t* grp, const float* zmean,

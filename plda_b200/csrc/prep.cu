@@ -174,120 +174,152 @@ __device__ __forceinline__ void load8<double>(const double* __restrict__ src, in
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void split8(const T (&v)[8], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[2 * j], h0, l0);
-    split_bf16(v[2 * j + 1], h1, l1);
-    h[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-    l[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// fp64 rows are scaled and split in fp64 (reference contract).  fp32 rows (the resident hot path) carry 24 bits:
-// the operand value is formed and split in fp32 (the split of an fp32 value is exact: x - hi is representable),
-// only the row / column terms -- sums of d products -- are accumulated in fp64.  This keeps the per-element work
-// off the fp64 conversion path (4 conversions per element -> 1).
-template <typename T>
-__global__ void __launch_bounds__(256)
-score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const T* __restrict__ test,
-                          long long nt, long long ld_t, long long test_row0, long long test_pad_end, int d, int count,
-                          const double* __restrict__ psi, __nv_bfloat16* __restrict__ l_hi,
-                          __nv_bfloat16* __restrict__ l_lo, float* __restrict__ row_term, const PrepDst tdst,
-                          int ld_out, unsigned enrol_blocks, int passes, int vec_e, int vec_t,
-                          const PrepSignal sig) {
-  __shared__ double s_s[1024];   // enrol: a/v (operand scale)
-  __shared__ double s_k[1024];   // enrol: a^2/v ; test: q   (weights of the squared terms)
-  __shared__ double s_red[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool is_enrol = blockIdx.x < enrol_blocks;
-  const double n = static_cast<double>(count);
-  double cpart = 0.0;
-  for (int c = threadIdx.x; c < d; c += 256) {
-    const double p = psi[c];
-    const double den = n * p + 1.0;
-    const double a = n * p / den;
-    const double v = 1.0 + p / den;
-    if (is_enrol) {
-      s_s[c] = a / v;
-      s_k[c] = a * a / v;
-      cpart += log1p(p) - log(v);
-    } else {
-      s_k[c] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
-    }
-  }
-  cpart = warp_sum(cpart);
-  if (lane == 0) s_red[warp] = cpart;
-  __syncthreads();
-  double cst = 0.0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) cst += s_red[i];
-
-  // a block owns 32 * passes rows; per pass a warp owns rows {warp, warp+8, warp+16, warp+24}; a lane owns
-  // 8-column groups
-  const long long nrows = is_enrol ? ne : nt;
-  const T* base = is_enrol ? enrol : test;
-  const long long ld_in = is_enrol ? ld_e : ld_t;
-  const bool vec = (is_enrol ? vec_e : vec_t) != 0;
-  for (int pass = 0; pass < passes; ++pass) {
-  const long long r0 = (static_cast<long long>(is_enrol ? blockIdx.x : blockIdx.x - enrol_blocks) * passes + pass) * 32;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int c = lane * 8; c < ld_out; c += 256) {
-    double kk[8];
-    T ks[8];
+// One 8-column group of one row: accumulate the weighted squares, scale, split into bf16 hi / lo planes.
+// fp64 rows are scaled and split in fp64 (reference contract).  fp32 rows (the resident hot path) carry 24 bits: the
+// operand value is formed and split in fp32 -- the split of an fp32 value is exact (x - hi is representable) and the
+// packed cvt.rn.bf16x2.f32 does two elements per instruction -- and the weighted squares are summed in fp32 over the
+// lane's 8 columns only; everything across lanes / column groups is accumulated in fp64.
+struct Group8F32 {
+  float sq[8], scale[8];
+  float part;
+  __device__ __forceinline__ void load_consts(const double* c_sq, const double* c_scale, bool scaled, int c, int d) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool in = c + j < d;
-      kk[j] = in ? s_k[c + j] : 0.0;
-      ks[j] = (in && is_enrol) ? static_cast<T>(s_s[c + j]) : static_cast<T>(in ? 1.0 : 0.0);
+      sq[j] = in ? static_cast<float>(__ldg(c_sq + c + j)) : 0.f;
+      scale[j] = in ? (scaled ? static_cast<float>(__ldg(c_scale + c + j)) : 1.f) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void run(float (&v)[8], uint4& hi, uint4& lo) {
+    float p = 0.f;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p = fmaf(sq[j], v[j] * v[j], p);
+      v[j] *= scale[j];                 // test side: x 1 (exact); padding columns: x 0
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long r = r0 + warp + 8 * i;
-      if (r >= nrows) continue;
-      T v[8];
-      load8<T>(base + r * ld_in, c, d, vec, v);
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hh, ll;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+      const float r0 = v[2 * j] - __uint_as_float(hh << 16);
+      const float r1 = v[2 * j + 1] - __uint_as_float(hh & 0xffff0000u);
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ll) : "f"(r1), "f"(r0));
+      h[j] = hh;
+      l[j] = ll;
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    part = p;
+  }
+};
+struct Group8F64 {
+  double sq[8], scale[8];
+  double part;
+  __device__ __forceinline__ void load_consts(const double* c_sq, const double* c_scale, bool scaled, int c, int d) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (sizeof(T) == 4) acc[i] += kk[j] * static_cast<double>(v[j] * v[j]);
-        else acc[i] += kk[j] * v[j] * v[j];
-        v[j] = v[j] * ks[j];          // test side: x 1 (exact); padding columns: x 0
+    for (int j = 0; j < 8; ++j) {
+      const bool in = c + j < d;
+      sq[j] = in ? __ldg(c_sq + c + j) : 0.0;
+      scale[j] = in ? (scaled ? __ldg(c_scale + c + j) : 1.0) : 0.0;
+    }
+  }
+  __device__ __forceinline__ void run(double (&v)[8], uint4& hi, uint4& lo) {
+    double p = 0.0;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p += sq[j] * v[j] * v[j];
+      v[j] *= scale[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * j], h0, l0);
+      split_bf16(v[2 * j + 1], h1, l1);
+      h[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      l[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    part = p;
+  }
+};
+template <typename T> struct Group8Of;
+template <> struct Group8Of<float> { typedef Group8F32 type; };
+template <> struct Group8Of<double> { typedef Group8F64 type; };
+
+// `consts` (kScoreConsts* layout, built once per (model, enrol count) by the engine): a/v, a^2/v, q and the
+// log-determinant term.  Grid: `enrol_blocks` blocks stride over the enrol rows, the rest over the test rows -- a
+// warp takes rows gw, gw + W, gw + 2W, gw + 3W (W = warps of its side) per round with the four row loads issued
+// together; a lane owns 8-column groups and keeps the constants of its columns in registers.
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const T* __restrict__ test,
+                          long long nt, long long ld_t, long long test_row0, long long test_pad_end, int d,
+                          const double* __restrict__ consts, __nv_bfloat16* __restrict__ l_hi,
+                          __nv_bfloat16* __restrict__ l_lo, float* __restrict__ row_term, const PrepDst tdst,
+                          int ld_out, unsigned enrol_blocks, int vec_e, int vec_t, const PrepSignal sig) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_enrol = blockIdx.x < enrol_blocks;
+  const double* __restrict__ c_scale = consts + kScoreConstsScale;
+  const double* __restrict__ c_sq = consts + (is_enrol ? kScoreConstsEnrolSq : kScoreConstsTestSq);
+  const double cst = __ldg(consts + kScoreConstsLogdet);
+  const long long nrows = is_enrol ? ne : nt;
+  const T* __restrict__ base = is_enrol ? enrol : test;
+  const long long ld_in = is_enrol ? ld_e : ld_t;
+  const bool vec = (is_enrol ? vec_e : vec_t) != 0;
+  const long long blk = is_enrol ? blockIdx.x : blockIdx.x - enrol_blocks;
+  const long long w_side = static_cast<long long>(is_enrol ? enrol_blocks : gridDim.x - enrol_blocks) * 8;
+  // destination 0 (the only one on a single GPU) lives in registers
+  __nv_bfloat16* __restrict__ o_hi = is_enrol ? l_hi : tdst.hi[0] + test_row0 * ld_out;
+  __nv_bfloat16* __restrict__ o_lo = is_enrol ? l_lo : tdst.lo[0] + test_row0 * ld_out;
+  float* __restrict__ o_term = is_enrol ? row_term : tdst.term[0] + test_row0;
+  const int extra = is_enrol ? 0 : tdst.n - 1;
+  const bool one_group = ld_out <= 256;        // d <= 256: the lane's constants are loaded once
+  typename Group8Of<T>::type g;
+  if (one_group && lane * 8 < ld_out) g.load_consts(c_sq, c_scale, is_enrol, lane * 8, d);
+  for (long long rb = blk * 8 + warp; rb < nrows; rb += 4 * w_side) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = lane * 8; c < ld_out; c += 256) {
+      if (!one_group) g.load_consts(c_sq, c_scale, is_enrol, c, d);
+      T v[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long r = rb + i * w_side;
+        if (r < nrows) load8<T>(base + r * ld_in, c, d, vec, v[i]);
       }
-      uint4 hi, lo;
-      split8<T>(v, hi, lo);
-      if (is_enrol) {
-        *reinterpret_cast<uint4*>(l_hi + r * ld_out + c) = hi;
-        *reinterpret_cast<uint4*>(l_lo + r * ld_out + c) = lo;
-      } else {
-        const long long o = (test_row0 + r) * ld_out + c;
-        for (int w = 0; w < tdst.n; ++w) {
-          *reinterpret_cast<uint4*>(tdst.hi[w] + o) = hi;
-          *reinterpret_cast<uint4*>(tdst.lo[w] + o) = lo;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long r = rb + i * w_side;
+        if (r >= nrows) continue;
+        uint4 hi, lo;
+        g.run(v[i], hi, lo);
+        acc[i] += static_cast<double>(g.part);
+        const long long o = r * ld_out + c;
+        *reinterpret_cast<uint4*>(o_hi + o) = hi;
+        *reinterpret_cast<uint4*>(o_lo + o) = lo;
+        for (int w = 1; w <= extra; ++w) {       // sharded grid: the other ranks' operand buffers (peer memory)
+          *reinterpret_cast<uint4*>(tdst.hi[w] + test_row0 * ld_out + o) = hi;
+          *reinterpret_cast<uint4*>(tdst.lo[w] + test_row0 * ld_out + o) = lo;
         }
       }
     }
-  }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long r = r0 + warp + 8 * i;
-    const double a = warp_sum(acc[i]);
-    if (lane != 0) continue;
-    if (is_enrol) {
-      if (r < ne) row_term[r] = static_cast<float>(0.5 * (cst - a));
-    } else {
-      const long long gr = test_row0 + r;          // row in the (global) operand
-      // rows past nt: zero padding of the column-term row, read (never stored) by the GEMM epilogue
-      const float t = r < nt ? static_cast<float>(a) : 0.f;
-      if (r < nt || gr < test_pad_end)
-        for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = t;
+    for (int i = 0; i < 4; ++i) {
+      const long long r = rb + i * w_side;
+      const double a = warp_sum(acc[i]);
+      if (lane != 0 || r >= nrows) continue;
+      const float t = is_enrol ? static_cast<float>(0.5 * (cst - a)) : static_cast<float>(a);
+      o_term[r] = t;
+      for (int w = 1; w <= extra; ++w) tdst.term[w][test_row0 + r] = t;
     }
   }
-  }  // pass
+  if (!is_enrol && blk == 0) {
+    // zero padding of the column-term row: read (never stored) by the GEMM epilogue
+    for (long long gr = test_row0 + nt + threadIdx.x; gr < test_pad_end; gr += 256)
+      for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = 0.f;
+  }
   if (sig.counter != nullptr) {
     // publish: every thread's peer stores are performed system-wide, then the LAST block raises the ready flag of
     // this source rank in every destination region
@@ -466,21 +498,27 @@ inline bool rows_vectorisable(const void* p, int64_t ld, bool is_f32) {
 void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, SplitBuf* l_out,
                               float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,
                               int64_t test_pad_end, const PrepDst& tdst, int64_t ld_out, bool is_f32, int64_t d,
-                              int count, const double* psi, const PrepSignal& sig) {
+                              const double* consts, const PrepSignal& sig) {
   PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
   PB_CHECK(ld_out % 16 == 0 && ld_out >= d, kInvalidArg, "score prep: operand pitch must be a multiple of 16");
   PB_CHECK(tdst.n >= 0 && tdst.n <= kMaxPeers && sig.n <= kMaxPeers, kInvalidArg, "score prep: too many destinations");
   if (l_out) l_out->reserve(ne, d);
   PB_CHECK(l_out == nullptr || l_out->ld == ld_out || nt == 0, kInvalidArg, "score prep: operand pitches differ");
   const int ldo = static_cast<int>(l_out ? l_out->ld : ld_out);
-  // 32 rows per block pass; enough passes per block that the grid is ONE wave (3 resident blocks per SM at 80 registers)
+  // two resident blocks per SM; the blocks are split between the sides in proportion to their rows, a small side
+  // gets one block per 32 rows (one round of four rows per warp)
   const int64_t e_rows = l_out ? ne : 0;
-  const int64_t t_rows = tdst.n > 0 ? std::max<int64_t>(test_pad_end - test_row0, nt) : 0;
-  const int64_t b32 = ceil_div(e_rows, 32) + ceil_div(t_rows, 32);
-  const int passes = static_cast<int>(std::max<int64_t>(1, ceil_div(b32, 3ll * ctx.num_sms)));
-  const unsigned eb = static_cast<unsigned>(ceil_div(e_rows, 32ll * passes));
-  unsigned tb = static_cast<unsigned>(ceil_div(t_rows, 32ll * passes));
-  if (sig.counter != nullptr && tb == 0) tb = 1;   // an empty shard still has to raise its ready flag
+  const int64_t t_rows = tdst.n > 0 ? nt : 0;
+  const int64_t slots = 2ll * ctx.num_sms;
+  auto side_blocks = [&](int64_t rows) -> unsigned {
+    if (rows <= 0) return 0u;
+    const int64_t share = std::max<int64_t>(1, slots * rows / (e_rows + t_rows));
+    return static_cast<unsigned>(std::min<int64_t>(ceil_div(rows, 32), share));
+  };
+  const unsigned eb = side_blocks(e_rows);
+  unsigned tb = side_blocks(t_rows);
+  // an empty shard still has to raise its ready flag / write the padding of the column-term row
+  if (tb == 0 && tdst.n > 0 && (sig.counter != nullptr || test_pad_end > test_row0 + nt)) tb = 1;
   if (eb + tb == 0) return;
   const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
   const int vec_t = test && rows_vectorisable(test, ld_t, is_f32) ? 1 : 0;
@@ -489,17 +527,17 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   if (is_f32)
     score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const float*>(enrol), l_out ? ne : 0, ld_e, static_cast<const float*>(test), nt, ld_t, test_row0,
-        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, passes, vec_e, vec_t, sig);
+        test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
   else
     score_prep_uniform_kernel<double><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const double*>(enrol), l_out ? ne : 0, ld_e, static_cast<const double*>(test), nt, ld_t, test_row0,
-        test_pad_end, static_cast<int>(d), count, psi, lhi, llo, row_term, tdst, ldo, eb, passes, vec_e, vec_t, sig);
+        test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }
 
 void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const void* test, int64_t nt,
-                        int64_t ld_t, bool is_f32, int64_t d, int count, const double* psi, SplitBuf& l_out,
+                        int64_t ld_t, bool is_f32, int64_t d, const double* consts, SplitBuf& l_out,
                         SplitBuf& r_out, float* row_term, float* col_term, int64_t col_ld) {
   r_out.reserve(nt, d);
   PrepDst tdst;
@@ -508,7 +546,7 @@ void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
   tdst.lo[0] = r_out.lo.get();
   tdst.term[0] = col_term;
   score_prep_uniform_multi(ctx, enrol, ne, ld_e, &l_out, row_term, test, nt, ld_t, 0, col_ld, tdst, r_out.ld, is_f32, d,
-                           count, psi, PrepSignal{});
+                           consts, PrepSignal{});
 }
 
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
