@@ -158,6 +158,11 @@ int plda_shard_push(plda_handle_t h, const void* test_shard, int64_t nt_local, i
                     int enrol_count);
 int plda_shard_score(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count,
                      const uint64_t* enrol_ids, int dtype, float* out, int64_t ldo);
+/* push + score in one call: the enrol-side operand producer shares the push kernel's launch (test blocks first,
+ * so their peer stores are in flight while the enrol rows are processed) */
+int plda_shard_step(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol,
+                    int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* enrol_ids, int dtype, float* out,
+                    int64_t ldo);
 int plda_shard_status(plda_handle_t h, int64_t* epoch, int64_t* timeouts);
 int plda_shard_close(plda_handle_t h);
 

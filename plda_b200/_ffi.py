@@ -56,6 +56,7 @@ SIGNATURES = {
     "plda_shard_connect": [_vp, _int, _vp, _vp],
     "plda_shard_push": [_vp, _vp, _i64, _i64, _int, _int],
     "plda_shard_score": [_vp, _vp, _i64, _i64, _int, _vp, _int, _vp, _i64],
+    "plda_shard_step": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _i64],
     "plda_shard_status": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "plda_shard_close": [_vp],
     "lda_create": [_int, C.POINTER(_vp)],

@@ -219,6 +219,13 @@ int plda_shard_score(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_
     e.shard_score(enrol, ne, ld_enrol, enrol_count, enrol_ids, dtype, out, ldo);
   });
 }
+int plda_shard_step(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol,
+                    int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* enrol_ids, int dtype, float* out,
+                    int64_t ldo) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.shard_step(test_shard, nt_local, ld_test, enrol, ne, ld_enrol, enrol_count, enrol_ids, dtype, out, ldo);
+  });
+}
 int plda_shard_status(plda_handle_t h, int64_t* epoch, int64_t* timeouts) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.shard_status(epoch, timeouts); });
 }

@@ -89,9 +89,19 @@ class PldaEngine {
   void shard_push(const void* test_shard, int64_t nt_local, int64_t ld, int dtype, int enrol_count);
   void shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids, int dtype,
                    float* out, int64_t ldo);
+  // push + score with the enrol-side producer fused into the push kernel (one launch less per step)
+  void shard_step(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
+                  int64_t ld_enrol, int enrol_count, const uint64_t* ids, int dtype, float* out, int64_t ldo);
   void shard_status(int64_t* epoch, int64_t* timeouts);
   void shard_close();
   ~PldaEngine();
+
+ private:
+  void shard_produce(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
+                     int64_t ld_enrol, int enrol_count, int dtype);
+  void shard_gemm(int64_t ne, const uint64_t* ids, float* out, int64_t ldo);
+
+ public:
   void test_gemm(const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit, float* out);
   void test_linalg(int op, const double* a, int64_t d, double* out, double* out2);
 

@@ -100,45 +100,45 @@ void PldaEngine::shard_connect(int peer_rank, const unsigned char* ipc_handle, v
   shard.peer_ipc[peer_rank] = true;
 }
 
-void PldaEngine::shard_push(const void* test_shard, int64_t nt_local, int64_t ld, int dtype, int enrol_count) {
+// Producer launch: this rank's test rows -> every region (+ ready flags); optionally the enrol-side operand in the
+// same launch.  Advances the epoch.
+void PldaEngine::shard_produce(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
+                               int64_t ld_enrol, int enrol_count, int dtype) {
   require_model();
-  PB_CHECK(shard.open, kInvalidArg, "shard_push: no open session");
-  for (int r = 0; r < shard.world; ++r) PB_CHECK(shard.peer[r] != nullptr, kInvalidArg, "shard_push: a peer is not connected");
+  PB_CHECK(shard.open, kInvalidArg, "shard: no open session");
+  for (int r = 0; r < shard.world; ++r) PB_CHECK(shard.peer[r] != nullptr, kInvalidArg, "shard: a peer is not connected");
   PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
   const int64_t row0 = shard.bounds[shard.rank];
-  PB_CHECK(nt_local == shard.bounds[shard.rank + 1] - row0, kInvalidArg, "shard_push: shard size does not match the bounds");
-  PB_CHECK(nt_local == 0 || (test_shard != nullptr && ld >= shard.dim), kInvalidArg, "shard_push: bad test rows");
-  PB_CHECK(enrol_count > 0, kInvalidArg, "shard_push: enrol count must be positive");
+  PB_CHECK(nt_local == shard.bounds[shard.rank + 1] - row0, kInvalidArg, "shard: shard size does not match the bounds");
+  PB_CHECK(nt_local == 0 || (test_shard != nullptr && ld_test >= shard.dim), kInvalidArg, "shard: bad test rows");
+  PB_CHECK(enrol_count > 0, kInvalidArg, "shard: enrol count must be positive");
+  PB_CHECK(ne == 0 || (enrol != nullptr && ld_enrol >= shard.dim), kInvalidArg, "shard: bad enrol rows");
+  const double* consts = score_consts_for(enrol_count, shard.dim);
   shard.epoch += 1;
   shard.push_count = enrol_count;
   const size_t gen = shard.off_gen[shard.epoch & 1u];
   PrepDst dst;
   PrepSignal sig;
   dst.n = sig.n = shard.world;
-  for (int r = 0; r < shard.world; ++r) {
+  // destination 0 is this rank's own region (the kernel keeps it in registers)
+  for (int i = 0; i < shard.world; ++i) {
+    const int r = (shard.rank + i) % shard.world;
     uint8_t* base = shard.peer[r];
-    dst.hi[r] = reinterpret_cast<__nv_bfloat16*>(base + gen);
-    dst.lo[r] = reinterpret_cast<__nv_bfloat16*>(base + gen + shard.off_lo);
-    dst.term[r] = reinterpret_cast<float*>(base + gen + shard.off_col);
-    sig.flag[r] = reinterpret_cast<unsigned*>(base + kFlagsOff) + shard.rank;
+    dst.hi[i] = reinterpret_cast<__nv_bfloat16*>(base + gen);
+    dst.lo[i] = reinterpret_cast<__nv_bfloat16*>(base + gen + shard.off_lo);
+    dst.term[i] = reinterpret_cast<float*>(base + gen + shard.off_col);
+    sig.flag[i] = reinterpret_cast<unsigned*>(base + kFlagsOff) + shard.rank;
   }
   sig.counter = reinterpret_cast<unsigned*>(shard.region + kCounterOff);
   sig.epoch = shard.epoch;
-  score_prep_uniform_multi(ctx, nullptr, 0, 0, nullptr, nullptr, test_shard, nt_local, ld, row0, row0 + nt_local, dst,
-                           shard.ldk, dtype == 1, shard.dim, score_consts_for(enrol_count, shard.dim), sig);
+  if (ne > 0) ws_row.reserve(ne);
+  score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, ne > 0 ? &ws_l : nullptr, ne > 0 ? ws_row.get() : nullptr,
+                           test_shard, nt_local, ld_test, row0, row0 + nt_local, dst, shard.ldk, dtype == 1, shard.dim,
+                           consts, sig);
 }
 
-void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids,
-                             int dtype, float* out, int64_t ldo) {
-  require_model();
-  PB_CHECK(shard.open, kInvalidArg, "shard_score: no open session");
-  PB_CHECK(shard.epoch > 0, kInvalidArg, "shard_score: nothing pushed yet");
-  PB_CHECK(enrol_count == shard.push_count, kInvalidArg,
-           "shard_score: the column terms were pushed for a different enrol count");
-  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
-  PB_CHECK(ne >= 0 && (ne == 0 || (enrol != nullptr && out != nullptr)), kInvalidArg, "shard_score: null pointer");
-  PB_CHECK(ld_enrol >= shard.dim && ldo >= shard.nt_total, kInvalidArg, "shard_score: pitch too small");
-  if (ne == 0) return;
+// The grid of this rank's enrol block (operand already in ws_l / ws_row) against the current generation.
+void PldaEngine::shard_gemm(int64_t ne, const uint64_t* ids, float* out, int64_t ldo) {
   const float* zmean = nullptr;
   const float* zinv = nullptr;
   if (ids != nullptr && !znorm.empty()) {
@@ -154,10 +154,6 @@ void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, in
     zmean = ws_zmean.get();
     zinv = ws_zmean.get() + ne;
   }
-  ws_row.reserve(ne);
-  PrepDst none;
-  score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, &ws_l, ws_row.get(), nullptr, 0, 0, 0, 0, none, shard.ldk,
-                           dtype == 1, shard.dim, score_consts_for(enrol_count, shard.dim), PrepSignal{});
   const size_t gen = shard.off_gen[shard.epoch & 1u];
   SplitOperand b;
   b.hi = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen);
@@ -181,6 +177,37 @@ void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, in
   gs.rank = shard.rank;
   for (int r = 0; r <= shard.world; ++r) gs.bounds[r] = static_cast<int>(shard.bounds[r]);
   gemm_bf16x3(ctx, ws_l.view(), b, ne, shard.nt_total, shard.dim, epi, &gs);
+}
+
+void PldaEngine::shard_push(const void* test_shard, int64_t nt_local, int64_t ld, int dtype, int enrol_count) {
+  shard_produce(test_shard, nt_local, ld, nullptr, 0, 0, enrol_count, dtype);
+}
+
+void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids,
+                             int dtype, float* out, int64_t ldo) {
+  require_model();
+  PB_CHECK(shard.open, kInvalidArg, "shard_score: no open session");
+  PB_CHECK(shard.epoch > 0, kInvalidArg, "shard_score: nothing pushed yet");
+  PB_CHECK(enrol_count == shard.push_count, kInvalidArg,
+           "shard_score: the column terms were pushed for a different enrol count");
+  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+  PB_CHECK(ne >= 0 && (ne == 0 || (enrol != nullptr && out != nullptr)), kInvalidArg, "shard_score: null pointer");
+  PB_CHECK(ld_enrol >= shard.dim && ldo >= shard.nt_total, kInvalidArg, "shard_score: pitch too small");
+  if (ne == 0) return;
+  ws_row.reserve(ne);
+  PrepDst none;
+  score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, &ws_l, ws_row.get(), nullptr, 0, 0, 0, 0, none, shard.ldk,
+                           dtype == 1, shard.dim, score_consts_for(enrol_count, shard.dim), PrepSignal{});
+  shard_gemm(ne, ids, out, ldo);
+}
+
+void PldaEngine::shard_step(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
+                            int64_t ld_enrol, int enrol_count, const uint64_t* ids, int dtype, float* out,
+                            int64_t ldo) {
+  PB_CHECK(ne >= 0 && (ne == 0 || out != nullptr), kInvalidArg, "shard_step: null output");
+  PB_CHECK(!shard.open || ldo >= shard.nt_total, kInvalidArg, "shard_step: output pitch too small");
+  shard_produce(test_shard, nt_local, ld_test, enrol, ne, ld_enrol, enrol_count, dtype);
+  if (ne > 0) shard_gemm(ne, ids, out, ldo);
 }
 
 void PldaEngine::shard_status(int64_t* epoch, int64_t* timeouts) {

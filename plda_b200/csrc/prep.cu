@@ -250,7 +250,7 @@ template <> struct Group8Of<float> { typedef Group8F32 type; };
 template <> struct Group8Of<double> { typedef Group8F64 type; };
 
 // `consts` (kScoreConsts* layout, built once per (model, enrol count) by the engine): a/v, a^2/v, q and the
-// log-determinant term.  Grid: `enrol_blocks` blocks stride over the enrol rows, the rest over the test rows -- a
+// log-determinant term.  Grid: the first `test_blocks` blocks stride over the test rows, the rest over the enrol rows -- a
 // warp takes rows gw, gw + W, gw + 2W, gw + 3W (W = warps of its side) per round with the four row loads issued
 // together; a lane owns 8-column groups and keeps the constants of its columns in registers.
 template <typename T>
@@ -259,9 +259,10 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
                           long long nt, long long ld_t, long long test_row0, long long test_pad_end, int d,
                           const double* __restrict__ consts, __nv_bfloat16* __restrict__ l_hi,
                           __nv_bfloat16* __restrict__ l_lo, float* __restrict__ row_term, const PrepDst tdst,
-                          int ld_out, unsigned enrol_blocks, int vec_e, int vec_t, const PrepSignal sig) {
+                          int ld_out, unsigned test_blocks, int vec_e, int vec_t, const PrepSignal sig) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool is_enrol = blockIdx.x < enrol_blocks;
+  // test blocks come first in the grid: on a sharded grid their stores travel over NVLink while the enrol blocks run
+  const bool is_enrol = blockIdx.x >= test_blocks;
   const double* __restrict__ c_scale = consts + kScoreConstsScale;
   const double* __restrict__ c_sq = consts + (is_enrol ? kScoreConstsEnrolSq : kScoreConstsTestSq);
   const double cst = __ldg(consts + kScoreConstsLogdet);
@@ -269,8 +270,8 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
   const T* __restrict__ base = is_enrol ? enrol : test;
   const long long ld_in = is_enrol ? ld_e : ld_t;
   const bool vec = (is_enrol ? vec_e : vec_t) != 0;
-  const long long blk = is_enrol ? blockIdx.x : blockIdx.x - enrol_blocks;
-  const long long w_side = static_cast<long long>(is_enrol ? enrol_blocks : gridDim.x - enrol_blocks) * 8;
+  const long long blk = is_enrol ? blockIdx.x - test_blocks : blockIdx.x;
+  const long long w_side = static_cast<long long>(is_enrol ? gridDim.x - test_blocks : test_blocks) * 8;
   // destination 0 (the only one on a single GPU) lives in registers
   __nv_bfloat16* __restrict__ o_hi = is_enrol ? l_hi : tdst.hi[0] + test_row0 * ld_out;
   __nv_bfloat16* __restrict__ o_lo = is_enrol ? l_lo : tdst.lo[0] + test_row0 * ld_out;
@@ -320,14 +321,14 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
     for (long long gr = test_row0 + nt + threadIdx.x; gr < test_pad_end; gr += 256)
       for (int w = 0; w < tdst.n; ++w) tdst.term[w][gr] = 0.f;
   }
-  if (sig.counter != nullptr) {
-    // publish: every thread's peer stores are performed system-wide, then the LAST block raises the ready flag of
-    // this source rank in every destination region
+  if (sig.counter != nullptr && !is_enrol) {
+    // publish: every thread's peer stores are performed system-wide, then the LAST test block raises the ready flag
+    // of this source rank in every destination region (block-uniform branch: the barrier is safe)
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned prev = atomicAdd(sig.counter, 1u);
-      if (prev == gridDim.x - 1) {
+      if (prev == test_blocks - 1) {
         atomicExch(sig.counter, 0u);
         __threadfence_system();
         for (int w = 0; w < sig.n; ++w)
@@ -527,11 +528,11 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   if (is_f32)
     score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const float*>(enrol), l_out ? ne : 0, ld_e, static_cast<const float*>(test), nt, ld_t, test_row0,
-        test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
+        test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, tb, vec_e, vec_t, sig);
   else
     score_prep_uniform_kernel<double><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const double*>(enrol), l_out ? ne : 0, ld_e, static_cast<const double*>(test), nt, ld_t, test_row0,
-        test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, eb, vec_e, vec_t, sig);
+        test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, tb, vec_e, vec_t, sig);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

@@ -167,9 +167,23 @@ class PeerShardedScorer:
         return out
 
     def score(self, enrol_block, enrol_count: int, test_shard, out=None, enrol_ids=None, sync: bool = True):
-        """One sharded scoring step: push + grid (+ a stream synchronisation unless ``sync=False``)."""
-        self.push(test_shard, enrol_count)
-        out = self.grid(enrol_block, enrol_count, out=out, enrol_ids=enrol_ids)
+        """One sharded scoring step (``plda_shard_step``): ONE producer launch (this rank's test rows -> every rank,
+        plus the enrol operand) and the grid GEMM (+ a stream synchronisation unless ``sync=False``)."""
+        import torch
+        tt, dtype = _cuda_matrix(test_shard)
+        et, dtype_e = _cuda_matrix(enrol_block)
+        if dtype != dtype_e:
+            raise ValueError("enrol and test dtypes differ")
+        ne = et.shape[0]
+        if out is None:
+            ldo = (self.n_test_total + 3) // 4 * 4
+            out = torch.empty((ne, ldo), dtype=torch.float32, device=et.device)[:, : self.n_test_total]
+        ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
+        C = self._C
+        self._ffi.check(self._lib.plda_shard_step(
+            self.plda._h, C.c_void_p(tt.data_ptr()), tt.shape[0], tt.stride(0) if tt.shape[0] else self.dim,
+            C.c_void_p(et.data_ptr()), ne, et.stride(0) if ne else self.dim, int(enrol_count), self._ffi.ptr(ids), dtype,
+            C.c_void_p(out.data_ptr()), out.stride(0)))
         if sync:
             self._ffi.check(self._lib.plda_synchronize(self.plda._h))
         return out

@@ -114,6 +114,45 @@ def test_grid_waits_for_a_late_push():
             sc.close()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_step_equals_push_then_grid(world):
+    """plda_shard_step (one producer launch for test push + enrol operand) == plda_shard_push + plda_shard_score.
+    Ranks are stepped one after the other without synchronisation: every GEMM but the last one launched waits on
+    flags of ranks that have not pushed yet (small grids, so the late producers find free SMs)."""
+    import torch
+    from plda_b200.dist import block_bounds
+    d, nt_total, count = 200, 700, 3
+    model = _model(d)
+    hs, scorers = _ranks(world, d, nt_total, model)
+    rng = np.random.RandomState(8)
+    try:
+        for step in range(2):
+            test = rng.randn(nt_total, d).astype(np.float32)
+            enrol = [rng.randn(150 + 20 * r, d).astype(np.float32) for r in range(world)]
+            t_dev = torch.from_numpy(test).cuda()
+            e_dev = [torch.from_numpy(e).cuda() for e in enrol]
+            torch.cuda.synchronize()
+            fused = []
+            for r, sc in enumerate(scorers):
+                lo, hi = block_bounds(nt_total, world, r)
+                fused.append(sc.score(e_dev[r], count, t_dev[lo:hi], sync=False))
+            torch.cuda.synchronize()
+            for r, sc in enumerate(scorers):
+                lo, hi = block_bounds(nt_total, world, r)
+                sc.push(t_dev[lo:hi], count)
+            split = [sc.grid(e_dev[r], count) for r, sc in enumerate(scorers)]
+            torch.cuda.synchronize()
+            for r, sc in enumerate(scorers):
+                assert sc.status() == (2 * step + 2, 0)
+                assert torch.equal(fused[r], split[r])
+                ref = _oracle_grid(model[2], enrol[r], count, test)
+                got = fused[r].cpu().numpy()
+                assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) <= 1e-3
+    finally:
+        for sc in scorers:
+            sc.close()
+
+
 def test_sharded_znorm_and_errors():
     import torch
     from plda_b200.dist import block_bounds
