@@ -149,7 +149,7 @@ int plda_znorm_set(plda_handle_t h, const uint64_t* ids, const double* mean, con
  *   connect  once per peer, with that peer's IPC handle (other process) or region pointer (same
  *            process); all ranks must have connected (barrier) before the first push
  *   push / score must be called the same number of times, in the same order, on every rank
- *   status   epoch = pushes so far; timeouts = waits that gave up after 5 s (results invalid if > 0) */
+ *   status   epoch = pushes so far; timeouts = waits that gave up (2 s; sticky) -- results are invalid if > 0      */
 #define PLDA_IPC_HANDLE_BYTES 64
 int plda_shard_open(plda_handle_t h, int world, int rank, const int64_t* bounds, int64_t dim,
                     unsigned char* ipc_handle_out, void** region_out);

@@ -87,18 +87,21 @@ struct Cfg {
 };
 static_assert(Cfg<true>::kStages * Cfg<true>::kStageBytes == STAGES * STAGE_BYTES, "smem budget");
 
-// Bounded poll of a peer's ready flag: a rank that never arrives is counted in shard.err (the host reports it)
-// instead of hanging the GPU.
+// Bounded poll of a peer's ready flag: a rank that never arrives is counted in *err (the host reports it) instead
+// of hanging the GPU.  The error is sticky: once any wait of the session has timed out (2 s), later waits give up at
+// once, so a broken exchange costs seconds, not seconds per tile.
 __device__ __noinline__ void shard_wait(const unsigned* f, unsigned epoch, unsigned* err) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
   if (static_cast<int>(v - epoch) >= 0) return;
+  if (*reinterpret_cast<volatile unsigned*>(err) != 0u) return;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (true) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
     if (static_cast<int>(v - epoch) >= 0) return;
-    if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 5000000000ull) {
+    if ((++spins & 0xff) == 0 &&
+        (global_timer_ns() - t0 > 2000000000ull || *reinterpret_cast<volatile unsigned*>(err) != 0u)) {
       atomicAdd(err, 1u);
       return;
     }
