@@ -208,6 +208,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the producer kernel's tail; its outputs (operands,
+  // row / column terms) are visible after this wait.  No-op for a normal launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
@@ -725,19 +728,24 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     PB_CUDA(cudaEventCreate(&e1));
     PB_CUDA(cudaEventRecord(e0, ctx.stream));
   }
+  // the events of the profiling pass sit between the producer and this launch: no overlap to declare then
+  const bool pdl = ctx.pdl_pending && !ctx.profile_gemm;
+  ctx.pdl_pending = false;
   if (pl.two_cta) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = ctx.stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 2 : 1;
     if (epi == 1)
       PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 1>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
                                  ttb_lo, tout, p));

@@ -260,6 +260,9 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
                           const double* __restrict__ consts, __nv_bfloat16* __restrict__ l_hi,
                           __nv_bfloat16* __restrict__ l_lo, float* __restrict__ row_term, const PrepDst tdst,
                           int ld_out, unsigned test_blocks, int vec_e, int vec_t, const PrepSignal sig) {
+  // the dependent GEMM may be scheduled as soon as every block of this grid is running: its prologue overlaps
+  // this kernel's tail, its griddepcontrol.wait returns when this grid has completed (and flushed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // test blocks come first in the grid: on a sharded grid their stores travel over NVLink while the enrol blocks run
   const bool is_enrol = blockIdx.x >= test_blocks;
@@ -535,6 +538,7 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
         test_pad_end, static_cast<int>(d), consts, lhi, llo, row_term, tdst, ldo, tb, vec_e, vec_t, sig);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
+  ctx.pdl_pending = ctx.pdl_enabled;
 }
 
 void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const void* test, int64_t nt,

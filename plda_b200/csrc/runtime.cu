@@ -33,6 +33,8 @@ Context::Context(int dev) : device(dev) {
     gemm_dbg.alloc(32);
     PB_CUDA(cudaMemset(gemm_dbg.get(), 0, 32 * sizeof(long long)));
   }
+  const char* pdl = getenv("PLDA_B200_PDL");
+  if (pdl && pdl[0] == '0') pdl_enabled = false;
   const char* gm = getenv("PLDA_B200_GEMM");
   gemm_two_cta = !(gm != nullptr && strcmp(gm, "1cta") == 0);
 }

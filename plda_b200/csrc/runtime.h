@@ -62,6 +62,11 @@ struct Context {
   DevBuf<long long> gemm_dbg;        // env PLDA_B200_DBG=1: stall counters written by CTA 0/1 of the last GEMM launch
   bool gemm_two_cta = true;          // env PLDA_B200_GEMM=1cta forces the single-CTA (cta_group::1) kernel
   // optional per-launch timing of the tensor-core GEMM (CUDA events on the launching stream); bench roofline
+  // programmatic dependent launch: set by a producer kernel that executes griddepcontrol.launch_dependents; the
+  // next tensor GEMM launch then carries the programmatic-serialization attribute, so its prologue (barrier init,
+  // TMEM allocation, descriptor prefetch) overlaps the producer's tail.  env PLDA_B200_PDL=0 disables it.
+  bool pdl_enabled = true;
+  bool pdl_pending = false;
   bool profile_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
   void profile_reset();

@@ -9,5 +9,6 @@ echo "== bench reference" ; timeout 900 python bench.py --impl reference --steps
 echo "== ncu launch list (bench)" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --skip-em > gpurun_out/ncu_launch.log 2>&1; echo "exit=$?"
 echo "== ncu launch list (fit)" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/fit_launches.csv python scripts/fit_once.py 200 1000 100 5 > gpurun_out/ncu_fit.log 2>&1; echo "exit=$?"
 echo "== ncu full gemm d=200" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 4 -c 1 -o gpurun_out/prof_gemm -f python scripts/bench_gemm.py 10000 10000 200 3 > gpurun_out/ncu_full.log 2>&1; echo "exit=$?"
+echo "== ncu full producer kernel" ; timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_prep -s 4 -c 1 -o gpurun_out/prof_prep -f python bench.py --steps 3 --warmup 3 --no-cpu --skip-em > gpurun_out/ncu_prep.log 2>&1; echo "exit=$?"
 echo "== ncu full gemm d=512" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 4 -c 1 -o gpurun_out/prof_gemm_d512 -f python scripts/bench_gemm.py 20000 20000 512 3 > gpurun_out/ncu_full2.log 2>&1; echo "exit=$?"
 ls gpurun_out | tr '\n' ' '

@@ -50,7 +50,9 @@ def ncu_raw(rep):
             "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
             "launch__grid_size", "launch__block_size", "launch__cluster_size",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
-            "sm__cycles_active.avg", "sm__cycles_elapsed.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+            "sm__cycles_active.avg", "sm__cycles_elapsed.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
     d = collections.OrderedDict()
     d["kernel"] = r[hdr.index("Kernel Name")][:120]
     for k in want:
@@ -68,7 +70,7 @@ if __name__ == "__main__":
         open(os.path.join(PR, "%s_launches_fit.md" % tag), "w").write(launch_table(
             os.path.join(GO, "fit_launches.csv"), "ncu launch list of PLDA.fit (C2: 100k x 200, 1k speakers, 5 EM iters, run twice)",
             "ncu --metrics gpu__time_duration.sum --clock-control none --csv python scripts/fit_once.py 200 1000 100 5"))
-    for name in ("prof_gemm", "prof_gemm_d512"):
+    for name in ("prof_gemm", "prof_gemm_d512", "prof_prep"):
         rep = os.path.join(GO, name + ".ncu-rep")
         if os.path.exists(rep):
             d = ncu_raw(rep)
