@@ -177,25 +177,26 @@ __device__ __forceinline__ void load8<double>(const double* __restrict__ src, in
 // One 8-column group of one row: accumulate the weighted squares, scale, split into bf16 hi / lo planes.
 // fp64 rows are scaled and split in fp64 (reference contract).  fp32 rows (the resident hot path) carry 24 bits: the
 // operand value is formed and split in fp32 -- the split of an fp32 value is exact (x - hi is representable) and the
-// packed cvt.rn.bf16x2.f32 does two elements per instruction -- and the weighted squares are summed in fp32 over the
-// lane's 8 columns only; everything across lanes / column groups is accumulated in fp64.
+// packed cvt.rn.bf16x2.f32 does two elements per instruction; the row / column terms (sums of d weighted squares)
+// are accumulated in fp64.
 struct Group8F32 {
-  float sq[8], scale[8];
-  float part;
+  double sq[8];
+  float scale[8];
+  double part;
   __device__ __forceinline__ void load_consts(const double* c_sq, const double* c_scale, bool scaled, int c, int d) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool in = c + j < d;
-      sq[j] = in ? static_cast<float>(__ldg(c_sq + c + j)) : 0.f;
+      sq[j] = in ? __ldg(c_sq + c + j) : 0.0;
       scale[j] = in ? (scaled ? static_cast<float>(__ldg(c_scale + c + j)) : 1.f) : 0.f;
     }
   }
   __device__ __forceinline__ void run(float (&v)[8], uint4& hi, uint4& lo) {
-    float p = 0.f;
+    double p = 0.0;
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      p = fmaf(sq[j], v[j] * v[j], p);
+      p = fma(sq[j], static_cast<double>(v[j] * v[j]), p);   // squares rounded to fp32 one by one, summed in fp64
       v[j] *= scale[j];                 // test side: x 1 (exact); padding columns: x 0
     }
 #pragma unroll
