@@ -510,8 +510,10 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   if (l_out) l_out->reserve(ne, d);
   PB_CHECK(l_out == nullptr || l_out->ld == ld_out || nt == 0, kInvalidArg, "score prep: operand pitches differ");
   const int ldo = static_cast<int>(l_out ? l_out->ld : ld_out);
-  // two resident blocks per SM; the blocks are split between the sides in proportion to their rows, a small side
-  // gets one block per 32 rows (one round of four rows per warp)
+  // two resident blocks per SM, split between the sides in proportion to their rows; a small side gets one block
+  // per 32 rows (one round of four rows per warp).  When the test rows travel to peers (tdst.n > 1) the test side
+  // instead gets one block per 8 rows, up to one per SM: the blocks are first in the grid, short, and many warps in
+  // flight hide the NVLink store latency; the enrol blocks take their slots as they retire.
   const int64_t e_rows = l_out ? ne : 0;
   const int64_t t_rows = tdst.n > 0 ? nt : 0;
   const int64_t slots = 2ll * ctx.num_sms;
@@ -522,6 +524,8 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   };
   const unsigned eb = side_blocks(e_rows);
   unsigned tb = side_blocks(t_rows);
+  if (tdst.n > 1 && t_rows > 0)
+    tb = static_cast<unsigned>(std::max<int64_t>(tb, std::min<int64_t>(ceil_div(t_rows, 8), ctx.num_sms)));
   // an empty shard still has to raise its ready flag / write the padding of the column-term row
   if (tb == 0 && tdst.n > 0 && (sig.counter != nullptr || test_pad_end > test_row0 + nt)) tb = 1;
   if (eb + tb == 0) return;
