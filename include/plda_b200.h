@@ -179,6 +179,13 @@ int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx
 /* lsqr solver (lda.py:223-251): coef = means cov^-1, cov = pooled class covariance; empirical priors only */
 int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                  const int64_t* labels, const double* priors, int64_t n_priors);
+/* eigen solver (lda.py:140-176): generalised symmetric eigenproblem Sb v = lambda Sw v (scipy eigh(Sb, Sw)),
+ * eigenvectors by descending eigenvalue rescaled to unit 2-norm, coef = means V V^T; empirical priors only.
+ * lda_get_svd then returns rank = d, xbar = 0 and scalings = V (transform is X V, lda.py:345-346);
+ * lda_get_eigenvalues the generalised eigenvalues (descending, floored at 0). */
+int lda_fit_eigen(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                  const int64_t* labels, const double* priors, int64_t n_priors);
+int lda_get_eigenvalues(lda_handle_t h, double* evals, int64_t capacity, int64_t* n);
 /* Sharded fit (SURVEY 8e "LDA fit": rows sharded by class, one d x d all-reduce + one all-gather of class rows).
  * lda_class_stats: statistics of THIS rank's rows -- k local classes, their means / counts / labels (ascending) and the
  * unscaled within-class scatter sum_i (x_i - m_class(i))(x_i - m_class(i))^T; read them with lda_get_class_stats
@@ -188,7 +195,7 @@ int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ld
 int lda_class_stats(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                     const int64_t* labels, int64_t* k);
 int lda_get_class_stats(lda_handle_t h, double* sw, double* means, int64_t* counts, int64_t* classes);
-int lda_fit_from_stats(lda_handle_t h, int solver, int64_t n, int64_t k, int64_t d, const double* sw,
+int lda_fit_from_stats(lda_handle_t h, int solver /* 0 svd, 1 lsqr, 2 eigen */, int64_t n, int64_t k, int64_t d, const double* sw,
                        const double* means, const int64_t* counts, const int64_t* classes, const double* priors,
                        int64_t n_priors);
 /* svd solver state: rank (0 for other solvers), xbar[d], scalings[d*rank] row-major (any pointer may be NULL) */

@@ -66,6 +66,8 @@ SIGNATURES = {
     "lda_synchronize": [_vp],
     "lda_fit_svd": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
     "lda_fit_lsqr": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
+    "lda_fit_eigen": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
+    "lda_get_eigenvalues": [_vp, _vp, _i64, C.POINTER(_i64)],
     "lda_class_stats": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, C.POINTER(_i64)],
     "lda_get_class_stats": [_vp, _vp, _vp, _vp, _vp],
     "lda_fit_from_stats": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64],

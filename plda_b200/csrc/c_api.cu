@@ -4,6 +4,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include "engine.h"
 
 struct plda_handle_s {
@@ -259,6 +261,18 @@ int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx
 int lda_fit_lsqr(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                  const int64_t* labels, const double* priors, int64_t n_priors) {
   return with_handle(h, [&](pb::LdaEngine& e) { e.fit_lsqr(x, n, d, ldx, dtype, loc, labels, priors, n_priors); });
+}
+int lda_fit_eigen(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                  const int64_t* labels, const double* priors, int64_t n_priors) {
+  return with_handle(h, [&](pb::LdaEngine& e) { e.fit_eigen(x, n, d, ldx, dtype, loc, labels, priors, n_priors); });
+}
+int lda_get_eigenvalues(lda_handle_t h, double* evals, int64_t capacity, int64_t* n) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    PB_CHECK(e.ready, pb::kNotFitted, "This LDA instance is not fitted yet");
+    const int64_t m = std::min<int64_t>(capacity, static_cast<int64_t>(e.h_evals.size()));
+    if (evals && m > 0) memcpy(evals, e.h_evals.data(), m * sizeof(double));
+    if (n) *n = static_cast<int64_t>(e.h_evals.size());
+  });
 }
 int lda_class_stats(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                     const int64_t* labels, int64_t* k) {

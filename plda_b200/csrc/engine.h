@@ -161,6 +161,10 @@ class LdaEngine {
   // lda.py:223-251 (_solve_lsqr): coef = means cov^-1 with cov = sum_k priors_k cov_k
   void fit_lsqr(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
                 const double* priors, int64_t n_priors);
+  // lda.py:140-176 (_solve_eigen): generalised symmetric eigenproblem of (Sb, Sw), unit-norm eigenvectors
+  void fit_eigen(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                 const double* priors, int64_t n_priors);
+  std::vector<double> h_evals;              // eigen solver: generalised eigenvalues, descending
   // lda.py:328-349 (transform, svd solver): (X - xbar) scalings[:, :n_components]
   void transform(const void* x, int64_t nt, int64_t d, int64_t ldx, int dtype, int loc, int64_t n_components,
                  float* out, int64_t ldo, int out_loc);
@@ -192,6 +196,8 @@ class LdaEngine {
   void finish_priors(ClassStats& out, const double* priors, int64_t n_priors);
   void solve_svd(const ClassStats& cs);
   void solve_lsqr(const ClassStats& cs);
+  void solve_eigen(const ClassStats& cs);
+  void refresh_transform_operands();
   SplitBuf ws_x;
   DevBuf<float> ws_out[2], ws_lmax, ws_lsum, ws_neglse;
   DevBuf<double> ws_gram;

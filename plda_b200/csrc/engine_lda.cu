@@ -225,7 +225,8 @@ void LdaEngine::fit_from_stats(int solver, int64_t n, int64_t kk, int64_t d_, co
   }
   PB_CHECK(total == n, kInvalidArg, "lda_fit_from_stats: class counts do not add up to n");
   finish_priors(cs, priors_in, n_priors);
-  if (solver == 0) solve_svd(cs); else solve_lsqr(cs);
+  PB_CHECK(solver >= 0 && solver <= 2, kInvalidArg, "lda_fit_from_stats: solver must be 0 (svd), 1 (lsqr) or 2 (eigen)");
+  if (solver == 0) solve_svd(cs); else if (solver == 1) solve_lsqr(cs); else solve_eigen(cs);
 }
 
 void LdaEngine::fit_svd(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
@@ -326,17 +327,23 @@ void LdaEngine::solve_svd(const ClassStats& cs) {
   h_scalings.resize(static_cast<size_t>(d_) * rank2);
   PB_CUDA(cudaMemcpyAsync(h_scalings.data(), dscal2.get(), d_ * rank2 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
-  // B operand of the projection GEMM: scalings^T [rank x d]
-  std::vector<double> st(static_cast<size_t>(rank2) * d_);
+  h_evals.clear();
+  refresh_transform_operands();
+  refresh_operands();
+}
+
+// device copies used by transform(): scalings^T [rank x d] as the B operand of the projection GEMM, xbar
+void LdaEngine::refresh_transform_operands() {
+  const int64_t d_ = d, r_ = rank;
+  std::vector<double> st(static_cast<size_t>(r_) * d_);
   for (int64_t j = 0; j < d_; ++j)
-    for (int64_t r = 0; r < rank2; ++r) st[r * d_ + j] = h_scalings[j * rank2 + r];
-  DevBuf<double> dst(rank2 * d_);
-  PB_CUDA(cudaMemcpyAsync(dst.get(), st.data(), rank2 * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
-  split_rows(ctx, dst.get(), false, rank2, d_, d_, nullptr, nullptr, nullptr, scal_split);
+    for (int64_t r = 0; r < r_; ++r) st[r * d_ + j] = h_scalings[j * r_ + r];
+  DevBuf<double> dst(r_ * d_);
+  PB_CUDA(cudaMemcpyAsync(dst.get(), st.data(), r_ * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  split_rows(ctx, dst.get(), false, r_, d_, d_, nullptr, nullptr, nullptr, scal_split);
   xbar_dev.reserve(d_);
   PB_CUDA(cudaMemcpyAsync(xbar_dev.get(), h_xbar.data(), d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   ctx.sync();
-  refresh_operands();
 }
 
 void LdaEngine::fit_lsqr(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
@@ -386,9 +393,94 @@ void LdaEngine::solve_lsqr(const ClassStats& cs) {
   refresh_operands();
 }
 
+void LdaEngine::fit_eigen(const void* x, int64_t n, int64_t d_, int64_t ldx, int dtype, int loc, const int64_t* labels,
+                          const double* priors_in, int64_t n_priors) {
+  ClassStats cs;
+  class_stats(x, n, d_, ldx, dtype, loc, labels, priors_in, n_priors, cs, false);
+  solve_eigen(cs);
+}
+
+// lda.py:140-176 (_solve_eigen): Sw = sum_k p_k cov_k, St = cov(X), Sb = St - Sw, generalised symmetric
+// eigenproblem Sb v = lambda Sw v (scipy eigh(Sb, Sw)), eigenvectors sorted by descending eigenvalue and rescaled
+// to unit 2-norm, coef = means V V^T, intercept = -1/2 diag(means coef^T) + log priors.
+// eigh(Sb, Sw) is done the way PLDA's GetOutput does it: Sw = C C^T, T1 = C^-1,
+// B' = T1 Sb T1^T = U diag(lambda) U^T, V = T1^T U  (so V^T Sw V = I, what LAPACK's dsygvd returns).
+// With empirical priors p_k = n_k/n:  Sw = S/n (S = pooled within scatter) and Sb = sum_k p_k (m_k - xbar)(.)^T.
+// When K - 1 < d the eigenvalue 0 is degenerate and the basis of its eigenspace is arbitrary (for LAPACK too);
+// that part of V V^T only moves every decision value of a sample by the same amount, so probabilities and
+// predictions do not depend on it, raw coef / decision values do.
+void LdaEngine::solve_eigen(const ClassStats& cs) {
+  const int64_t kk = cs.k, n = cs.n, d_ = cs.d;
+  const size_t dd = static_cast<size_t>(d_) * d_;
+  bool empirical = true;
+  for (int64_t c = 0; c < kk; ++c)
+    if (std::fabs(cs.priors[c] - static_cast<double>(cs.counts[c]) / static_cast<double>(n)) > 1e-12) empirical = false;
+  PB_CHECK(empirical, kInvalidArg, "lda eigen: only empirical priors (priors=None) are supported on the device path");
+  std::vector<double> sw(dd), xbar(d_, 0.0), mcw(static_cast<size_t>(kk) * d_);
+  for (size_t i = 0; i < dd; ++i) sw[i] = cs.sw[i] / static_cast<double>(n);
+  for (int64_t c = 0; c < kk; ++c)
+    for (int64_t j = 0; j < d_; ++j) xbar[j] += cs.priors[c] * cs.means[c * d_ + j];
+  for (int64_t c = 0; c < kk; ++c) {
+    const double w = std::sqrt(cs.priors[c]);
+    for (int64_t j = 0; j < d_; ++j) mcw[c * d_ + j] = w * (cs.means[c * d_ + j] - xbar[j]);
+  }
+  DevBuf<double> dsw(dd), dt1(dd), dsb(dd), dtmp(dd), dbp(dd), dut(dd), dvt(dd), dlam(d_);
+  DevBuf<double> dmcw(kk * d_), dmeans(kk * d_), dproj(kk * d_), dcoef(kk * d_);
+  DevBuf<int> info(1);
+  EigWork ew;
+  PB_CUDA(cudaMemcpyAsync(dsw.get(), sw.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(dmcw.get(), mcw.data(), kk * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(dmeans.get(), cs.means.data(), kk * d_ * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  gemm_f64(ctx, true, false, d_, d_, kk, 1.0, dmcw.get(), d_, dmcw.get(), d_, 0.0, dsb.get(), d_);       // Sb
+  cholesky_lower(ctx, dsw.get(), d_, info.get());                                                         // C
+  tri_inverse_lower(ctx, dsw.get(), dt1.get(), d_);                                                       // T1
+  gemm_f64(ctx, false, false, d_, d_, d_, 1.0, dt1.get(), d_, dsb.get(), d_, 0.0, dtmp.get(), d_);        // T1 Sb
+  gemm_f64(ctx, false, true, d_, d_, d_, 1.0, dtmp.get(), d_, dt1.get(), d_, 0.0, dbp.get(), d_);         // (.) T1^T
+  eig_sym_jacobi(ctx, dbp.get(), d_, nullptr, dlam.get(), dut.get(), ew, nullptr);     // rows of dut: eigenvectors
+  gemm_f64(ctx, false, false, d_, d_, d_, 1.0, dut.get(), d_, dt1.get(), d_, 0.0, dvt.get(), d_);         // V^T = U^T T1
+  int h_info = 0;
+  std::vector<double> vt(dd), lam(d_);
+  PB_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(vt.data(), dvt.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(lam.data(), dlam.get(), d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  PB_CHECK(h_info == 0, kValueError, "lda eigen: the pooled class covariance is singular (need more samples than dims)");
+  // unit 2-norm eigenvectors (lda.py:171); scalings[:, r] = r-th vector
+  for (int64_t r = 0; r < d_; ++r) {
+    double nrm = 0.0;
+    for (int64_t j = 0; j < d_; ++j) nrm += vt[r * d_ + j] * vt[r * d_ + j];
+    nrm = std::sqrt(nrm);
+    for (int64_t j = 0; j < d_; ++j) vt[r * d_ + j] /= nrm;
+  }
+  PB_CUDA(cudaMemcpyAsync(dvt.get(), vt.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  gemm_f64(ctx, false, true, kk, d_, d_, 1.0, dmeans.get(), d_, dvt.get(), d_, 0.0, dproj.get(), d_);     // means V
+  gemm_f64(ctx, false, false, kk, d_, d_, 1.0, dproj.get(), d_, dvt.get(), d_, 0.0, dcoef.get(), d_);     // (.) V^T
+  h_coef.resize(static_cast<size_t>(kk) * d_);
+  PB_CUDA(cudaMemcpyAsync(h_coef.data(), dcoef.get(), kk * d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  h_intercept.resize(kk);
+  h_classes = cs.classes;
+  for (int64_t c = 0; c < kk; ++c) {
+    double dot = 0.0;
+    for (int64_t j = 0; j < d_; ++j) dot += cs.means[c * d_ + j] * h_coef[c * d_ + j];
+    h_intercept[c] = -0.5 * dot + std::log(cs.priors[c]);
+  }
+  // transform for this solver is X scalings (no centring, lda.py:345-346)
+  h_scalings.assign(dd, 0.0);
+  for (int64_t r = 0; r < d_; ++r)
+    for (int64_t j = 0; j < d_; ++j) h_scalings[j * d_ + r] = vt[r * d_ + j];
+  h_xbar.assign(d_, 0.0);
+  h_evals = lam;
+  k = kk;
+  d = d_;
+  rank = d_;
+  refresh_operands();
+  refresh_transform_operands();
+}
+
 void LdaEngine::transform(const void* x, int64_t nt, int64_t d_, int64_t ldx, int dtype, int loc, int64_t n_components,
                           float* out, int64_t ldo, int out_loc) {
-  PB_CHECK(ready && rank > 0, kNotFitted, "transform needs a model fitted with the 'svd' solver");
+  PB_CHECK(ready && rank > 0, kNotFitted, "transform needs a model fitted with the 'svd' or 'eigen' solver");
   PB_CHECK(d_ == d, kValueError, "X has a different number of features than the model");
   PB_CHECK(n_components > 0 && n_components <= rank && ldo >= n_components, kInvalidArg, "transform: bad n_components");
   if (nt == 0) return;

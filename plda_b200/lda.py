@@ -6,9 +6,11 @@ Hot-path rows of SURVEY.md section 8 implemented here: ``fit`` with the default 
 solver (``lda.py:178-221``), ``decision_function`` (``:253-279``) and
 ``predict_log_proba`` (``:306-325``).  Section 8f "next" rows built on the same kernels: the
 ``lsqr`` solver (``:223-251``), ``predict_proba`` (``:281-304``) and ``transform`` (``:328-349``,
-evident intent -- the reference's svd branch is unreachable).  The ``eigen`` solver is not
-offered (its result depends on LAPACK's arbitrary null-space basis whenever K - 1 < d) and
-raises NotImplementedError -- there is no CPU fallback.
+evident intent -- the reference's svd branch is unreachable) and the ``eigen`` solver (``:140-176``).
+For ``eigen`` with K - 1 < d the generalised eigenvalue 0 is degenerate and the basis of its eigenspace is
+arbitrary (LAPACK's choice in the reference, the Jacobi solver's here): that part only moves all decision
+values of a sample by one common amount, so ``predict`` / ``predict_proba`` / ``predict_log_proba`` agree
+with the reference, raw ``coef`` / ``decision_function`` only when K > d.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -17,6 +19,8 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi
+
+_SOLVERS = {"svd": 0, "lsqr": 1, "eigen": 2}
 
 
 class LDA(object):
@@ -52,18 +56,16 @@ class LDA(object):
     # ------------------------------------------------------------------ fit
     def fit(self, features, labels):
         """``LDA.fit`` (``lda.py:106-138``).  Returns None."""
-        if self.solver not in ("svd", "lsqr"):
-            # 'eigen' (lda.py:140-176) normalises generalised eigenvectors column-wise, which makes coef depend on
-            # the arbitrary basis LAPACK picks inside the (d - K + 1)-dimensional null space of Sb whenever
-            # K - 1 < d: the reference's own result is not reproducible by construction, so it is not offered.
-            raise NotImplementedError("solver %r is not available on the device path; use 'svd' or 'lsqr'"
-                                      % (self.solver,))
+        if self.solver not in _SOLVERS:
+            # the reference silently fits nothing for an unknown solver (lda.py:131-138) and fails later
+            raise ValueError("unknown solver %r (expected 'svd', 'lsqr' or 'eigen')" % (self.solver,))
         x, dtype, y = self._check_xy(features, labels)
         n, d = x.shape
         pri = None
         if self.priors is not None:
             pri = np.ascontiguousarray(self.priors, dtype=np.float64)
-        fit_fn = self._lib.lda_fit_svd if self.solver == "svd" else self._lib.lda_fit_lsqr
+        fit_fn = {"svd": self._lib.lda_fit_svd, "lsqr": self._lib.lda_fit_lsqr,
+                  "eigen": self._lib.lda_fit_eigen}[self.solver]
         _ffi.check(fit_fn(self._h, _ffi.ptr(x), n, d, d, dtype, _ffi.HOST, _ffi.ptr(y), _ffi.ptr(pri),
                           0 if pri is None else pri.shape[0]))
         _, cnt = np.unique(y, return_counts=True)
@@ -93,7 +95,13 @@ class LDA(object):
         _ffi.check(self._lib.lda_get_coef(self._h, _ffi.ptr(self._coef), _ffi.ptr(self._intercept),
                                           _ffi.ptr(self._classes)))
         self._xbar = self._scalings = None
-        if self.solver == "svd":
+        self.explained_variance_ratio_ = None
+        if self.solver == "eigen":
+            ev = np.empty(dd.value)
+            nev = C.c_int64()
+            _ffi.check(self._lib.lda_get_eigenvalues(self._h, _ffi.ptr(ev), dd.value, C.byref(nev)))
+            self.explained_variance_ratio_ = np.sort(ev / np.sum(ev))[::-1]        # lda.py:167
+        if self.solver in ("svd", "eigen"):
             rank = C.c_int64()
             _ffi.check(self._lib.lda_get_svd(self._h, C.byref(rank), None, None))
             self._xbar = np.empty(dd.value)
@@ -112,9 +120,8 @@ class LDA(object):
         ``d x d`` scatter and ONE all-gather of the per-class rows (``plda_b200.dist.merge_class_stats``); the small
         solver runs replicated on every rank, so all ranks end with identical coefficients."""
         from . import dist as _dist
-        if self.solver not in ("svd", "lsqr"):
-            raise NotImplementedError("solver %r is not available on the device path; use 'svd' or 'lsqr'"
-                                      % (self.solver,))
+        if self.solver not in _SOLVERS:
+            raise ValueError("unknown solver %r (expected 'svd', 'lsqr' or 'eigen')" % (self.solver,))
         sw, means, counts, classes = self.local_class_stats(features, labels)
         sw, means, counts, classes = _dist.merge_class_stats(sw, means, counts, classes, group)
         self.fit_from_stats(sw, means, counts, classes)
@@ -146,7 +153,7 @@ class LDA(object):
         pri = None
         if self.priors is not None:
             pri = np.ascontiguousarray(self.priors, dtype=np.float64)
-        _ffi.check(self._lib.lda_fit_from_stats(self._h, 0 if self.solver == "svd" else 1, n, kk, d, _ffi.ptr(sw),
+        _ffi.check(self._lib.lda_fit_from_stats(self._h, _SOLVERS[self.solver], n, kk, d, _ffi.ptr(sw),
                                                 _ffi.ptr(means), _ffi.ptr(counts), _ffi.ptr(classes), _ffi.ptr(pri),
                                                 0 if pri is None else pri.shape[0]))
         self._read_back(counts, n)
@@ -208,8 +215,9 @@ class LDA(object):
         return prob
 
     def transform(self, X, n_components=None):
-        """``transform`` (``lda.py:328-349``) for the svd solver: ``(X - xbar) @ scalings[:, :n_components]``
-        (the reference's svd branch is unreachable -- SURVEY App. B -- this is its evident intent)."""
+        """``transform`` (``lda.py:328-349``): svd solver ``(X - xbar) @ scalings[:, :n_components]`` (the
+        reference's svd branch is unreachable -- SURVEY App. B -- this is its evident intent); eigen solver
+        ``X @ scalings[:, :n_components]`` (the handle keeps ``xbar = 0`` for it)."""
         if self.solver == "lsqr":
             raise NotImplementedError("transform not implemented for 'lsqr' solver (use 'svd' or 'eigen').")
         if self._coef is None:

@@ -53,6 +53,24 @@ def make_lda():
     np.savez_compressed(os.path.join(HERE, "lda_pytest_shapes.npz"), **out)
 
 
+def make_lda_eigen_full():
+    """eigen solver with MORE classes than dimensions (K - 1 >= d): every generalised eigenvalue is simple, so the
+    reference's coef / intercept / decision values are reproducible and can pin an independent eigensolver."""
+    ref = ref_lda.load()
+    rng = np.random.RandomState(13)
+    n, d, k, nt = 1500, 6, 15, 50
+    centers = rng.randn(k, d) * 1.2
+    y = np.arange(n) % k
+    x = centers[y] + rng.randn(n, d)
+    xt = centers[np.arange(nt) % k] + rng.randn(nt, d)
+    m = ref.LDA(solver="eigen")
+    m.fit(x, y)
+    np.savez_compressed(os.path.join(HERE, "lda_eigen_full.npz"), x=x, y=y, xt=xt, coef=m._coef,
+                        intercept=m._intercept, priors=m.priors, scalings=m._scalings,
+                        explained_variance_ratio=m.explained_variance_ratio_, decision=m.decision_function(xt),
+                        log_proba=m.predict_log_proba(xt), proba=m.predict_proba(xt), transform=m.transform(xt))
+
+
 def make_plda():
     d = 24
     a_b = kp.two_cov_generator(d, seed=1234)
@@ -81,6 +99,10 @@ def make_plda():
 
 
 if __name__ == "__main__":
+    if "--only-eigen-full" in sys.argv:
+        make_lda_eigen_full()
+        sys.exit(0)
     make_lda()
+    make_lda_eigen_full()
     make_plda()
     print("golden fixtures written to", HERE)

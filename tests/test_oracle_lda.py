@@ -22,6 +22,16 @@ def test_port_matches_reference_fixture(golden_dir, solver):
     assert np.all(g["log_proba"] <= 0)     # the only assertion the reference makes (tests/ldatest.py:18-20)
 
 
+def test_port_matches_reference_fixture_eigen_full(golden_dir):
+    """eigen solver with K - 1 >= d (no degenerate eigenspace): coef is reproducible."""
+    g = np.load(os.path.join(golden_dir, "lda_eigen_full.npz"))
+    m = LDAOracle(solver="eigen")
+    m.fit(g["x"], g["y"])
+    assert np.allclose(m._coef, g["coef"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(m.predict_log_proba(g["xt"]), g["log_proba"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(m.transform(g["xt"]), g["transform"], rtol=1e-9, atol=1e-11)
+
+
 def test_pytest_shapes_fixture(golden_dir):
     """python/test.py shapes: 100x10, 2 and 3 classes."""
     g = np.load(os.path.join(golden_dir, "lda_pytest_shapes.npz"))
