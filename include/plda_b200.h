@@ -166,6 +166,19 @@ int plda_shard_step(plda_handle_t h, const void* test_shard, int64_t nt_local, i
 int plda_shard_status(plda_handle_t h, int64_t* epoch, int64_t* timeouts);
 int plda_shard_close(plda_handle_t h);
 
+/* ---- d-vector pooling: replaces scoring/extractdvector.py:19-58 for a batch of utterances ------------- *
+ * frames [n_frames x d]: frame-level activations of ALL utterances, utterance u = rows [offsets[u], offsets[u+1])
+ * (offsets: HOST int64 [n_utts+1], ascending; every utterance needs >= 1 frame).  l2norm != 0: each frame is divided
+ * by its L2 norm first (getnormalizedvector, :19-29).  mode: mean (extractdvectormean :37-39), max
+ * (extractdvectormax :32-34), population variance (extractdvectorvar :42-46); l2norm = 0 gives the *_nol2 variants
+ * (:49-58).  out: fp64 [n_utts x d].  Needs no fitted model (any plda handle provides the device and stream). */
+#define PLDA_POOL_MEAN 0
+#define PLDA_POOL_MAX 1
+#define PLDA_POOL_VAR 2
+int plda_dvector_pool(plda_handle_t h, const void* frames, int64_t n_frames, int64_t d, int64_t ld, int dtype, int loc,
+                      const int64_t* offsets, int64_t n_utts, int mode, int l2norm, double* out, int64_t ldo,
+                      int out_loc);
+
 /* ---- LDA: replaces python/liblda/lda.py (LDA.fit svd :178-221, decision_function :253-279,
  *      predict_log_proba :306-325) ---------------------------------------------------------- */
 int lda_create(int device, lda_handle_t* out);

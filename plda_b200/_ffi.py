@@ -59,6 +59,7 @@ SIGNATURES = {
     "plda_shard_step": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _i64],
     "plda_shard_status": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "plda_shard_close": [_vp],
+    "plda_dvector_pool": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _int, _int, _vp, _i64, _int],
     "lda_create": [_int, C.POINTER(_vp)],
     "lda_destroy": [_vp],
     "lda_set_precision": [_vp, _int],

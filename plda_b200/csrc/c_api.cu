@@ -235,6 +235,39 @@ int plda_shard_close(plda_handle_t h) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.shard_close(); });
 }
 
+int plda_dvector_pool(plda_handle_t h, const void* frames, int64_t n_frames, int64_t d, int64_t ld, int dtype, int loc,
+                      const int64_t* offsets, int64_t n_utts, int mode, int l2norm, double* out, int64_t ldo,
+                      int out_loc) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(dtype == PLDA_F64 || dtype == PLDA_F32, pb::kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+    PB_CHECK((loc == 0 || loc == 1) && (out_loc == 0 || out_loc == 1), pb::kInvalidArg, "bad loc");
+    PB_CHECK(n_frames >= 0 && (frames != nullptr || n_frames == 0) && (out != nullptr || n_utts == 0), pb::kInvalidArg,
+             "dvector_pool: null pointer");
+    PB_CHECK(ld >= d && ldo >= d, pb::kInvalidArg, "dvector_pool: pitch smaller than the dimension");
+    if (n_utts == 0) return;
+    const size_t es = dtype == PLDA_F32 ? 4 : 8;
+    pb::DevBuf<uint8_t> stage;
+    const void* fd = frames;
+    int64_t ldf = ld;
+    if (loc == PLDA_HOST) {
+      stage.alloc(static_cast<size_t>(n_frames > 0 ? n_frames : 1) * d * es);
+      if (n_frames > 0)
+        PB_CUDA(cudaMemcpy2DAsync(stage.get(), d * es, frames, ld * es, d * es, n_frames, cudaMemcpyHostToDevice, e.ctx.stream));
+      fd = stage.get();
+      ldf = d;
+    }
+    if (out_loc == PLDA_DEVICE) {
+      pb::dvector_pool(e.ctx, fd, dtype == PLDA_F32, n_frames, d, ldf, offsets, n_utts, mode, l2norm != 0, out, ldo);
+      return;
+    }
+    pb::DevBuf<double> dout(static_cast<size_t>(n_utts) * d);
+    pb::dvector_pool(e.ctx, fd, dtype == PLDA_F32, n_frames, d, ldf, offsets, n_utts, mode, l2norm != 0, dout.get(), d);
+    PB_CUDA(cudaMemcpy2DAsync(out, ldo * sizeof(double), dout.get(), d * sizeof(double), d * sizeof(double), n_utts,
+                              cudaMemcpyDeviceToHost, e.ctx.stream));
+    e.ctx.sync();
+  });
+}
+
 int lda_create(int device, lda_handle_t* out) {
   if (out == nullptr) { g_last_error = "null output pointer"; return PLDA_E_INVALID; }
   *out = nullptr;

@@ -135,6 +135,13 @@ struct EigWork {
 void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t, double* evals, double* evecs_t,
                     EigWork& work, int* sweeps_out);
 
+// ---- d-vector pooling (scoring/extractdvector.py:19-58) ------------------------------------ //
+// frames [n_frames x d] (device), utterance u = frames [offsets[u], offsets[u+1]) (host CSR offsets);
+// out[u, :] = mean / max / population variance (mode 0 / 1 / 2) over the utterance's frames, each frame divided by
+// its L2 norm first when l2norm.  out is a device fp64 matrix.  Synchronises.
+void dvector_pool(Context& ctx, const void* frames, bool is_f32, int64_t n_frames, int64_t d, int64_t ld,
+                  const int64_t* offsets_host, int64_t n_utts, int mode, bool l2norm, double* out_dev, int64_t ldo);
+
 // ---- LDA ----------------------------------------------------------------------------- //
 // log-softmax finalisation: lse[m] from per-tile (max,sum) partials
 void lse_combine(Context& ctx, const float* lmax, const float* lsum, int64_t m, int n_tiles, float* neg_lse);

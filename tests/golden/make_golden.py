@@ -71,6 +71,31 @@ def make_lda_eigen_full():
                         log_proba=m.predict_log_proba(xt), proba=m.predict_proba(xt), transform=m.transform(xt))
 
 
+def reference_dvector_functions():
+    """The reference's own pooling functions: lines 19-58 of scoring/extractdvector.py executed as they are (the
+    module itself cannot be imported under Python 3: cPickle, htkfeature)."""
+    path = "/root/reference/scoring/extractdvector.py"
+    with open(path) as f:
+        lines = f.readlines()
+    ns = {"np": np}
+    exec(compile("".join(lines[18:58]), path, "exec"), ns)
+    return ns
+
+
+def make_dvector():
+    ns = reference_dvector_functions()
+    rng = np.random.RandomState(17)
+    d = 40
+    lens = [1, 7, 33, 64, 5, 130, 2]
+    utts = [rng.randn(n, d) * rng.uniform(0.5, 3.0) + rng.uniform(-1, 1) for n in lens]
+    out = dict(frames=np.concatenate(utts), offsets=np.concatenate([[0], np.cumsum(lens)]))
+    for name in ("extractdvectormean", "extractdvectormax", "extractdvectorvar", "extractdvectormean_nol2",
+                 "extractdvectorvar_nol2", "extractdvectormax_nol2"):
+        out[name] = np.stack([np.asarray(ns[name](u)).reshape(-1) for u in utts])
+    out["shape_nol2"] = np.array(np.asarray(ns["extractdvectormean_nol2"](utts[2])).shape)
+    np.savez_compressed(os.path.join(HERE, "dvector_pool.npz"), **out)
+
+
 def make_plda():
     d = 24
     a_b = kp.two_cov_generator(d, seed=1234)
@@ -102,7 +127,11 @@ if __name__ == "__main__":
     if "--only-eigen-full" in sys.argv:
         make_lda_eigen_full()
         sys.exit(0)
+    if "--only-dvector" in sys.argv:
+        make_dvector()
+        sys.exit(0)
     make_lda()
     make_lda_eigen_full()
+    make_dvector()
     make_plda()
     print("golden fixtures written to", HERE)
