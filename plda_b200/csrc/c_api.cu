@@ -328,7 +328,7 @@ int lda_fit_from_stats(lda_handle_t h, int solver, int64_t n, int64_t k, int64_t
                        const double* means, const int64_t* counts, const int64_t* classes, const double* priors,
                        int64_t n_priors) {
   return with_handle(h, [&](pb::LdaEngine& e) {
-    PB_CHECK(solver == 0 || solver == 1, pb::kInvalidArg, "lda_fit_from_stats: solver must be 0 (svd) or 1 (lsqr)");
+    PB_CHECK(solver >= 0 && solver <= 2, pb::kInvalidArg, "lda_fit_from_stats: solver must be 0 (svd), 1 (lsqr) or 2 (eigen)");
     e.fit_from_stats(solver, n, k, d, sw, means, counts, classes, priors, n_priors);
   });
 }

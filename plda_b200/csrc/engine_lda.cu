@@ -436,15 +436,28 @@ void LdaEngine::solve_eigen(const ClassStats& cs) {
   tri_inverse_lower(ctx, dsw.get(), dt1.get(), d_);                                                       // T1
   gemm_f64(ctx, false, false, d_, d_, d_, 1.0, dt1.get(), d_, dsb.get(), d_, 0.0, dtmp.get(), d_);        // T1 Sb
   gemm_f64(ctx, false, true, d_, d_, d_, 1.0, dtmp.get(), d_, dt1.get(), d_, 0.0, dbp.get(), d_);         // (.) T1^T
+  // The Jacobi solver recovers eigenvectors as normalised columns of B'V, which is noise for an eigenvalue 0 -- and
+  // B' has d - K + 1 of them when K - 1 < d.  Solve the shifted problem B' + sigma I (sigma = mean eigenvalue): same
+  // eigenvectors, all eigenvalues >= sigma > 0, the null space becomes an ordinary degenerate eigenspace.
+  std::vector<double> hbp(dd);
+  int h_info = 0;
+  PB_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(hbp.data(), dbp.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  ctx.sync();
+  PB_CHECK(h_info == 0, kValueError, "lda eigen: the pooled class covariance is singular (need more samples than dims)");
+  double sigma = 0.0;
+  for (int64_t i = 0; i < d_; ++i) sigma += hbp[i * d_ + i];
+  sigma = sigma / static_cast<double>(d_);
+  PB_CHECK(sigma > 0.0 && std::isfinite(sigma), kValueError, "lda eigen: the class means coincide (between scatter is zero)");
+  for (int64_t i = 0; i < d_; ++i) hbp[i * d_ + i] += sigma;
+  PB_CUDA(cudaMemcpyAsync(dbp.get(), hbp.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
   eig_sym_jacobi(ctx, dbp.get(), d_, nullptr, dlam.get(), dut.get(), ew, nullptr);     // rows of dut: eigenvectors
   gemm_f64(ctx, false, false, d_, d_, d_, 1.0, dut.get(), d_, dt1.get(), d_, 0.0, dvt.get(), d_);         // V^T = U^T T1
-  int h_info = 0;
   std::vector<double> vt(dd), lam(d_);
-  PB_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
   PB_CUDA(cudaMemcpyAsync(vt.data(), dvt.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   PB_CUDA(cudaMemcpyAsync(lam.data(), dlam.get(), d_ * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
-  PB_CHECK(h_info == 0, kValueError, "lda eigen: the pooled class covariance is singular (need more samples than dims)");
+  for (int64_t i = 0; i < d_; ++i) lam[i] = std::max(lam[i] - sigma, 0.0);
   // unit 2-norm eigenvectors (lda.py:171); scalings[:, r] = r-th vector
   for (int64_t r = 0; r < d_; ++r) {
     double nrm = 0.0;

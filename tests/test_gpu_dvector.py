@@ -2,7 +2,7 @@
 functions -- through the fixture they generated -- and against the CPU restatement on seeded inputs, including the
 shapes the reference's per-utterance functions return, ragged / single-frame / long (chunked) utterances, fp32 input
 and device-resident input.  Tolerance: fp64 arithmetic on both sides, different summation order -> 1e-12 relative
-(fp32 input: the reference normalises in fp32, the kernel in fp64 -> 2e-6)."""
+(fp32 input: the reference normalises in fp32, the kernel in fp64 -> 1e-5)."""
 import os
 
 import numpy as np
@@ -61,7 +61,7 @@ def test_float32_and_device_resident_input():
     want = dp.pool(frames.astype(np.float64), offsets, "mean", True)
     got_host = dv.pool_dvectors(frames, offsets, "mean", True)
     assert rel(got_host, want) <= 1e-12                       # fp32 values, fp64 arithmetic
-    assert rel(got_host, dp.pool(frames, offsets, "mean", True)) <= 2e-6   # the reference's fp32 arithmetic
+    assert rel(got_host, dp.pool(frames, offsets, "mean", True)) <= 1e-5   # the reference's fp32 arithmetic
     got_dev = dv.pool_dvectors(torch.from_numpy(frames).cuda(), offsets, "mean", True)
     assert got_dev.is_cuda and np.array_equal(got_dev.cpu().numpy(), got_host)
     # a view with a row pitch (every other column block of a wider matrix)
