@@ -407,8 +407,8 @@ void LdaEngine::fit_eigen(const void* x, int64_t n, int64_t d_, int64_t ldx, int
 // B' = T1 Sb T1^T = U diag(lambda) U^T, V = T1^T U  (so V^T Sw V = I, what LAPACK's dsygvd returns).
 // With empirical priors p_k = n_k/n:  Sw = S/n (S = pooled within scatter) and Sb = sum_k p_k (m_k - xbar)(.)^T.
 // When K - 1 < d the eigenvalue 0 is degenerate and the basis of its eigenspace is arbitrary (for LAPACK too);
-// that part of V V^T only moves every decision value of a sample by the same amount, so probabilities and
-// predictions do not depend on it, raw coef / decision values do.
+// that part of V V^T only moves every decision value of a sample by the same amount, so the log-softmax and the
+// predictions do not depend on it, raw coef / decision values (and the sigmoid-based predict_proba) do.
 void LdaEngine::solve_eigen(const ClassStats& cs) {
   const int64_t kk = cs.k, n = cs.n, d_ = cs.d;
   const size_t dd = static_cast<size_t>(d_) * d_;

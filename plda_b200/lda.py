@@ -9,8 +9,9 @@ solver (``lda.py:178-221``), ``decision_function`` (``:253-279``) and
 evident intent -- the reference's svd branch is unreachable) and the ``eigen`` solver (``:140-176``).
 For ``eigen`` with K - 1 < d the generalised eigenvalue 0 is degenerate and the basis of its eigenspace is
 arbitrary (LAPACK's choice in the reference, the Jacobi solver's here): that part only moves all decision
-values of a sample by one common amount, so ``predict`` / ``predict_proba`` / ``predict_log_proba`` agree
-with the reference, raw ``coef`` / ``decision_function`` only when K > d.  There is no CPU fallback.
+values of a sample by one common amount, so ``predict`` / ``predict_log_proba`` agree with the reference,
+raw ``coef`` / ``decision_function`` / ``predict_proba`` (a sigmoid of the raw values) only when K > d.
+There is no CPU fallback.
 """
 from __future__ import annotations
 
