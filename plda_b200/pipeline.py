@@ -1,4 +1,5 @@
-"""Trial-list scoring pipeline -- py3 port of the CALLER of the hot path, ``scoring/scorePLDA.py``.
+"""Trial-list scoring pipelines -- py3 ports of the CALLERS of the hot path, ``scoring/scorePLDA.py`` and
+``scoring/scoreLDA.py``.
 
 The reference parses a trial list, enumerates string labels to ``uint`` (``scorePLDA.py:243-255``), runs
 ``fit -> transform x2 -> [norm]`` (``:258-298``) and then scores every listed trial with one ``plda.score`` call in a
@@ -87,4 +88,41 @@ def score_trials(plda, bkg_vectors, bkg_labels: Sequence[str], enrol_vectors, en
                 continue
             score = float(grid[ei, t_pos[test_tab[testutt]]])
             lines.append("{} {}-{} {:.3f}\n".format(enrolmodel, targetmdl, testutt, score))
+    return lines, errors
+
+
+def score_trials_lda(lda, dvectors, labels: Sequence[str], test_vectors: Dict[str, np.ndarray],
+                     trials: Dict[str, Iterable[Sequence[str]]], fit: bool = True) -> Tuple[List[str], int]:
+    """The body of ``scoreLDA.main`` (``scoring/scoreLDA.py:212-246``): enumerate the speaker labels in ``np.unique``
+    order (``:212-214``), ``lda.fit`` (``:223``), then for every listed trial the log-probability of the ENROL model's
+    class for the test utterance (``:237-243``).  The reference calls ``predict_log_proba`` once per trial on a
+    1 x d matrix; here every distinct test utterance goes through ONE device call and the trials are gathered.
+
+    ``test_vectors``: ``{testutt: d-vector}`` (``testtofeature``, ``:205``); ``trials`` as produced by
+    ``parse_test_ref`` / ``parse_mlf``.  Returns (output lines ``"{model} {target}-{utt} {score:.3f}\n"``, errors).
+    """
+    uniq = np.unique(np.asarray(labels))
+    spktonum = {str(s): i for i, s in enumerate(uniq)}
+    if fit:
+        lda.fit(np.asarray(dvectors), np.array([spktonum[str(s)] for s in labels]))
+    wanted, errors = [], 0
+    for enrolmodel, vals in trials.items():
+        if enrolmodel not in spktonum:
+            errors += 1
+            continue
+        for testutt, targetmdl in vals:
+            if testutt not in test_vectors:
+                errors += 1
+                continue
+            wanted.append((enrolmodel, targetmdl, testutt))
+    utts = sorted({w[2] for w in wanted})
+    lines: List[str] = []
+    if not utts:
+        return lines, errors
+    pos = {u: i for i, u in enumerate(utts)}
+    x = np.stack([np.asarray(test_vectors[u], dtype=np.float64).reshape(-1) for u in utts])
+    logp = np.asarray(lda.predict_log_proba(x))
+    for enrolmodel, targetmdl, testutt in wanted:
+        lines.append("{} {}-{} {:.3f}\n".format(enrolmodel, targetmdl, testutt,
+                                                float(logp[pos[testutt], spktonum[enrolmodel]])))
     return lines, errors

@@ -61,3 +61,30 @@ def test_pipeline_equals_per_trial_loop():
         target, utt = rest.split("-", 1)
         want = ref.score(etab[model], te[etab[model]], tt[ttab[utt]])
         assert abs(float(score) - want) <= 2e-3 * max(1.0, abs(want)) + 5e-4     # "{:.3f}" rounding
+
+
+@pytest.mark.gpu
+def test_lda_pipeline_equals_per_trial_loop():
+    """scoreLDA.main (scoring/scoreLDA.py:212-246) per trial through the LDA oracle == one batched device call."""
+    from oracle.lda_port import LDAOracle
+    from plda_b200 import LDA
+    rng = np.random.RandomState(4)
+    k, d, per = 7, 16, 30
+    centers = rng.randn(k, d) * 1.5
+    names = ["spk%c" % c for c in "gcafbed"]                                # not in sorted order on purpose
+    labels = [names[i % k] for i in range(k * per)]
+    x = np.stack([centers[i % k] for i in range(k * per)]) + rng.randn(k * per, d)
+    tests = {"utt%02d" % i: centers[i % k] + rng.randn(d) for i in range(12)}
+    trials = {n: [["utt%02d" % i, names[i % k]] for i in range(12)] for n in names}
+    trials["ghost"] = [["utt00", names[0]]]
+    trials[names[0]].append(["missing", names[0]])
+    lines, errors = pipeline.score_trials_lda(LDA(solver="svd", precision="fp64"), x, labels, tests, trials)
+    assert errors == 2 and len(lines) == k * 12
+    ref = LDAOracle(solver="svd")
+    uniq = list(np.unique(labels))
+    ref.fit(x, np.array([uniq.index(l) for l in labels]))
+    for line in lines:
+        model, rest, score = line.split()
+        target, utt = rest.split("-", 1)
+        want = ref.predict_log_proba(tests[utt][np.newaxis, :])[0][uniq.index(model)]      # scoreLDA.py:239-243
+        assert abs(float(score) - want) <= 1e-3 * max(1.0, abs(want)) + 5e-4                # "{:.3f}" rounding
