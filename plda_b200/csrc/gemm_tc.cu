@@ -68,6 +68,7 @@ struct GemmParams {
   int direct_store;   // 3 TMA store via swizzled smem staging (default), 0 coalesced LSU stores, 1 register stores, 2 none
   int tail_cols;      // K columns of the last k-block when it uses a narrow box (16 -> 32B swizzle, 32 -> 64B), else 0
   long long* dbg;     // optional stall counters of CTA 0/1 (env PLDA_B200_DBG=1): see plda_debug_counters
+  int dbg_skip_a;     // timing experiment only (see Context::dbg_skip_a)
   int n_rot;          // column tiles are visited starting at this one (sharded B: the rank's own rows first)
   GemmEpilogue epi;
   GemmShard shard;    // flags == nullptr: B is complete before the launch
@@ -141,6 +142,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   constexpr bool FAST = EPI == 1;
   constexpr bool LSE = EPI == 2;
+  constexpr bool SECT = EPI == 3;   // score-grid path, accumulators stored straight from registers (no smem staging)
   constexpr int kStages = Cfg<TWO>::kStages;
   constexpr int kStageBytes = Cfg<TWO>::kStageBytes;
   constexpr int kBBytes = Cfg<TWO>::kBBytes;
@@ -255,7 +257,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           dbg_prod_wait += clock64() - t_w0;
           uint8_t* s = smem + stage * kStageBytes;
           const bool tail = p.tail_cols != 0 && kb == p.nkb_total - 1;
-          const uint32_t tx = tail ? tx_tail_cta : tx_cta;
+          const bool skip_a = p.dbg_skip_a != 0 && item != first_item;
+          uint32_t tx = tail ? tx_tail_cta : tx_cta;
+          if (skip_a) tx -= tail ? 2u * BM * p.tail_cols * 2u : 2u * A_TILE_BYTES;
           const CUtensorMap* ma_hi = tail ? &tt_a_hi : &tm_a_hi;
           const CUtensorMap* ma_lo = tail ? &tt_a_lo : &tm_a_lo;
           const CUtensorMap* mb_hi = tail ? &tt_b_hi : &tm_b_hi;
@@ -263,8 +267,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (TWO) {
             const uint32_t lead_full = stage == 0 ? lead_full_addr[0] : (stage == 1 ? lead_full_addr[1] : lead_full_addr[2]);
             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * tx);
-            tma_load_2d_2sm(s, ma_hi, lead_full, kb * BK, w.m_blk * BM);
-            tma_load_2d_2sm(s + A_TILE_BYTES, ma_lo, lead_full, kb * BK, w.m_blk * BM);
+            if (!skip_a) {
+              tma_load_2d_2sm(s, ma_hi, lead_full, kb * BK, w.m_blk * BM);
+              tma_load_2d_2sm(s + A_TILE_BYTES, ma_lo, lead_full, kb * BK, w.m_blk * BM);
+            }
             tma_load_2d_2sm(s + 2 * A_TILE_BYTES, mb_hi, lead_full, kb * BK, brow);
             tma_load_2d_2sm(s + 2 * A_TILE_BYTES + kBBytes, mb_lo, lead_full, kb * BK, brow);
           } else {
@@ -540,6 +546,69 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
         __syncwarp();
       }
+      if constexpr (SECT) {
+        // Register-direct epilogue: the 16x256b TMEM load shape hands four threads 8 consecutive columns of one row,
+        // so every 8-byte store of a warp completes 32-byte sectors (8 rows x 32 B per instruction) -- no shared
+        // memory staging, no TMA store: the shared-memory port is left to the operand fill and the MMA reads.
+        uint32_t rr[4][2][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc < nchunks) {
+            tmem_ld_16x256b_x4(tbase + cc * 32, rr[i][0]);
+            tmem_ld_16x256b_x4(tbase + (16u << 16) + cc * 32, rr[i][1]);
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));
+          else mbar_arrive(&tempty[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // the four rows of this thread: lane/4 + {0, 8, 16, 24} inside the warp's 32-row quarter
+        float radd4[4], zi4[4];
+        float* orow[4];
+        bool rok[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int mr = m0 + q * 32 + s4 * 8 + (lane >> 2);
+          rok[s4] = mr < p.m;
+          float ra4 = 0.f, zm4 = 0.f;
+          zi4[s4] = 1.f;
+          if (rok[s4]) {
+            if (e.row_add) ra4 = __ldg(e.row_add + mr);
+            if (e.zmean) { zm4 = __ldg(e.zmean + mr); zi4[s4] = __ldg(e.zinv + mr); }
+          }
+          radd4[s4] = ra4 - zm4;
+          orow[s4] = e.out + (static_cast<long long>(w.ks) * p.mpad + mr) * e.ldo + n0 + 2 * (lane & 3);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc >= nchunks) continue;
+#pragma unroll
+          for (int rep = 0; rep < 4; ++rep) {
+            const int cl = cc * 32 + rep * 8 + 2 * (lane & 3);     // column inside the tile
+            float2 ct = make_float2(0.f, 0.f);
+            if (col_cached) ct = *reinterpret_cast<const float2*>(colslot + cl);
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+              const int h2 = s4 >> 1, half = s4 & 1;
+              float2 v;
+              v.x = (__uint_as_float(rr[i][h2][rep * 4 + half * 2 + 0]) + ct.x + radd4[s4]) * zi4[s4];
+              v.y = (__uint_as_float(rr[i][h2][rep * 4 + half * 2 + 1]) + ct.y + radd4[s4]) * zi4[s4];
+              if (rok[s4]) {
+                const int col = n0 + cl;
+                if (col + 1 < p.n) *reinterpret_cast<float2*>(orow[s4] + cc * 32 + rep * 8) = v;
+                else if (col < p.n) orow[s4][cc * 32 + rep * 8] = v.x;
+              }
+            }
+          }
+        }
+        continue;
+      }
       // all of this warp's chunks are fetched with the TMEM loads in flight together (one ~1k-cycle latency per
       // tile instead of one per chunk), then the accumulator stage is handed back BEFORE the post-processing
       // and the stores, so the MMA warp never waits for the store path
@@ -577,7 +646,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     }
-    if ((FAST || p.direct_store == 3) && lane == 0) tma_store_wait<0>();
+    if (!SECT && (FAST || p.direct_store == 3) && lane == 0) tma_store_wait<0>();
     if (p.dbg != nullptr && blockIdx.x < 2 && lane == 0 && (ew == 0 || ew == 7)) {
       const int o = blockIdx.x * 16 + (ew == 0 ? 6 : 9);
       p.dbg[o + 0] = dbg_tfull;
@@ -708,10 +777,13 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     tout = ta_hi;  // never dereferenced
   }
   p.dbg = ctx.gemm_dbg.size() >= 32 ? ctx.gemm_dbg.get() : nullptr;
+  p.dbg_skip_a = ctx.dbg_skip_a;
   const GemmEpilogue& ep = p.epi;
   // 1: score-grid hot path, 2: LDA log-sum-exp pass (nothing stored), 0: everything else
   int epi = 0;
   if (out != nullptr && p.direct_store == 3 && ep.rsum == nullptr && ep.lse_max == nullptr && ep.grp == nullptr) epi = 1;
+  // register-direct sector stores (PLDA_B200_EPI=sector): same preconditions as the TMA path (8-byte aligned rows)
+  if (epi == 1 && ctx.epi_sector) epi = 3;
   else if (out == nullptr && ep.lse_max != nullptr && ep.rsum == nullptr && ep.grp == nullptr) epi = 2;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
@@ -721,6 +793,8 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx.profile_gemm) {
@@ -752,6 +826,9 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     else if (epi == 2)
       PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 2>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
                                  ttb_lo, tout, p));
+    else if (epi == 3)
+      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 3>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
+                                 ttb_lo, tout, p));
     else
       PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 0>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
                                  ttb_lo, tout, p));
@@ -760,6 +837,9 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
         ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
   } else if (epi == 2) {
     gemm_bf16x3_kernel<false, 2><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
+        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
+  } else if (epi == 3) {
+    gemm_bf16x3_kernel<false, 3><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
         ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
   } else {
     gemm_bf16x3_kernel<false, 0><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(

@@ -26,6 +26,7 @@ Context::Context(int dev) : device(dev) {
   const char* epi = getenv("PLDA_B200_EPI");
   epi_mode = epi == nullptr ? 0
              : (strcmp(epi, "direct") == 0 ? 1 : (strcmp(epi, "skip") == 0 ? 2 : (strcmp(epi, "lsu") == 0 ? 3 : 0)));
+  epi_sector = epi != nullptr && strcmp(epi, "sector") == 0;
   const char* kt = getenv("PLDA_B200_KTAIL");
   k_tail_boxes = !(kt != nullptr && strcmp(kt, "0") == 0);
   const char* dbg = getenv("PLDA_B200_DBG");
@@ -33,6 +34,8 @@ Context::Context(int dev) : device(dev) {
     gemm_dbg.alloc(32);
     PB_CUDA(cudaMemset(gemm_dbg.get(), 0, 32 * sizeof(long long)));
   }
+  const char* sk = getenv("PLDA_B200_DBGSKIPA");
+  dbg_skip_a = (sk != nullptr && sk[0] == '1') ? 1 : 0;
   const char* pdl = getenv("PLDA_B200_PDL");
   if (pdl && pdl[0] == '0') pdl_enabled = false;
   const char* gm = getenv("PLDA_B200_GEMM");

@@ -58,6 +58,10 @@ struct Context {
   bool owns_stream = true;
   std::atomic<long long> launches{0};   // number of OUR kernels launched (bench "gpu_launches")
   int epi_mode = 0;                  // debug (env PLDA_B200_EPI): 0 default (TMA store), 1 "direct" register stores, 2 "skip", 3 "lsu"
+  bool epi_sector = false;           // env PLDA_B200_EPI=sector: register-direct sector stores in the score-grid epilogue
+  int dbg_skip_a = 0;                // debug (env PLDA_B200_DBGSKIPA=1): timing experiment, the TMA producer loads the A
+                                     // tiles only for the first item of a CTA (WRONG results) -> upper bound of an
+                                     // A-resident schedule
   bool k_tail_boxes = true;          // env PLDA_B200_KTAIL=0 disables the narrow K-tail boxes
   DevBuf<long long> gemm_dbg;        // env PLDA_B200_DBG=1: stall counters written by CTA 0/1 of the last GEMM launch
   bool gemm_two_cta = true;          // env PLDA_B200_GEMM=1cta forces the single-CTA (cta_group::1) kernel
