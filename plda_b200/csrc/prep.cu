@@ -327,17 +327,20 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
   }
   if (sig.counter != nullptr && !is_enrol) {
     // publish: every thread's peer stores are performed system-wide, then the LAST test block raises the ready flag
-    // of this source rank in every destination region (block-uniform branch: the barrier is safe)
+    // of this source rank in every destination region -- one thread per destination, so the NVLink round trips of
+    // the flag stores overlap instead of adding up (block-uniform branch: the barriers are safe)
+    __shared__ int s_last;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned prev = atomicAdd(sig.counter, 1u);
-      if (prev == test_blocks - 1) {
-        atomicExch(sig.counter, 0u);
-        __threadfence_system();
-        for (int w = 0; w < sig.n; ++w)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sig.flag[w]), "r"(sig.epoch) : "memory");
-      }
+      s_last = prev == test_blocks - 1 ? 1 : 0;
+      if (s_last) atomicExch(sig.counter, 0u);
+    }
+    __syncthreads();
+    if (s_last && static_cast<int>(threadIdx.x) < sig.n) {
+      __threadfence_system();     // orders the counter observation (all blocks fenced before adding) before the flag
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sig.flag[threadIdx.x]), "r"(sig.epoch) : "memory");
     }
   }
 }

@@ -35,7 +35,7 @@ def pool_dvectors(frames, offsets, method: str = "mean", l2norm: bool = True, de
     if method not in _MODES:
         raise ValueError("method must be 'mean', 'max' or 'var'")
     off = np.ascontiguousarray(offsets, dtype=np.int64).reshape(-1)
-    if off.shape[0] < 1 or np.any(np.diff(off) <= 0) and off.shape[0] > 1:
+    if off.shape[0] < 1 or (off.shape[0] > 1 and np.any(np.diff(off) <= 0)):
         raise ValueError("offsets must be strictly increasing (every utterance needs at least one frame)")
     n_utts = off.shape[0] - 1
     lib = _ffi.lib()
