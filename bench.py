@@ -469,6 +469,9 @@ def run_main(args):
         "roofline": roofline,
         "em": em,
         "parity_spot_max_abs_diff": spot,
+        "parity_spot_note": "64x64 corner of the last timed slab (fp32 resident rows: operand formed in fp32) vs the e2e "
+                            "result (fp64 host rows: operand formed in fp64) -- two roundings of the same operand, both "
+                            "inside the 1e-3 score tolerance the GPU tests hold against the fp64 oracle",
     }
     os.sched_setaffinity(0, prev_affinity)       # the CPU baseline may use every host core
     if rank == 0 and world == 1 and not args.no_cpu:
