@@ -153,12 +153,25 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   const size_t dd = static_cast<size_t>(d) * d;
   PB_CUDA(cudaEventRecord(ev[0], ctx.stream));
 
+  // PLDA_B200_TRACE=1: host-clock laps of the stats pass, each after a stream synchronisation
+  const bool trace = getenv("PLDA_B200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx.stream);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    fprintf(stderr, "plda_b200 fit: %-32s +%.3f ms\n", what, ms);
+  };
+
   // ---- stats pass (PldaStats::AddSamples for every speaker) ----
   Staged sx;
   stage(x, n, d, ldx, dtype, loc, sx);
+  lap("rows staged");
   DevBuf<uint64_t> lab(n);
   PB_CUDA(cudaMemcpyAsync(lab.get(), labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+  lap("labels uploaded");
   build_segments(ctx, lab.get(), n, segs);                                  // K1
+  lap("segments built");
   const int64_t k = segs.nseg;
   if (k < 2 && reduce_fn == nullptr) {
     for (auto& e : ev) cudaEventDestroy(e);
@@ -169,6 +182,7 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   DevBuf<int32_t> counts(k);
   segment_sums(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get());        // K2
   segment_finalize_means(ctx, means.get(), d, segs, counts.get());
+  lap("class means");
   DevBuf<double> scatter(dd);
   if (precision == 1) {
     ws_gram.reserve(static_cast<size_t>(n) * d);
@@ -176,6 +190,7 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
     gemm_f64(ctx, true, false, d, d, n, 1.0, ws_gram.get(), d, ws_gram.get(), d, 0.0, scatter.get(), d);
   } else {
     center_scale_split_t(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_xt);   // K3 operand
+    lap("centred split operand");
     const int ks = choose_ksplit(ctx, d, d, n);
     const int eff = effective_ksplit(ctx, d, d, n, ks);
     const int64_t mpad = round_up(d, 128), npad = round_up(d, 4);
@@ -183,6 +198,7 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
     gemm_bf16x3_splitk(ctx, ws_xt.view(), ws_xt.view(), d, d, n, ks, ws_partial.get());   // K3: S = X~^T X~
     reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, scatter.get(), d, 1.0, true);
   }
+  lap("scatter SYRK");
   // sum_ = sum_s w_s m_s, class_weight = sum_s w_s ; mu = sum_/class_weight
   DevBuf<double> class_weight(1);
   model.d = d;
@@ -207,6 +223,7 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   if (precision != 1) split_rows(ctx, mc.get(), false, k, d, d, nullptr, nullptr, nullptr, ws_mc);
   PB_CUDA(cudaEventRecord(ev[1], ctx.stream));
   ctx.sync();
+  lap("stats pass done");
   // example_weight = sum w_s n_s = K;  W_count = (K - class_weight) + class_weight = K;  B_count = class_weight
   if (h_k < 2.0) {
     for (auto& e : ev) cudaEventDestroy(e);

@@ -195,6 +195,89 @@ center_scale_split_t_kernel(const T* __restrict__ x, int d, long long ld, const 
   }
 }
 
+// Wider version of the same producer for aligned rows: tile = 64 sorted positions x 64 columns.
+//   in   16 threads per row, 4 consecutive columns each (one 16-byte load for fp32 rows, two for fp64), 16 rows per
+//        pass; the per-row scalars (source row, class, 1/sqrt(n_class)) are resolved once per row in shared memory
+//        instead of once per element
+//   out  every warp store writes one full 128-byte line: 64 positions x bf16 of ONE column of one plane
+// Same arithmetic as the 32 x 32 kernel (fp64 centring and scaling before the split), so the operand bits are equal.
+template <typename T>
+__global__ void __launch_bounds__(256)
+center_scale_split_t64_kernel(const T* __restrict__ x, int d, long long ld, const int32_t* __restrict__ order,
+                              const int32_t* __restrict__ seg_of_pos, const int32_t* __restrict__ seg_start,
+                              long long n, const double* __restrict__ means, int scale_by_count,
+                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ld_out) {
+  constexpr int TP = 64, TC = 64, PITCH = TP + 2;       // bf16 elements per smem row (pad: 2-way conflicts at most)
+  __shared__ __align__(16) unsigned short s_hi[TC][PITCH];
+  __shared__ __align__(16) unsigned short s_lo[TC][PITCH];
+  __shared__ long long s_src[TP];
+  __shared__ long long s_mean[TP];
+  __shared__ double s_scale[TP];
+  const long long p0 = blockIdx.x * static_cast<long long>(TP);
+  const int c0 = blockIdx.y * TC;
+  if (threadIdx.x < TP) {
+    const long long p = p0 + threadIdx.x;
+    long long src = -1, mrow = 0;
+    double sc = 0.0;
+    if (p < n) {
+      const int sg = seg_of_pos[p];
+      src = static_cast<long long>(order[p]) * ld;
+      mrow = static_cast<long long>(sg) * d;
+      sc = scale_by_count ? rsqrt(static_cast<double>(seg_start[sg + 1] - seg_start[sg])) : 1.0;
+    }
+    s_src[threadIdx.x] = src;
+    s_mean[threadIdx.x] = mrow;
+    s_scale[threadIdx.x] = sc;
+  }
+  __syncthreads();
+  const int t16 = threadIdx.x & 15, r16 = threadIdx.x >> 4;
+  const int c = c0 + 4 * t16;
+#pragma unroll
+  for (int pass = 0; pass < TP / 16; ++pass) {
+    const int row = pass * 16 + r16;
+    const long long src = s_src[row];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (src >= 0 && c < d) {
+      if (c + 4 <= d) {
+        if (sizeof(T) == 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(x + src + c));
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(x + src + c));
+          const double2 b = __ldg(reinterpret_cast<const double2*>(x + src + c + 2));
+          v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (c + j < d) v[j] = static_cast<double>(x[src + c + j]);
+      }
+      const double sc = s_scale[row];
+      const double* m = means + s_mean[row] + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = c + j < d ? (v[j] - m[j]) * sc : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h, l;
+      split_bf16(v[j], h, l);
+      s_hi[4 * t16 + j][row] = __bfloat16_as_ushort(h);
+      s_lo[4 * t16 + j][row] = __bfloat16_as_ushort(l);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 128 line stores (64 columns x 2 planes), 16 per warp; a lane carries two positions
+  for (int i = warp; i < 2 * TC; i += 8) {
+    const int cl = i >> 1;
+    const int cg = c0 + cl;
+    if (cg >= d) continue;
+    const unsigned short* srow = (i & 1) ? s_lo[cl] : s_hi[cl];
+    const uint32_t pair = static_cast<uint32_t>(srow[2 * lane]) | (static_cast<uint32_t>(srow[2 * lane + 1]) << 16);
+    __nv_bfloat16* dst = ((i & 1) ? lo : hi) + static_cast<long long>(cg) * ld_out + p0;
+    if (p0 + 2 * lane + 1 < ld_out) *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pair;
+  }
+}
+
 template <typename T>
 __global__ void center_scale_f64_kernel(const T* __restrict__ x, int d, long long ld, const int32_t* __restrict__ order,
                                         const int32_t* __restrict__ seg_of_pos, const int32_t* __restrict__ seg_start,
@@ -323,6 +406,22 @@ void center_scale_split_t(Context& ctx, const void* x, bool is_f32, int64_t d, i
   xt.ld = npad;
   xt.hi.reserve(static_cast<size_t>(d) * npad);
   xt.lo.reserve(static_cast<size_t>(d) * npad);
+  // aligned rows take the 64 x 64 tile kernel (16-byte loads, full-line stores); npad is a multiple of 64
+  const bool wide = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld % (is_f32 ? 4 : 2) == 0;
+  if (wide) {
+    dim3 grid64(static_cast<unsigned>(npad / 64), static_cast<unsigned>(ceil_div(d, 64)));
+    if (is_f32)
+      center_scale_split_t64_kernel<float><<<grid64, 256, 0, ctx.stream>>>(
+          static_cast<const float*>(x), static_cast<int>(d), ld, seg.order.get(), seg.seg_of_pos.get(),
+          seg.seg_start.get(), seg.n, means, scale_by_count ? 1 : 0, xt.hi.get(), xt.lo.get(), npad);
+    else
+      center_scale_split_t64_kernel<double><<<grid64, 256, 0, ctx.stream>>>(
+          static_cast<const double*>(x), static_cast<int>(d), ld, seg.order.get(), seg.seg_of_pos.get(),
+          seg.seg_start.get(), seg.n, means, scale_by_count ? 1 : 0, xt.hi.get(), xt.lo.get(), npad);
+    PB_CUDA(cudaGetLastError());
+    ctx.count_launch();
+    return;
+  }
   dim3 grid(static_cast<unsigned>(npad / 32), static_cast<unsigned>(ceil_div(d, 32)));
   if (is_f32)
     center_scale_split_t_kernel<float><<<grid, 256, 0, ctx.stream>>>(

@@ -308,3 +308,30 @@ def test_smoothing_mutates_model_like_reference():
     s_g = g.score(0, a[0], a[1])
     s_r = ref.score(0, b[0], b[1])
     assert s_g == pytest.approx(s_r, rel=1e-5, abs=1e-5)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_fit_operand_kernels_agree(dtype):
+    """The transposing SYRK-operand producer has a 64 x 64 tile kernel for aligned rows (16-byte loads, full-line
+    stores) and a 32 x 32 one for everything else; same arithmetic -> the fitted model must be bit-identical whether
+    the rows arrive contiguous or as an odd-pitch, element-shifted view of a wider matrix."""
+    import torch
+    from plda_b200 import PLDA
+    d = 72
+    rng = np.random.RandomState(12)
+    counts = rng.randint(2, 9, size=90)
+    x, labels, _ = synth(d, counts, 77)
+    tdt = getattr(torch, dtype)
+    x_al = torch.from_numpy(x).to(tdt).cuda()
+    buf = torch.zeros((x.shape[0], d + 3), dtype=tdt, device="cuda")
+    x_un = buf[:, 1:d + 1]
+    x_un.copy_(x_al)
+    torch.cuda.synchronize()
+    a, b = PLDA(), PLDA()
+    a.fit(x_al, labels, 3)
+    b.fit(x_un, labels, 3)
+    ma, ta, pa = a.get_model()
+    mb, tb, pb_ = b.get_model()
+    assert np.array_equal(pa, pb_) and np.array_equal(ma, mb) and np.array_equal(ta, tb)
+    ref = oracle_fit(x_al.double().cpu().numpy(), labels, 3)
+    assert np.max(np.abs(pa - ref.plda.psi) / np.maximum(ref.plda.psi, 1e-12)) <= 2e-3
