@@ -557,13 +557,22 @@ void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dt
                          nullptr, nullptr, nullptr, 0, ws_rsum.get() + r0, ws_rsq.get() + r0);
     }
   } else {
+    // one enrol count (n = 1): the table-driven producer (no per-element log / divide); the two sides may differ in
+    // dtype (caller's enrol rows vs the fp64 transformed cohort), hence one launch per side
     ws_row.reserve(ne);
     ws_col.reserve(col_ld);
-    PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, col_ld * sizeof(float), ctx.stream));
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, nullptr, 1, model.psi.get(), &ws_l, nullptr,
-                     ws_row.get(), nullptr);
-    score_prep_test(ctx, bt.get(), false, numutts, dim, dim, nullptr, 1, 1, model.psi.get(), &ws_r, ws_col.get(),
-                    col_ld, nullptr);
+    const double* consts = score_consts_for(1, dim);
+    PrepDst none, cohort;
+    score_prep_uniform_multi(ctx, se.ptr, ne, se.ld, &ws_l, ws_row.get(), nullptr, 0, 0, 0, 0, none, round_up(dim, 16),
+                             se.is_f32, dim, consts, PrepSignal{});
+    ws_r.reserve(numutts, dim);
+    cohort.n = 1;
+    cohort.hi[0] = ws_r.hi.get();
+    cohort.lo[0] = ws_r.lo.get();
+    cohort.term[0] = ws_col.get();
+    score_prep_uniform_multi(ctx, nullptr, 0, 0, nullptr, nullptr, bt.get(), numutts, dim, 0, col_ld, cohort, ws_r.ld,
+                             false, dim, consts, PrepSignal{});
+    ctx.pdl_pending = false;     // the GEMM below does not directly follow a producer it may overlap
     GemmEpilogue epi;
     epi.row_add = ws_row.get();
     epi.col_add = ws_col.get();
