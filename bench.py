@@ -307,16 +307,9 @@ def run_main(args):
     if world > 1 and not args.nccl_allgather:
         from plda_b200.dist import PeerShardedScorer
         try:
-            peer = PeerShardedScorer(plda, nt_total, D)
-            okf = 1
+            peer = PeerShardedScorer(plda, nt_total, D)     # fails (or succeeds) on every rank together
         except Exception as e:  # pragma: no cover
-            log("rank %d: peer-memory scorer unavailable (%r)" % (rank, e))
-            okf = 0
-        t_ok = torch.tensor([okf], device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        if int(t_ok.item()) == 0:
-            if peer is not None:
-                peer.close()
+            log("rank %d: %s -- using the NCCL all-gather" % (rank, e))
             peer = None
         torch.cuda.current_stream().synchronize()
 

@@ -113,13 +113,34 @@ class PeerShardedScorer:
         self._handle = (C.c_ubyte * 64)()
         self._region = C.c_void_p()
         self._open = False
-        _ffi.check(self._lib.plda_shard_open(plda._h, self.world, self.rank, _ffi.ptr(self.bounds), self.dim,
-                                             C.cast(self._handle, C.c_void_p), C.byref(self._region)))
-        self._open = True
-        if not self._local_only:
-            self._exchange()
+        err = None
+        try:
+            _ffi.check(self._lib.plda_shard_open(plda._h, self.world, self.rank, _ffi.ptr(self.bounds), self.dim,
+                                                 C.cast(self._handle, C.c_void_p), C.byref(self._region)))
+            self._open = True
+        except Exception as e:          # decided collectively below: a rank must not leave the others in a collective
+            err = e
+        if self._local_only:
+            if err is not None:
+                raise err
+            return
+        self._agree(err, "allocating the exchange region")
+        self._exchange()
 
     # -- wiring ---------------------------------------------------------------------------------
+    def _agree(self, err, what):
+        """Collective: every rank learns whether ANY rank failed; then all of them release their region and raise
+        (so that a caller can fall back to the all-gather path on every rank), or none does."""
+        import torch
+        import torch.distributed as dist
+        flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=_coll_device(self.group))
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()) == 0:
+            return
+        self.close(barrier=False)
+        raise RuntimeError("peer-memory scorer unavailable (%s failed on %s): %r"
+                           % (what, "this rank" if err is not None else "another rank", err))
+
     def _exchange(self):
         import torch
         import torch.distributed as dist
@@ -128,12 +149,18 @@ class PeerShardedScorer:
         allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
         allh = allh.cpu().numpy()
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            buf = (self._C.c_ubyte * 64)(*allh[r].tolist())
-            self._ffi.check(self._lib.plda_shard_connect(self.plda._h, r, self._C.cast(buf, self._C.c_void_p), None))
-        dist.barrier(group=self.group)         # every region is mapped everywhere before the first push
+        err = None
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                buf = (self._C.c_ubyte * 64)(*allh[r].tolist())
+                self._ffi.check(self._lib.plda_shard_connect(self.plda._h, r, self._C.cast(buf, self._C.c_void_p),
+                                                             None))
+        except Exception as e:
+            err = e
+        # doubles as the barrier: every region is mapped everywhere before the first push
+        self._agree(err, "mapping the peers' regions (CUDA IPC)")
 
     @staticmethod
     def connect_local(scorers):
@@ -194,11 +221,11 @@ class PeerShardedScorer:
         self._ffi.check(self._lib.plda_shard_status(self.plda._h, self._C.byref(e), self._C.byref(t)))
         return int(e.value), int(t.value)
 
-    def close(self):
+    def close(self, barrier: bool = True):
         if not self._open:
             return
         self._open = False
-        if not self._local_only:
+        if barrier and not self._local_only:
             import torch.distributed as dist
             self._ffi.check(self._lib.plda_synchronize(self.plda._h))
             dist.barrier(group=self.group)     # nobody writes into a region that is about to be freed

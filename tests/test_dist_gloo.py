@@ -143,3 +143,36 @@ def test_sharded_lda_and_norm_plumbing_gloo(tmp_path, world):
     port = _free_port()
     mp.spawn(_lda_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "lda_ok_%d" % r)) for r in range(world))
+
+
+def _peer_fail_worker(rank, world, port, result_dir):
+    """No GPU here: plda_shard_open fails on every rank (null handle).  The point is the COLLECTIVE agreement of
+    PeerShardedScorer: all ranks raise together (so a caller can fall back to the all-gather path on every rank)
+    instead of one rank walking away from a collective the others are blocked in."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        from plda_b200.dist import PeerShardedScorer
+
+        class FakePlda:
+            _h = C.c_void_p(None)
+
+        outcome = "no error"
+        try:
+            PeerShardedScorer(FakePlda(), 100, 8)
+        except RuntimeError as e:
+            outcome = "RuntimeError" if "peer-memory scorer unavailable" in str(e) else "other: %r" % (e,)
+        dist.barrier()                          # both ranks are still in step
+        with open(os.path.join(result_dir, "peer_%d.txt" % rank), "w") as f:
+            f.write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_scorer_failure_is_collective(tmp_path):
+    world = 2
+    mp.spawn(_peer_fail_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / ("peer_%d.txt" % r)).read_text() == "RuntimeError"
