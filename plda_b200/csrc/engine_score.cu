@@ -341,22 +341,8 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     fprintf(stderr, "plda_b200 score_grid: %-28s +%.3f ms\n", what, ms);
   };
-  // Host rows in, host scores out, one enrol count: the grid is produced in enrol-row chunks and the whole call is
-  // a three-stage pipeline over PCIe -- upload of chunk i+1's enrol rows, producer + GEMM of chunk i, drain of chunk
-  // i-1's scores (the drain is the bottleneck: 4 B per trial; everything else hides behind it)
-  const bool pipelined = loc == 0 && out_loc == 0 && uniform && precision != 1 && ne >= 2048;
-  const size_t es_in = elem_size(dtype);
   Staged se, st;
-  if (pipelined) {
-    PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
-    PB_CHECK(enrol != nullptr && ld_enrol >= dim, kInvalidArg, "score_grid: bad enrol matrix");
-    ws_stage[0].reserve(static_cast<size_t>(ne) * dim * es_in);     // filled chunk by chunk
-    se.ptr = ws_stage[0].get();
-    se.ld = dim;
-    se.is_f32 = dtype == 1;
-  } else {
-    stage(enrol, ne, dim, ld_enrol, dtype, loc, se, &ws_stage[0]);
-  }
+  stage(enrol, ne, dim, ld_enrol, dtype, loc, se, &ws_stage[0]);
   stage(test, nt, dim, ld_test, dtype, loc, st, &ws_stage[1]);
   lap("inputs staged (enqueued)");
 
@@ -413,10 +399,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   } else {
     ws_row.reserve(ne);
     ws_col.reserve(static_cast<size_t>(ng) * col_ld);
-    if (pipelined) {
-      ws_l.reserve(ne, dim);       // all rows now: the chunks below fill their own rows
-      ws_r.reserve(nt, dim);
-    } else if (uniform) {
+    if (uniform) {
       score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, score_consts_for(uniform_count, dim), ws_l,
                          ws_r, ws_row.get(), ws_col.get(), col_ld);
     } else {
@@ -434,9 +417,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
     const int64_t budget = exact ? (512ll << 20) / 8 : (1ll << 30) / 4;   // elements per staging buffer
     chunk = std::max<int64_t>(128, (budget / std::max<int64_t>(ldo_dev, 1)) / 128 * 128);
     chunk = std::min(chunk, ne);
-    if (pipelined) chunk = std::min(chunk, std::max<int64_t>(1024, round_up(ceil_div(ne, 8), 256)));
   }
-  const double* pipe_consts = pipelined ? score_consts_for(uniform_count, dim) : nullptr;
   if (out_loc == 0) {
     ensure_copy_stream();
     const int nbuf = chunk < ne ? 2 : 1;   // the second staging buffer is only needed when the grid is chunked
@@ -457,28 +438,6 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
                          grp_dev ? grp_dev + r0 : nullptr, zmean ? zmean + r0 : nullptr, zinv ? zinv + r0 : nullptr, dst, ldo_dev,
                          nullptr, nullptr);
     } else {
-      if (pipelined) {
-        // this chunk's enrol rows: host -> device, then the producer (plus the whole test side with chunk 0)
-        uint8_t* dst_rows = ws_stage[0].get() + static_cast<size_t>(r0) * dim * es_in;
-        const uint8_t* src_rows = static_cast<const uint8_t*>(enrol) + static_cast<size_t>(r0) * ld_enrol * es_in;
-        if (ld_enrol == dim)
-          PB_CUDA(cudaMemcpyAsync(dst_rows, src_rows, static_cast<size_t>(rows) * dim * es_in, cudaMemcpyHostToDevice,
-                                  ctx.stream));
-        else
-          PB_CUDA(cudaMemcpy2DAsync(dst_rows, dim * es_in, src_rows, ld_enrol * es_in, dim * es_in, rows,
-                                    cudaMemcpyHostToDevice, ctx.stream));
-        PrepDst tdst;
-        const bool first = r0 == 0;
-        if (first) {
-          tdst.n = 1;
-          tdst.hi[0] = ws_r.hi.get();
-          tdst.lo[0] = ws_r.lo.get();
-          tdst.term[0] = ws_col.get();
-        }
-        score_prep_uniform_multi(ctx, dst_rows, rows, dim, &ws_l, ws_row.get(), first ? st.ptr : nullptr, first ? nt : 0,
-                                 st.ld, 0, first ? col_ld : 0, tdst, round_up(dim, 16), se.is_f32, dim, pipe_consts,
-                                 PrepSignal{}, r0);
-      }
       SplitOperand a = ws_l.view();
       a.hi += r0 * a.ld;
       a.lo += r0 * a.ld;

@@ -43,8 +43,7 @@ void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
 // ld_out and a column-term row each) at global row offset test_row0, and an optional completion signal: the last
 // block stores `epoch` (release, system scope) to each `flag[w]`.  Sharded score grid: the
 // destinations are every rank's operand buffer over NVLink peer memory -- producer and all-gather in one kernel.
-// l_out == nullptr skips the enrol side; tdst.n == 0 skips the test side.  enrol_row0: the `ne` enrol rows given are
-// rows [enrol_row0, enrol_row0 + ne) of the operand / row-term arrays (chunked, pipelined callers).
+// l_out == nullptr skips the enrol side; tdst.n == 0 skips the test side.
 constexpr int kMaxPeers = 16;
 struct PrepDst {
   __nv_bfloat16* hi[kMaxPeers];
@@ -61,7 +60,7 @@ struct PrepSignal {
 void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, SplitBuf* l_out,
                               float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,
                               int64_t test_pad_end, const PrepDst& tdst, int64_t ld_out, bool is_f32, int64_t d,
-                              const double* consts, const PrepSignal& sig, int64_t enrol_row0 = 0);
+                              const double* consts, const PrepSignal& sig);
 // exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
                         const double* col_term, int64_t col_ld, const int32_t* grp, const float* zmean,

@@ -506,12 +506,11 @@ inline bool rows_vectorisable(const void* p, int64_t ld, bool is_f32) {
 void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, SplitBuf* l_out,
                               float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,
                               int64_t test_pad_end, const PrepDst& tdst, int64_t ld_out, bool is_f32, int64_t d,
-                              const double* consts, const PrepSignal& sig, int64_t enrol_row0) {
+                              const double* consts, const PrepSignal& sig) {
   PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
-  PB_CHECK(enrol_row0 >= 0, kInvalidArg, "score prep: negative row offset");
   PB_CHECK(ld_out % 16 == 0 && ld_out >= d, kInvalidArg, "score prep: operand pitch must be a multiple of 16");
   PB_CHECK(tdst.n >= 0 && tdst.n <= kMaxPeers && sig.n <= kMaxPeers, kInvalidArg, "score prep: too many destinations");
-  if (l_out) l_out->reserve(enrol_row0 + ne, d);   // grow-only: a chunked caller reserves all rows before chunk 0
+  if (l_out) l_out->reserve(ne, d);
   PB_CHECK(l_out == nullptr || l_out->ld == ld_out || nt == 0, kInvalidArg, "score prep: operand pitches differ");
   const int ldo = static_cast<int>(l_out ? l_out->ld : ld_out);
   // two resident blocks per SM, split between the sides in proportion to their rows; a small side gets one block
@@ -535,9 +534,8 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   if (eb + tb == 0) return;
   const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
   const int vec_t = test && rows_vectorisable(test, ld_t, is_f32) ? 1 : 0;
-  __nv_bfloat16* lhi = l_out ? l_out->hi.get() + enrol_row0 * ldo : nullptr;
-  __nv_bfloat16* llo = l_out ? l_out->lo.get() + enrol_row0 * ldo : nullptr;
-  if (row_term != nullptr) row_term += enrol_row0;
+  __nv_bfloat16* lhi = l_out ? l_out->hi.get() : nullptr;
+  __nv_bfloat16* llo = l_out ? l_out->lo.get() : nullptr;
   if (is_f32)
     score_prep_uniform_kernel<float><<<eb + tb, 256, 0, ctx.stream>>>(
         static_cast<const float*>(enrol), l_out ? ne : 0, ld_e, static_cast<const float*>(test), nt, ld_t, test_row0,
