@@ -28,6 +28,9 @@
 //   TMEM        2 accumulator stages x 256 fp32 columns (all 512 columns): the epilogue of tile i
 //               overlaps the MMAs of tile i+1.
 // A cta_group::1 instantiation (tile 128 x BN x 64, 2 x 96 KB stages) serves single-row-tile problems.
+// Launch-level features: programmatic dependent launch behind the operand producer (the prologue above the
+// griddepcontrol.wait overlaps the producer's tail); sharded B operand (GemmShard): the TMA producer polls the
+// owner rank's ready flag before the first tile that touches its rows and the column tiles start at the rank's own.
 #include <algorithm>
 
 #include "runtime.h"

@@ -1,6 +1,9 @@
 // HBM-bound operand producers and row-wise epilogues of the scoring / transform path.
-// All are one-warp-per-row kernels with coalesced loads along the feature axis, fp64
-// arithmetic on the way in (inputs are the caller's fp64/fp32 rows), split-bf16 or fp32 out.
+// Warp-per-row kernels with coalesced loads along the feature axis; inputs are the caller's fp64 / fp32 rows,
+// outputs split-bf16 planes or fp32.  The score-grid producer for one enrol count (score_prep_uniform_kernel) is
+// the tuned one: table-driven constants, 16-byte loads and stores, balanced warp-stride rows, optional fan-out of
+// the test side to every rank's operand buffer (sharded grid); the per-row-count variants serve ragged enrol counts
+// and the exact fp64 mode.
 #include <algorithm>
 
 #include "kernels.h"

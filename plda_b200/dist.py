@@ -3,10 +3,19 @@
 One process per GPU (``torch.distributed``, NCCL on GPUs, gloo in the CPU tests).  The grid
 shards by ENROL BLOCK: rank g owns a contiguous block of enrol models (their operand rows, row
 terms and z-norm statistics) and the ``block x Nt`` slab of the score grid.  Test vectors are
-transformed shard-wise and exchanged with ONE all-gather; there is no other data-path collective.
+transformed shard-wise and every rank needs all of them -- the only exchange on the data path:
 
-The collective plumbing lives here so that it can be exercised with world_size-2 gloo tests on CPU
-(``tests/test_dist_gloo.py``) with a stand-in scorer; on GPUs the scorer is ``PLDA.score_grid``.
+* ``PeerShardedScorer`` (GPUs with peer access, uniform enrol counts): no collective at all.  The
+  operand-producer kernel of every rank writes its test rows into the operand buffer of every
+  other rank over NVLink peer memory (CUDA-IPC mapped regions) and the tcgen05 GEMM waits per
+  column tile for the owner's ready flag (C ABI ``plda_shard_*``, ``csrc/engine_shard.cu``).
+* ``ShardedScorer``: ONE NCCL all-gather of the transformed test vectors, then ``score_grid``.
+
+The host-side plumbing lives here so that it can be exercised with world_size-2 gloo tests on CPU
+(``tests/test_dist_gloo.py``: partition, ragged all-gather, slab assembly with a stand-in scorer,
+collective failure agreement of the peer scorer); the peer-memory protocol itself is tested on one
+GPU with several handles (``tests/test_gpu_shard.py``) and across processes
+(``scripts/dist_shard_check.py``).
 """
 from __future__ import annotations
 
