@@ -15,7 +15,9 @@ algorithm (``PldaStats``, ``PldaEstimator``, ``Plda`` in ivector/plda.cc, API wi
 the 4-argument ``TransformIvector`` used at ``src/pldamodule.cpp:171,224``) in the
 operation order Kaldi uses, and follows ``src/pldamodule.cpp`` line by line for
 everything the shim adds.  It is pinned only by the self-consistency invariants in
-``tests/test_oracle_plda.py``.
+``tests/test_oracle_plda.py`` and by the first-principles checks in
+``tests/test_oracle_first_principles.py`` (LLR, EM objective and EM step against brute-force
+multivariate-normal densities of the two-covariance model) -- not by any output of Kaldi.
 
 Two layers:
 
