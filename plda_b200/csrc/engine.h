@@ -130,6 +130,8 @@ class PldaEngine {
   struct ScoreConsts { int count = 0; int64_t dim = 0; DevBuf<double> dev; };
   std::vector<ScoreConsts> score_consts;
   const double* score_consts_for(int count, int64_t dim);
+  static void fill_score_consts(const double* psi, int64_t dim, int count, double* out /* kScoreConstsSize */);
+  DevBuf<double> ws_tables;   // ragged counts: [ng][kScoreConstsSize]
   // device->host drain of the score grid: second stream + events, created on first use
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};

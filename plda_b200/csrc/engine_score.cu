@@ -1,6 +1,7 @@
 // PldaEngine: model state, transform, pair / grid scoring, z-norm.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <chrono>
@@ -102,26 +103,30 @@ void PldaEngine::stage(const void* p, int64_t rows, int64_t cols, int64_t ld, in
   s.ld = cols;
 }
 
+// SURVEY App. A.7:  a = n psi/(n psi+1), v = 1 + psi/(n psi+1), q = 1/2 (1/(1+psi) - 1/v)
+void PldaEngine::fill_score_consts(const double* psi, int64_t dim, int count, double* out) {
+  const double n = static_cast<double>(count);
+  double logdet = 0.0;
+  for (int64_t i = 0; i < dim; ++i) {
+    const double p = psi[i];
+    const double den = n * p + 1.0;
+    const double a = n * p / den;
+    const double v = 1.0 + p / den;
+    out[kScoreConstsScale + i] = a / v;
+    out[kScoreConstsEnrolSq + i] = a * a / v;
+    out[kScoreConstsTestSq + i] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
+    logdet += log1p(p) - log(v);
+  }
+  out[kScoreConstsLogdet] = logdet;
+}
+
 const double* PldaEngine::score_consts_for(int count, int64_t dim) {
   for (auto& c : score_consts)
     if (c.count == count && c.dim == dim) return c.dev.get();
   PB_CHECK(dim > 0 && dim <= 1024 && dim <= static_cast<int64_t>(model.h_psi.size()), kInvalidArg,
            "score: dimension above 1024 is not supported");
-  // SURVEY App. A.7:  a = n psi/(n psi+1), v = 1 + psi/(n psi+1), q = 1/2 (1/(1+psi) - 1/v)
   std::vector<double> h(kScoreConstsSize, 0.0);
-  const double n = static_cast<double>(count);
-  double logdet = 0.0;
-  for (int64_t i = 0; i < dim; ++i) {
-    const double p = model.h_psi[i];
-    const double den = n * p + 1.0;
-    const double a = n * p / den;
-    const double v = 1.0 + p / den;
-    h[kScoreConstsScale + i] = a / v;
-    h[kScoreConstsEnrolSq + i] = a * a / v;
-    h[kScoreConstsTestSq + i] = 0.5 * (1.0 / (1.0 + p) - 1.0 / v);
-    logdet += log1p(p) - log(v);
-  }
-  h[kScoreConstsLogdet] = logdet;
+  fill_score_consts(model.h_psi.data(), dim, count, h.data());
   if (score_consts.size() >= 16) score_consts.erase(score_consts.begin());
   score_consts.emplace_back();
   ScoreConsts& c = score_consts.back();
@@ -346,6 +351,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   stage(test, nt, dim, ld_test, dtype, loc, st, &ws_stage[1]);
   lap("inputs staged (enqueued)");
 
+  std::vector<int32_t> ragged_counts;
   if (!uniform) {
     std::vector<int32_t> gcounts(counts, counts + ne);
     std::sort(gcounts.begin(), gcounts.end());
@@ -363,6 +369,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
     counts_dev = ws_counts.get();
     grp_dev = ws_grp.get();
     gcounts_dev = ws_gcounts.get();
+    ragged_counts = gcounts;
   }
 
   // optional z-norm affine per enrol row
@@ -404,10 +411,25 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
                          ws_r, ws_row.get(), ws_col.get(), col_ld);
     } else {
       PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(ng) * col_ld * sizeof(float), ctx.stream));
-      score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), &ws_l,
-                       nullptr, ws_row.get(), nullptr);
-      score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), &ws_r,
-                      ws_col.get(), col_ld, nullptr);
+      static const bool ragged_old = getenv("PLDA_B200_RAGGED") != nullptr && strcmp(getenv("PLDA_B200_RAGGED"), "old") == 0;
+      if (ragged_old) {      // A/B switch: per-element log / divide producers
+        score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), &ws_l,
+                         nullptr, ws_row.get(), nullptr);
+        score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), &ws_r,
+                        ws_col.get(), col_ld, nullptr);
+      } else {
+        // one constants table per distinct count, built on the host from the psi mirror
+        PB_CHECK(dim <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
+        std::vector<double> tabs(static_cast<size_t>(ng) * kScoreConstsSize, 0.0);
+        for (int g = 0; g < ng; ++g)
+          fill_score_consts(model.h_psi.data(), dim, ragged_counts[g], tabs.data() + static_cast<size_t>(g) * kScoreConstsSize);
+        ws_tables.reserve(tabs.size());
+        PB_CUDA(cudaMemcpyAsync(ws_tables.get(), tabs.data(), tabs.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                ctx.stream));
+        PB_CUDA(cudaStreamSynchronize(ctx.stream));   // tabs is a stack-lifetime staging buffer
+        score_prep_grouped(ctx, se.ptr, ne, se.ld, grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, ng, ws_tables.get(), ws_l,
+                           ws_r, ws_row.get(), ws_col.get(), col_ld);
+      }
     }
   }
 

@@ -61,6 +61,13 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
                               float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,
                               int64_t test_pad_end, const PrepDst& tdst, int64_t ld_out, bool is_f32, int64_t d,
                               const double* consts, const PrepSignal& sig);
+// Ragged enrol counts: one launch for both sides with the per-column constants read from one kScoreConsts* table per
+// distinct count (tables_dev: [ng][kScoreConstsSize]); grp_dev: group index per enrol row.  Writes one column-term row
+// per group (pitch col_ld; the caller zeroes the padding).
+void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
+                        const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
+                        const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term, float* col_term,
+                        int64_t col_ld);
 // exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
                         const double* col_term, int64_t col_ld, const int32_t* grp, const float* zmean,

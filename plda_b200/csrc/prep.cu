@@ -348,6 +348,55 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
   }
 }
 
+// Ragged enrol counts (tensor path): the same producer with the per-column constants read from one table per
+// distinct count (`tables`: [ng][kScoreConstsSize], built on the host once per call) instead of a log1p / log / three
+// divisions per element.  Blocks [0, eb) take 8 enrol rows each (row r uses the table of grp[r]); the rest take 8
+// test rows each and write the split row once plus one column term per group.  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+score_prep_grouped_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const int32_t* __restrict__ grp,
+                          const T* __restrict__ test, long long nt, long long ld_t, int d, int ng,
+                          const double* __restrict__ tables, __nv_bfloat16* __restrict__ l_hi,
+                          __nv_bfloat16* __restrict__ l_lo, __nv_bfloat16* __restrict__ r_hi,
+                          __nv_bfloat16* __restrict__ r_lo, int ld_out, float* __restrict__ row_term,
+                          float* __restrict__ col_term, long long col_ld, unsigned enrol_blocks) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x < enrol_blocks) {
+    const long long r = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
+    if (r >= ne) return;
+    const double* tab = tables + static_cast<long long>(grp[r]) * kScoreConstsSize;
+    const T* src = enrol + r * ld_e;
+    double acc = 0.0;
+    for (int c = lane; c < ld_out; c += 32) {
+      double lv = 0.0;
+      if (c < d) {
+        const double e = static_cast<double>(src[c]);
+        lv = e * __ldg(tab + kScoreConstsScale + c);
+        acc += __ldg(tab + kScoreConstsEnrolSq + c) * e * e;
+      }
+      store_split(l_hi, l_lo, r * ld_out + c, lv);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) row_term[r] = static_cast<float>(0.5 * (__ldg(tab + kScoreConstsLogdet) - acc));
+  } else {
+    const long long r = static_cast<long long>(blockIdx.x - enrol_blocks) * kWarpsPerBlock + warp;
+    if (r >= nt) return;
+    const T* src = test + r * ld_t;
+    for (int c = lane; c < ld_out; c += 32)
+      store_split(r_hi, r_lo, r * ld_out + c, c < d ? static_cast<double>(src[c]) : 0.0);
+    for (int g = 0; g < ng; ++g) {
+      const double* tab = tables + static_cast<long long>(g) * kScoreConstsSize + kScoreConstsTestSq;
+      double acc = 0.0;
+      for (int c = lane; c < d; c += 32) {
+        const double t = static_cast<double>(src[c]);
+        acc += __ldg(tab + c) * t * t;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) col_term[g * col_ld + r] = static_cast<float>(acc);
+    }
+  }
+}
+
 __global__ void score_epilogue_f64_kernel(const double* __restrict__ gram, long long ne, long long nt,
                                           const double* __restrict__ row_term, const double* __restrict__ col_term,
                                           long long col_ld, const int32_t* __restrict__ grp,
@@ -563,6 +612,29 @@ void score_prep_uniform(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
   tdst.term[0] = col_term;
   score_prep_uniform_multi(ctx, enrol, ne, ld_e, &l_out, row_term, test, nt, ld_t, 0, col_ld, tdst, r_out.ld, is_f32, d,
                            consts, PrepSignal{});
+}
+
+void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
+                        const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
+                        const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term, float* col_term,
+                        int64_t col_ld) {
+  PB_CHECK(d <= 1024 && ng >= 1, kInvalidArg, "score: dimension above 1024 is not supported");
+  l_out.reserve(ne, d);
+  r_out.reserve(nt, d);
+  const unsigned eb = row_blocks(ne), tb = row_blocks(nt);
+  if (eb + tb == 0) return;
+  if (is_f32)
+    score_prep_grouped_kernel<float><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
+        static_cast<const float*>(enrol), ne, ld_e, grp_dev, static_cast<const float*>(test), nt, ld_t,
+        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
+        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb);
+  else
+    score_prep_grouped_kernel<double><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
+        static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
+        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
+        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
 }
 
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
