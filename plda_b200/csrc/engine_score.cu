@@ -391,7 +391,6 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
 
   const int64_t col_ld = round_up(nt, 32);
   const bool exact = precision == 1;
-  bool folded = false;     // ragged counts scored in the K = 2 dim form (no column terms in the epilogue)
   const int64_t ldo_dev = out_loc == 1 ? ldo : round_up(nt, 4);
 
   if (exact) {
@@ -428,17 +427,8 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
         PB_CUDA(cudaMemcpyAsync(ws_tables.get(), tabs.data(), tabs.size() * sizeof(double), cudaMemcpyHostToDevice,
                                 ctx.stream));
         PB_CUDA(cudaStreamSynchronize(ctx.stream));   // tabs is a stack-lifetime staging buffer
-        static const bool ragged_groups =
-            getenv("PLDA_B200_RAGGED") != nullptr && strcmp(getenv("PLDA_B200_RAGGED"), "groups") == 0;
-        if (ragged_groups || 2 * dim > 1024) {
-          score_prep_grouped(ctx, se.ptr, ne, se.ld, grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, ng, ws_tables.get(),
-                             ws_l, ws_r, ws_row.get(), ws_col.get(), col_ld);
-        } else {
-          // folded form: the per-count column term rides in the contraction (K = 2 dim), hot-path epilogue
-          score_prep_folded(ctx, se.ptr, ne, se.ld, grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, ws_tables.get(), ws_l,
-                            ws_r, ws_row.get());
-          folded = true;
-        }
+        score_prep_grouped(ctx, se.ptr, ne, se.ld, grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, ng, ws_tables.get(), ws_l,
+                           ws_r, ws_row.get(), ws_col.get(), col_ld);
       }
     }
   }
@@ -478,14 +468,12 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
       epi.out = dst;
       epi.ldo = ldo_dev;
       epi.row_add = ws_row.get() + r0;
-      if (!folded) {
-        epi.col_add = ws_col.get();
-        epi.col_ld = col_ld;
-        epi.grp = grp_dev ? grp_dev + r0 : nullptr;
-      }
+      epi.col_add = ws_col.get();
+      epi.col_ld = col_ld;
+      epi.grp = grp_dev ? grp_dev + r0 : nullptr;
       epi.zmean = zmean ? zmean + r0 : nullptr;
       epi.zinv = zinv ? zinv + r0 : nullptr;
-      gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, folded ? 2 * dim : dim, epi);
+      gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, dim, epi);
     }
     if (out_loc == 0) PB_CUDA(cudaEventRecord(ev_done[b], ctx.stream));
   };

@@ -68,11 +68,6 @@ void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
                         const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
                         const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term, float* col_term,
                         int64_t col_ld);
-// Ragged enrol counts, folded form: operands [2d] wide (L = [e a/v ; q(n_e)], R = [t ; t*t]) so that the GEMM itself
-// adds the count-dependent column term; only the row term is left for the epilogue.
-void score_prep_folded(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
-                       const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, const double* tables_dev,
-                       SplitBuf& l_out, SplitBuf& r_out, float* row_term);
 // exact-mode epilogue applied in place on an fp64 grid: s = (s + row[m] + col[grp[m]][n] - zmean[m]) * zinv[m] -> fp32 out
 void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt, const double* row_term,
                         const double* col_term, int64_t col_ld, const int32_t* grp, const float* zmean,

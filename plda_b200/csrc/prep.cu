@@ -397,50 +397,6 @@ score_prep_grouped_kernel(const T* __restrict__ enrol, long long ne, long long l
   }
 }
 
-// Ragged enrol counts, folded form (L = [e a/v ; q(n_e)], R = [t ; t*t], K = 2d): the count-dependent
-// column term sum_i q_i(n_e) t_i^2 becomes part of the contraction, so the GEMM epilogue needs no per-row gathers and
-// the hot-path (FAST) epilogue applies -- at twice the MMA work.  Operand rows are [2d] wide (pitch ld_out).
-template <typename T>
-__global__ void __launch_bounds__(256)
-score_prep_folded_kernel(const T* __restrict__ enrol, long long ne, long long ld_e, const int32_t* __restrict__ grp,
-                         const T* __restrict__ test, long long nt, long long ld_t, int d,
-                         const double* __restrict__ tables, __nv_bfloat16* __restrict__ l_hi,
-                         __nv_bfloat16* __restrict__ l_lo, __nv_bfloat16* __restrict__ r_hi,
-                         __nv_bfloat16* __restrict__ r_lo, int ld_out, float* __restrict__ row_term,
-                         unsigned enrol_blocks) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x < enrol_blocks) {
-    const long long r = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
-    if (r >= ne) return;
-    const double* tab = tables + static_cast<long long>(grp[r]) * kScoreConstsSize;
-    const T* src = enrol + r * ld_e;
-    double acc = 0.0;
-    for (int c = lane; c < ld_out; c += 32) {
-      double lv = 0.0;
-      if (c < d) {
-        const double e = static_cast<double>(src[c]);
-        lv = e * __ldg(tab + kScoreConstsScale + c);
-        acc += __ldg(tab + kScoreConstsEnrolSq + c) * e * e;
-      } else if (c < 2 * d) {
-        lv = __ldg(tab + kScoreConstsTestSq + (c - d));
-      }
-      store_split(l_hi, l_lo, r * ld_out + c, lv);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) row_term[r] = static_cast<float>(0.5 * (__ldg(tab + kScoreConstsLogdet) - acc));
-  } else {
-    const long long r = static_cast<long long>(blockIdx.x - enrol_blocks) * kWarpsPerBlock + warp;
-    if (r >= nt) return;
-    const T* src = test + r * ld_t;
-    for (int c = lane; c < ld_out; c += 32) {
-      double v = 0.0;
-      if (c < d) v = static_cast<double>(src[c]);
-      else if (c < 2 * d) { const double t = static_cast<double>(src[c - d]); v = t * t; }
-      store_split(r_hi, r_lo, r * ld_out + c, v);
-    }
-  }
-}
-
 __global__ void score_epilogue_f64_kernel(const double* __restrict__ gram, long long ne, long long nt,
                                           const double* __restrict__ row_term, const double* __restrict__ col_term,
                                           long long col_ld, const int32_t* __restrict__ grp,
@@ -677,28 +633,6 @@ void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
         static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
         static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
         static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb);
-  PB_CUDA(cudaGetLastError());
-  ctx.count_launch();
-}
-
-void score_prep_folded(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
-                       const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, const double* tables_dev,
-                       SplitBuf& l_out, SplitBuf& r_out, float* row_term) {
-  PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
-  l_out.reserve(ne, 2 * d);
-  r_out.reserve(nt, 2 * d);
-  const unsigned eb = row_blocks(ne), tb = row_blocks(nt);
-  if (eb + tb == 0) return;
-  if (is_f32)
-    score_prep_folded_kernel<float><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
-        static_cast<const float*>(enrol), ne, ld_e, grp_dev, static_cast<const float*>(test), nt, ld_t,
-        static_cast<int>(d), tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
-        static_cast<int>(l_out.ld), row_term, eb);
-  else
-    score_prep_folded_kernel<double><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
-        static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
-        static_cast<int>(d), tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
-        static_cast<int>(l_out.ld), row_term, eb);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }
