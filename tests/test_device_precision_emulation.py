@@ -121,3 +121,54 @@ def test_emulated_device_arithmetic_meets_parity_bar(name):
     got = device_grid(dev, device_transform(dev, me, ce), ce, device_transform(dev, mt, ct))
     err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
     assert err.max() < 5e-4, err.max()      # bar is 1e-3
+
+
+def device_grid_f32_rows(m, e, n, t):
+    """The resident hot path: fp32 rows in.  The operand producer (score_prep_uniform_kernel, csrc/prep.cu) forms the
+    enrol operand in fp32 (e * fp32(a/v), ONE fp32 rounding), splits fp32 values (hi = bf16(x), lo = bf16(x - hi),
+    the subtraction is exact), rounds each square to fp32 and accumulates the row / column terms in fp64."""
+    f32 = np.float32
+    e = np.asarray(e, dtype=f32)
+    t = np.asarray(t, dtype=f32)
+    psi = m.psi
+    out = np.empty((e.shape[0], t.shape[0]))
+    t_hi = bf16(t)
+    t_lo = bf16(t.astype(np.float64) - t_hi)
+    tsq = (t * t).astype(np.float64)                   # fp32 products
+    for count in np.unique(n):
+        sel = np.nonzero(n == count)[0]
+        a = count * psi / (count * psi + 1)
+        v = 1 + psi / (count * psi + 1)
+        lm = (e[sel] * (a / v).astype(f32)).astype(f32)               # fp32 multiply
+        l_hi = bf16(lm)
+        l_lo = bf16(lm.astype(np.float64) - l_hi)
+        esq = (e[sel] * e[sel]).astype(np.float64)
+        row = (0.5 * (np.sum(np.log1p(psi) - np.log(v)) - esq @ (a * a / v))).astype(f32)
+        col = (tsq @ (0.5 * (1 / (1 + psi) - 1 / v))).astype(f32)
+        g = (l_hi @ t_hi.T + l_hi @ t_lo.T + l_lo @ t_hi.T).astype(f32)
+        out[sel] = ((g + col[None, :]) + row[:, None]).astype(f32).astype(np.float64)
+    return out
+
+
+@pytest.mark.parametrize("d", [40, 200])
+def test_emulated_fp32_row_producer_meets_parity_bar(d):
+    """Scores from fp32 transformed vectors through the fp32 operand path against the fp64 oracle on the SAME fp32
+    values: the producer's fp32 rounding is far inside the bar the bf16x3 contraction already sets."""
+    a_b = kp.two_cov_generator(d, 1234)
+    rng = np.random.RandomState(8)
+    x, labels, _ = kp.synth_speakers(a_b, [10] * 120, 1234)
+    xe, le, _ = kp.synth_speakers(a_b, [3] * 60, 1235)
+    xt, lt, _ = kp.synth_speakers(a_b, [1] * 80, 1236)
+    ref = kp.MPlda()
+    ref.fit(x, labels, 8)
+    _, ce, me = kp.group_means(xe, le)
+    _, ct, mt = kp.group_means(xt, lt)
+    e32 = kp.transform_batch(ref.plda, me, ce).astype(np.float32)
+    t32 = kp.transform_batch(ref.plda, mt, ct).astype(np.float32)
+    want = kp.score_grid(ref.plda, e32.astype(np.float64), ce, t32.astype(np.float64))
+    got = device_grid_f32_rows(ref.plda, e32, ce, t32)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+    assert err.max() < 5e-4, err.max()
+    # and the fp32 path stays close to the fp64-row path of the same design (the bench's parity_spot check)
+    alt = device_grid(ref.plda, e32.astype(np.float64), ce, t32.astype(np.float64))
+    assert np.max(np.abs(got - alt)) < 2e-4
