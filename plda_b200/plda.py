@@ -248,6 +248,36 @@ class PLDA(object):
                                        _ffi.ptr(enrol), ne, dim, dim, _ffi.F64, _ffi.HOST, int(numutts), int(seed)))
         return None
 
+    def norm_batch(self, vectors, enrol_ids, enrol_vectors, numutts=0, seed=0):
+        """Batched form of ``norm`` for large enrol sets: ``enrol_ids`` (uint64 ``[Ne]``) and ``enrol_vectors``
+        (transformed, ``[Ne, dim]``) as arrays instead of the ``{id: (n, vec)}`` dict -- same statistics
+        (``src/pldamodule.cpp:196-256``; the per-model utterance count is not used by the reference's ``norm`` either,
+        ``:235`` scores with ``n = 1``).  numpy arrays or CUDA tensors (both operands on the same side)."""
+        ids = np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
+        if _is_torch_cuda(vectors) or _is_torch_cuda(enrol_vectors):
+            if not (_is_torch_cuda(vectors) and _is_torch_cuda(enrol_vectors)):
+                raise ValueError("norm_batch: background and enrol vectors must both be CUDA tensors or both host arrays")
+            bt, bdt = _torch_matrix(vectors)
+            et, edt = _torch_matrix(enrol_vectors)
+            if et.shape[0] != ids.shape[0]:
+                raise ValueError("norm_batch: enrol_ids length mismatch")
+            if et.shape[0] == 0:
+                return None
+            _ffi.check(self._lib.plda_norm(self._h, C.c_void_p(bt.data_ptr()), bt.shape[0], bt.shape[1], bt.stride(0),
+                                           bdt, _ffi.DEVICE, _ffi.ptr(ids), C.c_void_p(et.data_ptr()), et.shape[0],
+                                           et.stride(0), et.shape[1], edt, _ffi.DEVICE, int(numutts), int(seed)))
+            return None
+        bkg, bdt = _ffi.as_matrix(vectors, "vectors")
+        enrol, edt = _ffi.as_matrix(enrol_vectors, "enrol_vectors")
+        if enrol.shape[0] != ids.shape[0]:
+            raise ValueError("norm_batch: enrol_ids length mismatch")
+        if enrol.shape[0] == 0:
+            return None
+        _ffi.check(self._lib.plda_norm(self._h, _ffi.ptr(bkg), bkg.shape[0], bkg.shape[1], bkg.shape[1], bdt, _ffi.HOST,
+                                       _ffi.ptr(ids), _ffi.ptr(enrol), enrol.shape[0], enrol.shape[1], enrol.shape[1],
+                                       edt, _ffi.HOST, int(numutts), int(seed)))
+        return None
+
     def znorm_tables(self):
         n = C.c_int64()
         _ffi.check(self._lib.plda_znorm_size(self._h, C.byref(n)))

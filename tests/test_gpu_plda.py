@@ -338,3 +338,29 @@ def test_fit_operand_kernels_agree(dtype):
     assert np.allclose(ta.T @ ta, tb.T @ tb, rtol=1e-6, atol=1e-8)
     ref = oracle_fit(x_al.double().cpu().numpy(), labels, 3)
     assert np.max(np.abs(pa - ref.plda.psi) / np.maximum(ref.plda.psi, 1e-12)) <= 2e-3
+
+
+def test_norm_batch_equals_dict_norm(small_problem):
+    """norm_batch (arrays, host or device) stores the same z-norm tables as the reference-shaped dict call."""
+    import torch
+    from plda_b200 import PLDA
+    p = small_problem
+    g = PLDA()
+    g.fit(p["x"], p["labels"], p["iters"])
+    te = g.transform(p["xe"], p["le"])
+    g.norm(p["bkg"], te)
+    ids_ref, mean_ref, std_ref = g.znorm_tables()
+    keys = np.array(sorted(te), dtype=np.uint64)
+    vecs = np.stack([te[int(k)][1] for k in keys])
+    for device in (False, True):
+        h = PLDA()
+        h.set_model(*g.get_model())
+        if device:
+            h.norm_batch(torch.from_numpy(p["bkg"]).cuda(), keys, torch.from_numpy(vecs).cuda())
+        else:
+            h.norm_batch(p["bkg"], keys, vecs)
+        ids, mean, std = h.znorm_tables()
+        assert np.array_equal(ids, ids_ref)
+        assert np.allclose(mean, mean_ref, rtol=1e-6, atol=1e-6) and np.allclose(std, std_ref, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        h.norm_batch(p["bkg"], keys[:-1], vecs)
