@@ -58,6 +58,11 @@ int plda_set_precision(plda_handle_t h, int precision);
 /* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
 int plda_set_stream(plda_handle_t h, void* cuda_stream);
 int plda_synchronize(plda_handle_t h);
+/* Order the handle's stream AFTER everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the legacy
+ * default stream): callers that fill DEVICE operands with their own kernels / copies (e.g. torch's current stream) call
+ * this before a plda_* call that reads them, instead of synchronising the host.  DEVICE outputs are complete when a
+ * call returns on the handle's own stream; on a stream installed with plda_set_stream they are stream-ordered. */
+int plda_stream_wait(plda_handle_t h, void* producer_stream);
 /* number of plda_b200 kernels launched through this handle so far (bench "gpu_launches") */
 int plda_launch_count(plda_handle_t h, int64_t* out);
 
@@ -80,6 +85,9 @@ int plda_set_allreduce(plda_handle_t h, plda_allreduce_fn fn, void* user, double
  * Errors: PLDA_E_VALUE if only one distinct label (:83-86).                                 */
 int plda_fit(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
              const uint64_t* labels, int iters);
+/* same with the labels at `labels_loc` (PLDA_DEVICE: uint64 [n] on the handle's device -- no 8 B/row upload) */
+int plda_fit_labels(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                    const uint64_t* labels, int labels_loc, int iters);
 /* timing breakdown of the last fit in milliseconds: [0] ingest+stats pass, [1] EM iterations,
  * [2] GetOutput, [3] total; [4] EM iterations run */
 int plda_fit_timings(plda_handle_t h, double out[5]);
@@ -111,7 +119,8 @@ int plda_transform_rows(plda_handle_t h, const void* x, int64_t n, int64_t d, in
 
 /* ---- score: replaces MPlda_score (src/pldamodule.cpp:258-277) --------------------------- *
  * One (enrol, test) pair, already transformed, HOST fp64 [dim]; z-normalised iff model_id was
- * seen by plda_norm (:269-273).  Result is rounded through float32 like Py_BuildValue("f").  */
+ * seen by plda_norm (:269-273).  The reference returns the fp64 LLR (Py_BuildValue("f", ...) takes a C double, :276);
+ * this entry point hands back fp32 (the grid dtype): <= 6e-8 relative, far inside the 1e-3 score tolerance. */
 int plda_score_pair(plda_handle_t h, uint64_t model_id, int64_t n_enrol, const double* enrol, const double* test,
                     int64_t dim, float* out);
 /* All-pairs grid: out[e, t] = LLR(enrol_e (n = counts[e]), test_t)  [ne x nt] fp32.
@@ -121,6 +130,31 @@ int plda_score_grid(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_e
                     const uint64_t* enrol_ids, const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype,
                     int loc, float* out, int64_t ldo, int out_loc);
 
+/* plda_score_grid with the z-norm given as arrays (fp64 [ne] at z_loc, from plda_norm_rows; NULL = none) */
+int plda_score_grid_z(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                      const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc, float* out,
+                      int64_t ldo, int out_loc, const double* zmean, const double* zstd, int z_loc);
+/* Listed trials -- what the reference's callers actually need (scoring/scorePLDA.py:302-318 calls MPlda_score once per
+ * line of the trial list): out[i] = LLR(enrol[trial_enrol[i]], test[trial_test[i]]), z-normalised like plda_score_grid
+ * (ids seen by plda_norm) or by the zmean / zstd arrays.  trial_* : int32 [n_trials] at idx_loc (HOST indices are range
+ * checked; DEVICE indices must be valid); out: fp32 [n_trials] at out_loc.  mode 0 picks the cheaper of 1 = direct
+ * (one warp per trial, fp64 accumulation, wins below ~0.5/dim list density) and 2 = grid slabs + gather on the device. */
+int plda_score_trials(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                      const uint64_t* enrol_ids, const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype,
+                      int loc, const int32_t* trial_enrol, const int32_t* trial_test, int64_t n_trials, int idx_loc,
+                      float* out, int out_loc, const double* zmean, const double* zstd, int z_loc, int mode);
+/* Histogram sink for the EER (scoring/eer.py:68-73) of a grid that is never materialised: trial (e, t) is a TARGET iff
+ * enrol_spk[e] == test_spk[t] (int32 at spk_loc).  bin = clamp(floor((score - lo) * nbins / (hi - lo)), 0, nbins-1);
+ * every target goes into hist_target, a non-target into hist_nontarget only if score >= theta_lo and otherwise into the
+ * single counter *below (theta_lo = -inf histograms everything; choose it below the EER threshold, e.g. a low quantile of
+ * the target scores, and the bulk of the grid costs no atomic).  One enrol count for all rows.  Outputs: uint64
+ * [nbins], [nbins], [1] at out_loc, overwritten (the caller sums slabs / ranks). */
+int plda_score_hist(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, int32_t enrol_count,
+                    const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc,
+                    const int32_t* enrol_spk, const int32_t* test_spk, int spk_loc, double lo, double hi, int nbins,
+                    double theta_lo, const double* zmean, const double* zstd, int z_loc, uint64_t* hist_target,
+                    uint64_t* hist_nontarget, uint64_t* below, int out_loc);
+
 /* ---- norm: replaces MPlda_norm (src/pldamodule.cpp:196-256) ------------------------------ *
  * bkg: [m x d] RAW (untransformed) background vectors; each selected row is transformed with
  * num_examples = m (sic, :224) and scored as LLR(bkg, n=1, enrol_k) against every enrol vector
@@ -129,6 +163,16 @@ int plda_score_grid(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_e
 int plda_norm(plda_handle_t h, const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc,
               const uint64_t* enrol_ids, const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype,
               int enrol_loc, int64_t numutts, uint64_t seed);
+/* Array form of plda_norm for large enrol sets (same statistics, src/pldamodule.cpp:196-256): nothing is inserted into
+ * the id table; mean_out / std_out (fp64 [ne], HOST or DEVICE) receive the per-row mean and population std and go
+ * back into plda_score_grid_z / plda_score_trials / plda_score_hist as `zmean` / `zstd`. */
+int plda_norm_rows(plda_handle_t h, const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc,
+                   const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype, int enrol_loc,
+                   int64_t numutts, uint64_t seed, double* mean_out, double* std_out, int out_loc);
+/* The background rows plda_norm / plda_norm_rows use for (m, numutts, seed): the first numutts entries of a
+ * Fisher-Yates shuffle of 0..m-1 driven by splitmix64(seed) (the reference shuffles with an unseeded
+ * std::random_shuffle, :204-213); numutts = 0 -> all m rows in order.  rows_out: HOST int32 [numutts or m]. */
+int plda_norm_selection(int64_t m, int64_t numutts, uint64_t seed, int32_t* rows_out);
 int plda_znorm_size(plda_handle_t h, int64_t* n);
 int plda_znorm_get(plda_handle_t h, uint64_t* ids, double* mean, double* stdv, int64_t capacity, int64_t* n);
 int plda_znorm_clear(plda_handle_t h);
@@ -186,6 +230,7 @@ int lda_destroy(lda_handle_t h);
 int lda_set_precision(lda_handle_t h, int precision);
 int lda_launch_count(lda_handle_t h, int64_t* out);
 int lda_synchronize(lda_handle_t h);
+int lda_stream_wait(lda_handle_t h, void* producer_stream);   /* see plda_stream_wait */
 /* labels: HOST int64 [n] (any values; classes = sorted unique, lda.py:118); priors NULL = empirical */
 int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
                 const int64_t* labels, const double* priors, int64_t n_priors);

@@ -32,11 +32,13 @@ SIGNATURES = {
     "plda_set_precision": [_vp, _int],
     "plda_set_stream": [_vp, _vp],
     "plda_synchronize": [_vp],
+    "plda_stream_wait": [_vp, _vp],
     "plda_launch_count": [_vp, C.POINTER(_i64)],
     "plda_profile_gemm": [_vp, _int],
     "plda_profile_collect": [_vp, C.POINTER(C.c_double), C.POINTER(_i64)],
     "plda_set_allreduce": [_vp, _vp, _vp, _vp, _i64],
     "plda_fit": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _int],
+    "plda_fit_labels": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _int, _int],
     "plda_fit_timings": [_vp, C.POINTER(C.c_double)],
     "plda_dim": [_vp, C.POINTER(_i64)],
     "plda_get_model": [_vp, _vp, _vp, _vp],
@@ -48,6 +50,14 @@ SIGNATURES = {
     "plda_score_pair": [_vp, C.c_uint64, _i64, _vp, _vp, _i64, C.POINTER(C.c_float)],
     "plda_score_grid": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _int],
     "plda_norm": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64, _i64, _i64, _int, _int, _i64, C.c_uint64],
+    "plda_norm_rows": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _i64, _i64, _int, _int, _i64, C.c_uint64,
+                       _vp, _vp, _int],
+    "plda_norm_selection": [_i64, _i64, C.c_uint64, _vp],
+    "plda_score_grid_z": [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _int, _vp, _vp, _int],
+    "plda_score_trials": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64, _int, _vp,
+                          _int, _vp, _vp, _int, _int],
+    "plda_score_hist": [_vp, _vp, _i64, _i64, C.c_int32, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _int, C.c_double,
+                        C.c_double, _int, C.c_double, _vp, _vp, _int, _vp, _vp, _vp, _int],
     "plda_znorm_size": [_vp, C.POINTER(_i64)],
     "plda_znorm_get": [_vp, _vp, _vp, _vp, _i64, C.POINTER(_i64)],
     "plda_znorm_clear": [_vp],
@@ -65,6 +75,7 @@ SIGNATURES = {
     "lda_set_precision": [_vp, _int],
     "lda_launch_count": [_vp, C.POINTER(_i64)],
     "lda_synchronize": [_vp],
+    "lda_stream_wait": [_vp, _vp],
     "lda_fit_svd": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
     "lda_fit_lsqr": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],
     "lda_fit_eigen": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp, _i64],

@@ -93,6 +93,18 @@ int plda_set_stream(plda_handle_t h, void* cuda_stream) {
     }
   });
 }
+int plda_stream_wait(plda_handle_t h, void* producer_stream) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    cudaStream_t ps = static_cast<cudaStream_t>(producer_stream);
+    if (ps == e.ctx.stream) return;
+    cudaEvent_t ev;
+    PB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t err = cudaEventRecord(ev, ps);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(e.ctx.stream, ev, 0);
+    cudaEventDestroy(ev);      // released once the wait has been satisfied
+    PB_CUDA(err);
+  });
+}
 int plda_synchronize(plda_handle_t h) { return with_handle(h, [&](pb::PldaEngine& e) { e.ctx.sync(); }); }
 int plda_launch_count(plda_handle_t h, int64_t* out) {
   return with_handle(h, [&](pb::PldaEngine& e) { *out = e.ctx.launches.load(); });
@@ -122,6 +134,13 @@ int plda_set_allreduce(plda_handle_t h, plda_allreduce_fn fn, void* user, double
 int plda_fit(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
              const uint64_t* labels, int iters) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.fit(x, n, d, ldx, dtype, loc, labels, iters); });
+}
+int plda_fit_labels(plda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,
+                    const uint64_t* labels, int labels_loc, int iters) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(labels_loc == PLDA_HOST || labels_loc == PLDA_DEVICE, pb::kInvalidArg, "fit: bad label location");
+    e.fit(x, n, d, ldx, dtype, loc, labels, iters, labels_loc);
+  });
 }
 int plda_fit_timings(plda_handle_t h, double out[5]) {
   return with_handle(h, [&](pb::PldaEngine& e) { memcpy(out, e.fit_ms, sizeof(e.fit_ms)); });
@@ -178,6 +197,53 @@ int plda_norm(plda_handle_t h, const void* bkg, int64_t m, int64_t d, int64_t ld
               int enrol_loc, int64_t numutts, uint64_t seed) {
   return with_handle(h, [&](pb::PldaEngine& e) {
     e.norm(bkg, m, d, ldb, dtype, loc, enrol_ids, enrol, ne, ld_enrol, dim, enrol_dtype, enrol_loc, numutts, seed);
+  });
+}
+int plda_norm_rows(plda_handle_t h, const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc,
+                   const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype, int enrol_loc,
+                   int64_t numutts, uint64_t seed, double* mean_out, double* std_out, int out_loc) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(ne == 0 || (mean_out != nullptr && std_out != nullptr), pb::kInvalidArg, "norm_rows: null output");
+    PB_CHECK(out_loc == PLDA_HOST || out_loc == PLDA_DEVICE, pb::kInvalidArg, "norm_rows: bad output location");
+    e.norm(bkg, m, d, ldb, dtype, loc, nullptr, enrol, ne, ld_enrol, dim, enrol_dtype, enrol_loc, numutts, seed, mean_out,
+           std_out, out_loc);
+  });
+}
+int plda_norm_selection(int64_t m, int64_t numutts, uint64_t seed, int32_t* rows_out) {
+  return guarded([&] {
+    PB_CHECK(m > 0 && m < (1ll << 31) && numutts >= 0 && numutts <= m && rows_out != nullptr, pb::kInvalidArg,
+             "norm_selection: bad arguments");
+    pb::norm_selection(m, numutts == 0 ? m : numutts, seed, rows_out);
+  });
+}
+int plda_score_grid_z(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                      const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc, float* out,
+                      int64_t ldo, int out_loc, const double* zmean, const double* zstd, int z_loc) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK((zmean == nullptr) == (zstd == nullptr), pb::kInvalidArg, "score_grid_z: zmean and zstd go together");
+    e.score_grid(enrol, ne, ld_enrol, enrol_counts, nullptr, test, nt, ld_test, dim, dtype, loc, out, ldo, out_loc, zmean,
+                 zstd, z_loc);
+  });
+}
+int plda_score_trials(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                      const uint64_t* enrol_ids, const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype,
+                      int loc, const int32_t* trial_enrol, const int32_t* trial_test, int64_t n_trials, int idx_loc,
+                      float* out, int out_loc, const double* zmean, const double* zstd, int z_loc, int mode) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK((zmean == nullptr) == (zstd == nullptr), pb::kInvalidArg, "score_trials: zmean and zstd go together");
+    e.score_trials(enrol, ne, ld_enrol, enrol_counts, enrol_ids, test, nt, ld_test, dim, dtype, loc, trial_enrol,
+                   trial_test, n_trials, idx_loc, out, out_loc, zmean, zstd, z_loc, mode);
+  });
+}
+int plda_score_hist(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_enrol, int32_t enrol_count,
+                    const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc,
+                    const int32_t* enrol_spk, const int32_t* test_spk, int spk_loc, double lo, double hi, int nbins,
+                    double theta_lo, const double* zmean, const double* zstd, int z_loc, uint64_t* hist_target,
+                    uint64_t* hist_nontarget, uint64_t* below, int out_loc) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK((zmean == nullptr) == (zstd == nullptr), pb::kInvalidArg, "score_hist: zmean and zstd go together");
+    e.score_hist(enrol, ne, ld_enrol, enrol_count, test, nt, ld_test, dim, dtype, loc, enrol_spk, test_spk, spk_loc, lo, hi,
+                 nbins, theta_lo, zmean, zstd, z_loc, hist_target, hist_nontarget, below, out_loc);
   });
 }
 int plda_znorm_size(plda_handle_t h, int64_t* n) {
@@ -285,6 +351,18 @@ int lda_set_precision(lda_handle_t h, int precision) {
 }
 int lda_launch_count(lda_handle_t h, int64_t* out) {
   return with_handle(h, [&](pb::LdaEngine& e) { *out = e.ctx.launches.load(); });
+}
+int lda_stream_wait(lda_handle_t h, void* producer_stream) {
+  return with_handle(h, [&](pb::LdaEngine& e) {
+    cudaStream_t ps = static_cast<cudaStream_t>(producer_stream);
+    if (ps == e.ctx.stream) return;
+    cudaEvent_t ev;
+    PB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t err = cudaEventRecord(ev, ps);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(e.ctx.stream, ev, 0);
+    cudaEventDestroy(ev);
+    PB_CUDA(err);
+  });
 }
 int lda_synchronize(lda_handle_t h) { return with_handle(h, [&](pb::LdaEngine& e) { e.ctx.sync(); }); }
 int lda_fit_svd(lda_handle_t h, const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc,

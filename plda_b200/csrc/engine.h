@@ -49,6 +49,9 @@ struct ShardSession {
   int push_count = 0;                   // enrol count the column terms of the current generation were built for
 };
 
+// rows of the background set used by norm(numutts, seed): defined splitmix64 Fisher-Yates (engine_score.cu)
+void norm_selection(int64_t m, int64_t numutts, uint64_t seed, int32_t* out);
+
 class PldaEngine {
  public:
   explicit PldaEngine(int device) : ctx(device) {}
@@ -68,19 +71,36 @@ class PldaEngine {
   void get_model(double* mean, double* transform, double* psi);
   void get_covariances(double* within, double* between);
   void smooth(double factor);
-  void fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels, int iters);
+  // labels: uint64 [n], HOST (labels_loc 0) or DEVICE (1)
+  void fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels, int iters,
+           int labels_loc = 0);
+  DevBuf<uint64_t> ws_labels;
   void transform_grouped(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,
                          int64_t targetdim, uint64_t* out_labels, int64_t* out_counts, double* out_vecs,
                          int64_t* n_out);
   void transform_rows(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const int32_t* counts,
                       int32_t const_count, int64_t targetdim, void* out, int64_t ldo, int out_dtype, int out_loc);
   void score_pair(uint64_t id, int64_t n_enrol, const double* enrol, const double* test, int64_t dim, float* out);
+  // zmean_in / zstd_in (fp64 [ne] at z_loc, both or neither): per-row z-norm given as arrays instead of the id table
   void score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* counts, const uint64_t* ids,
                   const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc, float* out,
-                  int64_t ldo, int out_loc);
+                  int64_t ldo, int out_loc, const double* zmean_in = nullptr, const double* zstd_in = nullptr,
+                  int z_loc = 0);
+  // enrol_ids may be null when mean_out / std_out (fp64 [ne] at out_loc) receive the statistics instead of the table
   void norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc, const uint64_t* enrol_ids,
             const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim, int enrol_dtype, int enrol_loc,
-            int64_t numutts, uint64_t seed);
+            int64_t numutts, uint64_t seed, double* mean_out = nullptr, double* std_out = nullptr, int out_loc = 0);
+  // listed trials (engine_sinks.cu): out[i] = LLR(enrol[te[i]], test[tt[i]]); mode 0 auto, 1 direct, 2 grid + gather
+  void score_trials(const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* counts, const uint64_t* ids,
+                    const void* test, int64_t nt, int64_t ld_test, int64_t dim, int dtype, int loc, const int32_t* te,
+                    const int32_t* tt, int64_t n_trials, int idx_loc, float* out, int out_loc, const double* zmean_in,
+                    const double* zstd_in, int z_loc, int mode);
+  // target / tail non-target histograms of the grid, nothing materialised (engine_sinks.cu)
+  void score_hist(const void* enrol, int64_t ne, int64_t ld_enrol, int32_t enrol_count, const void* test, int64_t nt,
+                  int64_t ld_test, int64_t dim, int dtype, int loc, const int32_t* enrol_spk, const int32_t* test_spk,
+                  int spk_loc, double lo, double hi, int nbins, double theta_lo, const double* zmean_in,
+                  const double* zstd_in, int z_loc, uint64_t* hist_target, uint64_t* hist_nontarget, uint64_t* below,
+                  int out_loc);
   // sharded score grid (engine_shard.cu)
   ShardSession shard;
   void shard_open(int world, int rank, const int64_t* bounds, int64_t dim, unsigned char* ipc_handle_out,
@@ -100,6 +120,7 @@ class PldaEngine {
   void shard_produce(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
                      int64_t ld_enrol, int enrol_count, int dtype);
   void shard_gemm(int64_t ne, const uint64_t* ids, float* out, int64_t ldo);
+  GemmShard shard_desc() const;
 
  public:
   void test_gemm(const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit, float* out);
@@ -108,6 +129,29 @@ class PldaEngine {
  private:
   void require_model() const { PB_CHECK(model.ready, kNotFitted, "PLDA model is not fitted (call fit or set_model)"); }
   void refresh_model_operands();
+  // enrol counts -> groups of equal count + their constants tables (engine_score.cu)
+  struct ScoreGroups {
+    bool uniform = true;
+    int32_t uniform_count = 1;
+    int ng = 1;
+    const int32_t* counts_dev = nullptr;   // ragged only
+    const int32_t* grp_dev = nullptr;      // ragged only: table index per enrol row
+    const int32_t* gcounts_dev = nullptr;  // ragged only: count of each group
+    const double* tables = nullptr;        // [ng][kScoreConstsSize]
+  };
+  ScoreGroups prepare_groups(const int32_t* counts, int64_t ne, int64_t dim);
+  void znorm_affine(const uint64_t* ids, int64_t ne, const double* zmean_in, const double* zstd_in, int z_loc,
+                    const float** zmean, const float** zinv);
+  void produce_score_operands(const Staged& se, int64_t ne, const Staged& st, int64_t nt, int64_t dim,
+                              const ScoreGroups& g, int64_t col_ld);
+  std::vector<int32_t> ragged_key;   // distinct counts ws_tables was built for
+  int64_t ragged_dim = 0;
+  DevBuf<float4> ws_mom;
+  DevBuf<unsigned long long> ws_hist;
+  DevBuf<int32_t> ws_te, ws_tt, ws_spk;
+  DevBuf<float> ws_trial_out;
+  DevBuf<double> ws_bt, ws_zstat;
+  DevBuf<uint8_t> ws_gather;
   // `keep`: grow-only staging buffer owned by the engine (hot host paths must not cudaMalloc/cudaFree per call)
   void stage(const void* p, int64_t rows, int64_t cols, int64_t ld, int dtype, int loc, Staged& s,
              DevBuf<uint8_t>* keep = nullptr);

@@ -143,7 +143,7 @@ void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const
 }
 
 void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,
-                     int iters) {
+                     int iters, int labels_loc) {
   PB_CHECK(n > 0 && d > 0, kInvalidArg, "fit: empty input");
   PB_CHECK(d <= 1024, kInvalidArg, "fit: feature dimension above 1024 is not supported");
   PB_CHECK(labels != nullptr, kInvalidArg, "fit: labels are required");
@@ -167,10 +167,14 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   Staged sx;
   stage(x, n, d, ldx, dtype, loc, sx);
   lap("rows staged");
-  DevBuf<uint64_t> lab(n);
-  PB_CUDA(cudaMemcpyAsync(lab.get(), labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+  const uint64_t* lab_dev = labels;
+  if (labels_loc == 0) {
+    ws_labels.reserve(n);
+    PB_CUDA(cudaMemcpyAsync(ws_labels.get(), labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+    lab_dev = ws_labels.get();
+  }
   lap("labels uploaded");
-  build_segments(ctx, lab.get(), n, segs);                                  // K1
+  build_segments(ctx, lab_dev, n, segs);                                    // K1
   lap("segments built");
   const int64_t k = segs.nseg;
   if (k < 2 && reduce_fn == nullptr) {

@@ -133,13 +133,14 @@ const double* PldaEngine::score_consts_for(int count, int64_t dim) {
   c.count = count;
   c.dim = dim;
   c.dev.alloc(kScoreConstsSize);
+  // pageable source: the runtime copies it to its staging buffer before the call returns (no sync needed)
   PB_CUDA(cudaMemcpyAsync(c.dev.get(), h.data(), kScoreConstsSize * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
-  PB_CUDA(cudaStreamSynchronize(ctx.stream));   // h is stack-lifetime
   return c.dev.get();
 }
 
 void PldaEngine::refresh_model_operands() {
   score_consts.clear();
+  ragged_key.clear();
   const int64_t d = model.d;
   split_rows(ctx, model.transform.get(), false, d, d, d, nullptr, nullptr, nullptr, model.a_split);
   model.h_psi.resize(d);
@@ -315,29 +316,139 @@ void PldaEngine::score_pair(uint64_t id, int64_t n_enrol, const double* enrol, c
   *out = static_cast<float>(s);                                                                 // "f" :276
 }
 
+// Enrol counts -> groups of equal count.  Uniform counts (the common case) use the single cached table of that
+// count; ragged counts get one table per distinct count, built on the host from the psi mirror and kept on the
+// device until the set of counts (or the model) changes.
+PldaEngine::ScoreGroups PldaEngine::prepare_groups(const int32_t* counts, int64_t ne, int64_t dim) {
+  PB_CHECK(counts != nullptr, kInvalidArg, "score: enrol counts are required");
+  PB_CHECK(dim > 0 && dim <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
+  ScoreGroups g;
+  g.uniform = true;
+  for (int64_t i = 0; i < ne; ++i) {
+    PB_CHECK(counts[i] > 0, kInvalidArg, "score: enrol counts must be positive");
+    g.uniform = g.uniform && counts[i] == counts[0];
+  }
+  g.uniform_count = counts[0];
+  if (g.uniform) {
+    g.tables = score_consts_for(g.uniform_count, dim);
+    return g;
+  }
+  std::vector<int32_t> gcounts(counts, counts + ne);
+  std::sort(gcounts.begin(), gcounts.end());
+  gcounts.erase(std::unique(gcounts.begin(), gcounts.end()), gcounts.end());
+  g.ng = static_cast<int>(gcounts.size());
+  std::vector<int32_t> grp(ne);
+  for (int64_t i = 0; i < ne; ++i)
+    grp[i] = static_cast<int32_t>(std::lower_bound(gcounts.begin(), gcounts.end(), counts[i]) - gcounts.begin());
+  ws_counts.reserve(ne);
+  ws_grp.reserve(ne);
+  ws_gcounts.reserve(g.ng);
+  PB_CUDA(cudaMemcpyAsync(ws_counts.get(), counts, ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(ws_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(ws_gcounts.get(), gcounts.data(), g.ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+  g.counts_dev = ws_counts.get();
+  g.grp_dev = ws_grp.get();
+  g.gcounts_dev = ws_gcounts.get();
+  if (ragged_key != gcounts || ragged_dim != dim) {
+    std::vector<double> tabs(static_cast<size_t>(g.ng) * kScoreConstsSize, 0.0);
+    for (int i = 0; i < g.ng; ++i)
+      fill_score_consts(model.h_psi.data(), dim, gcounts[i], tabs.data() + static_cast<size_t>(i) * kScoreConstsSize);
+    ws_tables.reserve(tabs.size());
+    PB_CUDA(cudaMemcpyAsync(ws_tables.get(), tabs.data(), tabs.size() * sizeof(double), cudaMemcpyHostToDevice,
+                            ctx.stream));
+    ragged_key = gcounts;
+    ragged_dim = dim;
+  }
+  g.tables = ws_tables.get();
+  return g;
+}
+
+namespace {
+__global__ void znorm_affine_kernel(const double* __restrict__ mean, const double* __restrict__ stdv, long long n,
+                                    float* __restrict__ zmean, float* __restrict__ zinv) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  zmean[i] = static_cast<float>(mean[i]);
+  zinv[i] = static_cast<float>(1.0 / stdv[i]);
+}
+}  // namespace
+
+// Per-enrol-row z-norm affine (s - mean) / std as fp32 device vectors: from caller arrays (host or device fp64) when
+// given, else from the id table filled by norm() (rows whose id is unknown stay unnormalised, pldamodule.cpp:269-273).
+void PldaEngine::znorm_affine(const uint64_t* ids, int64_t ne, const double* zmean_in, const double* zstd_in, int z_loc,
+                              const float** zmean, const float** zinv) {
+  *zmean = nullptr;
+  *zinv = nullptr;
+  if (zmean_in != nullptr && zstd_in != nullptr) {
+    ws_zmean.reserve(2 * ne);
+    if (z_loc == 1) {
+      znorm_affine_kernel<<<static_cast<unsigned>(ceil_div(ne, 256)), 256, 0, ctx.stream>>>(
+          zmean_in, zstd_in, ne, ws_zmean.get(), ws_zmean.get() + ne);
+      PB_CUDA(cudaGetLastError());
+      ctx.count_launch();
+    } else {
+      std::vector<float> hz(2 * ne);
+      for (int64_t i = 0; i < ne; ++i) {
+        hz[i] = static_cast<float>(zmean_in[i]);
+        hz[ne + i] = static_cast<float>(1.0 / zstd_in[i]);
+      }
+      PB_CUDA(cudaMemcpyAsync(ws_zmean.get(), hz.data(), 2 * ne * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+    }
+    *zmean = ws_zmean.get();
+    *zinv = ws_zmean.get() + ne;
+    return;
+  }
+  if (ids == nullptr || znorm.empty()) return;
+  std::vector<float> hz(2 * ne);
+  for (int64_t i = 0; i < ne; ++i) {
+    auto it = znorm.find(ids[i]);
+    hz[i] = it == znorm.end() ? 0.f : static_cast<float>(it->second.first);
+    hz[ne + i] = it == znorm.end() ? 1.f : static_cast<float>(1.0 / it->second.second);
+  }
+  ws_zmean.reserve(2 * ne);
+  PB_CUDA(cudaMemcpyAsync(ws_zmean.get(), hz.data(), 2 * ne * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
+  *zmean = ws_zmean.get();
+  *zinv = ws_zmean.get() + ne;
+}
+
+// Tensor-path operands of one grid: ws_l / ws_row (enrol side), ws_r / ws_col (test side, one column-term row per
+// distinct enrol count).
+void PldaEngine::produce_score_operands(const Staged& se, int64_t ne, const Staged& st, int64_t nt, int64_t dim,
+                                        const ScoreGroups& g, int64_t col_ld) {
+  ws_row.reserve(ne);
+  ws_col.reserve(static_cast<size_t>(g.ng) * col_ld);
+  if (g.uniform) {
+    score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, g.tables, ws_l, ws_r, ws_row.get(),
+                       ws_col.get(), col_ld);
+    return;
+  }
+  PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(g.ng) * col_ld * sizeof(float), ctx.stream));
+  static const char* mode = getenv("PLDA_B200_RAGGED");
+  if (mode != nullptr && strcmp(mode, "old") == 0) {            // A/B switch: per-element log / divide producers
+    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, g.counts_dev, g.uniform_count, model.psi.get(), &ws_l,
+                     nullptr, ws_row.get(), nullptr);
+    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, g.gcounts_dev, g.ng, g.uniform_count, model.psi.get(), &ws_r,
+                    ws_col.get(), col_ld, nullptr);
+  } else if (mode != nullptr && strcmp(mode, "scalar") == 0) {  // A/B switch: table-driven, 2-byte stores
+    score_prep_grouped(ctx, se.ptr, ne, se.ld, g.grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, g.ng, g.tables, ws_l, ws_r,
+                       ws_row.get(), ws_col.get(), col_ld);
+  } else {
+    score_prep_grouped_vec(ctx, se.ptr, ne, se.ld, g.grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, g.ng, g.tables, ws_l,
+                           ws_r, ws_row.get(), ws_col.get(), col_ld);
+  }
+}
+
 void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* counts,
                             const uint64_t* ids, const void* test, int64_t nt, int64_t ld_test, int64_t dim,
-                            int dtype, int loc, float* out, int64_t ldo, int out_loc) {
+                            int dtype, int loc, float* out, int64_t ldo, int out_loc, const double* zmean_in,
+                            const double* zstd_in, int z_loc) {
   require_model();
   PB_CHECK(dim > 0 && dim <= model.d, kInvalidArg, "score_grid: vector dimension does not match the model");
   PB_CHECK(ne >= 0 && nt >= 0, kInvalidArg, "score_grid: negative size");
   PB_CHECK(out != nullptr || ne * nt == 0, kInvalidArg, "score_grid: null output");
   PB_CHECK(ldo >= nt, kInvalidArg, "score_grid: output pitch too small");
   if (ne == 0 || nt == 0) return;
-  PB_CHECK(counts != nullptr, kInvalidArg, "score_grid: enrol counts are required");
-
-  // distinct enrol counts -> groups (host; ne ints).  Uniform counts (the common case) need no per-row
-  // tables on the device at all.
-  bool uniform = true;
-  for (int64_t i = 0; i < ne; ++i) {
-    PB_CHECK(counts[i] > 0, kInvalidArg, "score_grid: enrol counts must be positive");
-    uniform = uniform && counts[i] == counts[0];
-  }
-  const int32_t uniform_count = counts[0];
-  int ng = 1;
-  const int32_t* counts_dev = nullptr;
-  const int32_t* grp_dev = nullptr;
-  const int32_t* gcounts_dev = nullptr;
+  const ScoreGroups g = prepare_groups(counts, ne, dim);
 
   const bool trace = getenv("PLDA_B200_TRACE") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
@@ -351,43 +462,10 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   stage(test, nt, dim, ld_test, dtype, loc, st, &ws_stage[1]);
   lap("inputs staged (enqueued)");
 
-  std::vector<int32_t> ragged_counts;
-  if (!uniform) {
-    std::vector<int32_t> gcounts(counts, counts + ne);
-    std::sort(gcounts.begin(), gcounts.end());
-    gcounts.erase(std::unique(gcounts.begin(), gcounts.end()), gcounts.end());
-    ng = static_cast<int>(gcounts.size());
-    std::vector<int32_t> grp(ne);
-    for (int64_t i = 0; i < ne; ++i)
-      grp[i] = static_cast<int32_t>(std::lower_bound(gcounts.begin(), gcounts.end(), counts[i]) - gcounts.begin());
-    ws_counts.reserve(ne);
-    ws_grp.reserve(ne);
-    ws_gcounts.reserve(ng);
-    PB_CUDA(cudaMemcpyAsync(ws_counts.get(), counts, ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-    PB_CUDA(cudaMemcpyAsync(ws_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-    PB_CUDA(cudaMemcpyAsync(ws_gcounts.get(), gcounts.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-    counts_dev = ws_counts.get();
-    grp_dev = ws_grp.get();
-    gcounts_dev = ws_gcounts.get();
-    ragged_counts = gcounts;
-  }
-
   // optional z-norm affine per enrol row
   const float* zmean = nullptr;
   const float* zinv = nullptr;
-  std::vector<float> hz;
-  if (ids != nullptr && !znorm.empty()) {
-    hz.resize(2 * ne);
-    for (int64_t i = 0; i < ne; ++i) {
-      auto it = znorm.find(ids[i]);
-      hz[i] = it == znorm.end() ? 0.f : static_cast<float>(it->second.first);
-      hz[ne + i] = it == znorm.end() ? 1.f : static_cast<float>(1.0 / it->second.second);
-    }
-    ws_zmean.reserve(2 * ne);
-    PB_CUDA(cudaMemcpyAsync(ws_zmean.get(), hz.data(), 2 * ne * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
-    zmean = ws_zmean.get();
-    zinv = ws_zmean.get() + ne;
-  }
+  znorm_affine(ids, ne, zmean_in, zstd_in, z_loc, &zmean, &zinv);
 
   const int64_t col_ld = round_up(nt, 32);
   const bool exact = precision == 1;
@@ -396,41 +474,15 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
   if (exact) {
     ws_f64a.reserve(ne * dim);                       // L (fp64)
     ws_row64.reserve(ne);
-    ws_col64.reserve(static_cast<size_t>(ng) * col_ld);
-    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), nullptr,
+    ws_col64.reserve(static_cast<size_t>(g.ng) * col_ld);
+    score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, g.counts_dev, g.uniform_count, model.psi.get(), nullptr,
                      ws_f64a.get(), nullptr, ws_row64.get());
-    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), nullptr,
+    score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, g.gcounts_dev, g.ng, g.uniform_count, model.psi.get(), nullptr,
                     nullptr, col_ld, ws_col64.get());
     ws_f64b.reserve(nt * dim);
     convert_to_f64(ctx, st.ptr, st.is_f32, nt, dim, st.ld, ws_f64b.get(), dim);
   } else {
-    ws_row.reserve(ne);
-    ws_col.reserve(static_cast<size_t>(ng) * col_ld);
-    if (uniform) {
-      score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, score_consts_for(uniform_count, dim), ws_l,
-                         ws_r, ws_row.get(), ws_col.get(), col_ld);
-    } else {
-      PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(ng) * col_ld * sizeof(float), ctx.stream));
-      static const bool ragged_old = getenv("PLDA_B200_RAGGED") != nullptr && strcmp(getenv("PLDA_B200_RAGGED"), "old") == 0;
-      if (ragged_old) {      // A/B switch: per-element log / divide producers
-        score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, counts_dev, uniform_count, model.psi.get(), &ws_l,
-                         nullptr, ws_row.get(), nullptr);
-        score_prep_test(ctx, st.ptr, st.is_f32, nt, dim, st.ld, gcounts_dev, ng, uniform_count, model.psi.get(), &ws_r,
-                        ws_col.get(), col_ld, nullptr);
-      } else {
-        // one constants table per distinct count, built on the host from the psi mirror
-        PB_CHECK(dim <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
-        std::vector<double> tabs(static_cast<size_t>(ng) * kScoreConstsSize, 0.0);
-        for (int g = 0; g < ng; ++g)
-          fill_score_consts(model.h_psi.data(), dim, ragged_counts[g], tabs.data() + static_cast<size_t>(g) * kScoreConstsSize);
-        ws_tables.reserve(tabs.size());
-        PB_CUDA(cudaMemcpyAsync(ws_tables.get(), tabs.data(), tabs.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                ctx.stream));
-        PB_CUDA(cudaStreamSynchronize(ctx.stream));   // tabs is a stack-lifetime staging buffer
-        score_prep_grouped(ctx, se.ptr, ne, se.ld, grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, ng, ws_tables.get(), ws_l,
-                           ws_r, ws_row.get(), ws_col.get(), col_ld);
-      }
-    }
+    produce_score_operands(se, ne, st, nt, dim, g, col_ld);
   }
 
   // enrol-row chunks: bounded staging when the result goes back to the host, one chunk otherwise
@@ -457,8 +509,8 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
       gemm_f64(ctx, false, true, rows, nt, dim, 1.0, ws_f64a.get() + r0 * dim, dim, ws_f64b.get(), dim, 0.0,
                ws_gram.get(), nt);
       score_epilogue_f64(ctx, ws_gram.get(), rows, nt, ws_row64.get() + r0, ws_col64.get(), col_ld,
-                         grp_dev ? grp_dev + r0 : nullptr, zmean ? zmean + r0 : nullptr, zinv ? zinv + r0 : nullptr, dst, ldo_dev,
-                         nullptr, nullptr);
+                         g.grp_dev ? g.grp_dev + r0 : nullptr, zmean ? zmean + r0 : nullptr, zinv ? zinv + r0 : nullptr, dst,
+                         ldo_dev, nullptr, nullptr);
     } else {
       SplitOperand a = ws_l.view();
       a.hi += r0 * a.ld;
@@ -470,7 +522,7 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
       epi.row_add = ws_row.get() + r0;
       epi.col_add = ws_col.get();
       epi.col_ld = col_ld;
-      epi.grp = grp_dev ? grp_dev + r0 : nullptr;
+      epi.grp = g.grp_dev ? g.grp_dev + r0 : nullptr;
       epi.zmean = zmean ? zmean + r0 : nullptr;
       epi.zinv = zinv ? zinv + r0 : nullptr;
       gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, dim, epi);
@@ -512,15 +564,37 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
 // ------------------------------------------------------------------------- //
 // z-norm statistics
 // ------------------------------------------------------------------------- //
+// Rows of the background set a z-norm pass uses: all of them (numutts == 0 or m), else the first `numutts` entries
+// of a Fisher-Yates shuffle of 0..m-1 driven by splitmix64(seed) -- a DEFINED sequence (the reference's
+// std::random_shuffle is unseeded, src/pldamodule.cpp:204-213), so a caller or a test can reproduce the subset.
+void norm_selection(int64_t m, int64_t numutts, uint64_t seed, int32_t* out) {
+  std::vector<int32_t> idx(m);
+  std::iota(idx.begin(), idx.end(), 0);
+  uint64_t state = seed;
+  auto next = [&state]() {
+    uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  for (int64_t i = m - 1; i > 0; --i) {
+    const int64_t j = static_cast<int64_t>(next() % static_cast<uint64_t>(i + 1));
+    std::swap(idx[i], idx[j]);
+  }
+  std::copy(idx.begin(), idx.begin() + numutts, out);
+}
+
 void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dtype, int loc,
                       const uint64_t* enrol_ids, const void* enrol, int64_t ne, int64_t ld_enrol, int64_t dim,
-                      int enrol_dtype, int enrol_loc, int64_t numutts, uint64_t seed) {
+                      int enrol_dtype, int enrol_loc, int64_t numutts, uint64_t seed, double* mean_out,
+                      double* std_out, int out_loc) {
   require_model();
   PB_CHECK(d == model.d, kInvalidArg, "norm: background dimension does not match the model");
   PB_CHECK(dim > 0 && dim <= model.d, kInvalidArg, "norm: enrol dimension does not match the model");
-  PB_CHECK(m > 0, kInvalidArg, "norm: no background vectors");
+  PB_CHECK(m > 0 && m < (1ll << 31), kInvalidArg, "norm: no background vectors");
   PB_CHECK(numutts >= 0 && numutts <= m, kInvalidArg, "norm: numutts out of range");
-  PB_CHECK(enrol_ids != nullptr || ne == 0, kInvalidArg, "norm: enrol ids are required");
+  PB_CHECK(enrol_ids != nullptr || (mean_out != nullptr && std_out != nullptr) || ne == 0, kInvalidArg,
+           "norm: enrol ids or output arrays are required");
   if (ne == 0) return;
   if (numutts == 0) numutts = m;
 
@@ -528,56 +602,54 @@ void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dt
   stage(bkg, m, d, ldb, dtype, loc, sb);
   const void* rows_ptr = sb.ptr;
   int64_t rows_ld = sb.ld;
-  DevBuf<uint8_t> gathered;
   if (numutts < m) {
-    // seeded shuffle, first numutts rows (the reference uses an unseeded std::random_shuffle, :204-213)
-    std::vector<int32_t> idx(m);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::mt19937_64 rng(seed);
-    std::shuffle(idx.begin(), idx.end(), rng);
-    idx.resize(numutts);
-    DevBuf<int32_t> didx(numutts);
-    PB_CUDA(cudaMemcpyAsync(didx.get(), idx.data(), numutts * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    std::vector<int32_t> idx(numutts);
+    norm_selection(m, numutts, seed, idx.data());
+    ws_te.reserve(numutts);
+    PB_CUDA(cudaMemcpyAsync(ws_te.get(), idx.data(), numutts * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
     const size_t es = sb.is_f32 ? 4 : 8;
-    gathered.alloc(static_cast<size_t>(numutts) * d * es);
+    ws_gather.reserve(static_cast<size_t>(numutts) * d * es);
     gather_rows_kernel<<<static_cast<unsigned>(numutts), 128, 0, ctx.stream>>>(
-        static_cast<const uint8_t*>(sb.ptr), sb.ld * es, didx.get(), numutts, d * es, gathered.get());
+        static_cast<const uint8_t*>(sb.ptr), sb.ld * es, ws_te.get(), numutts, d * es, ws_gather.get());
     PB_CUDA(cudaGetLastError());
     ctx.count_launch();
-    ctx.sync();
-    rows_ptr = gathered.get();
+    rows_ptr = ws_gather.get();
     rows_ld = d;
   }
   // background rows transformed with num_examples = m  (src/pldamodule.cpp:224)
-  DevBuf<double> bt(static_cast<size_t>(numutts) * dim);
+  ws_bt.reserve(static_cast<size_t>(numutts) * dim);
   transform_device_rows(rows_ptr, sb.is_f32, numutts, d, rows_ld, model.mean.get(), nullptr,
-                        static_cast<int32_t>(std::min<int64_t>(m, INT32_MAX)), dim, bt.get(), dim, nullptr, 0);
+                        static_cast<int32_t>(std::min<int64_t>(m, INT32_MAX)), dim, ws_bt.get(), dim, nullptr, 0);
   stage(enrol, ne, dim, ld_enrol, enrol_dtype, enrol_loc, se);
 
   // S[e, b] = LLR(train = bkg_b, n = 1, test = enrol_e): symmetric in (e,b) for n = 1, so enrol rows are the
   // M side (row reduction over the cohort happens in the GEMM epilogue; the grid is never materialised).
-  ws_rsum.reserve(ne);
-  ws_rsq.reserve(ne);
-  PB_CUDA(cudaMemsetAsync(ws_rsum.get(), 0, ne * sizeof(double), ctx.stream));
-  PB_CUDA(cudaMemsetAsync(ws_rsq.get(), 0, ne * sizeof(double), ctx.stream));
+  ws_zstat.reserve(2 * ne);
+  double* dmean = ws_zstat.get();
+  double* dstd = ws_zstat.get() + ne;
   const int64_t col_ld = round_up(numutts, 32);
   if (precision == 1) {
+    ws_rsum.reserve(ne);
+    ws_rsq.reserve(ne);
+    PB_CUDA(cudaMemsetAsync(ws_rsum.get(), 0, ne * sizeof(double), ctx.stream));
+    PB_CUDA(cudaMemsetAsync(ws_rsq.get(), 0, ne * sizeof(double), ctx.stream));
     ws_f64a.reserve(ne * dim);
     ws_row64.reserve(ne);
     ws_col64.reserve(col_ld);
     score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, nullptr, 1, model.psi.get(), nullptr, ws_f64a.get(),
                      nullptr, ws_row64.get());
-    score_prep_test(ctx, bt.get(), false, numutts, dim, dim, nullptr, 1, 1, model.psi.get(), nullptr, nullptr,
+    score_prep_test(ctx, ws_bt.get(), false, numutts, dim, dim, nullptr, 1, 1, model.psi.get(), nullptr, nullptr,
                     col_ld, ws_col64.get());
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ne, (512ll << 20) / 8 / numutts));
     ws_gram.reserve(static_cast<size_t>(chunk) * numutts);
     for (int64_t r0 = 0; r0 < ne; r0 += chunk) {
       const int64_t rows = std::min(chunk, ne - r0);
-      gemm_f64(ctx, false, true, rows, numutts, dim, 1.0, ws_f64a.get() + r0 * dim, dim, bt.get(), dim, 0.0,
+      gemm_f64(ctx, false, true, rows, numutts, dim, 1.0, ws_f64a.get() + r0 * dim, dim, ws_bt.get(), dim, 0.0,
                ws_gram.get(), numutts);
       score_epilogue_f64(ctx, ws_gram.get(), rows, numutts, ws_row64.get() + r0, ws_col64.get(), col_ld, nullptr,
                          nullptr, nullptr, nullptr, 0, ws_rsum.get() + r0, ws_rsq.get() + r0);
     }
+    znorm_finalize(ctx, ws_rsum.get(), ws_rsq.get(), ne, numutts, nullptr, nullptr, dmean, dstd);
   } else {
     // one enrol count (n = 1): the table-driven producer (no per-element log / divide); the two sides may differ in
     // dtype (caller's enrol rows vs the fp64 transformed cohort), hence one launch per side
@@ -592,24 +664,41 @@ void PldaEngine::norm(const void* bkg, int64_t m, int64_t d, int64_t ldb, int dt
     cohort.hi[0] = ws_r.hi.get();
     cohort.lo[0] = ws_r.lo.get();
     cohort.term[0] = ws_col.get();
-    score_prep_uniform_multi(ctx, nullptr, 0, 0, nullptr, nullptr, bt.get(), numutts, dim, 0, col_ld, cohort, ws_r.ld,
+    score_prep_uniform_multi(ctx, nullptr, 0, 0, nullptr, nullptr, ws_bt.get(), numutts, dim, 0, col_ld, cohort, ws_r.ld,
                              false, dim, consts, PrepSignal{});
     ctx.pdl_pending = false;     // the GEMM below does not directly follow a producer it may overlap
+    // moments sink: per-(row, column tile, epilogue half) shifted fp32 partials, merged in fp64 -- no atomics, and
+    // no cancellation when |mean| >> std
+    const int n_tiles = gemm_n_tiles(numutts);
+    ws_mom.reserve(static_cast<size_t>(ne) * n_tiles * 2);
     GemmEpilogue epi;
     epi.row_add = ws_row.get();
     epi.col_add = ws_col.get();
     epi.col_ld = col_ld;
-    epi.rsum = ws_rsum.get();
-    epi.rsq = ws_rsq.get();
+    epi.mom = ws_mom.get();
     gemm_bf16x3(ctx, ws_l.view(), ws_r.view(), ne, numutts, dim, epi);
+    moments_reduce(ctx, ws_mom.get(), ne, n_tiles, nullptr, nullptr, dmean, dstd);
   }
-  DevBuf<double> dmean(ne), dstd(ne);
-  znorm_finalize(ctx, ws_rsum.get(), ws_rsq.get(), ne, numutts, nullptr, nullptr, dmean.get(), dstd.get());
-  std::vector<double> hm(ne), hs(ne);
-  PB_CUDA(cudaMemcpyAsync(hm.data(), dmean.get(), ne * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(hs.data(), dstd.get(), ne * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  if (mean_out != nullptr && std_out != nullptr && out_loc == 1) {
+    PB_CUDA(cudaMemcpyAsync(mean_out, dmean, ne * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(std_out, dstd, ne * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+  }
+  const bool to_host = enrol_ids != nullptr || (mean_out != nullptr && out_loc == 0);
+  if (!to_host) {
+    if (ctx.owns_stream) ctx.sync();
+    return;
+  }
+  std::vector<double> hm(2 * ne);
+  PB_CUDA(cudaMemcpyAsync(hm.data(), ws_zstat.get(), 2 * ne * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
-  for (int64_t i = 0; i < ne; ++i) znorm.emplace(enrol_ids[i], std::make_pair(hm[i], hs[i]));   // insert: first wins
+  if (mean_out != nullptr && std_out != nullptr && out_loc == 0) {
+    std::copy(hm.begin(), hm.begin() + ne, mean_out);
+    std::copy(hm.begin() + ne, hm.end(), std_out);
+  }
+  if (enrol_ids != nullptr) {
+    znorm.reserve(znorm.size() + ne);
+    for (int64_t i = 0; i < ne; ++i) znorm.emplace(enrol_ids[i], std::make_pair(hm[i], hm[ne + i]));   // insert: first wins
+  }
 }
 
 // ------------------------------------------------------------------------- //

@@ -138,22 +138,21 @@ void PldaEngine::shard_produce(const void* test_shard, int64_t nt_local, int64_t
 }
 
 // The grid of this rank's enrol block (operand already in ws_l / ws_row) against the current generation.
+GemmShard PldaEngine::shard_desc() const {
+  GemmShard gs;
+  gs.flags = reinterpret_cast<const unsigned*>(shard.region + kFlagsOff);
+  gs.err = reinterpret_cast<unsigned*>(shard.region + kErrOff);
+  gs.epoch = shard.epoch;
+  gs.world = shard.world;
+  gs.rank = shard.rank;
+  for (int r = 0; r <= shard.world; ++r) gs.bounds[r] = static_cast<int>(shard.bounds[r]);
+  return gs;
+}
+
 void PldaEngine::shard_gemm(int64_t ne, const uint64_t* ids, float* out, int64_t ldo) {
   const float* zmean = nullptr;
   const float* zinv = nullptr;
-  if (ids != nullptr && !znorm.empty()) {
-    std::vector<float> hz(2 * ne);
-    for (int64_t i = 0; i < ne; ++i) {
-      auto it = znorm.find(ids[i]);
-      hz[i] = it == znorm.end() ? 0.f : static_cast<float>(it->second.first);
-      hz[ne + i] = it == znorm.end() ? 1.f : static_cast<float>(1.0 / it->second.second);
-    }
-    ws_zmean.reserve(2 * ne);
-    PB_CUDA(cudaMemcpyAsync(ws_zmean.get(), hz.data(), 2 * ne * sizeof(float), cudaMemcpyHostToDevice, ctx.stream));
-    PB_CUDA(cudaStreamSynchronize(ctx.stream));   // hz is a stack-lifetime staging buffer
-    zmean = ws_zmean.get();
-    zinv = ws_zmean.get() + ne;
-  }
+  znorm_affine(ids, ne, nullptr, nullptr, 0, &zmean, &zinv);
   const size_t gen = shard.off_gen[shard.epoch & 1u];
   SplitOperand b;
   b.hi = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen);
@@ -169,13 +168,7 @@ void PldaEngine::shard_gemm(int64_t ne, const uint64_t* ids, float* out, int64_t
   epi.col_ld = shard.col_ld;
   epi.zmean = zmean;
   epi.zinv = zinv;
-  GemmShard gs;
-  gs.flags = reinterpret_cast<const unsigned*>(shard.region + kFlagsOff);
-  gs.err = reinterpret_cast<unsigned*>(shard.region + kErrOff);
-  gs.epoch = shard.epoch;
-  gs.world = shard.world;
-  gs.rank = shard.rank;
-  for (int r = 0; r <= shard.world; ++r) gs.bounds[r] = static_cast<int>(shard.bounds[r]);
+  const GemmShard gs = shard_desc();
   gemm_bf16x3(ctx, ws_l.view(), b, ne, shard.nt_total, shard.dim, epi, &gs);
 }
 
@@ -192,8 +185,12 @@ void PldaEngine::shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, in
            "shard_score: the column terms were pushed for a different enrol count");
   PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
   PB_CHECK(ne >= 0 && (ne == 0 || (enrol != nullptr && out != nullptr)), kInvalidArg, "shard_score: null pointer");
-  PB_CHECK(ld_enrol >= shard.dim && ldo >= shard.nt_total, kInvalidArg, "shard_score: pitch too small");
-  if (ne == 0) return;
+  PB_CHECK(ne == 0 || (ld_enrol >= shard.dim && ldo >= shard.nt_total), kInvalidArg, "shard_score: pitch too small");
+  if (ne == 0) {
+    // no grid to compute, but the step's back-pressure still applies: see every peer's flag before the next push
+    shard_wait_all(ctx, shard_desc());
+    return;
+  }
   ws_row.reserve(ne);
   PrepDst none;
   score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, &ws_l, ws_row.get(), nullptr, 0, 0, 0, 0, none, shard.ldk,
@@ -208,6 +205,7 @@ void PldaEngine::shard_step(const void* test_shard, int64_t nt_local, int64_t ld
   PB_CHECK(!shard.open || ldo >= shard.nt_total, kInvalidArg, "shard_step: output pitch too small");
   shard_produce(test_shard, nt_local, ld_test, enrol, ne, ld_enrol, enrol_count, dtype);
   if (ne > 0) shard_gemm(ne, ids, out, ldo);
+  else shard_wait_all(ctx, shard_desc());     // an empty enrol block must not run ahead of its peers
 }
 
 void PldaEngine::shard_status(int64_t* epoch, int64_t* timeouts) {

@@ -146,6 +146,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   constexpr bool FAST = EPI == 1;
   constexpr bool LSE = EPI == 2;
   constexpr bool SECT = EPI == 3;   // score-grid path, accumulators stored straight from registers (no smem staging)
+  constexpr bool MOM = EPI == 4;    // z-norm sink: per-row shifted moments of the scores, nothing stored
+  constexpr bool HIST = EPI == 5;   // EER sink: target / tail non-target histograms of the scores, nothing stored
   constexpr int kStages = Cfg<TWO>::kStages;
   constexpr int kStageBytes = Cfg<TWO>::kStageBytes;
   constexpr int kBBytes = Cfg<TWO>::kBBytes;
@@ -384,6 +386,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (e.zmean) { zm = __ldg(e.zmean + m); zi = __ldg(e.zinv + m); }
       }
       const float radd = ra - zm;
+      int row_spk = 0;
+      if (HIST && mvalid) row_spk = __ldg(e.row_spk + m);
       float rs = 0.f, rq = 0.f;
       float lmax = -INFINITY, lsum = 0.f;
       const int ncols = min(p.bn, p.n - n0);
@@ -529,6 +533,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       };
 
+      if constexpr (HIST) {
+        // speaker ids of this warp's columns, parked in the warp's own (otherwise unused) staging box
+        int* sidx = reinterpret_cast<int*>(sb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          const int col = n0 + cc * 32 + lane;
+          sidx[i * 32 + lane] = (cc < nchunks && col < p.n) ? __ldg(e.col_spk + col) : 0;
+        }
+        __syncwarp();
+      }
       const long long t_w0 = clock64();
       mbar_wait(&tfull[acc], acc_phase);
       dbg_tfull += clock64() - t_w0;
@@ -631,6 +646,71 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         else mbar_arrive(&tempty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if constexpr (MOM) {
+        // Shifted moments of this thread's row over the warp's chunks: pivot = the slot's first score, so the
+        // fp32 sums carry deviations of the size of the cohort spread, not of the score itself (no cancellation
+        // when |mean| >> std); the slots of a row are merged in fp64 (moments_reduce, Chan's update).
+        float s1 = 0.f, s2 = 0.f, piv = 0.f;
+        int cnt = 0;
+        if (h < nchunks) {
+          piv = (__uint_as_float(r[0][0]) + (col_cached ? colslot[h * 32] : 0.f) + radd) * zi;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int cc = h + 2 * i;
+            if (cc >= nchunks) continue;
+            const int nbase = n0 + cc * 32;
+            const float4* cp = reinterpret_cast<const float4*>(colslot + cc * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col_cached) t = cp[j4];
+              const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * j4 + jj;
+                if (nbase + j < p.n) {
+                  const float dv = (__uint_as_float(r[i][j]) + tv[jj] + radd) * zi - piv;
+                  s1 += dv;
+                  s2 = fmaf(dv, dv, s2);
+                  ++cnt;
+                }
+              }
+            }
+          }
+        }
+        if (mvalid)
+          e.mom[(static_cast<long long>(m) * p.n_tiles + w.n_blk) * 2 + h] = make_float4(s1, s2, piv, static_cast<float>(cnt));
+        continue;
+      }
+      if constexpr (HIST) {
+        const int* sidx = reinterpret_cast<const int*>(sb);
+        unsigned below = 0;
+        const int top = e.nbins - 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc >= nchunks) continue;
+          const int nbase = n0 + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (!mvalid || nbase + j >= p.n) continue;
+            const float v = (__uint_as_float(r[i][j]) + (col_cached ? colslot[cc * 32 + j] : 0.f) + radd) * zi;
+            const bool tgt = sidx[i * 32 + j] == row_spk;
+            if (tgt || v >= e.theta_lo) {
+              int b = __float2int_rd((v - e.hist_lo) * e.hist_scale);
+              b = b < 0 ? 0 : (b > top ? top : b);
+              atomicAdd((tgt ? e.hist_t : e.hist_n) + b, 1ull);
+            } else {
+              ++below;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if (lane == 0 && below != 0) atomicAdd(e.below, static_cast<unsigned long long>(below));
+        __syncwarp();     // the next item's speaker ids overwrite the staging box
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int cc = h + 2 * i;
@@ -743,6 +823,47 @@ Plan make_plan(const Context& ctx, int64_t m, int64_t n, int64_t k, int ksplit) 
   return pl;
 }
 
+struct TmapSet {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo, ta_hi, ta_lo, tb_hi, tb_lo, out;
+};
+
+template <bool TWO, int EPI>
+void launch_one(Context& ctx, const Plan& pl, const TmapSet& tm, bool pdl) {
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(gemm_bf16x3_kernel<TWO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = ctx.stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (TWO) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl && TWO) {     // the single-CTA kernel keeps plain stream order (as before)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<TWO, EPI>, tm.a_hi, tm.a_lo, tm.b_hi, tm.b_lo, tm.ta_hi, tm.ta_lo,
+                             tm.tb_hi, tm.tb_lo, tm.out, pl.p));
+}
+
+template <int EPI>
+void launch_epi(Context& ctx, const Plan& pl, const TmapSet& tm, bool pdl) {
+  if (pl.two_cta) launch_one<true, EPI>(ctx, pl, tm, pdl);
+  else launch_one<false, EPI>(ctx, pl, tm, pdl);
+}
+
 void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl, float* out, int64_t ldo,
             int64_t out_rows) {
   GemmParams& p = pl.p;
@@ -788,17 +909,11 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
   // register-direct sector stores (PLDA_B200_EPI=sector): same preconditions as the TMA path (8-byte aligned rows)
   if (epi == 1 && ctx.epi_sector) epi = 3;
   else if (out == nullptr && ep.lse_max != nullptr && ep.rsum == nullptr && ep.grp == nullptr) epi = 2;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_bf16x3_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  });
+  else if (out == nullptr && ep.mom != nullptr) epi = 4;
+  else if (out == nullptr && ep.hist_n != nullptr) epi = 5;
+  if (epi == 4 || epi == 5)
+    PB_CHECK(ep.grp == nullptr && ep.rsum == nullptr && ep.lse_max == nullptr, kInvalidArg,
+             "gemm: the moments / histogram sinks need uniform column terms and no other reduction");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx.profile_gemm) {
     PB_CUDA(cudaEventCreate(&e0));
@@ -808,45 +923,14 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
   // the events of the profiling pass sit between the producer and this launch: no overlap to declare then
   const bool pdl = ctx.pdl_pending && !ctx.profile_gemm;
   ctx.pdl_pending = false;
-  if (pl.two_cta) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = ctx.stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 2 : 1;
-    if (epi == 1)
-      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 1>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
-                                 ttb_lo, tout, p));
-    else if (epi == 2)
-      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 2>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
-                                 ttb_lo, tout, p));
-    else if (epi == 3)
-      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 3>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
-                                 ttb_lo, tout, p));
-    else
-      PB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<true, 0>, ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi,
-                                 ttb_lo, tout, p));
-  } else if (epi == 1) {
-    gemm_bf16x3_kernel<false, 1><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
-        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
-  } else if (epi == 2) {
-    gemm_bf16x3_kernel<false, 2><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
-        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
-  } else if (epi == 3) {
-    gemm_bf16x3_kernel<false, 3><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
-        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
-  } else {
-    gemm_bf16x3_kernel<false, 0><<<pl.grid, NUM_THREADS, SMEM_BYTES, ctx.stream>>>(
-        ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout, p);
+  const TmapSet tm{ta_hi, ta_lo, tb_hi, tb_lo, tta_hi, tta_lo, ttb_hi, ttb_lo, tout};
+  switch (epi) {
+    case 1: launch_epi<1>(ctx, pl, tm, pdl); break;
+    case 2: launch_epi<2>(ctx, pl, tm, pdl); break;
+    case 3: launch_epi<3>(ctx, pl, tm, pdl); break;
+    case 4: launch_epi<4>(ctx, pl, tm, pdl); break;
+    case 5: launch_epi<5>(ctx, pl, tm, pdl); break;
+    default: launch_epi<0>(ctx, pl, tm, pdl); break;
   }
   PB_CUDA(cudaGetLastError());
   if (ctx.profile_gemm) {
@@ -898,6 +982,27 @@ void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int
              kInvalidArg, "gemm: col_add must be 16B aligned with pitch >= round_up(n,32)");
   }
   launch(ctx, a, b, pl, epi.out, epi.ldo, m);
+}
+
+namespace {
+// A rank without enrol rows launches no GEMM; it still has to observe every peer's flag for the epoch before it may
+// push again (the protocol's only back-pressure), or it could overwrite a generation a peer is still reading.
+__global__ void shard_wait_all_kernel(GemmShard sh) {
+  if (static_cast<int>(threadIdx.x) < sh.world) shard_wait(sh.flags + threadIdx.x, sh.epoch, sh.err);
+}
+}  // namespace
+
+void shard_wait_all(Context& ctx, const GemmShard& shard) {
+  PB_CHECK(shard.flags != nullptr && shard.err != nullptr && shard.world >= 1 && shard.world <= 16, kInvalidArg,
+           "shard_wait_all: bad shard description");
+  shard_wait_all_kernel<<<1, 32, 0, ctx.stream>>>(shard);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+int gemm_n_tiles(int64_t n) {
+  const int64_t bn = n >= BN_MAX ? BN_MAX : round_up(n, 16);
+  return static_cast<int>(ceil_div(n, bn));
 }
 
 int choose_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k) {

@@ -76,6 +76,27 @@ void score_epilogue_f64(Context& ctx, const double* gram, int64_t ne, int64_t nt
 void znorm_finalize(Context& ctx, const double* rsum, const double* rsq, int64_t ne, int64_t m, float* zmean,
                     float* zinv, double* mean_out, double* std_out);
 
+// ---- sinks of the score grid other than "whole fp32 matrix" (sinks.cu) ------------------------------- //
+// z-norm moments from the MOM epilogue's per-slot partials (GemmEpilogue::mom, [ne][n_tiles][2] float4): Chan's
+// pairwise update in fp64 -> mean and POPULATION std per enrol row (src/pldamodule.cpp:240-253); any output may be null
+void moments_reduce(Context& ctx, const float4* mom, int64_t ne, int n_tiles, float* zmean, float* zinv,
+                    double* mean_out, double* std_out);
+// Listed trials, scored directly (one warp per trial, fp64 accumulation): out[i] = LLR(enrol[te[i]], test[tt[i]]) in
+// the Gram form of SURVEY App. A.7 with the per-count constants of `tables` ([ng][kScoreConstsSize]; grp == null ->
+// table 0), optional z-norm affine per enrol row.  Replaces the per-trial loop of scoring/scorePLDA.py:302-318 when
+// the list is sparse (the grid + gather_trials wins above ~0.5/dim density).
+void score_trials_direct(Context& ctx, const void* enrol, int64_t ld_e, const void* test, int64_t ld_t, bool is_f32,
+                         int64_t dim, const double* tables, const int32_t* grp, const float* zmean, const float* zinv,
+                         const int32_t* te, const int32_t* tt, int64_t n_trials, float* out);
+// out[i] = slab[(te[i] - r0) * ld + tt[i]] for the trials with r0 <= te[i] < r0 + rows (others untouched)
+void gather_trials(Context& ctx, const float* slab, int64_t ld, int64_t r0, int64_t rows, const int32_t* te,
+                   const int32_t* tt, int64_t n_trials, float* out);
+// Vectorised operand producer for ragged enrol counts (16-byte loads / stores, per-row constants table)
+void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
+                            const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
+                            const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term,
+                            float* col_term, int64_t col_ld);
+
 // ---- label segmentation (K1) + segmented sums (K2/K4) --------------------------- //
 struct Segments {
   DevBuf<int32_t> order;       // [n] row index of sorted position p

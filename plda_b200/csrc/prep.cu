@@ -397,6 +397,64 @@ score_prep_grouped_kernel(const T* __restrict__ enrol, long long ne, long long l
   }
 }
 
+// Vectorised form of the ragged-count producer: one warp per row, a lane owns 8-column groups (16-byte loads, one
+// 16-byte store per plane), constants read from the row's table (L1 / L2 resident: 24 KB per distinct count).
+// Test rows: the split row is written once together with the column term of group 0; the other groups re-read the
+// row from L1.
+template <typename T>
+__global__ void __launch_bounds__(256)
+score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long long ld_e,
+                              const int32_t* __restrict__ grp, const T* __restrict__ test, long long nt,
+                              long long ld_t, int d, int ng, const double* __restrict__ tables,
+                              __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo,
+                              __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo, int ld_out,
+                              float* __restrict__ row_term, float* __restrict__ col_term, long long col_ld,
+                              unsigned enrol_blocks, int vec_e, int vec_t) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  typename Group8Of<T>::type g;
+  if (blockIdx.x < enrol_blocks) {
+    const long long r = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
+    if (r >= ne) return;
+    const double* tab = tables + static_cast<long long>(__ldg(grp + r)) * kScoreConstsSize;
+    const T* src = enrol + r * ld_e;
+    double acc = 0.0;
+    for (int c = lane * 8; c < ld_out; c += 256) {
+      g.load_consts(tab + kScoreConstsEnrolSq, tab + kScoreConstsScale, true, c, d);
+      T v[8];
+      load8<T>(src, c, d, vec_e != 0, v);
+      uint4 hi, lo;
+      g.run(v, hi, lo);
+      acc += g.part;
+      *reinterpret_cast<uint4*>(l_hi + r * ld_out + c) = hi;
+      *reinterpret_cast<uint4*>(l_lo + r * ld_out + c) = lo;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) row_term[r] = static_cast<float>(0.5 * (__ldg(tab + kScoreConstsLogdet) - acc));
+  } else {
+    const long long r = static_cast<long long>(blockIdx.x - enrol_blocks) * kWarpsPerBlock + warp;
+    if (r >= nt) return;
+    const T* src = test + r * ld_t;
+    for (int gi = 0; gi < ng; ++gi) {
+      const double* tab = tables + static_cast<long long>(gi) * kScoreConstsSize;
+      double acc = 0.0;
+      for (int c = lane * 8; c < ld_out; c += 256) {
+        g.load_consts(tab + kScoreConstsTestSq, tab + kScoreConstsScale, false, c, d);
+        T v[8];
+        load8<T>(src, c, d, vec_t != 0, v);
+        uint4 hi, lo;
+        g.run(v, hi, lo);
+        acc += g.part;
+        if (gi == 0) {
+          *reinterpret_cast<uint4*>(r_hi + r * ld_out + c) = hi;
+          *reinterpret_cast<uint4*>(r_lo + r * ld_out + c) = lo;
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) col_term[gi * col_ld + r] = static_cast<float>(acc);
+    }
+  }
+}
+
 __global__ void score_epilogue_f64_kernel(const double* __restrict__ gram, long long ne, long long nt,
                                           const double* __restrict__ row_term, const double* __restrict__ col_term,
                                           long long col_ld, const int32_t* __restrict__ grp,
@@ -633,6 +691,31 @@ void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
         static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
         static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
         static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
+                            const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
+                            const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term,
+                            float* col_term, int64_t col_ld) {
+  PB_CHECK(d <= 1024 && ng >= 1, kInvalidArg, "score: dimension above 1024 is not supported");
+  l_out.reserve(ne, d);
+  r_out.reserve(nt, d);
+  const unsigned eb = row_blocks(ne), tb = row_blocks(nt);
+  if (eb + tb == 0) return;
+  const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
+  const int vec_t = test && rows_vectorisable(test, ld_t, is_f32) ? 1 : 0;
+  if (is_f32)
+    score_prep_grouped_vec_kernel<float><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
+        static_cast<const float*>(enrol), ne, ld_e, grp_dev, static_cast<const float*>(test), nt, ld_t,
+        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
+        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t);
+  else
+    score_prep_grouped_vec_kernel<double><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
+        static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
+        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
+        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

@@ -131,6 +131,21 @@ struct GemmEpilogue {
   // online log-sum-exp per row over the columns (LDA): rmax/rsumexp are [M x n_tiles]
   float* lse_max = nullptr;
   float* lse_sum = nullptr;
+  // moments sink (z-norm, nothing stored): per (row, column tile, epilogue half) the fp32 partials
+  // {sum(v - p), sum((v - p)^2), p, count} with the pivot p = the first score of that slot -- combined in fp64 by
+  // moments_reduce (Chan's update); [M][n_tiles][2] float4
+  float4* mom = nullptr;
+  // tail-histogram sink (EER at sizes where the grid is not materialised, nothing stored): a trial (m, n) is a
+  // TARGET iff row_spk[m] == col_spk[n].  Targets are always binned into hist_t; non-targets are binned into hist_n
+  // only when v >= theta_lo and otherwise just counted in *below (the bulk of the non-target mass never touches an
+  // atomic).  bin = clamp(floor((v - hist_lo) * hist_scale), 0, nbins - 1)
+  const int32_t* row_spk = nullptr;
+  const int32_t* col_spk = nullptr;
+  unsigned long long* hist_t = nullptr;
+  unsigned long long* hist_n = nullptr;
+  unsigned long long* below = nullptr;
+  float hist_lo = 0.f, hist_scale = 0.f, theta_lo = 0.f;
+  int nbins = 0;
 };
 
 // Sharded B operand (scoring grid): rows [bounds[r], bounds[r+1]) of B (and of the column-term row)
@@ -146,6 +161,10 @@ struct GemmShard {
   int bounds[17] = {0};
 };
 
+// waits (bounded, like the GEMM's own polls) until every rank's flag has reached shard.epoch -- for a rank that has
+// no GEMM to launch in a step
+void shard_wait_all(Context& ctx, const GemmShard& shard);
+
 // C[M,N] = A[M,K] * B[N,K]^T with bf16x3 split operands on tcgen05 (fp32 TMEM accumulate).
 // ksplit > 1: reduction axis split into ksplit chunks, partial tiles written to
 // `partial` ([ksplit][Mpad][Npad] fp32, Mpad = round_up(M,128), Npad = round_up(N,4)) and
@@ -155,6 +174,8 @@ void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int
 void gemm_bf16x3_splitk(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
                         int ksplit, float* partial);
 int choose_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k);
+// number of column tiles gemm_bf16x3 uses for n columns (slot count of the per-tile epilogue outputs)
+int gemm_n_tiles(int64_t n);
 // number of partial planes gemm_bf16x3_splitk actually writes for a requested ksplit
 int effective_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k, int ksplit);
 // out[m*ldo+n] = alpha * sum_s partial[s][m][n]  (+ beta * out) in fp64; optional symmetrise

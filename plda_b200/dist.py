@@ -184,6 +184,7 @@ class PeerShardedScorer:
         """Producer + exchange: this rank's transformed test rows (CUDA tensor ``[bounds[rank+1]-bounds[rank], dim]``,
         fp32 or fp64) -> every rank's operand buffer.  Stream-ordered, does not synchronise."""
         tt, dtype = _cuda_matrix(test_shard)
+        self.plda._after_torch(tt)
         self._ffi.check(self._lib.plda_shard_push(self.plda._h, self._C.c_void_p(tt.data_ptr()), tt.shape[0],
                                                   tt.stride(0) if tt.shape[0] else self.dim, dtype, int(enrol_count)))
 
@@ -196,6 +197,7 @@ class PeerShardedScorer:
             ldo = (self.n_test_total + 3) // 4 * 4
             out = torch.empty((ne, ldo), dtype=torch.float32, device=et.device)[:, : self.n_test_total]
         ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
+        self.plda._after_torch(et)
         self._ffi.check(self._lib.plda_shard_score(self.plda._h, self._C.c_void_p(et.data_ptr()), ne,
                                                    et.stride(0) if ne else self.dim, int(enrol_count),
                                                    self._ffi.ptr(ids), dtype, self._C.c_void_p(out.data_ptr()),
@@ -216,13 +218,23 @@ class PeerShardedScorer:
             out = torch.empty((ne, ldo), dtype=torch.float32, device=et.device)[:, : self.n_test_total]
         ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
         C = self._C
+        self.plda._after_torch(tt)
         self._ffi.check(self._lib.plda_shard_step(
             self.plda._h, C.c_void_p(tt.data_ptr()), tt.shape[0], tt.stride(0) if tt.shape[0] else self.dim,
             C.c_void_p(et.data_ptr()), ne, et.stride(0) if ne else self.dim, int(enrol_count), self._ffi.ptr(ids), dtype,
             C.c_void_p(out.data_ptr()), out.stride(0)))
         if sync:
-            self._ffi.check(self._lib.plda_synchronize(self.plda._h))
+            self.check()
         return out
+
+    def check(self):
+        """Synchronise and raise if any wait on a peer's flag has timed out (a stalled or dead peer): the slab was then
+        computed on stale operands and must not be used."""
+        self._ffi.check(self._lib.plda_synchronize(self.plda._h))
+        epoch, timeouts = self.status()
+        if timeouts:
+            raise RuntimeError("peer-memory exchange: %d wait(s) on a peer's ready flag timed out by step %d; the "
+                               "scores of this rank are invalid" % (timeouts, epoch))
 
     def status(self):
         """``(pushes so far, waits that timed out)`` -- a non-zero second value invalidates the results."""
@@ -234,11 +246,20 @@ class PeerShardedScorer:
         if not self._open:
             return
         self._open = False
+        timeouts = 0
+        if barrier:
+            try:
+                self._ffi.check(self._lib.plda_synchronize(self.plda._h))
+                timeouts = self.status()[1]
+            except Exception:
+                timeouts = -1
         if barrier and not self._local_only:
             import torch.distributed as dist
-            self._ffi.check(self._lib.plda_synchronize(self.plda._h))
             dist.barrier(group=self.group)     # nobody writes into a region that is about to be freed
         self._ffi.check(self._lib.plda_shard_close(self.plda._h))
+        if timeouts:
+            raise RuntimeError("peer-memory exchange: waits on a peer's ready flag timed out during this session; "
+                               "slabs computed after the first timeout are invalid")
 
 
 def _cuda_matrix(x):
@@ -304,8 +325,10 @@ def merge_class_stats(sw, means, counts, classes, group=None):
 
 
 def broadcast_lda(lda, src: int = 0, group=None):
-    """Replicate a fitted LDA's ``coef`` / ``intercept`` from rank ``src`` (SURVEY 8e "LDA predict": test rows are
-    sharded, the K x d coefficients are broadcast once after the fit)."""
+    """Replicate a fitted LDA from rank ``src`` (SURVEY 8e "LDA predict": test rows are sharded, the model is
+    broadcast once after the fit): ``coef`` / ``intercept`` / the class label of every row, so ``predict`` returns the
+    same labels on every rank.  (``transform`` needs the fitted projection and stays with the fitting rank /
+    ``fit_distributed``, which fits replicas everywhere.)"""
     import torch
     import torch.distributed as dist
     rank = dist.get_rank(group)
@@ -316,13 +339,16 @@ def broadcast_lda(lda, src: int = 0, group=None):
     dist.broadcast(shape, src=src, group=group)
     k, d = int(shape[0].item()), int(shape[1].item())
     buf = torch.empty((k, d + 1), dtype=torch.float64, device=dev)
+    cls = torch.empty(k, dtype=torch.int64, device=dev)
     if rank == src:
         buf[:, :d] = torch.from_numpy(np.asarray(lda._coef, dtype=np.float64)).to(dev)
         buf[:, d] = torch.from_numpy(np.asarray(lda._intercept, dtype=np.float64)).to(dev)
+        cls.copy_(torch.from_numpy(np.asarray(lda._classes, dtype=np.int64)).to(dev))
     dist.broadcast(buf, src=src, group=group)
+    dist.broadcast(cls, src=src, group=group)
     if rank != src:
         h = buf.cpu().numpy()
-        lda.set_coef(np.ascontiguousarray(h[:, :d]), np.ascontiguousarray(h[:, d]))
+        lda.set_coef(np.ascontiguousarray(h[:, :d]), np.ascontiguousarray(h[:, d]), classes=cls.cpu().numpy())
     return lda
 
 

@@ -54,19 +54,48 @@ class LDA(object):
         _ffi.check(self._lib.lda_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def _after_torch(self, t) -> None:
+        """Order the handle's stream after torch's current stream on ``t``'s device (``lda_stream_wait``; see
+        ``PLDA._after_torch`` for the stream contract of CUDA-tensor operands)."""
+        import torch
+        s = torch.cuda.current_stream(t.device)
+        _ffi.check(self._lib.lda_stream_wait(self._h, C.c_void_p(s.cuda_stream)))
+
     # ------------------------------------------------------------------ fit
     def fit(self, features, labels):
         """``LDA.fit`` (``lda.py:106-138``).  Returns None."""
         if self.solver not in _SOLVERS:
             # the reference silently fits nothing for an unknown solver (lda.py:131-138) and fails later
             raise ValueError("unknown solver %r (expected 'svd', 'lsqr' or 'eigen')" % (self.solver,))
-        x, dtype, y = self._check_xy(features, labels)
-        n, d = x.shape
         pri = None
         if self.priors is not None:
             pri = np.ascontiguousarray(self.priors, dtype=np.float64)
         fit_fn = {"svd": self._lib.lda_fit_svd, "lsqr": self._lib.lda_fit_lsqr,
                   "eigen": self._lib.lda_fit_eigen}[self.solver]
+        if hasattr(features, "is_cuda") and features.is_cuda:
+            # resident rows (superset): no host round trip of the N x d matrix; labels are 8 B / row on the host
+            import torch
+            x = features
+            if x.dim() != 2 or x.dtype not in (torch.float32, torch.float64):
+                raise ValueError("features must be a 2-D float32 / float64 tensor")
+            if x.stride(1) != 1:
+                x = x.contiguous()
+            y = labels.detach().cpu().numpy() if hasattr(labels, "detach") else np.asarray(labels)
+            if y.dtype.kind not in "iub":
+                raise ValueError("labels must be integers")
+            y = np.ascontiguousarray(y.astype(np.int64).reshape(-1))
+            n, d = x.shape
+            if y.shape[0] != n:
+                raise ValueError("labels and features disagree on the number of samples")
+            self._after_torch(x)
+            _ffi.check(fit_fn(self._h, C.c_void_p(x.data_ptr()), n, d, x.stride(0),
+                              _ffi.F32 if x.dtype == torch.float32 else _ffi.F64, _ffi.DEVICE, _ffi.ptr(y),
+                              _ffi.ptr(pri), 0 if pri is None else pri.shape[0]))
+            _, cnt = np.unique(y, return_counts=True)
+            self._read_back(cnt, n)
+            return None
+        x, dtype, y = self._check_xy(features, labels)
+        n, d = x.shape
         _ffi.check(fit_fn(self._h, _ffi.ptr(x), n, d, d, dtype, _ffi.HOST, _ffi.ptr(y), _ffi.ptr(pri),
                           0 if pri is None else pri.shape[0]))
         _, cnt = np.unique(y, return_counts=True)
@@ -159,12 +188,17 @@ class LDA(object):
                                                 0 if pri is None else pri.shape[0]))
         self._read_back(counts, n)
 
-    def set_coef(self, coef, intercept):
+    def set_coef(self, coef, intercept, classes=None):
+        """Install decision coefficients (replica of a model fitted elsewhere).  ``classes``: the label value of every
+        row of ``coef`` (default ``arange(K)``) -- what ``predict`` returns."""
         coef = np.ascontiguousarray(coef, dtype=np.float64)
         intercept = np.ascontiguousarray(intercept, dtype=np.float64)
         _ffi.check(self._lib.lda_set_coef(self._h, coef.shape[0], coef.shape[1], _ffi.ptr(coef), _ffi.ptr(intercept)))
         self._coef, self._intercept = coef, intercept
-        self._classes = np.arange(coef.shape[0])
+        self._classes = np.arange(coef.shape[0]) if classes is None else np.asarray(classes, dtype=np.int64).copy()
+        if self._classes.shape[0] != coef.shape[0]:
+            raise ValueError("set_coef: one class label per coefficient row")
+        self._xbar = self._scalings = None
 
     # ------------------------------------------------------------------ predict
     def _predict(self, x, log_proba):
@@ -180,6 +214,7 @@ class LDA(object):
             k = self._coef.shape[0]
             ldo = (k + 3) // 4 * 4
             buf = torch.empty((nt, ldo), dtype=torch.float32, device=x.device)
+            self._after_torch(x)
             _ffi.check(self._lib.lda_predict(self._h, C.c_void_p(x.data_ptr()), nt, d, x.stride(0),
                                              _ffi.F32 if x.dtype == torch.float32 else _ffi.F64, _ffi.DEVICE,
                                              int(log_proba), C.c_void_p(buf.data_ptr()), ldo, _ffi.DEVICE))
@@ -223,6 +258,9 @@ class LDA(object):
             raise NotImplementedError("transform not implemented for 'lsqr' solver (use 'svd' or 'eigen').")
         if self._coef is None:
             raise ValueError("This %(name)s instance is not fitted yet" % {"name": type(self).__name__})
+        if getattr(self, "_scalings", None) is None:
+            raise ValueError("transform needs the fitted projection (this instance only holds coefficients installed "
+                             "with set_coef)")
         xa = np.asarray(X)
         if xa.dtype.kind != "f":
             xa = xa.astype(np.float64)

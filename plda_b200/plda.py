@@ -59,6 +59,19 @@ class PLDA(object):
         _ffi.check(self._lib.plda_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def _after_torch(self, *tensors) -> None:
+        """Stream contract of the CUDA-tensor entry points: the library launches on the handle's own stream, so it is
+        first ordered AFTER torch's current stream on the tensors' device (``plda_stream_wait``: an event, no host
+        synchronisation) -- operands still being produced by torch kernels / ``.to(device)`` copies are safe to pass,
+        and so are output buffers the caching allocator has just recycled.  Outputs are complete when the call
+        returns (own stream) or stream-ordered (a stream installed with ``plda_set_stream``)."""
+        import torch
+        for t in tensors:
+            if t is not None and _is_torch_cuda(t):
+                s = torch.cuda.current_stream(t.device)
+                _ffi.check(self._lib.plda_stream_wait(self._h, C.c_void_p(s.cuda_stream)))
+                return
+
     # ------------------------------------------------------------------ fit
     def fit(self, x, y, iters=10):
         """``MPlda_fit`` (``src/pldamodule.cpp:42-109``).  x: (n, d) float array (or a CUDA
@@ -69,7 +82,22 @@ class PLDA(object):
         if _is_torch_cuda(x):
             xt, dtype = _torch_matrix(x)
             n, d = xt.shape
+            if _is_torch_cuda(y):
+                # resident labels (superset): no 8 B / row upload; must be a non-negative integer tensor
+                import torch
+                if y.dtype in (torch.float16, torch.float32, torch.float64, torch.bfloat16):
+                    raise ValueError("Given labels (argument 2) are not an unsigned! Set the dtype to uint!")
+                if y.numel() != n:
+                    raise ValueError("labels and features disagree on the number of samples")
+                yl = y.reshape(-1).to(torch.int64).contiguous()
+                if n and int(yl.min().item()) < 0:
+                    raise ValueError("Given labels (argument 2) are not an unsigned! Set the dtype to uint!")
+                self._after_torch(xt)
+                _ffi.check(self._lib.plda_fit_labels(self._h, C.c_void_p(xt.data_ptr()), n, d, xt.stride(0), dtype,
+                                                     _ffi.DEVICE, C.c_void_p(yl.data_ptr()), _ffi.DEVICE, iters))
+                return None
             lab = _ffi.as_labels(_to_numpy_labels(y), n)
+            self._after_torch(xt)
             _ffi.check(self._lib.plda_fit(self._h, C.c_void_p(xt.data_ptr()), n, d, xt.stride(0), dtype, _ffi.DEVICE,
                                           _ffi.ptr(lab), iters))
             return None
@@ -163,10 +191,10 @@ class PLDA(object):
         """npz checkpoint of the model and z-norm tables (the reference has none)."""
         mean, tr, psi = self.get_model()
         ids, zm, zs = self.znorm_tables()
-        np.savez(path, mean=mean, transform=tr, psi=psi, z_ids=ids, z_mean=zm, z_std=zs)
+        np.savez(_npz_path(path), mean=mean, transform=tr, psi=psi, z_ids=ids, z_mean=zm, z_std=zs)
 
     def load(self, path) -> None:
-        g = np.load(path)
+        g = np.load(_npz_path(path))
         self.set_model(g["mean"], g["transform"], g["psi"])
         ids = np.ascontiguousarray(g["z_ids"], dtype=np.uint64)
         zm = np.ascontiguousarray(g["z_mean"], dtype=np.float64)
@@ -215,6 +243,7 @@ class PLDA(object):
             dim = int(targetdim) if targetdim else d
             tdt = torch.float32 if np.dtype(out_dtype) == np.float32 else torch.float64
             out = torch.empty((n, dim), dtype=tdt, device=xt.device)
+            self._after_torch(xt)
             _ffi.check(self._lib.plda_transform_rows(
                 self._h, C.c_void_p(xt.data_ptr()), n, d, xt.stride(0), dtype, _ffi.DEVICE, _ffi.ptr(cnt), const_count,
                 int(targetdim), C.c_void_p(out.data_ptr()), dim, _ffi.F32 if tdt == torch.float32 else _ffi.F64,
@@ -263,6 +292,7 @@ class PLDA(object):
                 raise ValueError("norm_batch: enrol_ids length mismatch")
             if et.shape[0] == 0:
                 return None
+            self._after_torch(bt)
             _ffi.check(self._lib.plda_norm(self._h, C.c_void_p(bt.data_ptr()), bt.shape[0], bt.shape[1], bt.stride(0),
                                            bdt, _ffi.DEVICE, _ffi.ptr(ids), C.c_void_p(et.data_ptr()), et.shape[0],
                                            et.stride(0), et.shape[1], edt, _ffi.DEVICE, int(numutts), int(seed)))
@@ -277,6 +307,47 @@ class PLDA(object):
                                        _ffi.ptr(ids), _ffi.ptr(enrol), enrol.shape[0], enrol.shape[1], enrol.shape[1],
                                        edt, _ffi.HOST, int(numutts), int(seed)))
         return None
+
+    def norm_rows(self, vectors, enrol_vectors, numutts=0, seed=0):
+        """Array form of ``norm`` for large enrol sets (``plda_norm_rows``): returns ``(mean, std)`` of every enrol row
+        against the cohort (fp64 ``[Ne]``; CUDA tensors for CUDA operands, numpy otherwise) without touching the id
+        table -- pass them to ``score_grid(..., znorm=(mean, std))`` / ``score_trials`` / ``score_hist``.  Same
+        statistics as ``MPlda_norm`` (``src/pldamodule.cpp:196-256``)."""
+        if _is_torch_cuda(vectors) or _is_torch_cuda(enrol_vectors):
+            import torch
+            if not (_is_torch_cuda(vectors) and _is_torch_cuda(enrol_vectors)):
+                raise ValueError("norm_rows: background and enrol vectors must both be CUDA tensors or both host arrays")
+            bt, bdt = _torch_matrix(vectors)
+            et, edt = _torch_matrix(enrol_vectors)
+            ne = et.shape[0]
+            mean = torch.empty(ne, dtype=torch.float64, device=et.device)
+            std = torch.empty(ne, dtype=torch.float64, device=et.device)
+            if ne == 0:
+                return mean, std
+            self._after_torch(bt)
+            _ffi.check(self._lib.plda_norm_rows(self._h, C.c_void_p(bt.data_ptr()), bt.shape[0], bt.shape[1],
+                                                bt.stride(0), bdt, _ffi.DEVICE, C.c_void_p(et.data_ptr()), ne,
+                                                et.stride(0), et.shape[1], edt, _ffi.DEVICE, int(numutts), int(seed),
+                                                C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()), _ffi.DEVICE))
+            return mean, std
+        bkg, bdt = _ffi.as_matrix(vectors, "vectors")
+        enrol, edt = _ffi.as_matrix(enrol_vectors, "enrol_vectors")
+        ne = enrol.shape[0]
+        mean = np.empty(ne)
+        std = np.empty(ne)
+        if ne == 0:
+            return mean, std
+        _ffi.check(self._lib.plda_norm_rows(self._h, _ffi.ptr(bkg), bkg.shape[0], bkg.shape[1], bkg.shape[1], bdt,
+                                            _ffi.HOST, _ffi.ptr(enrol), ne, enrol.shape[1], enrol.shape[1], edt,
+                                            _ffi.HOST, int(numutts), int(seed), _ffi.ptr(mean), _ffi.ptr(std), _ffi.HOST))
+        return mean, std
+
+    def norm_selection(self, m, numutts, seed=0):
+        """Rows of an ``m``-row background set that ``norm(..., numutts, seed)`` uses (``plda_norm_selection``)."""
+        m, numutts = int(m), int(numutts)
+        rows = np.empty(m if numutts == 0 else numutts, dtype=np.int32)
+        _ffi.check(self._lib.plda_norm_selection(m, numutts, int(seed), _ffi.ptr(rows)))
+        return rows
 
     def znorm_tables(self):
         n = C.c_int64()
@@ -303,52 +374,167 @@ class PLDA(object):
                                              C.byref(out)))
         return float(out.value)
 
-    def score_grid(self, enrol, enrol_counts, test, enrol_ids=None, out=None):
+    def score_grid(self, enrol, enrol_counts, test, enrol_ids=None, out=None, znorm=None):
         """All-pairs LLR grid: ``out[e, t] = LogLikelihoodRatio(enrol[e], enrol_counts[e], test[t])``
         as float32 (Ne, Nt).  Inputs are transformed vectors: numpy (host) or CUDA torch tensors
         (resident; the result is then a CUDA tensor too).  ``enrol_ids``: apply z-norm for ids seen
-        by ``norm``."""
-        cnt = np.ascontiguousarray(enrol_counts, dtype=np.int32).reshape(-1)
+        by ``norm``; ``znorm=(mean, std)``: z-norm given as per-row arrays (``norm_rows``) instead."""
+        cnt = _counts_array(enrol_counts, enrol.shape[0] if hasattr(enrol, "shape") else len(enrol))
         ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
         if _is_torch_cuda(enrol):
             import torch
-            et, dtype = _torch_matrix(enrol)
-            tt, dtype2 = _torch_matrix(test)
-            if dtype != dtype2:
-                raise ValueError("score_grid: enrol and test dtypes differ")
+            et, tt, dtype = self._cuda_pair(enrol, test, "score_grid")
             ne, dim = et.shape
             nt = tt.shape[0]
             if cnt.shape[0] != ne:
                 raise ValueError("score_grid: enrol_counts length mismatch")
+            if ids is not None and ids.shape[0] != ne:
+                raise ValueError("score_grid: enrol_ids length mismatch")
             if out is None:
                 ldo = (nt + 3) // 4 * 4
                 buf = torch.empty((ne, ldo), dtype=torch.float32, device=et.device)
                 out = buf[:, :nt]
+            if ne == 0 or nt == 0:
+                return out
+            self._after_torch(et)
+            if znorm is not None:
+                zm, zs, zloc, _keep = _znorm_arrays(znorm, ne, et.device)
+                _ffi.check(self._lib.plda_score_grid_z(
+                    self._h, C.c_void_p(et.data_ptr()), ne, et.stride(0), _ffi.ptr(cnt), C.c_void_p(tt.data_ptr()), nt,
+                    tt.stride(0), dim, dtype, _ffi.DEVICE, C.c_void_p(out.data_ptr()), out.stride(0), _ffi.DEVICE, zm, zs,
+                    zloc))
+                return out
             _ffi.check(self._lib.plda_score_grid(
                 self._h, C.c_void_p(et.data_ptr()), ne, et.stride(0), _ffi.ptr(cnt), _ffi.ptr(ids),
                 C.c_void_p(tt.data_ptr()), nt, tt.stride(0), dim, dtype, _ffi.DEVICE, C.c_void_p(out.data_ptr()),
                 out.stride(0), _ffi.DEVICE))
             return out
-        ea, dtype = _ffi.as_matrix(enrol, "enrol")
-        ta, dtype2 = _ffi.as_matrix(test, "test")
-        if dtype != dtype2:
-            ea = ea.astype(np.float64)
-            ta = ta.astype(np.float64)
-            dtype = _ffi.F64
+        ea, ta, dtype = _host_pair(enrol, test, "score_grid")
         ne, dim = ea.shape
         nt = ta.shape[0]
-        if ta.shape[1] != dim:
-            raise ValueError("score_grid: enrol and test dimensions differ")
         if cnt.shape[0] != ne:
             raise ValueError("score_grid: enrol_counts length mismatch")
+        if ids is not None and ids.shape[0] != ne:
+            raise ValueError("score_grid: enrol_ids length mismatch")
         if out is None:
             out = np.empty((ne, nt), dtype=np.float32)
         if ne == 0 or nt == 0:
+            return out
+        if znorm is not None:
+            zm, zs, zloc, _keep = _znorm_arrays(znorm, ne, None)
+            _ffi.check(self._lib.plda_score_grid_z(self._h, _ffi.ptr(ea), ne, dim, _ffi.ptr(cnt), _ffi.ptr(ta), nt, dim,
+                                                   dim, dtype, _ffi.HOST, _ffi.ptr(out), out.strides[0] // 4, _ffi.HOST,
+                                                   zm, zs, zloc))
             return out
         _ffi.check(self._lib.plda_score_grid(self._h, _ffi.ptr(ea), ne, dim, _ffi.ptr(cnt), _ffi.ptr(ids), _ffi.ptr(ta),
                                              nt, dim, dim, dtype, _ffi.HOST, _ffi.ptr(out), out.strides[0] // 4,
                                              _ffi.HOST))
         return out
+
+    def _cuda_pair(self, enrol, test, what):
+        et, dtype = _torch_matrix(enrol)
+        if not _is_torch_cuda(test):
+            raise ValueError("%s: enrol and test must both be CUDA tensors or both host arrays" % what)
+        tt, dtype2 = _torch_matrix(test)
+        if dtype != dtype2:
+            raise ValueError("%s: enrol and test dtypes differ" % what)
+        if tt.shape[1] != et.shape[1]:
+            raise ValueError("%s: enrol and test dimensions differ" % what)
+        if tt.device != et.device:
+            raise ValueError("%s: enrol and test live on different devices" % what)
+        return et, tt, dtype
+
+    def score_trials(self, enrol, enrol_counts, test, trial_enrol, trial_test, enrol_ids=None, znorm=None, mode="auto"):
+        """Scores of LISTED trials, computed and gathered on the device (``plda_score_trials``): what
+        ``scoring/scorePLDA.py:302-318`` asks of ``MPlda_score`` one trial at a time.  ``trial_enrol[i]`` /
+        ``trial_test[i]`` index rows of ``enrol`` / ``test``; returns float32 ``[n_trials]`` (CUDA tensor for CUDA
+        operands).  ``mode``: 'direct' (one warp per trial, fp64 accumulation), 'grid' (grid slabs + gather on the
+        device) or 'auto' (direct below ~0.5/dim list density)."""
+        code = {"auto": 0, "direct": 1, "grid": 2}.get(mode)
+        if code is None:
+            raise ValueError("mode must be 'auto', 'direct' or 'grid'")
+        cnt = _counts_array(enrol_counts, enrol.shape[0] if hasattr(enrol, "shape") else len(enrol))
+        ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
+        if _is_torch_cuda(enrol):
+            import torch
+            et, tt, dtype = self._cuda_pair(enrol, test, "score_trials")
+            ne, dim = et.shape
+            nt = tt.shape[0]
+            if cnt.shape[0] != ne:
+                raise ValueError("score_trials: enrol_counts length mismatch")
+            if _is_torch_cuda(trial_enrol):
+                te = trial_enrol.reshape(-1).to(torch.int32).contiguous()
+                tq = trial_test.reshape(-1).to(device=et.device, dtype=torch.int32).contiguous()
+                n = te.numel()
+                if tq.numel() != n:
+                    raise ValueError("score_trials: index arrays differ in length")
+                if n and (int(te.min()) < 0 or int(te.max()) >= ne or int(tq.min()) < 0 or int(tq.max()) >= nt):
+                    raise ValueError("score_trials: trial index out of range")
+                pe, pt, iloc = C.c_void_p(te.data_ptr()), C.c_void_p(tq.data_ptr()), _ffi.DEVICE
+            else:
+                te = np.ascontiguousarray(trial_enrol, dtype=np.int32).reshape(-1)
+                tq = np.ascontiguousarray(trial_test, dtype=np.int32).reshape(-1)
+                n = te.shape[0]
+                if tq.shape[0] != n:
+                    raise ValueError("score_trials: index arrays differ in length")
+                pe, pt, iloc = _ffi.ptr(te), _ffi.ptr(tq), _ffi.HOST
+            out = torch.empty(n, dtype=torch.float32, device=et.device)
+            if n == 0:
+                return out
+            zm, zs, zloc, _keep = _znorm_arrays(znorm, ne, et.device)
+            self._after_torch(et)
+            _ffi.check(self._lib.plda_score_trials(
+                self._h, C.c_void_p(et.data_ptr()), ne, et.stride(0), _ffi.ptr(cnt), _ffi.ptr(ids),
+                C.c_void_p(tt.data_ptr()), nt, tt.stride(0), dim, dtype, _ffi.DEVICE, pe, pt, n, iloc,
+                C.c_void_p(out.data_ptr()), _ffi.DEVICE, zm, zs, zloc, code))
+            return out
+        ea, ta, dtype = _host_pair(enrol, test, "score_trials")
+        ne, dim = ea.shape
+        nt = ta.shape[0]
+        if cnt.shape[0] != ne:
+            raise ValueError("score_trials: enrol_counts length mismatch")
+        te = np.ascontiguousarray(trial_enrol, dtype=np.int32).reshape(-1)
+        tq = np.ascontiguousarray(trial_test, dtype=np.int32).reshape(-1)
+        if te.shape[0] != tq.shape[0]:
+            raise ValueError("score_trials: index arrays differ in length")
+        out = np.empty(te.shape[0], dtype=np.float32)
+        if te.shape[0] == 0:
+            return out
+        zm, zs, zloc, _keep = _znorm_arrays(znorm, ne, None)
+        _ffi.check(self._lib.plda_score_trials(self._h, _ffi.ptr(ea), ne, dim, _ffi.ptr(cnt), _ffi.ptr(ids), _ffi.ptr(ta),
+                                               nt, dim, dim, dtype, _ffi.HOST, _ffi.ptr(te), _ffi.ptr(tq), te.shape[0],
+                                               _ffi.HOST, _ffi.ptr(out), _ffi.HOST, zm, zs, zloc, code))
+        return out
+
+    def score_hist(self, enrol, enrol_count, test, enrol_spk, test_spk, lo, hi, nbins=1 << 16, theta_lo=-np.inf,
+                   znorm=None):
+        """Histogram sink (``plda_score_hist``): target / non-target score histograms of the whole ``Ne x Nt`` grid
+        without materialising it.  Trial ``(e, t)`` is a target iff ``enrol_spk[e] == test_spk[t]``.  Non-targets
+        scoring below ``theta_lo`` are only counted.  Returns ``(hist_target, hist_nontarget, below)`` (uint64
+        numpy arrays of ``nbins`` and an int); ``plda_b200.eer.eer_from_hist`` turns them into the EER.  CUDA tensors
+        only (resident operands), one enrol count for all rows."""
+        import torch
+        et, tt, dtype = self._cuda_pair(enrol, test, "score_hist")
+        ne, dim = et.shape
+        nt = tt.shape[0]
+        es = torch.as_tensor(enrol_spk).reshape(-1).to(device=et.device, dtype=torch.int32).contiguous()
+        ts = torch.as_tensor(test_spk).reshape(-1).to(device=et.device, dtype=torch.int32).contiguous()
+        if es.numel() != ne or ts.numel() != nt:
+            raise ValueError("score_hist: speaker id arrays must match the enrol / test rows")
+        nbins = int(nbins)
+        ht = np.zeros(nbins, dtype=np.uint64)
+        hn = np.zeros(nbins, dtype=np.uint64)
+        below = np.zeros(1, dtype=np.uint64)
+        zm, zs, zloc, _keep = _znorm_arrays(znorm, ne, et.device)
+        th = float(theta_lo)
+        if not np.isfinite(th):
+            th = -3.0e38
+        self._after_torch(et)
+        _ffi.check(self._lib.plda_score_hist(
+            self._h, C.c_void_p(et.data_ptr()), ne, et.stride(0), int(enrol_count), C.c_void_p(tt.data_ptr()), nt,
+            tt.stride(0), dim, dtype, _ffi.DEVICE, C.c_void_p(es.data_ptr()), C.c_void_p(ts.data_ptr()), _ffi.DEVICE,
+            float(lo), float(hi), nbins, th, zm, zs, zloc, _ffi.ptr(ht), _ffi.ptr(hn), _ffi.ptr(below), _ffi.HOST))
+        return ht, hn, int(below[0])
 
     # ------------------------------------------------------------------ kernel-level hooks (tests)
     def _test_gemm(self, a, b, ksplit=1):
@@ -382,6 +568,58 @@ def _torch_matrix(x):
     if x.stride(1) != 1:
         x = x.contiguous()
     return x, dtype
+
+
+def _npz_path(path):
+    """``np.savez`` appends '.npz' to a bare name; ``save`` and ``load`` agree on the final path."""
+    if isinstance(path, (str, bytes)) or hasattr(path, "__fspath__"):
+        import os
+        p = os.fspath(path)
+        if isinstance(p, bytes):
+            p = p.decode()
+        return p if p.endswith(".npz") else p + ".npz"
+    return path         # an open file object
+
+
+def _counts_array(enrol_counts, ne):
+    if np.isscalar(enrol_counts):
+        return np.full(int(ne), int(enrol_counts), dtype=np.int32)
+    if hasattr(enrol_counts, "detach"):
+        enrol_counts = enrol_counts.detach().cpu().numpy()
+    return np.ascontiguousarray(enrol_counts, dtype=np.int32).reshape(-1)
+
+
+def _host_pair(enrol, test, what):
+    ea, dtype = _ffi.as_matrix(enrol, "enrol")
+    ta, dtype2 = _ffi.as_matrix(test, "test")
+    if dtype != dtype2:
+        ea = ea.astype(np.float64)
+        ta = ta.astype(np.float64)
+        dtype = _ffi.F64
+    if ta.shape[1] != ea.shape[1]:
+        raise ValueError("%s: enrol and test dimensions differ" % what)
+    return ea, ta, dtype
+
+
+def _znorm_arrays(znorm, ne, device):
+    """(mean, std) -> (void* mean, void* std, loc, keep-alive).  CUDA fp64 tensors stay on the device."""
+    if znorm is None:
+        return C.c_void_p(None), C.c_void_p(None), _ffi.HOST, None
+    mean, std = znorm
+    if _is_torch_cuda(mean) and _is_torch_cuda(std):
+        import torch
+        m = mean.reshape(-1).to(torch.float64).contiguous()
+        s = std.reshape(-1).to(torch.float64).contiguous()
+        if m.numel() != ne or s.numel() != ne:
+            raise ValueError("znorm arrays must have one entry per enrol row")
+        return C.c_void_p(m.data_ptr()), C.c_void_p(s.data_ptr()), _ffi.DEVICE, (m, s)
+    if hasattr(mean, "detach"):
+        mean, std = mean.detach().cpu().numpy(), std.detach().cpu().numpy()
+    m = np.ascontiguousarray(mean, dtype=np.float64).reshape(-1)
+    s = np.ascontiguousarray(std, dtype=np.float64).reshape(-1)
+    if m.shape[0] != ne or s.shape[0] != ne:
+        raise ValueError("znorm arrays must have one entry per enrol row")
+    return _ffi.ptr(m), _ffi.ptr(s), _ffi.HOST, (m, s)
 
 
 def _to_numpy_labels(y):
