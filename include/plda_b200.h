@@ -284,6 +284,12 @@ int plda_test_gemm(plda_handle_t h, const double* a, const double* b, int64_t m,
  * per CTA 16 slots: 0 producer wait-empty, 1 producer total, 2 mma wait-full, 3 mma wait-tmem-empty, 4 mma total,
  * 5 tiles, 6/7/8 epilogue warp 0 wait-tmem-full / wait-store / total, 9/10/11 same for epilogue warp 7 */
 int plda_debug_counters(plda_handle_t h, int64_t* out, int n);
+/* the fused stats pass on its own (csrc/scatter_tc.cu): HOST rows [n x d] (contiguous) and labels in; scatter [d*d] =
+ * sum_p w_p (x_p - m_c)(x_p - m_c)^T with w_p = 1/n_c (scale_by_count != 0, PldaStats::AddSamples with the reference's
+ * weights, src/pldamodule.cpp:97) or 1; class means [k*d] in ascending label order if means_capacity >= k*d; d <= 512 */
+int plda_test_scatter(plda_handle_t h, const void* x, int64_t n, int64_t d, int dtype, const uint64_t* labels,
+                      int scale_by_count, double* scatter_out, double* means_out, int64_t means_capacity,
+                      int64_t* k_out);
 /* fp64 d x d helpers exposed for tests: op 0 = cholesky (lower), 1 = lower-triangular inverse,
  * 2 = symmetric eig (out = eigenvectors as columns, out2 = eigenvalues descending) */
 int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2);

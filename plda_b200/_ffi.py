@@ -96,6 +96,7 @@ SIGNATURES = {
     "plda_memcpy": [_vp, _vp, C.c_size_t, _int],
     "plda_test_gemm": [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp],
     "plda_debug_counters": [_vp, _vp, _int],
+    "plda_test_scatter": [_vp, _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _i64, C.POINTER(_i64)],
     "plda_test_linalg": [_vp, _int, _vp, _i64, _vp, _vp],
 }
 STRING_FUNCS = ("plda_last_error", "plda_version")

@@ -475,6 +475,14 @@ int plda_debug_counters(plda_handle_t h, int64_t* out, int n) {
     PB_CUDA(cudaMemcpy(out, e.ctx.gemm_dbg.get(), n * sizeof(long long), cudaMemcpyDeviceToHost));
   });
 }
+int plda_test_scatter(plda_handle_t h, const void* x, int64_t n, int64_t d, int dtype, const uint64_t* labels,
+                      int scale_by_count, double* scatter_out, double* means_out, int64_t means_capacity,
+                      int64_t* k_out) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    PB_CHECK(x && labels && scatter_out, pb::kInvalidArg, "test_scatter: null pointer");
+    e.test_scatter(x, n, d, dtype, labels, scale_by_count, scatter_out, means_out, means_capacity, k_out);
+  });
+}
 int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.test_linalg(op, a, d, out, out2); });
 }

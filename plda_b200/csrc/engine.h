@@ -125,6 +125,8 @@ class PldaEngine {
  public:
   void test_gemm(const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit, float* out);
   void test_linalg(int op, const double* a, int64_t d, double* out, double* out2);
+  void test_scatter(const void* x, int64_t n, int64_t d, int dtype, const uint64_t* labels, int scale_by_count,
+                    double* scatter_out, double* means_out, int64_t means_capacity, int64_t* k_out);
 
  private:
   void require_model() const { PB_CHECK(model.ready, kNotFitted, "PLDA model is not fitted (call fit or set_model)"); }
@@ -181,6 +183,7 @@ class PldaEngine {
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   void ensure_copy_stream();
   Segments segs;
+  ScatterWork scat;
   EigWork eig;
   // EM state (d x d, fp64)
   DevBuf<double> em_c, em_t1, em_bp, em_u, em_a, em_ainv, em_psi, em_tmp, em_tmp2, em_bs, em_ws, em_db, em_dw;

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "engine.h"
 
@@ -184,23 +185,32 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   }
   DevBuf<double> means(static_cast<size_t>(k) * d);
   DevBuf<int32_t> counts(k);
-  segment_sums(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get());        // K2
-  segment_finalize_means(ctx, means.get(), d, segs, counts.get());
-  lap("class means");
   DevBuf<double> scatter(dd);
-  if (precision == 1) {
-    ws_gram.reserve(static_cast<size_t>(n) * d);
-    center_scale_f64(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_gram.get());
-    gemm_f64(ctx, true, false, d, d, n, 1.0, ws_gram.get(), d, ws_gram.get(), d, 0.0, scatter.get(), d);
+  static const char* stats_mode = getenv("PLDA_B200_STATS");    // "legacy": round-1 materialised-operand path (A/B)
+  const bool fused = precision != 1 && d <= scatter_fused_max_dim() &&
+                     !(stats_mode != nullptr && strcmp(stats_mode, "legacy") == 0);
+  if (fused) {
+    // K2 + K3 in one read of the rows: anchor-centred SYRK on tcgen05, class sums from the same registers
+    scatter_fused(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, true, scatter.get(), means.get(), counts.get(), scat);
+    lap("fused scatter + class means");
   } else {
-    center_scale_split_t(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_xt);   // K3 operand
-    lap("centred split operand");
-    const int ks = choose_ksplit(ctx, d, d, n);
-    const int eff = effective_ksplit(ctx, d, d, n, ks);
-    const int64_t mpad = round_up(d, 128), npad = round_up(d, 4);
-    ws_partial.reserve(static_cast<size_t>(eff) * mpad * npad);
-    gemm_bf16x3_splitk(ctx, ws_xt.view(), ws_xt.view(), d, d, n, ks, ws_partial.get());   // K3: S = X~^T X~
-    reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, scatter.get(), d, 1.0, true);
+    segment_sums(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get());        // K2
+    segment_finalize_means(ctx, means.get(), d, segs, counts.get());
+    lap("class means");
+    if (precision == 1) {
+      ws_gram.reserve(static_cast<size_t>(n) * d);
+      center_scale_f64(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_gram.get());
+      gemm_f64(ctx, true, false, d, d, n, 1.0, ws_gram.get(), d, ws_gram.get(), d, 0.0, scatter.get(), d);
+    } else {
+      center_scale_split_t(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, means.get(), true, ws_xt);   // K3 operand
+      lap("centred split operand");
+      const int ks = choose_ksplit(ctx, d, d, n);
+      const int eff = effective_ksplit(ctx, d, d, n, ks);
+      const int64_t mpad = round_up(d, 128), npad = round_up(d, 4);
+      ws_partial.reserve(static_cast<size_t>(eff) * mpad * npad);
+      gemm_bf16x3_splitk(ctx, ws_xt.view(), ws_xt.view(), d, d, n, ks, ws_partial.get());   // K3: S = X~^T X~
+      reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, scatter.get(), d, 1.0, true);
+    }
   }
   lap("scatter SYRK");
   // sum_ = sum_s w_s m_s, class_weight = sum_s w_s ; mu = sum_/class_weight
@@ -266,6 +276,27 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   PB_CHECK(h_info == 0, kInternal, "within-class covariance is not positive definite (Cholesky failed at column " +
                                       std::to_string(h_info) + ")");
   refresh_model_operands();
+}
+
+// test hook: the fused stats pass on its own (HOST rows and labels in; scatter [d*d], class means [k*d] (label order
+// ascending) and k out)
+void PldaEngine::test_scatter(const void* x, int64_t n, int64_t d, int dtype, const uint64_t* labels, int scale_by_count,
+                              double* scatter_out, double* means_out, int64_t means_capacity, int64_t* k_out) {
+  PB_CHECK(n > 0 && d > 0 && d <= scatter_fused_max_dim(), kInvalidArg, "test_scatter: bad shape");
+  Staged sx;
+  stage(x, n, d, d, dtype, 0, sx);
+  DevBuf<uint64_t> lab(n);
+  PB_CUDA(cudaMemcpyAsync(lab.get(), labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+  build_segments(ctx, lab.get(), n, segs);
+  const int64_t k = segs.nseg;
+  DevBuf<double> sc(static_cast<size_t>(d) * d), means(static_cast<size_t>(k) * d);
+  DevBuf<int32_t> counts(k);
+  scatter_fused(ctx, sx.ptr, sx.is_f32, d, sx.ld, segs, scale_by_count != 0, sc.get(), means.get(), counts.get(), scat);
+  PB_CUDA(cudaMemcpyAsync(scatter_out, sc.get(), d * d * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  if (means_out != nullptr && means_capacity >= k * d)
+    PB_CUDA(cudaMemcpyAsync(means_out, means.get(), k * d * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  if (k_out) *k_out = k;
+  ctx.sync();
 }
 
 void PldaEngine::test_linalg(int op, const double* a, int64_t d, double* out, double* out2) {

@@ -129,6 +129,17 @@ void length_normalise(Context& ctx, const void* y, bool y_is_f32, int64_t rows, 
 // row index, which is the SYRK reduction axis): xt[c, p] = (x[order[p], c] - mean[seg(p), c]) / sqrt(n_seg).
 void center_scale_split_t(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
                           const double* means, bool scale_by_count, SplitBuf& xt);
+// Fused stats pass (scatter_tc.cu): within-class scatter + class means + counts in ONE read of the rows, no
+// materialised operand.  scatter_out [d x d] fp64 symmetric = sum_p w_p (x_p - m_c)(x_p - m_c)^T with w_p = 1/n_c
+// (scale_by_count; PldaStats::AddSamples with the reference's weights) or 1; means_out [nseg x d] fp64; counts_out
+// [nseg].  Tensor path (split-bf16 x3), d <= scatter_fused_max_dim().
+struct ScatterWork {
+  DevBuf<int4> meta;
+  DevBuf<float> csum, delta, partial;
+};
+int scatter_fused_max_dim();
+void scatter_fused(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
+                   bool scale_by_count, double* scatter_out, double* means_out, int32_t* counts_out, ScatterWork& w);
 // exact mode: same rows, fp64, not transposed [n x d]
 void center_scale_f64(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,
                       const double* means, bool scale_by_count, double* out);

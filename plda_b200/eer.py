@@ -38,3 +38,37 @@ def eer_percent(scores, target_mask=None, enrol_labels=None, test_labels=None, m
     frr = torch.searchsorted(tar_s, thr, right=False).double() / n_tar          # targets with score <  thr
     i = torch.argmin(torch.abs(far - frr))
     return float((far[i] + frr[i]) / 2.0 * 100.0)
+
+
+def eer_from_hist(target_scores, hist_nontarget, below, lo, hi):
+    """EER (%) from the histogram sink (``PLDA.score_hist`` / ``plda_score_hist``) -- for grids that are never
+    materialised (BASELINE configs[3]: 2e11 trials).
+
+    ``target_scores``: the EXACT target scores (few: one per test utterance; ``PLDA.score_trials`` on the target
+    pairs), so FRR is exact.  ``hist_nontarget`` (uint64 ``[nbins]`` over ``[lo, hi)``, last bin closed above) holds the
+    non-targets that scored at least ``theta_lo``; ``below`` counts the rest.  Candidate thresholds are the bin edges at
+    or above the lowest populated non-target bin: FAR is exact at a bin edge, FRR exact everywhere, so the result is
+    the reference's EER (``scoring/eer.py:68-73``: threshold minimising |FAR - FRR|, report their mean) up to the
+    restriction of the threshold to bin edges (one non-target bin of FAR, at most one target step of FRR).
+
+    Returns ``(eer_percent, valid)``; ``valid`` is False when the crossing lies below the histogrammed tail
+    (FAR at the lowest usable edge is already below FRR there) -- re-run the sink with a lower ``theta_lo``.  A safe
+    choice is a quantile q of the target scores with q below the expected EER (FRR(theta_lo) = q <= EER puts the
+    crossing at or above theta_lo); ``theta_lo = -inf`` always works (every non-target is then binned)."""
+    import numpy as np
+    hn = np.asarray(hist_nontarget, dtype=np.float64)
+    nbins = hn.shape[0]
+    tar = np.sort(np.asarray(target_scores, dtype=np.float64).reshape(-1))
+    n_non = float(hn.sum() + float(below))
+    if tar.shape[0] == 0 or n_non == 0:
+        raise ValueError("EER needs at least one target and one non-target trial")
+    edges = lo + (hi - lo) * np.arange(nbins, dtype=np.float64) / nbins          # lower edge of every bin
+    above = np.cumsum(hn[::-1])[::-1]                                           # non-targets with bin >= b
+    nz = np.nonzero(hn)[0]
+    first = int(nz[0]) + 1 if nz.size else nbins - 1        # edges above the bin that may hold clamped / cut scores
+    first = min(first, nbins - 1)
+    far = above[first:] / n_non
+    frr = np.searchsorted(tar, edges[first:], side="left") / tar.shape[0]
+    i = int(np.argmin(np.abs(far - frr)))
+    valid = bool(far[0] >= frr[0])
+    return float((far[i] + frr[i]) / 2.0 * 100.0), valid

@@ -72,11 +72,12 @@ def score_trials(plda, bkg_vectors, bkg_labels: Sequence[str], enrol_vectors, en
     e = np.stack([enrol_t[k][1] for k in ek])
     n = np.array([enrol_t[k][0] for k in ek], dtype=np.int32)
     t = np.stack([test_t[k][1] for k in tk])
-    # the reference scores test vectors as transformed with their own utterance count; LLR uses n of the enrol side
-    grid = plda.score_grid(e, n, t, enrol_ids=np.array(ek, dtype=np.uint64) if znorm_vectors is not None else None)
+    # the reference scores test vectors as transformed with their own utterance count; LLR uses n of the enrol side.
+    # Only the LISTED trials are scored and brought back (plda_score_trials): the index arrays go to the device, the
+    # scores of the list come back -- not the Ne x Nt grid the reference's per-trial loop would walk.
     e_pos = {k: i for i, k in enumerate(ek)}
     t_pos = {k: i for i, k in enumerate(tk)}
-    lines, errors = [], 0
+    wanted, te, tt, errors = [], [], [], 0
     for enrolmodel, vals in trials.items():
         if enrolmodel not in enrol_tab:
             errors += 1
@@ -86,8 +87,14 @@ def score_trials(plda, bkg_vectors, bkg_labels: Sequence[str], enrol_vectors, en
             if testutt not in test_tab:
                 errors += 1
                 continue
-            score = float(grid[ei, t_pos[test_tab[testutt]]])
-            lines.append("{} {}-{} {:.3f}\n".format(enrolmodel, targetmdl, testutt, score))
+            wanted.append((enrolmodel, targetmdl, testutt))
+            te.append(ei)
+            tt.append(t_pos[test_tab[testutt]])
+    if not wanted:
+        return [], errors
+    scores = plda.score_trials(e, n, t, np.asarray(te, dtype=np.int32), np.asarray(tt, dtype=np.int32),
+                               enrol_ids=np.array(ek, dtype=np.uint64) if znorm_vectors is not None else None)
+    lines = ["{} {}-{} {:.3f}\n".format(m, tg, u, float(sc)) for (m, tg, u), sc in zip(wanted, scores)]
     return lines, errors
 
 

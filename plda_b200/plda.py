@@ -546,6 +546,19 @@ class PLDA(object):
         _ffi.check(self._lib.plda_test_gemm(self._h, _ffi.ptr(a), _ffi.ptr(b), m, n, k, int(ksplit), _ffi.ptr(out)))
         return out
 
+    def _test_scatter(self, x, labels, scale_by_count=True):
+        xa, dtype = _ffi.as_matrix(x, "features")
+        lab = _ffi.as_labels(labels, xa.shape[0])
+        n, d = xa.shape
+        k_max = int(np.unique(lab).shape[0])
+        sc = np.empty((d, d))
+        means = np.empty((k_max, d))
+        k = C.c_int64()
+        _ffi.check(self._lib.plda_test_scatter(self._h, _ffi.ptr(xa), n, d, dtype, _ffi.ptr(lab),
+                                               1 if scale_by_count else 0, _ffi.ptr(sc), _ffi.ptr(means), means.size,
+                                               C.byref(k)))
+        return sc, means[:k.value]
+
     def _test_linalg(self, op, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         d = a.shape[0]

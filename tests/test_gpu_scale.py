@@ -171,3 +171,88 @@ def test_grid_is_bitwise_repeatable(model200):
     for _ in range(60):
         again = g.score_grid(e, n, t)
         assert torch.equal(again, first)
+
+
+def test_c2_full_size_fit_vs_oracle():
+    """BASELINE configs[1] at FULL size: fit 100k x 200, 1k speakers, 10 EM iterations on the device (fused stats pass
+    + diagonalised EM) against the oracle's Kaldi loop on the same rows: psi, within and between covariances."""
+    from plda_b200 import PLDA
+    d = 200
+    a_b = kp.two_cov_generator(d, seed=1234)
+    x, labels, _ = kp.synth_speakers(a_b, [100] * 1000, seed=1234)
+    ref = kp.MPlda()
+    ref.fit(x, labels, 10)
+    g = PLDA()
+    g.fit(x, labels, 10)
+    mean, a, psi = g.get_model()
+    w, b = g.get_covariances()
+    assert np.allclose(mean, ref.plda.mean, rtol=1e-6, atol=1e-7)
+    assert np.allclose(psi, ref.plda.psi, rtol=1e-3, atol=1e-6)
+    est = ref.estimator
+    assert np.max(np.abs(w - est.within_var)) <= 1e-3 * np.abs(est.within_var).max()
+    assert np.max(np.abs(b - est.between_var)) <= 1e-3 * np.abs(est.between_var).max()
+    assert np.allclose(a @ w @ a.T, np.eye(d), atol=1e-8)
+    # fp32 rows (the resident bench path) give the same model
+    import torch
+    g32 = PLDA()
+    g32.fit(torch.from_numpy(x).to("cuda", dtype=torch.float32), torch.from_numpy(labels.astype(np.int64)).to("cuda"), 10)
+    _, _, psi32 = g32.get_model()
+    assert np.allclose(psi32, ref.plda.psi, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("targetdim", [0, 150])
+def test_d512_fit_and_random_tiles(targetdim):
+    """BASELINE configs[3]'s dimension (d = 512): device fit vs oracle fit, then >= 16 random 1024 x 1024 tiles of an
+    8192 x 8192 grid (SURVEY 8d parity reporting) -- full dimension and targetdim = 150 -- and the EER of the sampled
+    tiles, each side scoring with ITS OWN fitted model (scores are invariant to eigenvector signs)."""
+    from plda_b200 import PLDA
+    d = 512
+    a_b = kp.two_cov_generator(d, seed=1234)
+    x, labels, _ = kp.synth_speakers(a_b, [40] * 600, seed=1234)
+    ref = kp.MPlda()
+    ref.fit(x, labels, 3)
+    g = PLDA()
+    g.fit(x, labels, 3)
+    _, _, psi = g.get_model()
+    w, b = g.get_covariances()
+    assert np.allclose(psi, ref.plda.psi, rtol=1e-3, atol=1e-6)
+    assert np.max(np.abs(w - ref.estimator.within_var)) <= 1e-3 * np.abs(ref.estimator.within_var).max()
+    assert np.max(np.abs(b - ref.estimator.between_var)) <= 1e-3 * np.abs(ref.estimator.between_var).max()
+
+    n_side, tile = 8192, 1024
+    xe, _, z = kp.synth_speakers(a_b, [3] * n_side, seed=1235)
+    rng = np.random.RandomState(1236)
+    xt = 0.5 + z @ a_b.T + rng.randn(n_side, d)              # test t belongs to enrol speaker t
+    means = xe.reshape(n_side, 3, d).mean(axis=1)
+    r = targetdim if targetdim else d
+
+    def ref_transform(rows, n):
+        y = (rows - ref.plda.mean) @ ref.plda.transform[:r].T
+        f = np.sqrt(r / np.sum(y * y / (ref.plda.psi[:r] + 1.0 / n), axis=1))
+        return y * f[:, None]
+
+    pr = kp.Plda()
+    pr.mean, pr.transform, pr.psi = ref.plda.mean[:r], np.eye(r), ref.plda.psi[:r]
+    pr.compute_derived_vars()
+    e_r, t_r = ref_transform(means, 3), ref_transform(xt, 1)
+    import torch
+    e_g = g.transform_batch(torch.from_numpy(means).cuda(), counts=3, targetdim=targetdim, out_dtype=np.float32)
+    t_g = g.transform_batch(torch.from_numpy(xt).cuda(), counts=1, targetdim=targetdim, out_dtype=np.float32)
+    grid = g.score_grid(e_g, 3, t_g)                          # 8192 x 8192 on the device
+    pick = np.random.RandomState(7)
+    tiles = [(0, 0), (7, 7), (3, 3), (5, 5)] + [tuple(pick.randint(0, n_side // tile, 2)) for _ in range(12)]
+    worst, tar_g, non_g, tar_r, non_r = 0.0, [], [], [], []
+    for (bi, bj) in tiles:
+        rs, cs = slice(bi * tile, (bi + 1) * tile), slice(bj * tile, (bj + 1) * tile)
+        got = grid[rs, cs].cpu().numpy().astype(np.float64)
+        want = kp.score_grid(pr, e_r[rs], np.full(tile, 3), t_r[cs])
+        worst = max(worst, float(tol_err(got, want).max()))
+        if bi == bj:
+            m = np.eye(tile, dtype=bool)
+            tar_g.append(got[m]); tar_r.append(want[m]); non_g.append(got[~m]); non_r.append(want[~m])
+        else:
+            non_g.append(got.ravel()); non_r.append(want.ravel())
+    assert worst <= 1e-3, worst
+    eer_g = kp.eer_percent(np.concatenate(tar_g), np.concatenate(non_g))
+    eer_r = kp.eer_percent(np.concatenate(tar_r), np.concatenate(non_r))
+    assert abs(eer_g - eer_r) <= 0.01, (eer_g, eer_r)

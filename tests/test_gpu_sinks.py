@@ -1,0 +1,255 @@
+"""GPU parity of the round-2 pieces against the fp64 oracle:
+
+* the fused stats pass (csrc/scatter_tc.cu) -- scatter and class means vs numpy, every template instantiation
+* sinks of the score grid that do not return the matrix: listed trials (direct and grid + gather), array-form z-norm
+  moments (incl. the seeded cohort subset, src/pldamodule.cpp:204-213), the tail-histogram sink and its EER
+* persistence (save / load incl. z-norm tables), plda_znorm_set, EER of a CUDA grid
+"""
+import numpy as np
+import pytest
+
+from oracle import kaldi_plda as kp
+
+pytestmark = pytest.mark.gpu
+
+
+def tol_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    return np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+
+
+def ref_scatter(x, labels, scale):
+    x = np.asarray(x, dtype=np.float64)
+    d = x.shape[1]
+    s = np.zeros((d, d))
+    means = []
+    for c in np.unique(labels):
+        g = x[labels == c]
+        m = g.mean(axis=0)
+        means.append(m)
+        c0 = g - m
+        s += (c0.T @ c0) / (g.shape[0] if scale else 1.0)
+    return s, np.stack(means)
+
+
+@pytest.mark.parametrize("n,d,k,dtype,scale", [
+    (1000, 32, 10, np.float64, True),        # one 128-column block half empty, 16 k-blocks
+    (5000, 200, 37, np.float32, True),       # C2's dimension: NBLK = 1
+    (3000, 256, 20, np.float64, False),      # LDA weights, block edge
+    (4100, 300, 33, np.float32, True),       # NBLK = 2, second super-block partly empty, ragged tail k-block
+    (6000, 512, 45, np.float32, True),       # C4's dimension
+    (2500, 512, 12, np.float64, False),      # fp64 rows, NBLK = 2 (2-row batches)
+])
+def test_fused_scatter_vs_numpy(n, d, k, dtype, scale):
+    from plda_b200 import PLDA
+    rng = np.random.RandomState(n + d)
+    labels = rng.randint(0, k, n).astype(np.uint64)              # unsorted, ragged class sizes
+    centres = 3.0 * rng.randn(k, d)                              # between-class spread >> within: centring matters
+    x = (centres[labels.astype(np.int64)] + rng.randn(n, d) * (0.5 + rng.rand(d))).astype(dtype)
+    want_s, want_m = ref_scatter(x, labels, scale)
+    g = PLDA()
+    got_s, got_m = g._test_scatter(x, labels, scale)
+    assert got_m.shape == want_m.shape
+    assert np.max(np.abs(got_m - want_m)) <= 2e-5 * max(1.0, np.max(np.abs(want_m)))
+    assert np.allclose(got_s, got_s.T, rtol=0, atol=0)
+    err = np.max(np.abs(got_s - want_s)) / np.max(np.abs(want_s))
+    assert err <= 3e-5, err
+
+
+def test_fused_scatter_sorted_single_row_classes():
+    """Sorted labels (identity gather), classes of one row (zero scatter contribution) mixed with large ones."""
+    from plda_b200 import PLDA
+    rng = np.random.RandomState(3)
+    sizes = [1, 1, 130, 1, 64, 7, 1, 300]
+    labels = np.repeat(np.arange(len(sizes)), sizes).astype(np.uint64)
+    x = rng.randn(labels.shape[0], 96) + 2.0 * rng.randn(len(sizes), 96)[labels.astype(np.int64)]
+    want_s, want_m = ref_scatter(x, labels, True)
+    got_s, got_m = PLDA()._test_scatter(x, labels, True)
+    assert np.max(np.abs(got_m - want_m)) <= 1e-5
+    assert np.max(np.abs(got_s - want_s)) / np.max(np.abs(want_s)) <= 3e-5
+
+
+@pytest.fixture(scope="module")
+def fitted():
+    """d = 64 model fitted by the oracle and installed on the device; transformed enrol / test sets from the oracle."""
+    from plda_b200 import PLDA
+    d = 64
+    a_b = kp.two_cov_generator(d, seed=1234)
+    x, labels, _ = kp.synth_speakers(a_b, [12] * 90, seed=1234)
+    ref = kp.MPlda()
+    ref.fit(x, labels, 4)
+    g = PLDA()
+    g.set_model(ref.plda.mean, ref.plda.transform, ref.plda.psi)
+    ne, nt = 700, 900
+    xe, _, z = kp.synth_speakers(a_b, [1] * ne, seed=5)
+    rng = np.random.RandomState(6)
+    spk_t = rng.randint(0, ne, nt)
+    xt = 0.5 + z[spk_t] @ a_b.T + rng.randn(nt, d)
+    counts = rng.randint(1, 5, ne).astype(np.int32)             # ragged enrol counts
+    e = kp.transform_batch(ref.plda, xe, counts)
+    t = kp.transform_batch(ref.plda, xt, np.ones(nt, dtype=np.int64))
+    return dict(ref=ref, g=g, a_b=a_b, e=e, t=t, counts=counts, spk_t=spk_t, d=d)
+
+
+@pytest.mark.parametrize("mode", ["direct", "grid", "auto"])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_score_trials_vs_oracle(fitted, mode, ragged):
+    f = fitted
+    rng = np.random.RandomState(11)
+    n_trials = 5000
+    te = rng.randint(0, f["e"].shape[0], n_trials).astype(np.int32)
+    tt = rng.randint(0, f["t"].shape[0], n_trials).astype(np.int32)
+    counts = f["counts"] if ragged else np.full(f["e"].shape[0], 3, dtype=np.int32)
+    want = np.array([f["ref"].plda.log_likelihood_ratio(f["e"][a], int(counts[a]), f["t"][b]) for a, b in zip(te, tt)])
+    got = f["g"].score_trials(f["e"], counts, f["t"], te, tt, mode=mode)
+    assert got.dtype == np.float32 and got.shape == (n_trials,)
+    assert tol_err(got, want).max() <= (1e-5 if mode == "direct" else 1e-3)
+    import torch
+    dev = torch.device("cuda", 0)
+    got_d = f["g"].score_trials(torch.from_numpy(f["e"]).to(dev), counts, torch.from_numpy(f["t"]).to(dev),
+                                torch.from_numpy(te).to(dev), torch.from_numpy(tt).to(dev), mode=mode)
+    assert tol_err(got_d.cpu().numpy(), want).max() <= (1e-5 if mode == "direct" else 1e-3)
+    with pytest.raises(ValueError):
+        f["g"].score_trials(f["e"], counts, f["t"], np.array([f["e"].shape[0]], dtype=np.int32), np.array([0], dtype=np.int32))
+
+
+def test_norm_rows_and_subset_vs_oracle(fitted):
+    """Array-form z-norm statistics vs the oracle's MPlda.norm -- all cohort rows and a seeded subset
+    (src/pldamodule.cpp:204-213 selects `numutts` shuffled rows; the selection is exposed so the oracle uses the same)."""
+    import torch
+    f = fitted
+    g, ref = f["g"], f["ref"]
+    bkg, _, _ = kp.synth_speakers(f["a_b"], [1] * 333, seed=8)
+    e = f["e"][:150]
+    enrol = {i + 100: (1, e[i]) for i in range(e.shape[0])}
+    for numutts in (0, 77):
+        rows = g.norm_selection(bkg.shape[0], numutts, seed=42)
+        assert len(set(rows.tolist())) == (bkg.shape[0] if numutts == 0 else numutts)
+        r = kp.MPlda()
+        r.plda = ref.plda
+        r.norm(bkg, enrol, numutts, rows=rows.tolist())
+        want_m = np.array([r.meanz[k] for k in sorted(enrol)])
+        want_s = np.array([r.stdvz[k] for k in sorted(enrol)])
+        m, s = g.norm_rows(bkg, e, numutts=numutts, seed=42)
+        assert np.max(np.abs(m - want_m)) <= 1e-3 * max(1.0, np.max(np.abs(want_m)))
+        assert np.max(np.abs(s - want_s) / want_s) <= 1e-3
+        dev = torch.device("cuda", 0)
+        md, sd = g.norm_rows(torch.from_numpy(bkg).to(dev), torch.from_numpy(e).to(dev), numutts=numutts, seed=42)
+        assert np.allclose(md.cpu().numpy(), m, rtol=1e-6, atol=1e-6) and np.allclose(sd.cpu().numpy(), s, rtol=1e-5)
+        # the dict form fills the id table with the same numbers
+        g2_ids = np.array(sorted(enrol), dtype=np.uint64)
+        from plda_b200 import _ffi
+        _ffi.check(g._lib.plda_znorm_clear(g._h))
+        g.norm(bkg, enrol, numutts, seed=42)
+        ids, zm, zs = g.znorm_tables()
+        assert np.array_equal(ids, g2_ids)
+        assert np.allclose(zm, m, rtol=1e-6, atol=1e-6) and np.allclose(zs, s, rtol=1e-5)
+        # z-normalised grid through the arrays == through the id table
+        t = f["t"][:200]
+        cnt = np.ones(e.shape[0], dtype=np.int32)
+        a = g.score_grid(e, cnt, t, enrol_ids=g2_ids)
+        b = g.score_grid(e, cnt, t, znorm=(m, s))
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-5)
+        raw = kp.score_grid(ref.plda, e, cnt, t)
+        want = (raw - want_m[:, None]) / want_s[:, None]
+        assert tol_err(b, want).max() <= 1e-3
+        _ffi.check(g._lib.plda_znorm_clear(g._h))
+
+
+def test_score_hist_and_eer(fitted):
+    """Histogram sink: bins of the whole grid (theta_lo = -inf) equal numpy's histogram of the materialised grid;
+    with a tail threshold the EER equals the oracle's exact EER within 0.01 % absolute."""
+    import torch
+    from plda_b200.eer import eer_from_hist, eer_percent
+    f = fitted
+    g = f["g"]
+    dev = torch.device("cuda", 0)
+    e = torch.from_numpy(f["e"]).to(dev).float()
+    t = torch.from_numpy(f["t"]).to(dev).float()
+    ne, nt = e.shape[0], t.shape[0]
+    enrol_spk = np.arange(ne, dtype=np.int32)
+    test_spk = f["spk_t"].astype(np.int32)
+    grid = g.score_grid(e, 3, t).cpu().numpy().astype(np.float64)
+    mask = enrol_spk[:, None] == test_spk[None, :]
+    lo, hi, nbins = float(grid.min()) - 1.0, float(grid.max()) + 1.0, 4096
+    ht, hn, below = g.score_hist(e, 3, t, enrol_spk, test_spk, lo, hi, nbins)
+    assert below == 0
+    assert int(ht.sum()) == int(mask.sum()) and int(hn.sum()) == int((~mask).sum())
+    bins = np.clip(np.floor((grid.astype(np.float32) - np.float32(lo)) * np.float32(nbins / (hi - lo))), 0, nbins - 1)
+    want_n = np.bincount(bins[~mask].astype(np.int64), minlength=nbins)
+    want_t = np.bincount(bins[mask].astype(np.int64), minlength=nbins)
+    # fp32 rounding at a bin edge may move a handful of scores to the neighbouring bin
+    assert np.abs(np.cumsum(hn.astype(np.int64)) - np.cumsum(want_n)).max() <= 8
+    assert np.abs(np.cumsum(ht.astype(np.int64)) - np.cumsum(want_t)).max() <= 2
+    # tail sink: non-targets below a low quantile of the target scores (FRR there < EER) are only counted
+    tar = grid[mask]
+    theta = float(np.quantile(tar, 0.002))
+    ht2, hn2, below2 = g.score_hist(e, 3, t, enrol_spk, test_spk, theta, hi, 1 << 16, theta_lo=theta)
+    assert int(hn2.sum()) + below2 == int((~mask).sum())
+    assert below2 == int((grid[~mask].astype(np.float32) < np.float32(theta)).sum())
+    want_eer = kp.eer_percent(tar, grid[~mask])
+    got_eer, valid = eer_from_hist(tar, hn2, below2, theta, hi)
+    assert valid
+    assert abs(got_eer - want_eer) <= 0.01, (got_eer, want_eer)
+    # the torch EER on the CUDA grid (VERDICT missing item 7)
+    cuda_grid = g.score_grid(e, 3, t)
+    got_cuda = eer_percent(cuda_grid, enrol_labels=enrol_spk, test_labels=test_spk)
+    assert abs(got_cuda - want_eer) <= 1e-6
+
+
+def test_save_load_and_znorm_set(fitted, tmp_path):
+    from plda_b200 import PLDA, _ffi
+    f = fitted
+    g = f["g"]
+    bkg, _, _ = kp.synth_speakers(f["a_b"], [1] * 64, seed=9)
+    e = f["e"][:40]
+    enrol = {i: (2, e[i]) for i in range(e.shape[0])}
+    _ffi.check(g._lib.plda_znorm_clear(g._h))
+    g.norm(bkg, enrol)
+    cnt = np.full(e.shape[0], 2, dtype=np.int32)
+    ids = np.arange(e.shape[0], dtype=np.uint64)
+    want = g.score_grid(e, cnt, f["t"][:50], enrol_ids=ids)
+    g.save(str(tmp_path / "model"))                      # np.savez appends .npz; load must find it
+    h = PLDA()
+    h.load(str(tmp_path / "model"))
+    m0, t0, p0 = g.get_model()
+    m1, t1, p1 = h.get_model()
+    assert np.array_equal(m0, m1) and np.array_equal(t0, t1) and np.array_equal(p0, p1)
+    for a, b in zip(g.znorm_tables(), h.znorm_tables()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(h.score_grid(e, cnt, f["t"][:50], enrol_ids=ids), want)
+    h.save(str(tmp_path / "again.npz"))
+    h.load(str(tmp_path / "again.npz"))
+    # plda_znorm_set: first insert wins (like MPlda_norm's map insert, src/pldamodule.cpp:245,250)
+    k = PLDA()
+    k.set_model(m0, t0, p0)
+    zi, zm, zs = g.znorm_tables()
+    _ffi.check(k._lib.plda_znorm_set(k._h, _ffi.ptr(zi), _ffi.ptr(zm), _ffi.ptr(zs), zi.shape[0]))
+    bogus = np.zeros_like(zm)
+    _ffi.check(k._lib.plda_znorm_set(k._h, _ffi.ptr(zi), _ffi.ptr(bogus), _ffi.ptr(bogus + 1.0), zi.shape[0]))
+    for a, b in zip(g.znorm_tables(), k.znorm_tables()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(k.score_grid(e, cnt, f["t"][:50], enrol_ids=ids), want)
+    _ffi.check(g._lib.plda_znorm_clear(g._h))
+
+
+def test_stream_order_with_pending_torch_work(fitted):
+    """CUDA-tensor operands produced by still-pending torch kernels on a side stream are read after they are ready
+    (plda_stream_wait), without the caller synchronising."""
+    import torch
+    f = fitted
+    g = f["g"]
+    dev = torch.device("cuda", 0)
+    e_host = torch.from_numpy(f["e"][:256]).float().pin_memory()
+    t_host = torch.from_numpy(f["t"][:512]).float().pin_memory()
+    want = g.score_grid(f["e"][:256].astype(np.float32), 3, f["t"][:512].astype(np.float32))
+    side = torch.cuda.Stream(device=dev)
+    big = torch.empty(64 * 1024 * 1024, device=dev)
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(8):
+                big.normal_()                                  # keeps the side stream busy ahead of the copies
+            e = e_host.to(dev, non_blocking=True) * 1.0
+            t = t_host.to(dev, non_blocking=True) * 1.0
+            got = g.score_grid(e, 3, t)
+        assert np.array_equal(got.cpu().numpy(), want)
