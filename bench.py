@@ -3,7 +3,7 @@
 
     PLDA trial-scores/sec (enrol x test LLR)  [+ EM-iters/sec reported beside it]
 
-Workload (config.workload): BASELINE configs[1] = "100k x 200 d-vectors, 1k speakers, 10 EM
+Headline workload (config.workload): BASELINE configs[1] = "100k x 200 d-vectors, 1k speakers, 10 EM
 iters + 10k x 10k scoring grid on 1 x B200", synthetic two-covariance d-vectors.
 A *step* is one pass of the scoring hot path over one batch: the all-pairs LLR grid of
 10 000 enrol models (3 utterances each) x 10 000 test vectors (1e8 trials) per GPU.
@@ -12,20 +12,28 @@ A *step* is one pass of the scoring hot path over one batch: the all-pairs LLR g
                matrix sink in HBM, CUDA-event timed per step with an L2 flush between steps
   e2e          same metric through the public API with HOST (pinned) buffers: host->device
                copy of both vector sets and device->host copy of the fp32 score matrix inside
-               the timed region
+               the timed region;  e2e_trials: the same call pattern for a 1 %-dense TRIAL LIST
+               (plda_score_trials: indices up, listed scores down -- what scorePLDA.py needs)
   roofline     the tcgen05 Gram kernel: algorithmic 2*d flop per trial / its CUDA-event time
                (measured on the launching stream), against MEASURED_PEAKS.json bf16 burst peak
-  cpu_baseline the C restatement of the reference's per-pair loop (oracle/plda_ref.c) on a
-               bounded sub-grid, all host threads (N=1, rank 0 only)
+  cpu_baseline CPU-A: the C restatement of the reference's per-pair loop (oracle/plda_ref.c) on a
+               bounded sub-grid, all host threads; cpu_best: CPU-B, the numpy/OpenBLAS Gram-form grid and
+               vectorised EM on all cores (N=1, rank 0 only)
   em           EM iterations/s of plda.fit on the same config (stats pass / GetOutput excluded)
+  configs      the other BASELINE configs measured in the same run (N = 1): c3 (1M x 256, targetdim 150,
+               z-norm, 50k x 100k grid), c4_slab (fit 5M x 512 + one GPU's 25k x 1M slab of the 200k x 1M grid),
+               c5 (LDA 1M x 200, 5k classes, predict_log_proba over 1M rows), each with its own roofline numbers
 
 N > 1 (torchrun): weak scaling -- every rank owns 10 000 enrol models, the test vectors are
 sharded.  Each step exchanges the transformed test vectors and scores the local slab: the operand
 producer kernel of every rank writes its rows into the operand buffers of ALL ranks over NVLink
 peer memory and the GEMM waits per column tile for the owner's flag (no collective on the data
 path; `--nccl-allgather` or a failed CUDA-IPC setup selects ONE NCCL all-gather per step instead).
+`sharded` then records, per N: the sharded fit (stats pass + EM all-reduces; EM-iters/s), the C4 per-GPU slab
+(25k x 1M, d = 512) over the same exchange, sharded z-norm and the sharded LDA fit / predict, each checked
+against the single-GPU result.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--headline-only]
 """
 from __future__ import annotations
 
@@ -47,6 +55,7 @@ N_TRAIN, K_TRAIN, EM_ITERS = 100_000, 1_000, 10
 NE, NT, ENROL_UTTS = 10_000, 10_000, 3
 METRIC = "plda_trial_scores_per_sec"
 UNIT = "trials/s"
+WORKLOAD = "C2: 100k x 200 d-vectors, 1k speakers, 10 EM iters + 10k x 10k scoring grid"
 
 
 def log(*a):
@@ -58,8 +67,17 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             j = json.load(f)
-        return dict(bf16_tflops=j.get("bf16_tflops", 1590.0), hbm_gbs=j.get("hbm_gbs", 6650.0), source="measured")
-    return dict(bf16_tflops=1590.0, hbm_gbs=6650.0, source="fallback")
+        return dict(bf16_tflops=j.get("bf16_tflops", 1590.0), bf16_sustained=j.get("bf16_tflops_sustained", 1400.0),
+                    hbm_gbs=j.get("hbm_gbs", 6650.0), source="measured")
+    return dict(bf16_tflops=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+def bench_config(world):
+    """`config` of the JSON line -- the same dict in both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": WORKLOAD, "d": D, "enrol_per_gpu": NE, "test": NT, "enrol_utts": ENROL_UTTS,
+            "gpus": world,
+            "sink": "fp32 score matrix (400 MB per step per GPU), resident in HBM for `value`",
+            "l2": "GPU arm: a 256 MB buffer is written between timed steps (L2 flush); per-step CUDA events summed"}
 
 
 # --------------------------------------------------------------------------- #
@@ -79,6 +97,21 @@ def speakers(a_b, k, per, seed):
     labels = np.repeat(np.arange(k), per)
     x = 0.5 + (z @ a_b.T)[labels] + rng.randn(k * per, d)
     return x, labels.astype(np.uint64), z
+
+
+def device_speakers(torch, dev, a_b, k, per, seed, dtype=None):
+    """The same generator on the device (Philox, seeded): rows fp32 [k*per, d], labels int64, z [k, d]."""
+    dtype = dtype or torch.float32
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    d = a_b.shape[0]
+    ab = torch.from_numpy(a_b).to(dev, dtype=dtype)
+    z = torch.randn(k, d, device=dev, generator=g, dtype=dtype)
+    centre = z @ ab.T + 0.5
+    labels = torch.arange(k, device=dev).repeat_interleave(per)
+    x = torch.randn(k * per, d, device=dev, generator=g, dtype=dtype)
+    x += centre.repeat_interleave(per, dim=0) if per > 1 else centre
+    return x, labels, z
 
 
 # --------------------------------------------------------------------------- #
@@ -156,11 +189,15 @@ def cpu_reference_model():
     return dict(mean=mean, transform=tr, psi=psi, em_iters_per_sec=n_it / t_em, stats_s=t_stats, a_b=a_b)
 
 
+def host_threads():
+    # explicit: torchrun exports OMP_NUM_THREADS=1, the reference arm may use every host core
+    return len(os.sched_getaffinity(0))
+
+
 def cpu_grid_sample(psi, sub_ne, sub_nt, steps, warmup, threads=0):
     from oracle import c_ref
     if threads <= 0:
-        # explicit: torchrun exports OMP_NUM_THREADS=1, the reference arm may use every host core
-        threads = len(os.sched_getaffinity(0))
+        threads = host_threads()
     rng = np.random.RandomState(7)
     e = rng.randn(sub_ne, D)
     t = rng.randn(sub_nt, D)
@@ -175,16 +212,69 @@ def cpu_grid_sample(psi, sub_ne, sub_nt, steps, warmup, threads=0):
     return steps * sub_ne * sub_nt / dt, used, dt / steps
 
 
+def cpu_best(mean, tr, psi, x, labels):
+    """CPU-B "best CPU" (SURVEY 8d / BASELINE.md section 3): the Gram-form grid in fp64 numpy / OpenBLAS on every
+    host core -- the FULL 10k x 10k C2 grid -- and one vectorised (diagonalised) EM iteration."""
+    from oracle import kaldi_plda as kp
+    out = {"kind": "port-gram", "cores": host_threads()}
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=host_threads())
+    except Exception:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        pl = kp.Plda()
+        pl.mean, pl.transform, pl.psi = mean, tr, psi
+        pl.compute_derived_vars()
+        rng = np.random.RandomState(7)
+        e = rng.randn(NE, D)
+        t = rng.randn(NT, D)
+        cnt = np.full(NE, ENROL_UTTS)
+        kp.score_grid(pl, e[:512], cnt[:512], t[:512])
+        t0 = time.perf_counter()
+        kp.score_grid(pl, e, cnt, t)
+        dt = time.perf_counter() - t0
+        out.update({"value": NE * NT / dt, "unit": UNIT, "sample": "full %d x %d grid, Gram form (kp.score_grid: dgemm "
+                    "+ row / column terms), %.2f s" % (NE, NT, dt)})
+        try:
+            st = kp.PldaStats()
+            order = np.argsort(labels, kind="stable")
+            xs, ls = x[order], labels[order]
+            bounds = np.flatnonzero(np.r_[True, ls[1:] != ls[:-1], True])
+            t0 = time.perf_counter()
+            means = np.add.reduceat(xs, bounds[:-1], axis=0) / np.diff(bounds)[:, None]
+            counts = np.diff(bounds).astype(np.float64)
+            xc = (xs - np.repeat(means, np.diff(bounds), axis=0)) / np.sqrt(np.repeat(counts, np.diff(bounds)))[:, None]
+            scatter = xc.T @ xc
+            out["stats_pass_s"] = time.perf_counter() - t0
+            weights = 1.0 / counts
+            mu = (weights[:, None] * means).sum(0) / weights.sum()
+            w, b = np.eye(D), np.eye(D)
+            kp.em_iter_diag(scatter, means, counts, weights, mu, w, b)
+            t0 = time.perf_counter()
+            n_it = 3
+            for _ in range(n_it):
+                w, b = kp.em_iter_diag(scatter, means, counts, weights, mu, w, b)
+            out["em_iters_per_sec"] = n_it / (time.perf_counter() - t0)
+            del st
+        except Exception as e:  # the EM leg is reported when the oracle exposes it
+            out["em_error"] = repr(e)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     from oracle import c_ref
     c_ref.build()
     model = cpu_reference_model()
-    sub = 2000
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 2))
+    # K steps exactly as asked; each step is a bounded sample of the workload (a sub-grid), sized so that the whole
+    # run stays within a few minutes on the box's host cores
+    sub = 2000 if args.steps <= 60 else 1000
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     v, used, spp = cpu_grid_sample(model["psi"], sub, sub, steps, warm)
     sample = "%dx%d sub-grid of the %dx%d grid per step (per-pair LogLikelihoodRatio loop), %d steps" % (
         sub, sub, NE, NT, steps)
@@ -192,8 +282,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 100k x 200 d-vectors, 1k speakers, 10 EM iters + 10k x 10k scoring grid",
-                   "d": D, "enrol": NE, "test": NT, "enrol_utts": ENROL_UTTS},
+        "config": bench_config(max(world, args.gpus)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "em": {"em_iters_per_sec": model["em_iters_per_sec"], "cores": 1, "stats_pass_s": model["stats_s"],
@@ -204,7 +293,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- #
-# main arm
+# main arm helpers
 # --------------------------------------------------------------------------- #
 def pinned_array(lib, shape, dtype):
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
@@ -235,6 +324,469 @@ def bind_to_gpu_numa(index):
     return prev
 
 
+def event_time(torch, fn, reps, flush=None, stream=None):
+    """Mean ms of fn() over `reps` runs, CUDA events on the current stream, optional L2 flush between runs."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        if flush is not None:
+            flush.zero_()
+        a.record(stream)
+        fn()
+        b.record(stream)
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def gemm_kernel_ms(lib, plda, fn, reps):
+    """Average CUDA-event time of the tensor GEMM launches inside fn() (library-side events on the launching stream)."""
+    from plda_b200 import _ffi
+    _ffi.check(lib.plda_profile_gemm(plda._h, 1))
+    for _ in range(reps):
+        fn()
+    g_ms, g_n = C.c_double(), C.c_int64()
+    _ffi.check(lib.plda_profile_collect(plda._h, C.byref(g_ms), C.byref(g_n)))
+    _ffi.check(lib.plda_profile_gemm(plda._h, 0))
+    return g_ms.value / max(1, g_n.value), int(g_n.value)
+
+
+def run_c3(torch, dev, pk, steps):
+    """BASELINE configs[2]: fit 1M x 256 (10k speakers), targetdim = 150, z-norm against a 10k cohort, 50k x 100k grid
+    (20 GB fp32, resident).  Everything generated and kept on the device."""
+    from plda_b200 import PLDA, _ffi
+    lib = _ffi.lib()
+    d, r, k, per, ne, nt, m = 256, 150, 10_000, 100, 50_000, 100_000, 10_000
+    a_b = two_cov(d)
+    rec = {"workload": "C3: 1M x 256 d-vectors, 10k speakers, fit targetdim=150 + z-norm (10k cohort) + 50k x 100k grid"}
+    plda = PLDA(device=dev.index)
+    x, labels, _ = device_speakers(torch, dev, a_b, k, per, 1234)
+    plda.fit(x, labels, EM_ITERS)
+    plda.fit(x, labels, EM_ITERS)
+    ft = plda.fit_timings()
+    rec["fit"] = {"stats_pass_ms": ft["stats"], "stats_pass_gbs": x.numel() * 4 / (ft["stats"] * 1e-3) / 1e9,
+                  "stats_pass_hbm_frac": x.numel() * 4 / (ft["stats"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                  "em_ms_per_iter": ft["em"] / ft["iters"], "em_iters_per_sec": ft["iters"] / (ft["em"] * 1e-3),
+                  "get_output_ms": ft["output"], "total_ms": ft["total"], "input": "fp32 rows + labels resident in HBM"}
+    del x
+    xe, _, ze = device_speakers(torch, dev, a_b, ne, ENROL_UTTS, 1235)
+    enrol_means = xe.view(ne, ENROL_UTTS, d).mean(dim=1)
+    del xe
+    g = torch.Generator(device=dev)
+    g.manual_seed(1236)
+    ab = torch.from_numpy(a_b).to(dev, dtype=torch.float32)
+    spk_t = torch.randint(0, ne, (nt,), device=dev, generator=g)
+    xt = 0.5 + ze[spk_t] @ ab.T + torch.randn(nt, d, device=dev, generator=g)
+    cohort, _, _ = device_speakers(torch, dev, a_b, m, 1, 1237)
+    enrol_t = plda.transform_batch(enrol_means, counts=ENROL_UTTS, targetdim=r, out_dtype=np.float32)
+    test_t = plda.transform_batch(xt, counts=1, targetdim=r, out_dtype=np.float32)
+    rec["transform_test_ms"] = event_time(torch, lambda: plda.transform_batch(xt, counts=1, targetdim=r,
+                                                                              out_dtype=np.float32), 3)
+    zm, zs = plda.norm_rows(cohort, enrol_t)
+    z_ms = event_time(torch, lambda: plda.norm_rows(cohort, enrol_t), 5)
+    zk_ms, _ = gemm_kernel_ms(lib, plda, lambda: plda.norm_rows(cohort, enrol_t), 3)
+    rec["znorm"] = {"ms": z_ms, "cohort_trials_per_sec": ne * m / (z_ms * 1e-3), "kernel_ms": zk_ms,
+                    "kernel_cohort_trials_per_sec": ne * m / (zk_ms * 1e-3),
+                    "sink": "per-row shifted moments (never materialised), fp64 merge"}
+    ldo = (nt + 3) // 4 * 4
+    out = torch.empty((ne, ldo), dtype=torch.float32, device=dev)
+    fn = lambda: plda.score_grid(enrol_t, ENROL_UTTS, test_t, out=out[:, :nt], znorm=(zm, zs))
+    fn()
+    ms = event_time(torch, fn, max(3, min(steps, 10)))
+    k_ms, _ = gemm_kernel_ms(lib, plda, fn, 3)
+    flops = 2.0 * r * ne * nt
+    rec["grid"] = {"ms_per_step": ms, "trials_per_sec": ne * nt / (ms * 1e-3), "kernel_ms": k_ms,
+                   "algorithmic_tflops": flops / (k_ms * 1e-3) / 1e12,
+                   "roofline_frac": flops / (k_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                   "issued_frac": flops * 3 * 160 / 150 / (k_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                   "hbm_write_gbs": 4.0 * ne * nt / (k_ms * 1e-3) / 1e9,
+                   "hbm_write_frac": 4.0 * ne * nt / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                   "peak": "measured bf16 sustained (ms-scale kernel)",
+                   "sink": "z-normalised fp32 matrix in HBM (20 GB)", "inputs": "grid (20 GB) > L2"}
+    # EER of the materialised grid vs the histogram sink (nothing materialised)
+    from plda_b200.eer import eer_from_hist
+    tgt_e, tgt_t = spk_t.to(torch.int32), torch.arange(nt, device=dev, dtype=torch.int32)
+    tar = plda.score_trials(enrol_t, ENROL_UTTS, test_t, tgt_e, tgt_t, znorm=(zm, zs)).double().cpu().numpy()
+    theta = float(np.quantile(tar, 0.0005))
+    hi = float(max(tar.max(), float(out[:, :nt].max().item()))) + 1.0
+    es, ts = torch.arange(ne, device=dev, dtype=torch.int32), spk_t.to(torch.int32)
+    hfn = lambda: plda.score_hist(enrol_t, ENROL_UTTS, test_t, es, ts, theta, hi, 1 << 16, theta_lo=theta, znorm=(zm, zs))
+    ht, hn, below = hfn()
+    h_ms = event_time(torch, hfn, 3)
+    eer_h, valid = eer_from_hist(tar, hn, below, theta, hi)
+    # exact EER on the device grid: sort-free counting against the sorted target scores
+    tar_sorted = torch.sort(torch.from_numpy(tar).to(dev).float())[0]
+    rec["eer"] = {"hist_sink_percent": eer_h, "hist_valid": valid, "hist_sink_ms": h_ms,
+                  "hist_sink_trials_per_sec": ne * nt / (h_ms * 1e-3),
+                  "nontargets_binned_frac": float(hn.sum()) / float(hn.sum() + below)}
+    try:
+        rec["eer"]["grid_percent"] = eer_exact_grid(torch, out[:, :nt], es, ts, tar_sorted)
+    except Exception as e:
+        rec["eer"]["grid_error"] = repr(e)
+    rec["mem_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+    del out, plda
+    return rec
+
+
+def eer_exact_grid(torch, grid, enrol_spk, test_spk, tar_sorted):
+    """Exact EER of a resident grid without sorting its 5e9 non-targets: candidate thresholds are the target scores
+    (FRR steps only there); FAR at each comes from one counting pass (row chunks)."""
+    n_t = tar_sorted.numel()
+    # thresholds: a quantile sub-grid of the target scores around the crossing is enough for +-0.01 %
+    cand = tar_sorted[:: max(1, n_t // 4096)]
+    ge = torch.zeros(cand.numel(), dtype=torch.float64, device=grid.device)
+    n_non = 0
+    for r0 in range(0, grid.shape[0], 2048):
+        blk = grid[r0:r0 + 2048]
+        mask = enrol_spk[r0:r0 + 2048].view(-1, 1) != test_spk.view(1, -1)
+        vals = torch.sort(blk[mask])[0]
+        n_non += vals.numel()
+        ge += (vals.numel() - torch.searchsorted(vals, cand, right=False)).double()
+    far = ge / n_non
+    frr = torch.searchsorted(tar_sorted, cand, right=False).double() / n_t
+    i = torch.argmin(torch.abs(far - frr))
+    return float((far[i] + frr[i]) / 2.0 * 100.0)
+
+
+def run_c4_slab(torch, dev, pk, steps, plda=None, rows_fit=5_000_000, materialise=True):
+    """BASELINE configs[3], one GPU's share: fit 5M x 512 (50k speakers) and the 25k x 1M slab (1/8 of the enrol rows)
+    of the 200k x 1M grid, d = 512."""
+    from plda_b200 import PLDA, _ffi
+    lib = _ffi.lib()
+    d, per, ne, nt = 512, 100, 25_000, 1_000_000
+    a_b = two_cov(d)
+    rec = {"workload": "C4 slab: fit 5M x 512 x-vectors (50k speakers) + 25k x 1M slab of the 200k x 1M grid (1 of 8 GPUs)"}
+    own = plda is None
+    if own:
+        plda = PLDA(device=dev.index)
+        k = rows_fit // per
+        x, labels, _ = device_speakers(torch, dev, a_b, k, per, 1234)
+        plda.fit(x, labels, EM_ITERS)
+        plda.fit(x, labels, EM_ITERS)
+        ft = plda.fit_timings()
+        rec["fit"] = {"rows": rows_fit, "stats_pass_ms": ft["stats"],
+                      "stats_pass_gbs": x.numel() * 4 / (ft["stats"] * 1e-3) / 1e9,
+                      "stats_pass_hbm_frac": x.numel() * 4 / (ft["stats"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                      "stats_pass_algorithmic_tflops": rows_fit * d * (d + 1) / (ft["stats"] * 1e-3) / 1e12,
+                      "em_ms_per_iter": ft["em"] / ft["iters"], "em_iters_per_sec": ft["iters"] / (ft["em"] * 1e-3),
+                      "get_output_ms": ft["output"], "total_ms": ft["total"],
+                      "input": "fp32 rows + labels resident in HBM"}
+        del x, labels
+        torch.cuda.empty_cache()
+    xe, _, ze = device_speakers(torch, dev, a_b, ne, ENROL_UTTS, 1235)
+    enrol_means = xe.view(ne, ENROL_UTTS, d).mean(dim=1)
+    del xe
+    g = torch.Generator(device=dev)
+    g.manual_seed(1236)
+    ab = torch.from_numpy(a_b).to(dev, dtype=torch.float32)
+    spk_t = torch.randint(0, ne, (nt,), device=dev, generator=g)
+    xt = torch.randn(nt, d, device=dev, generator=g)
+    for r0 in range(0, nt, 100_000):
+        xt[r0:r0 + 100_000] += 0.5 + ze[spk_t[r0:r0 + 100_000]] @ ab.T
+    enrol_t = plda.transform_batch(enrol_means, counts=ENROL_UTTS, out_dtype=np.float32)
+    test_t = plda.transform_batch(xt, counts=1, out_dtype=np.float32)
+    rec["transform_test_ms"] = event_time(torch, lambda: plda.transform_batch(xt, counts=1, out_dtype=np.float32), 2)
+    del xt
+    torch.cuda.empty_cache()
+    flops = 2.0 * d * ne * nt
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    reps = max(2, min(steps, 5))
+    if materialise and free_b > 4 * ne * nt + (12 << 30):
+        out = torch.empty((ne, nt), dtype=torch.float32, device=dev)
+        fn = lambda: plda.score_grid(enrol_t, ENROL_UTTS, test_t, out=out)
+        fn()
+        ms = event_time(torch, fn, reps)
+        k_ms, _ = gemm_kernel_ms(lib, plda, fn, 2)
+        rec["grid"] = {"ms_per_step": ms, "trials_per_sec": ne * nt / (ms * 1e-3), "kernel_ms": k_ms,
+                       "algorithmic_tflops": flops / (k_ms * 1e-3) / 1e12,
+                       "roofline_frac": flops / (k_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                       "issued_frac": flops * 3 / (k_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                       "hbm_write_gbs": 4.0 * ne * nt / (k_ms * 1e-3) / 1e9,
+                       "peak": "measured bf16 sustained (ms-scale kernel)",
+                       "sink": "fp32 slab in HBM (100 GB)", "inputs": "slab (100 GB) > L2"}
+        del out
+        torch.cuda.empty_cache()
+    else:
+        rec["grid"] = {"skipped": "not enough free HBM for the 100 GB slab (%.0f GB free)" % (free_b / 1e9)}
+    # the sink that scales to the whole 200k x 1M grid: target scores (listed trials) + tail histogram -> EER
+    from plda_b200.eer import eer_from_hist
+    tgt_e, tgt_t = spk_t.to(torch.int32), torch.arange(nt, device=dev, dtype=torch.int32)
+    tar = plda.score_trials(enrol_t, ENROL_UTTS, test_t, tgt_e, tgt_t).double().cpu().numpy()
+    t_ms = event_time(torch, lambda: plda.score_trials(enrol_t, ENROL_UTTS, test_t, tgt_e, tgt_t), 3)
+    theta = float(np.quantile(tar, 0.0005))
+    hi = float(tar.max()) + 50.0
+    es = torch.arange(ne, device=dev, dtype=torch.int32)
+    hfn = lambda: plda.score_hist(enrol_t, ENROL_UTTS, test_t, es, tgt_e, theta, hi, 1 << 16, theta_lo=theta)
+    ht, hn, below = hfn()
+    h_ms = event_time(torch, hfn, reps)
+    eer_h, valid = eer_from_hist(tar, hn, below, theta, hi)
+    rec["hist_sink"] = {"ms_per_step": h_ms, "trials_per_sec": ne * nt / (h_ms * 1e-3),
+                        "algorithmic_tflops": flops / (h_ms * 1e-3) / 1e12,
+                        "roofline_frac": flops / (h_ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                        "eer_percent": eer_h, "valid": valid, "target_trials_ms": t_ms,
+                        "nontargets_binned_frac": float(hn.sum()) / float(hn.sum() + below),
+                        "sink": "exact target scores (1M listed trials) + 2^16-bin tail histogram of the non-targets; "
+                                "nothing materialised"}
+    rec["mem_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+    if own:
+        del plda
+    return rec
+
+
+def run_c5(torch, dev, pk, steps):
+    """BASELINE configs[4]: LDA fit (svd) on 1M x 200, 5k classes + predict_log_proba over 1M test rows (20 GB out)."""
+    from plda_b200 import LDA
+    n, d, k, nt = 1_000_000, 200, 5_000, 1_000_000
+    rec = {"workload": "C5: LDA 1M x 200, 5k classes, fit(svd) + predict_log_proba over 1M test vectors"}
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    centres = torch.randn(k, d, device=dev, generator=g) * 0.7
+    y = torch.arange(n, device=dev) % k
+    x = centres[y] + torch.randn(n, d, device=dev, generator=g)
+    yt = torch.randint(0, k, (nt,), device=dev, generator=g)
+    t = centres[yt] + torch.randn(nt, d, device=dev, generator=g)
+    lda = LDA(device=dev.index)
+    y_host = y.cpu().numpy()
+    lda.fit(x, y_host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lda.fit(x, y_host)
+    torch.cuda.synchronize()
+    rec["fit_ms"] = (time.perf_counter() - t0) * 1e3
+    rec["fit_input"] = "fp32 rows resident in HBM, int64 labels from the host (8 MB)"
+    fn = lambda: lda.predict_log_proba(t)
+    lp = fn()
+    acc = float((lp.argmax(dim=1) == yt).float().mean().item())
+    del lp
+    torch.cuda.empty_cache()
+    reps = max(2, min(steps, 5))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o = fn()
+        del o
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    df = lambda: lda.decision_function(t)
+    o = df()
+    del o
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o = df()
+        del o
+    torch.cuda.synchronize()
+    ms_df = (time.perf_counter() - t0) / reps * 1e3
+    flops = 2.0 * d * k * nt
+    rec["predict_log_proba"] = {"ms": ms, "rows_per_sec": nt / (ms * 1e-3),
+                                "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                                "roofline_frac": flops / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                                "hbm_write_gbs": 4.0 * nt * k / (ms * 1e-3) / 1e9,
+                                "hbm_write_frac": 4.0 * nt * k / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                "note": "wall clock incl. torch's allocation of the 20 GB result; two GEMM passes "
+                                        "(online log-sum-exp, then z - lse stored)",
+                                "accuracy_on_synthetic": acc}
+    rec["decision_function_ms"] = ms_df
+    rec["mem_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+    # CPU side: the oracle's numpy port on a bounded sample of the test rows, all cores
+    try:
+        from oracle.lda_port import LDAOracle
+        sub_n, sub_t = 100_000, 20_000
+        xs = x[:sub_n].double().cpu().numpy()
+        ys = y_host[:sub_n]
+        o = LDAOracle("svd")
+        t0 = time.perf_counter()
+        o.fit(xs, ys)
+        fit_s = time.perf_counter() - t0
+        ts = t[:sub_t].double().cpu().numpy()
+        t0 = time.perf_counter()
+        o.predict_log_proba(ts)
+        pr_s = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"kind": "port (oracle/lda_port.py = python/liblda/lda.py, numpy/OpenBLAS)",
+                               "cores": host_threads(), "fit_rows_per_sec": sub_n / fit_s,
+                               "predict_rows_per_sec": sub_t / pr_s,
+                               "sample": "fit on the first %d rows, predict_log_proba on %d rows" % (sub_n, sub_t)}
+    except Exception as e:
+        rec["cpu_baseline"] = {"error": repr(e)}
+    del lda
+    return rec
+
+
+def run_sharded_extras(torch, dist, dev, pk, rank, world, steps):
+    """N > 1 records (SURVEY 8e rows other than the score grid), each checked against a single-GPU result."""
+    from plda_b200 import PLDA, LDA
+    from plda_b200 import dist as pdist
+    rec = {}
+
+    def all_equal(t):
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        ok = torch.tensor([1 if torch.equal(ref, t) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item())
+
+    # ---- sharded fit, C2-shaped (every rank holds whole speakers), checked against the single-GPU fit ----
+    try:
+        a_b = two_cov(D)
+        x, labels, _ = speakers(a_b, K_TRAIN, N_TRAIN // K_TRAIN, 1234)
+        lo, hi = pdist.block_bounds(K_TRAIN, world, rank)
+        per = N_TRAIN // K_TRAIN
+        xs = torch.from_numpy(x[lo * per:hi * per]).to(dev)
+        ls = labels[lo * per:hi * per]
+        single = PLDA(device=dev.index)
+        single.fit(torch.from_numpy(x).to(dev), labels, EM_ITERS)
+        _, _, psi_single = single.get_model()
+        p = PLDA(device=dev.index)
+        p.fit_distributed(xs, ls, EM_ITERS)
+        p.fit_distributed(xs, ls, EM_ITERS)
+        ft = p.fit_timings()
+        _, tr, psi = p.get_model()
+        ident = all_equal(torch.from_numpy(psi).to(dev)) and all_equal(torch.from_numpy(tr).to(dev))
+        rec["fit_c2"] = {"rows_per_gpu": int(xs.shape[0]), "scaling": "strong (100k rows split over N GPUs)",
+                         "stats_pass_ms": ft["stats"], "em_ms_per_iter": ft["em"] / ft["iters"],
+                         "em_iters_per_sec": ft["iters"] / (ft["em"] * 1e-3), "get_output_ms": ft["output"],
+                         "allreduces_per_fit": 1 + EM_ITERS, "allreduce_ms_per_fit": getattr(p, "last_allreduce_ms", None),
+                         "replicas_bit_identical": ident,
+                         "psi_max_rel_diff_vs_single_gpu": float(np.max(np.abs(psi - psi_single) / np.maximum(psi_single, 1e-6)))}
+        del single, p, xs
+    except Exception as e:
+        rec["fit_c2"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
+    # ---- sharded fit, C4-shaped: 625k x 512 rows per GPU (5M at N = 8), weak scaling ----
+    try:
+        d4, per4, k_gpu = 512, 100, 6250
+        a4 = two_cov(d4)
+        x4, l4, _ = device_speakers(torch, dev, a4, k_gpu, per4, 1234 + rank)
+        p4 = PLDA(device=dev.index)
+        p4.fit_distributed(x4, l4 + rank * k_gpu, EM_ITERS)
+        p4.fit_distributed(x4, l4 + rank * k_gpu, EM_ITERS)
+        ft = p4.fit_timings()
+        _, _, psi4 = p4.get_model()
+        rec["fit_c4"] = {"rows_per_gpu": int(x4.shape[0]), "rows_total": int(x4.shape[0]) * world, "d": d4,
+                         "scaling": "weak (625k rows per GPU; N = 8 is BASELINE configs[3]'s 5M x 512)",
+                         "stats_pass_ms": ft["stats"],
+                         "stats_pass_gbs_per_gpu": x4.numel() * 4 / (ft["stats"] * 1e-3) / 1e9,
+                         "em_ms_per_iter": ft["em"] / ft["iters"], "em_iters_per_sec": ft["iters"] / (ft["em"] * 1e-3),
+                         "get_output_ms": ft["output"], "allreduce_ms_per_fit": getattr(p4, "last_allreduce_ms", None),
+                         "replicas_bit_identical": all_equal(torch.from_numpy(psi4).to(dev))}
+        del x4
+        # ---- the C4 grid slab of this rank over the peer-memory exchange: 25k enrol rows x 1M test rows ----
+        ne4, nt4 = 25_000, 1_000_000
+        lo, hi = pdist.block_bounds(nt4, world, rank)
+        xe, _, ze = device_speakers(torch, dev, a4, ne4, ENROL_UTTS, 1235 + 1000 * rank)
+        enrol_t = p4.transform_batch(xe.view(ne4, ENROL_UTTS, d4).mean(dim=1), counts=ENROL_UTTS, out_dtype=np.float32)
+        del xe
+        g = torch.Generator(device=dev)
+        g.manual_seed(1236 + rank)
+        xt = 0.5 + torch.randn(hi - lo, d4, device=dev, generator=g)
+        test_shard = p4.transform_batch(xt, counts=1, out_dtype=np.float32)
+        del xt
+        torch.cuda.empty_cache()
+        out = torch.empty((ne4, nt4), dtype=torch.float32, device=dev)
+        peer = pdist.PeerShardedScorer(p4, nt4, d4)
+        reps = max(2, min(steps, 5))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        peer.score(enrol_t, ENROL_UTTS, test_shard, out=out, sync=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in evs:
+            a.record()
+            peer.score(enrol_t, ENROL_UTTS, test_shard, out=out, sync=False)
+            b.record()
+        peer.check()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        t_ms = torch.tensor([ms], device=dev)
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms = float(t_ms.item())
+        # cross-check a corner of the slab against the all-gather path
+        full = pdist.all_gather_rows(test_shard, nt4)
+        chk = p4.score_grid(enrol_t[:512], ENROL_UTTS, full)
+        ok = torch.tensor([1 if torch.equal(chk, out[:512]) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        peer.close()
+        flops = 2.0 * d4 * ne4 * nt4
+        rec["c4_slab"] = {"enrol_per_gpu": ne4, "test_total": nt4, "d": d4, "ms_per_step": ms,
+                          "trials_per_sec_all_gpus": ne4 * nt4 * world / (ms * 1e-3),
+                          "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+                          "roofline_frac": flops / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+                          "exchange": "producer kernel pushes the rank's test rows into every rank's operand buffer "
+                                      "(NVLink peer memory); the GEMM waits per column tile",
+                          "matches_allgather_path": bool(ok.item()),
+                          "sink": "fp32 slab in HBM (100 GB per GPU)"}
+        del out, full, p4
+    except Exception as e:
+        rec["fit_c4_or_slab_error"] = repr(e)
+    torch.cuda.empty_cache()
+
+    # ---- sharded z-norm (enrol-block ownership, cohort all-gathered) ----
+    try:
+        d = 64
+        a_b = two_cov(d)
+        x, labels, _ = speakers(a_b, 200, 20, 1234)
+        p = PLDA(device=dev.index)
+        p.fit(x, labels, 4)
+        cohort, _, _ = speakers(a_b, 512, 1, 1237)
+        xe, _, _ = speakers(a_b, 64 * world, 1, 1235)
+        e_all = p.transform_batch(xe, counts=1)
+        lo, hi = pdist.block_bounds(e_all.shape[0], world, rank)
+        clo, chi = pdist.block_bounds(cohort.shape[0], world, rank)
+        block = {int(i): (1, e_all[i]) for i in range(lo, hi)}
+        t0 = time.perf_counter()
+        pdist.sharded_norm(p, cohort[clo:chi], cohort.shape[0], block)
+        dt = time.perf_counter() - t0
+        ids, zm, zs = p.znorm_tables()
+        q = PLDA(device=dev.index)
+        q.set_model(*p.get_model())
+        m_ref, s_ref = q.norm_rows(cohort, e_all[lo:hi])
+        ok = bool(np.allclose(zm, m_ref, rtol=1e-6, atol=1e-6) and np.allclose(zs, s_ref, rtol=1e-5))
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        rec["znorm"] = {"enrol_per_gpu": hi - lo, "cohort": int(cohort.shape[0]), "ms": dt * 1e3,
+                        "matches_single_gpu": bool(okt.item())}
+        del p, q
+    except Exception as e:
+        rec["znorm"] = {"error": repr(e)}
+
+    # ---- sharded LDA: fit from merged class statistics, broadcast-free replicas, row-sharded predict ----
+    try:
+        rng = np.random.RandomState(3)
+        k, d, per = 40 * world, 48, 50
+        centres = rng.randn(k, d)
+        y = np.repeat(np.arange(k), per)
+        x = centres[y] + rng.randn(k * per, d)
+        lo, hi = pdist.block_bounds(k, world, rank)
+        sel = (y >= lo) & (y < hi)
+        m = LDA(device=dev.index)
+        t0 = time.perf_counter()
+        m.fit_distributed(x[sel], y[sel])
+        fit_ms = (time.perf_counter() - t0) * 1e3
+        ref = LDA(device=dev.index)
+        ref.fit(x, y)
+        coef_ok = bool(np.allclose(m._coef, ref._coef, rtol=1e-5, atol=1e-6))
+        tt = centres[rng.randint(0, k, 256 * world)] + rng.randn(256 * world, d)
+        tlo, thi = pdist.block_bounds(tt.shape[0], world, rank)
+        lp = m.predict_log_proba(tt[tlo:thi])
+        lp_ref = ref.predict_log_proba(tt[tlo:thi])
+        pred_ok = bool(np.max(np.abs(lp - lp_ref)) <= 1e-3)
+        # a replica installed by broadcast predicts the same labels
+        rep = LDA(device=dev.index)
+        if rank == 0:
+            rep = m
+        pdist.broadcast_lda(rep, src=0)
+        same = bool(np.array_equal(rep.predict(tt[tlo:thi]), m.predict(tt[tlo:thi])))
+        okt = torch.tensor([1 if (coef_ok and pred_ok and same) else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        rec["lda"] = {"classes": k, "fit_distributed_ms": fit_ms, "matches_single_gpu": bool(okt.item())}
+    except Exception as e:
+        rec["lda"] = {"error": repr(e)}
+    return rec
+
+
+# --------------------------------------------------------------------------- #
+# main arm
+# --------------------------------------------------------------------------- #
 def run_main(args):
     import torch
     import torch.distributed as dist
@@ -250,6 +802,7 @@ def run_main(args):
     dev = torch.device("cuda", local)
     lib = _ffi.lib()
     prev_affinity = bind_to_gpu_numa(local)
+    pk = peaks()
 
     # ---- model: fit on C2 (also the EM-iters/s measurement) ----
     a_b = two_cov(D)
@@ -264,16 +817,19 @@ def run_main(args):
         em = None
     else:
         plda.fit(x, labels, EM_ITERS)                 # warm-up fit (first-touch allocations)
-        launches0 = plda.launch_count()
         xd = torch.from_numpy(x).to(dev)
-        plda.fit(xd, labels, EM_ITERS)                # timed by the library's own CUDA events
+        ld = torch.from_numpy(labels.astype(np.int64)).to(dev)
+        plda.fit(xd, ld, EM_ITERS)
+        launches0 = plda.launch_count()
+        plda.fit(xd, ld, EM_ITERS)                    # timed by the library's own CUDA events
         ft = plda.fit_timings()
         fit_launches = plda.launch_count() - launches0
         em = {"em_iters_per_sec": ft["iters"] / (ft["em"] * 1e-3), "em_ms_per_iter": ft["em"] / ft["iters"],
               "stats_pass_ms": ft["stats"], "stats_pass_gbs": N_TRAIN * D * 8 / (ft["stats"] * 1e-3) / 1e9,
+              "stats_pass_hbm_frac": N_TRAIN * D * 8 / (ft["stats"] * 1e-3) / 1e9 / pk["hbm_gbs"],
               "get_output_ms": ft["output"], "fit_total_ms": ft["total"], "iters": ft["iters"],
-              "launches_per_fit": fit_launches, "input": "fp64 rows resident in HBM"}
-        del xd
+              "launches_per_fit": fit_launches, "input": "fp64 rows + labels resident in HBM"}
+        del xd, ld
 
     # ---- scoring inputs: enrol models (3 utts each) and test vectors, transformed on the device ----
     ne_local, nt_total = NE, NT
@@ -373,7 +929,10 @@ def run_main(args):
     if peer is not None and not peer_ok():
         # never report a number from an exchange that timed out or disagreed: redo the region over NCCL
         log("rank %d: peer-memory exchange failed its cross-check; falling back to the NCCL all-gather" % rank)
-        peer.close()
+        try:
+            peer.close()
+        except Exception as e:
+            log("rank %d: %s" % (rank, e))
         peer, peer_used = None, False
         for i in range(args.warmup):
             step(i)
@@ -404,6 +963,33 @@ def run_main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = trials_per_step * e2e_steps / e2e_s
+
+    # ---- e2e for a 1 %-dense trial list: indices up, listed scores down (plda_score_trials) ----
+    n_list = ne_local * nt_total // 100
+    rl = np.random.RandomState(17 + rank)
+    te_host, _p4 = pinned_array(lib, (n_list,), np.int32)
+    tt_host, _p5 = pinned_array(lib, (n_list,), np.int32)
+    te_host[:] = np.sort(rl.randint(0, ne_local, n_list)).astype(np.int32)
+    tt_host[:] = rl.randint(0, nt_total, n_list).astype(np.int32)
+    got_list = plda.score_trials(e_host, counts, t_host, te_host, tt_host)
+    list_err = float(np.max(np.abs(got_list - o_host[te_host, tt_host])))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plda.score_trials(e_host, counts, t_host, te_host, tt_host)
+    barrier()
+    list_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([list_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        list_s = float(t.item())
+    e2e_trials = {"value": n_list * world * e2e_steps / list_s, "unit": "listed trials/s",
+                  "grid_cells_covered_per_sec": trials_per_step * e2e_steps / list_s,
+                  "ms_per_step": list_s / e2e_steps * 1e3, "listed_trials_per_gpu": n_list, "density": 0.01,
+                  "h2d_bytes_per_step": int((ne_local + nt_total) * D * 8 + 8 * n_list),
+                  "d2h_bytes_per_step": int(4 * n_list),
+                  "max_abs_diff_vs_matrix_sink": list_err,
+                  "sink": "plda_score_trials: grid slabs + gather on the device, only the listed scores cross PCIe"}
     clocks = sampler.stop()
     torch.cuda.synchronize()
     _ffi.check(lib.plda_set_stream(plda._h, C.c_void_p(None)))
@@ -413,26 +999,28 @@ def run_main(args):
     dev_out = outs[(args.steps - 1) & 1][:64, :64].cpu().numpy()
     spot = float(np.max(np.abs(dev_out - o_host[:64, :64])))
 
-    pk = peaks()
     # DRAM traffic of the same kernel / shape from the committed ncu --set full capture (profiles/), per launch
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_prof_gemm.json")) as f:
-            nc = json.load(f)
-        to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            val, unit = nc[key].split()
-            traffic += float(val) * to_bytes[unit]
-    except Exception:
-        traffic = None
+    traffic, traffic_src = None, None
+    for name in ("r02_ncu_prof_gemm.json", "r01_ncu_prof_gemm.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                nc = json.load(f)
+            to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                val, unit = nc[key].split()
+                traffic += float(val) * to_bytes[unit]
+            traffic_src = "profiles/" + name
+            break
+        except Exception:
+            traffic = None
     gemm_ms_avg = gemm_ms_total / max(1, gemm_n)
     algo_flops = 2.0 * D * ne_local * nt_total                       # per launch (2*d flop per trial)
     achieved = algo_flops / (gemm_ms_avg * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "traffic": traffic,
-                "traffic_note": "dram read+write bytes per launch, ncu --set full of this kernel at this shape "
-                                "(profiles/r01_ncu_prof_gemm.json); algorithmic = 4 B x 1e8 scores + 16 MB operands",
+                "traffic_note": "dram read+write bytes per launch, ncu --set full of this kernel at this shape (%s); "
+                                "algorithmic = 4 B x 1e8 scores + 16 MB operands" % traffic_src,
                 "peak_source": pk["source"] + " bf16 burst",
                 "kernel": "gemm_bf16x3_kernel", "kernel_ms": gemm_ms_avg, "launches_timed": int(gemm_n),
                 "issued_tflops": achieved * 3 * 208 / 200,
@@ -441,22 +1029,23 @@ def run_main(args):
                 "hbm_write_frac": 4.0 * ne_local * nt_total / (gemm_ms_avg * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "note": "algorithmic = 2*d flop/trial; issued = x3 (bf16 split) on K padded 200->208; "
                         "co-bound by the 4 B/trial fp32 score write"}
+    cfg = bench_config(world)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate, fp32 scores)", "data": "synthetic",
-        "config": {"workload": "C2: 100k x 200 d-vectors, 1k speakers, 10 EM iters + 10k x 10k scoring grid",
-                   "d": D, "enrol_per_gpu": ne_local, "test": nt_total, "enrol_utts": ENROL_UTTS,
-                   "sink": "fp32 score matrix in HBM (400 MB per step per GPU)",
-                   "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events summed",
-                   "parallelism": ("single GPU" if world == 1 else
-                                   "enrol-block shard per GPU; each rank's producer kernel pushes its test rows into "
-                                   "every rank's operand buffer over NVLink peer memory (CUDA IPC), the GEMM waits per "
-                                   "column tile on the owner's flag; no NCCL on the data path" if peer_used else
-                                   "enrol-block shard per GPU, 1 NCCL all-gather of test vectors per step")},
+        "config": cfg,
+        "parallelism": ("single GPU" if world == 1 else
+                        "enrol-block shard per GPU; each rank's producer kernel pushes its test rows into "
+                        "every rank's operand buffer over NVLink peer memory (CUDA IPC), the GEMM waits per "
+                        "column tile on the owner's flag; no NCCL on the data path" if peer_used else
+                        "enrol-block shard per GPU, 1 NCCL all-gather of test vectors per step"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((ne_local + nt_total) * D * 8),
                 "d2h_bytes_per_step": int(ne_local * nt_total * 4), "steps": e2e_steps,
-                "ms_per_step": e2e_s / e2e_steps * 1e3, "host_buffers": "pinned fp64 in, pinned fp32 out"},
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "host_buffers": "pinned fp64 in, pinned fp32 out",
+                "bound": "PCIe: the 400 MB fp32 matrix per GPU per step is the payload (see e2e_trials for the sink "
+                         "that returns only listed trials)"},
+        "e2e_trials": e2e_trials,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -466,12 +1055,40 @@ def run_main(args):
                             "result (fp64 host rows: operand formed in fp64) -- two roundings of the same operand, both "
                             "inside the 1e-3 score tolerance the GPU tests hold against the fp64 oracle",
     }
+    for p in (_p1, _p2, _p3, _p4, _p5):
+        lib.plda_host_free_pinned(p)
+    model = plda.get_model()
+    del plda, outs, flush, enrol_t, test_shard, test_full
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, same run ----
+    if not args.headline_only:
+        if world == 1:
+            configs = {}
+            for name, fn in (("c3", run_c3), ("c4_slab", run_c4_slab), ("c5", run_c5)):
+                t0 = time.perf_counter()
+                try:
+                    torch.cuda.reset_peak_memory_stats(dev)
+                    configs[name] = fn(torch, dev, pk, args.steps)
+                except Exception as e:  # a failed side record never takes the headline line down
+                    configs[name] = {"error": repr(e)}
+                configs[name]["wall_s"] = time.perf_counter() - t0
+                torch.cuda.empty_cache()
+            out["configs"] = configs
+        else:
+            t0 = time.perf_counter()
+            try:
+                out["sharded"] = run_sharded_extras(torch, dist, dev, pk, rank, world, args.steps)
+            except Exception as e:
+                out["sharded"] = {"error": repr(e)}
+            out["sharded"]["wall_s"] = time.perf_counter() - t0
+
     os.sched_setaffinity(0, prev_affinity)       # the CPU baseline may use every host core
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             from oracle import c_ref
             c_ref.build()
-            mean, tr, psi = plda.get_model()
+            mean, tr, psi = model
             sub = 4000
             v, used, spp = cpu_grid_sample(psi, sub, sub, 1, 1)
             ref = c_ref.RefPlda(x, labels)
@@ -483,12 +1100,11 @@ def run_main(args):
                                    "sample": "%dx%d sub-grid of the 10k x 10k grid, per-pair LLR loop "
                                              "(oracle/plda_ref.c), %.1f s" % (sub, sub, spp),
                                    "em_iters_per_sec": cpu_em, "em_cores": 1}
+            out["cpu_best"] = cpu_best(mean, tr, psi, x, labels)
         except Exception as e:  # the baseline is reported, never required for the GPU number
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     if rank == 0:
         print(json.dumps(out), flush=True)
-    for p in (_p1, _p2, _p3):
-        lib.plda_host_free_pinned(p)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -504,6 +1120,8 @@ def main():
     ap.add_argument("--nccl-allgather", action="store_true",
                     help="N > 1: exchange the test vectors with one NCCL all-gather per step instead of peer memory")
     ap.add_argument("--skip-em", action="store_true", help="profiling aid: 1 EM iteration, no fit timing")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="only the C2 headline (no c3 / c4_slab / c5 / sharded side records)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -135,7 +135,8 @@ void center_scale_split_t(Context& ctx, const void* x, bool is_f32, int64_t d, i
 // [nseg].  Tensor path (split-bf16 x3), d <= scatter_fused_max_dim().
 struct ScatterWork {
   DevBuf<int4> meta;
-  DevBuf<float> csum, delta, partial;
+  DevBuf<uint8_t> csum;          // class sums in the rows' own type
+  DevBuf<float> delta, partial;
 };
 int scatter_fused_max_dim();
 void scatter_fused(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg,

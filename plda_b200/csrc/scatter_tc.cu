@@ -44,7 +44,7 @@ struct ScatterParams {
   long long ld;
   int d;
   const int4* meta;      // [nkb * 64] {source row (-1: padding), anchor row (-1: none), scale bits, class}
-  float* csum;           // [classes][csum_ld] class sums of (x - anchor), or null
+  void* csum;            // [classes][csum_ld] class sums of (x - anchor) in the rows' own type T, or null
   int csum_ld;
   float* partial;        // [ranges][dp][dp]
   int dp;
@@ -247,18 +247,23 @@ scatter_syrk_kernel(const ScatterParams p) {
     int4 m0 = load_meta(0), m1 = load_meta(1);
     issue_loads(m0);
     T g[CPL];
-    float acc[CPL];
+    T acc[CPL];      // class sums in the rows' own precision: fp64 rows keep fp64 class means
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) { g[c] = T(0); acc[c] = 0.f; }
+    for (int c = 0; c < CPL; ++c) { g[c] = T(0); acc[c] = T(0); }
     int g_row = -1, cur_cls = -1;
     auto flush = [&]() {
       if (cur_cls >= 0) {
-        float* dst = p.csum + static_cast<long long>(cur_cls) * p.csum_ld + gcol;
-        red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
-        if (CPL == 8) red_add_v4(dst + 4, acc[CPL - 4], acc[CPL - 3], acc[CPL - 2], acc[CPL - 1]);
+        T* dst = static_cast<T*>(p.csum) + static_cast<long long>(cur_cls) * p.csum_ld + gcol;
+        if constexpr (sizeof(T) == 4) {
+          red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+          if (CPL == 8) red_add_v4(dst + 4, acc[CPL - 4], acc[CPL - 3], acc[CPL - 2], acc[CPL - 1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) atomicAdd(dst + c, acc[c]);
+        }
       }
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+      for (int c = 0; c < CPL; ++c) acc[c] = T(0);
     };
     int stage = 0;
     uint32_t phase = 0;
@@ -296,9 +301,8 @@ scatter_syrk_kernel(const ScatterParams p) {
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
             const T dv = cur[jj][c] - g[c];                             // fp32 rows: exact to the ulp of a small value
-            const float df = static_cast<float>(dv);
-            acc[c] += df;
-            v[c] = sizeof(T) == 8 ? static_cast<float>(dv * static_cast<T>(scl)) : df * scl;
+            acc[c] += dv;
+            v[c] = static_cast<float>(dv * static_cast<T>(scl));
           }
         } else {
 #pragma unroll
@@ -396,7 +400,7 @@ __global__ void plain_meta_kernel(long long n, long long n_pad, int4* __restrict
 // delta_c = csum_c / n_c (scaled by sqrt(n_c w_c) for the correction SYRK);  mean_c = anchor_c + csum_c / n_c
 template <typename T>
 __global__ void scatter_means_kernel(const T* __restrict__ x, long long ld, int d, const int32_t* __restrict__ order,
-                                     const int32_t* __restrict__ seg_start, const float* __restrict__ csum, int csum_ld,
+                                     const int32_t* __restrict__ seg_start, const T* __restrict__ csum, int csum_ld,
                                      int scale_by_count, float* __restrict__ delta, int delta_ld,
                                      double* __restrict__ means, int32_t* __restrict__ counts) {
   const long long s = blockIdx.x;
@@ -457,7 +461,7 @@ void launch_syrk(Context& ctx, const ScatterParams& p) {
 
 // one pass of the fused kernel over `rows` rows described by w.meta; returns the number of ranges written
 int run_syrk(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, int64_t rows, const int4* meta,
-             float* csum, int csum_ld, float* partial, int dp) {
+             void* csum, int csum_ld, float* partial, int dp) {
   const int nblk = dp / 256;
   ScatterParams p;
   p.x = x;
@@ -493,12 +497,13 @@ void scatter_fused(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t 
   const int max_ranges = pairs / (dp / 256);
   const int64_t n_pad = round_up(seg.n, SC_KROWS), k_pad = round_up(seg.nseg, SC_KROWS);
   w.meta.reserve(static_cast<size_t>(std::max(n_pad, k_pad)));
-  w.csum.reserve(static_cast<size_t>(seg.nseg) * dp);
+  const size_t csum_bytes = static_cast<size_t>(seg.nseg) * dp * (is_f32 ? 4 : 8);
+  w.csum.reserve(csum_bytes);
   w.delta.reserve(static_cast<size_t>(seg.nseg) * dp);
   w.partial.reserve(static_cast<size_t>(2) * max_ranges * dp * dp);
   float* part_main = w.partial.get();
   float* part_corr = part_main + static_cast<size_t>(max_ranges) * dp * dp;
-  PB_CUDA(cudaMemsetAsync(w.csum.get(), 0, static_cast<size_t>(seg.nseg) * dp * sizeof(float), ctx.stream));
+  PB_CUDA(cudaMemsetAsync(w.csum.get(), 0, csum_bytes, ctx.stream));
   scatter_meta_kernel<<<static_cast<unsigned>(ceil_div(n_pad, 256)), 256, 0, ctx.stream>>>(
       seg.order.get(), seg.seg_of_pos.get(), seg.seg_start.get(), seg.n, n_pad, scale_by_count ? 1 : 0, w.meta.get());
   PB_CUDA(cudaGetLastError());
@@ -506,11 +511,13 @@ void scatter_fused(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t 
   const int r1 = run_syrk(ctx, x, is_f32, d, ld, seg.n, w.meta.get(), w.csum.get(), dp, part_main, dp);
   if (is_f32)
     scatter_means_kernel<float><<<static_cast<unsigned>(seg.nseg), 128, 0, ctx.stream>>>(
-        static_cast<const float*>(x), ld, static_cast<int>(d), seg.order.get(), seg.seg_start.get(), w.csum.get(), dp,
+        static_cast<const float*>(x), ld, static_cast<int>(d), seg.order.get(), seg.seg_start.get(),
+        reinterpret_cast<const float*>(w.csum.get()), dp,
         scale_by_count ? 1 : 0, w.delta.get(), dp, means_out, counts_out);
   else
     scatter_means_kernel<double><<<static_cast<unsigned>(seg.nseg), 128, 0, ctx.stream>>>(
-        static_cast<const double*>(x), ld, static_cast<int>(d), seg.order.get(), seg.seg_start.get(), w.csum.get(), dp,
+        static_cast<const double*>(x), ld, static_cast<int>(d), seg.order.get(), seg.seg_start.get(),
+        reinterpret_cast<const double*>(w.csum.get()), dp,
         scale_by_count ? 1 : 0, w.delta.get(), dp, means_out, counts_out);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();

@@ -79,10 +79,11 @@ def test_sharded_scoring_gloo(tmp_path, world, ne, nt):
 class _FakeLda:
     """Stand-in with the attributes broadcast_lda touches (the real LDA needs a GPU)."""
     def __init__(self):
-        self._coef = self._intercept = None
+        self._coef = self._intercept = self._classes = None
 
-    def set_coef(self, coef, intercept):
+    def set_coef(self, coef, intercept, classes=None):
         self._coef, self._intercept = coef, intercept
+        self._classes = np.arange(coef.shape[0]) if classes is None else np.asarray(classes)
 
 
 class _FakePlda:
@@ -123,11 +124,13 @@ def _lda_worker(rank, world, port, result_dir):
         if rank == 0:
             o = LDAOracle("svd")
             o.fit(x, y)
-            lda.set_coef(np.asarray(o._coef), np.asarray(o._intercept))
+            lda.set_coef(np.asarray(o._coef), np.asarray(o._intercept), classes=classes)
         broadcast_lda(lda, src=0)
         o = LDAOracle("svd")
         o.fit(x, y)
         assert np.array_equal(lda._coef, o._coef) and np.array_equal(lda._intercept, o._intercept)
+        # the label VALUES travel too (sparse, partly negative here): predict() agrees on every rank
+        assert np.array_equal(lda._classes, classes)
         # cohort all-gather in front of norm
         cohort = rng.randn(9, d)
         lo, hi = block_bounds(9, world, rank)

@@ -115,6 +115,11 @@ class _OraclePldaAdapter:
             g = (g - mean[:, None]) / std[:, None]
         return g
 
+    def score_trials(self, enrol, counts, test, trial_enrol, trial_test, enrol_ids=None):
+        """Listed trials (plda_score_trials): here simply a gather of the oracle's grid."""
+        g = self.score_grid(enrol, counts, test, enrol_ids)
+        return g[np.asarray(trial_enrol), np.asarray(trial_test)]
+
 
 def test_plda_pipeline_host_logic_with_oracle():
     """Label enumeration, transform / norm plumbing, grid -> trial gather and the error count of score_trials,
