@@ -163,7 +163,7 @@ class PldaEngine {
                              float* out32, int64_t ld32);
   void em_iteration(int64_t k, int64_t d, const double* scatter, const SplitBuf& mc_split, const double* mc_f64,
                     const int32_t* counts_dev, double w_count, double b_count, bool warm);
-  void joint_diagonalise(int64_t d, bool warm);
+  void joint_diagonalise(int64_t d, bool warm, bool final_pass);
 
   // persistent workspaces (grow-only)
   SplitBuf ws_l, ws_r, ws_x, ws_xt, ws_pt, ws_qt, ws_mc;

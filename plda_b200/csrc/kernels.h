@@ -172,8 +172,11 @@ struct EigWork {
   DevBuf<int> flags;
   DevBuf<int32_t> perm;
 };
+// stop_rotation: the solve ends after the first sweep whose largest rotation |gamma| / sqrt(alpha beta) stayed below
+// it; Jacobi converges quadratically, so the couplings left are ~stop_rotation^2 relative (1e-7 -> full fp64
+// accuracy; the EM iterations in between use a looser value, see PldaEngine::joint_diagonalise)
 void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t, double* evals, double* evecs_t,
-                    EigWork& work, int* sweeps_out);
+                    EigWork& work, int* sweeps_out, double stop_rotation = 1e-7);
 
 // ---- d-vector pooling (scoring/extractdvector.py:19-58) ------------------------------------ //
 // frames [n_frames x d] (device), utterance u = frames [offsets[u], offsets[u+1]) (host CSR offsets);

@@ -4,6 +4,9 @@
 // (reached from src/pldamodule.cpp:106) and are also what lets the EM iteration run in the jointly
 // diagonalising basis.  They are latency-bound (no meaningful roofline); the design goal is a small,
 // fixed number of device-wide synchronisations, all matrices L2-resident.
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 #include "kernels.h"
@@ -149,8 +152,13 @@ __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __
 //   3. C <- C Q              (written straight back to global memory)
 // Steps 1 and 3 are GEMM-shaped and use every thread; only step 2 is sequential, on a 32x32 / 64x64 matrix.
 // ------------------------------------------------------------------------- //
+// CLUSTER: the whole grid is ONE thread-block cluster (<= 16 CTAs): the per-round barrier is the hardware cluster
+// barrier (release / acquire at cluster scope orders the __stcg / __ldcg column exchange through L2) instead of an
+// atomic counter polled through L2.  big2: a sweep whose largest rotation satisfied gamma^2 <= big2 alpha beta is
+// the last one (quadratic convergence: the remaining couplings are ~big2 relative).
+template <bool CLUSTER>
 __global__ void __launch_bounds__(1024, 1)
-block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, int max_sweeps,
+block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, double big2, int max_sweeps,
                          unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated,
                          int* __restrict__ sweeps_done) {
   extern __shared__ double sm[];
@@ -225,7 +233,7 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
           if (warp == 0) { x = m2 - 1; y = lr; }
           else { x = (lr + warp) % (m2 - 1); y = (lr - warp + (m2 - 1)) % (m2 - 1); }
           const double alpha = gl[x * gp + x], beta = gl[y * gp + y], gamma = gl[x * gp + y];
-          if (lane == 0 && gamma * gamma > 1e-14 * alpha * beta) s_big = 1;
+          if (lane == 0 && gamma * gamma > big2 * alpha * beta) s_big = 1;
           if (gamma * gamma > tol * tol * alpha * beta && fabs(gamma) > abs_tol) {
             // rotation angle in fp32 (a 1e-7 relative error in the angle only leaves a 1e-7 * gamma residual),
             // but (c, s) exactly orthonormal in fp64: c = rsqrt(1 + t^2) by two Newton steps, s = c t
@@ -290,7 +298,13 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
         // without paying for a verification sweep.
         if (threadIdx.x == 0) atomicOr(rotated + sweep, s_big ? 3 : 1);
       }
-      grid_barrier(barrier_counter, target, gridDim.x);
+      if (CLUSTER) {
+        __threadfence();
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      } else {
+        grid_barrier(barrier_counter, target, gridDim.x);
+      }
     }
     const int flags = *reinterpret_cast<volatile int*>(rotated + sweep);
     if ((flags & 2) == 0) { ++sweep; break; }
@@ -350,7 +364,7 @@ void tri_inverse_lower(Context& ctx, const double* l, double* inv, int64_t d) {
 }
 
 void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t, double* evals, double* evecs_t,
-                    EigWork& w, int* sweeps_out) {
+                    EigWork& w, int* sweeps_out, double stop_rotation) {
   PB_CHECK(d > 0 && d <= 1024, kInvalidArg, "eig: d <= 1024");
   const int max_sweeps = 40;
   w.g.reserve(d * d);
@@ -381,16 +395,46 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   PB_CHECK(blocks <= ctx.num_sms, kInvalidArg, "eig: too many blocks for a cooperative launch");
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(block_jacobi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   });
   double* gp = w.g.get();
   unsigned int* counter = reinterpret_cast<unsigned int*>(w.flags.get());
   int* sweeps_done = w.flags.get() + 1;
   int* rotated = w.flags.get() + 2;
   int ms = max_sweeps;
-  void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &ms, &counter, &rotated, &sweeps_done};
-  PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(block_jacobi_gram_kernel), dim3(blocks),
-                                      dim3(512), args, smem, ctx.stream));
+  double big2 = stop_rotation * stop_rotation;
+  // one cluster for the whole solve when the hardware can place it (<= 16 CTAs, one per SM in a GPC)
+  bool use_cluster = blocks <= 16 && !(getenv("PLDA_B200_EIG") != nullptr && strcmp(getenv("PLDA_B200_EIG"), "grid") == 0);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (use_cluster) {
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx.stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = blocks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, block_jacobi_gram_kernel<true>, &cfg) != cudaSuccess ||
+        max_clusters < 1) {
+      cudaGetLastError();
+      use_cluster = false;
+    }
+  }
+  if (use_cluster) {
+    PB_CUDA(cudaLaunchKernelEx(&cfg, block_jacobi_gram_kernel<true>, gp, di, bw, nblk_pad, tol, big2, ms, counter, rotated,
+                               sweeps_done));
+  } else {
+    void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &big2, &ms, &counter, &rotated, &sweeps_done};
+    PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(block_jacobi_gram_kernel<false>), dim3(blocks),
+                                        dim3(512), args, smem, ctx.stream));
+  }
   ctx.count_launch();
   eig_normalise_kernel<<<static_cast<unsigned>(ceil_div(d, 8)), 256, 0, ctx.stream>>>(w.g.get(), di, w.lam.get(),
                                                                                      w.v.get());

@@ -35,15 +35,15 @@ constexpr int SC_KROWS = 64;                                  // reduction rows 
 constexpr int SC_TILE_BYTES = SC_KROWS * 128 * 2;             // one 128-column block, one plane: 16 KB
 constexpr int SC_BLOCK_BYTES = 2 * SC_TILE_BYTES;             // hi + lo
 constexpr int SC_STAGES = 3;
-constexpr int SC_PROD_WARPS = 8;
-constexpr int SC_THREADS = 64 + 32 * SC_PROD_WARPS;           // warp 0 relay, warp 1 MMA issuer, warps 2..9 producers
+constexpr int SC_PROD_WARPS = 16;
+constexpr int SC_THREADS = 64 + 32 * SC_PROD_WARPS;           // warp 0 relay, warp 1 MMA issuer, warps 2..17 producers
 constexpr int SC_BAR_BYTES = 256;
 
 struct ScatterParams {
   const void* x;
   long long ld;
   int d;
-  const int4* meta;      // [nkb * 64] {source row (-1: padding), anchor row (-1: none), scale bits, class}
+  const int4* meta;      // [nkb * 64] {source row, anchor row (-1: none), sqrt(weight) bits, class}
   void* csum;            // [classes][csum_ld] class sums of (x - anchor) in the rows' own type T, or null
   int csum_ld;
   float* partial;        // [ranges][dp][dp]
@@ -94,37 +94,16 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
-template <typename T, int CPL>
-__device__ __forceinline__ void load_cols(const T* __restrict__ row, int col, int d, bool vec, T (&v)[CPL]) {
-  if (vec && col + CPL <= d) {
-    if constexpr (sizeof(T) == 4) {
-#pragma unroll
-      for (int j = 0; j < CPL / 4; ++j) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(row + col) + j);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CPL / 2; ++j) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(row + col) + j);
-        v[2 * j] = t.x; v[2 * j + 1] = t.y;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) v[j] = col + j < d ? __ldg(row + col + j) : T(0);
-  }
-}
-
 // One CTA pair = (block row I of S, row range).  T: float / double rows.  NBLK: 128-column blocks staged per CTA
 // (1: d <= 256, 2: d <= 512) = number of 256-column accumulators = number of pair types.
 template <typename T, int NBLK>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 scatter_syrk_kernel(const ScatterParams p) {
   constexpr int CPL = 4 * NBLK;                          // columns per producer lane
-  // rows a producer warp converts per batch (register double buffering: one batch in flight while one is converted)
-  constexpr int SC_BATCH = (sizeof(T) == 8 && NBLK == 2) ? 2 : 4;
-  constexpr int BPK = 8 / SC_BATCH;                      // batches per k-block and warp
+  // a producer warp owns 4 rows of every k-block and converts them in NB batches of RB rows; the next batch is in
+  // flight (registers, ping-pong) while one is converted
+  constexpr int RB = (sizeof(T) == 8 && NBLK == 2) ? 1 : 2;
+  constexpr int NB = 4 / RB;
   constexpr int STAGE_BYTES = NBLK * SC_BLOCK_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -208,51 +187,63 @@ scatter_syrk_kernel(const ScatterParams p) {
     }
   } else {
     // ===== producers (both CTAs): rows -> centred, scaled, split operand tiles =====
+    // 16 warps; warp pw converts the k rows pw, pw + 16, pw + 32, pw + 48 of every k-block (one BATCH) -- its next
+    // batch is in flight (registers, ping-pong) while the current one is converted.  Everything that does not change
+    // from row to row is hoisted: the column state of the lane, the swizzled store offset (k row & 7 == pw & 7).
     const int pw = warp - 2;
     const int cl = lane * CPL;                                         // column inside the CTA's staged span
     const int lb = cl >> 7;                                            // local block (0 .. NBLK-1)
     const int cb = cl & 127;                                           // column inside the block
     const int gcol = 128 * (2 * lb + static_cast<int>(rank)) + cb;     // column of x
-    const T* __restrict__ xb = static_cast<const T*>(p.x);
-    const bool vec = ((reinterpret_cast<uintptr_t>(p.x) | (static_cast<uintptr_t>(p.ld) * sizeof(T))) & 15) == 0;
-    // byte offset of this lane's 16-byte chunk (minus the k-row terms) inside a stage
-    const uint32_t tile_off = lb * SC_BLOCK_BYTES + (cb >> 6) * 8192;
-    const uint32_t chunk = (cb & 63) >> 3;
-    const uint32_t sub = (cb & 7) * 2;                                 // CPL = 4: second half of the chunk
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p.x) | (static_cast<uintptr_t>(p.ld) * sizeof(T))) & 15) == 0;
+    // 1: all CPL columns exist and 16-byte loads are legal; 2: guarded scalar loads; 0: beyond d (zeros, nothing loaded)
+    const int cmode = gcol + CPL <= p.d ? (aligned ? 1 : 2) : (gcol < p.d ? 2 : 0);
+    const T* __restrict__ xcol = static_cast<const T*>(p.x) + gcol;
+    const int ncol = min(CPL, p.d - gcol);                             // valid columns of this lane (cmode 2)
+    const uint32_t st_off = lb * SC_BLOCK_BYTES + (cb >> 6) * 8192 + pw * 128 +
+                            ((((cb & 63) >> 3) ^ (pw & 7)) << 4) + (cb & 7) * 2;
     const bool do_sums = p.csum != nullptr && blk_row == 0;
+    const int4* __restrict__ mrow = p.meta + static_cast<long long>(kb0) * SC_KROWS + pw + 16 * (lane & 3);
 
-    const int batches = BPK * cnt;
-    auto load_meta = [&](int t) -> int4 {
-      int4 m = make_int4(-1, -1, 0, -1);
-      if (t < batches && lane < SC_BATCH) {
-        const int kb = kb0 + t / BPK;
-        const int row = pw + 8 * (SC_BATCH * (t % BPK) + lane);
-        m = __ldg(p.meta + static_cast<long long>(kb) * SC_KROWS + row);
-      }
-      return m;
-    };
-    T nxt[SC_BATCH][CPL];
-    auto issue_loads = [&](const int4& m) {
+    auto load_row = [&](T (&v)[CPL], long long row) {
+      const T* src = xcol + row * p.ld;
+      if (cmode == 1) {
+        if constexpr (sizeof(T) == 4) {
 #pragma unroll
-      for (int jj = 0; jj < SC_BATCH; ++jj) {
-        const int src = __shfl_sync(0xffffffffu, m.x, jj);
-        if (src >= 0 && gcol < p.d) {
-          load_cols<T, CPL>(xb + static_cast<long long>(src) * p.ld, gcol, p.d, vec, nxt[jj]);
+          for (int j = 0; j < CPL / 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src) + j);
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) nxt[jj][c] = T(0);
+          for (int j = 0; j < CPL / 2; ++j) {
+            const double2 t = __ldg(reinterpret_cast<const double2*>(src) + j);
+            v[2 * j] = t.x; v[2 * j + 1] = t.y;
+          }
         }
+      } else if (cmode == 2) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) v[j] = j < ncol ? __ldg(src + j) : T(0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) v[j] = T(0);
       }
     };
-    int4 m0 = load_meta(0), m1 = load_meta(1);
-    issue_loads(m0);
+    // meta of a batch: lane r (and r + 4, ...) holds the record of the warp's r-th row of k-block i
+    auto load_meta = [&](int i) -> int4 {
+      return i < cnt ? __ldg(mrow + static_cast<long long>(i) * SC_KROWS) : make_int4(0, 0, 0, 0);
+    };
+    auto issue_loads = [&](T (&buf)[RB][CPL], const int4& m, int b) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) load_row(buf[r], __shfl_sync(0xffffffffu, m.x, b * RB + r));
+    };
     T g[CPL];
     T acc[CPL];      // class sums in the rows' own precision: fp64 rows keep fp64 class means
 #pragma unroll
     for (int c = 0; c < CPL; ++c) { g[c] = T(0); acc[c] = T(0); }
     int g_row = -1, cur_cls = -1;
     auto flush = [&]() {
-      if (cur_cls >= 0) {
+      if (cur_cls >= 0 && cmode != 0) {
         T* dst = static_cast<T*>(p.csum) + static_cast<long long>(cur_cls) * p.csum_ld + gcol;
         if constexpr (sizeof(T) == 4) {
           red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
@@ -267,46 +258,31 @@ scatter_syrk_kernel(const ScatterParams p) {
     };
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = 0; t < batches; ++t) {
-      const int4 m2 = load_meta(t + 2);
-      T cur[SC_BATCH][CPL];
+    auto convert = [&](T (&buf)[RB][CPL], const int4& m, int b) {
+      if (b == 0) mbar_wait(&empty[stage], phase ^ 1);
+      const uint32_t sbase = smem_u32(smem + stage * STAGE_BYTES) + st_off;
 #pragma unroll
-      for (int jj = 0; jj < SC_BATCH; ++jj)
+      for (int r = 0; r < RB; ++r) {
+        const int wr = b * RB + r;                                      // the warp's wr-th row: k row pw + 16 wr
+        const int anc = __shfl_sync(0xffffffffu, m.y, wr);
+        const float scl = __int_as_float(__shfl_sync(0xffffffffu, m.z, wr));
+        const int cls = __shfl_sync(0xffffffffu, m.w, wr);
+        if (anc != g_row) {                                             // new class: its anchor row (warp uniform)
+          if (anc >= 0) {
+            load_row(g, anc);
+          } else {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) cur[jj][c] = nxt[jj][c];
-      const int4 mc = m0;
-      if (t + 1 < batches) issue_loads(m1);
-      const int bi = t % BPK;
-      if (bi == 0) mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* sbase = smem + stage * STAGE_BYTES + tile_off;
-#pragma unroll
-      for (int jj = 0; jj < SC_BATCH; ++jj) {
-        const int src = __shfl_sync(0xffffffffu, mc.x, jj);
-        const int anc = __shfl_sync(0xffffffffu, mc.y, jj);
-        const float scl = __int_as_float(__shfl_sync(0xffffffffu, mc.z, jj));
-        const int cls = __shfl_sync(0xffffffffu, mc.w, jj);
-        const int krow = pw + 8 * (SC_BATCH * bi + jj);
+            for (int c = 0; c < CPL; ++c) g[c] = T(0);
+          }
+          g_row = anc;
+        }
+        if (do_sums && cls != cur_cls) { flush(); cur_cls = cls; }
         float v[CPL];
-        if (src >= 0 && gcol < p.d) {
-          if (anc != g_row) {                                           // new class: its anchor row
-            if (anc >= 0) {
-              load_cols<T, CPL>(xb + static_cast<long long>(anc) * p.ld, gcol, p.d, vec, g);
-            } else {
 #pragma unroll
-              for (int c = 0; c < CPL; ++c) g[c] = T(0);
-            }
-            g_row = anc;
-          }
-          if (do_sums && cls != cur_cls) { flush(); cur_cls = cls; }
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            const T dv = cur[jj][c] - g[c];                             // fp32 rows: exact to the ulp of a small value
-            acc[c] += dv;
-            v[c] = static_cast<float>(dv * static_cast<T>(scl));
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) v[c] = 0.f;
+        for (int c = 0; c < CPL; ++c) {
+          const T dv = buf[r][c] - g[c];                                // fp32 rows: exact to the ulp of a small value
+          if (do_sums) acc[c] += dv;
+          v[c] = static_cast<float>(dv * static_cast<T>(scl));
         }
         uint32_t hi[CPL / 2], lo[CPL / 2];
 #pragma unroll
@@ -319,7 +295,7 @@ scatter_syrk_kernel(const ScatterParams p) {
           hi[c] = hh;
           lo[c] = ll;
         }
-        const uint32_t addr = smem_u32(sbase) + krow * 128 + ((chunk ^ (krow & 7)) << 4) + sub;
+        const uint32_t addr = sbase + wr * (16 * 128);
         if (CPL == 8) {
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hi[0]), "r"(hi[1]), "r"(hi[CPL / 2 - 2]),
                        "r"(hi[CPL / 2 - 1]) : "memory");
@@ -330,14 +306,30 @@ scatter_syrk_kernel(const ScatterParams p) {
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + SC_TILE_BYTES), "r"(lo[0]), "r"(lo[1]) : "memory");
         }
       }
-      if (bi == BPK - 1) {
-        fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core's (async proxy) reads
+      if (b == NB - 1) {
+        fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's (async proxy) reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[stage]);
         if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
       }
-      m0 = m1;
-      m1 = m2;
+    };
+    T bufa[RB][CPL], bufb[RB][CPL];
+    int4 m_cur = load_meta(0), m_nxt = load_meta(1);
+    issue_loads(bufa, m_cur, 0);
+    for (int i = 0; i < cnt; ++i) {
+      const int4 m_nn = load_meta(i + 2);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        // prefetch: the next batch of this k-block, or the first batch of the next one (NB is even: it is bufa's turn)
+        if (b + 1 < NB) {
+          if ((b + 1) & 1) issue_loads(bufb, m_cur, b + 1); else issue_loads(bufa, m_cur, b + 1);
+        } else if (i + 1 < cnt) {
+          issue_loads(bufa, m_nxt, 0);
+        }
+        if (b & 1) convert(bufb, m_cur, b); else convert(bufa, m_cur, b);
+      }
+      m_cur = m_nxt;
+      m_nxt = m_nn;
     }
     if (do_sums) flush();
 
@@ -348,7 +340,7 @@ scatter_syrk_kernel(const ScatterParams p) {
     const int h = pw >> 2;
     const int row = 256 * blk_row + 128 * static_cast<int>(rank) + 32 * q + lane;
     float* prow = p.partial + (static_cast<long long>(range) * p.dp + row) * p.dp;
-    for (int c = h; c < 8 * NBLK; c += 2) {
+    for (int c = h; c < 8 * NBLK; c += SC_PROD_WARPS / 4) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
       tmem_ld_wait();
@@ -377,16 +369,17 @@ __global__ void scatter_meta_kernel(const int32_t* __restrict__ order, const int
                                     int scale_by_count, int4* __restrict__ meta) {
   const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (p >= n_pad) return;
-  int4 m = make_int4(-1, -1, 0, -1);
-  if (p < n) {
-    const int s = seg_of_pos[p];
-    const int first = seg_start[s];
-    const int cnt = seg_start[s + 1] - first;
-    m.x = order[p];
-    m.y = order[first];
-    m.z = __float_as_int(scale_by_count ? static_cast<float>(rsqrt(static_cast<double>(cnt))) : 1.f);
-    m.w = s;
-  }
+  // padding positions repeat the anchor row of the last class: (x - anchor) is exactly zero there, so they add
+  // nothing to the scatter or to the class sums and the producer needs no branch for them
+  const long long q = p < n ? p : n - 1;
+  const int s = seg_of_pos[q];
+  const int first = seg_start[s];
+  const int cnt = seg_start[s + 1] - first;
+  int4 m;
+  m.x = p < n ? order[p] : order[first];
+  m.y = order[first];
+  m.z = __float_as_int(scale_by_count ? static_cast<float>(rsqrt(static_cast<double>(cnt))) : 1.f);
+  m.w = s;
   meta[p] = m;
 }
 
@@ -394,7 +387,8 @@ __global__ void scatter_meta_kernel(const int32_t* __restrict__ order, const int
 __global__ void plain_meta_kernel(long long n, long long n_pad, int4* __restrict__ meta) {
   const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (p >= n_pad) return;
-  meta[p] = p < n ? make_int4(static_cast<int>(p), -1, __float_as_int(1.f), 0) : make_int4(-1, -1, 0, -1);
+  // padding: row 0 with weight 0
+  meta[p] = p < n ? make_int4(static_cast<int>(p), -1, __float_as_int(1.f), 0) : make_int4(0, -1, __float_as_int(0.f), 0);
 }
 
 // delta_c = csum_c / n_c (scaled by sqrt(n_c w_c) for the correction SYRK);  mean_c = anchor_c + csum_c / n_c

@@ -312,9 +312,10 @@ def test_smoothing_mutates_model_like_reference():
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
 def test_fit_operand_kernels_agree(dtype):
-    """The transposing SYRK-operand producer has a 64 x 64 tile kernel for aligned rows (16-byte loads, full-line
-    stores) and a 32 x 32 one for everything else; same arithmetic -> the fitted model must not depend on whether
-    the rows arrive contiguous or as an odd-pitch, element-shifted view of a wider matrix."""
+    """The fused stats pass loads aligned rows with 16-byte loads and everything else with guarded scalar loads; same
+    arithmetic -> the fitted model must not depend on whether the rows arrive contiguous or as an odd-pitch,
+    element-shifted view of a wider matrix.  (Class sums are accumulated in the rows' own precision with atomics, so
+    fp32 rows agree to fp32 summation-order noise, fp64 rows to fp64 noise.)"""
     import torch
     from plda_b200 import PLDA
     d = 72
@@ -334,8 +335,12 @@ def test_fit_operand_kernels_agree(dtype):
     mb, tb, pb_ = b.get_model()
     # (the class-mean kernel also has a vectorised and a scalar variant with different fp64 summation orders, so the
     # two fits agree to rounding noise, not bit for bit; eigenvector signs may flip, so A is compared through A^T A)
-    assert np.allclose(pa, pb_, rtol=1e-7, atol=1e-12) and np.allclose(ma, mb, rtol=1e-10, atol=1e-12)
-    assert np.allclose(ta.T @ ta, tb.T @ tb, rtol=1e-6, atol=1e-8)
+    if dtype == "float64":
+        assert np.allclose(pa, pb_, rtol=1e-7, atol=1e-12) and np.allclose(ma, mb, rtol=1e-10, atol=1e-12)
+        assert np.allclose(ta.T @ ta, tb.T @ tb, rtol=1e-6, atol=1e-8)
+    else:
+        assert np.allclose(pa, pb_, rtol=3e-5, atol=1e-9) and np.allclose(ma, mb, rtol=1e-6, atol=1e-7)
+        assert np.allclose(ta.T @ ta, tb.T @ tb, rtol=1e-4, atol=1e-5)
     ref = oracle_fit(x_al.double().cpu().numpy(), labels, 3)
     assert np.max(np.abs(pa - ref.plda.psi) / np.maximum(ref.plda.psi, 1e-12)) <= 2e-3
 
