@@ -406,7 +406,7 @@ def run_c3(torch, dev, pk, steps):
     from plda_b200.eer import eer_from_hist
     tgt_e, tgt_t = spk_t.to(torch.int32), torch.arange(nt, device=dev, dtype=torch.int32)
     tar = plda.score_trials(enrol_t, ENROL_UTTS, test_t, tgt_e, tgt_t, znorm=(zm, zs)).double().cpu().numpy()
-    theta = float(np.quantile(tar, 0.0005))
+    theta = float(tar.min()) - 1e-3                  # FRR(theta) = 0 <= EER: always a valid tail
     hi = float(max(tar.max(), float(out[:, :nt].max().item()))) + 1.0
     es, ts = torch.arange(ne, device=dev, dtype=torch.int32), spk_t.to(torch.int32)
     hfn = lambda: plda.score_hist(enrol_t, ENROL_UTTS, test_t, es, ts, theta, hi, 1 << 16, theta_lo=theta, znorm=(zm, zs))
@@ -432,7 +432,7 @@ def eer_exact_grid(torch, grid, enrol_spk, test_spk, tar_sorted):
     (FRR steps only there); FAR at each comes from one counting pass (row chunks)."""
     n_t = tar_sorted.numel()
     # thresholds: a quantile sub-grid of the target scores around the crossing is enough for +-0.01 %
-    cand = tar_sorted[:: max(1, n_t // 4096)]
+    cand = tar_sorted[:: max(1, n_t // 4096)].contiguous()
     ge = torch.zeros(cand.numel(), dtype=torch.float64, device=grid.device)
     n_non = 0
     for r0 in range(0, grid.shape[0], 2048):
@@ -512,7 +512,8 @@ def run_c4_slab(torch, dev, pk, steps, plda=None, rows_fit=5_000_000, materialis
     tgt_e, tgt_t = spk_t.to(torch.int32), torch.arange(nt, device=dev, dtype=torch.int32)
     tar = plda.score_trials(enrol_t, ENROL_UTTS, test_t, tgt_e, tgt_t).double().cpu().numpy()
     t_ms = event_time(torch, lambda: plda.score_trials(enrol_t, ENROL_UTTS, test_t, tgt_e, tgt_t), 3)
-    theta = float(np.quantile(tar, 0.0005))
+    # tail threshold: just below the lowest target score -> FRR(theta) = 0 <= EER, always a valid tail
+    theta = float(tar.min()) - 1e-3
     hi = float(tar.max()) + 50.0
     es = torch.arange(ne, device=dev, dtype=torch.int32)
     hfn = lambda: plda.score_hist(enrol_t, ENROL_UTTS, test_t, es, tgt_e, theta, hi, 1 << 16, theta_lo=theta)

@@ -291,7 +291,8 @@ int plda_test_scatter(plda_handle_t h, const void* x, int64_t n, int64_t d, int 
                       int scale_by_count, double* scatter_out, double* means_out, int64_t means_capacity,
                       int64_t* k_out);
 /* fp64 d x d helpers exposed for tests: op 0 = cholesky (lower), 1 = lower-triangular inverse,
- * 2 = symmetric eig (out = eigenvectors as columns, out2 = eigenvalues descending) */
+ * 2 = symmetric eig (out = eigenvectors as columns, out2 = eigenvalues descending),
+ * 3 / 4 = the fused single-launch Cholesky + inverse (out = L / out = L^-1; d <= 512) */
 int plda_test_linalg(plda_handle_t h, int op, const double* a, int64_t d, double* out, double* out2);
 
 #ifdef __cplusplus

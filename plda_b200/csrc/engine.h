@@ -75,6 +75,8 @@ class PldaEngine {
   void fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels, int iters,
            int labels_loc = 0);
   DevBuf<uint64_t> ws_labels;
+  DevBuf<double> fit_means, fit_scatter, fit_scalars, fit_mc;
+  DevBuf<int32_t> fit_counts;
   void transform_grouped(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,
                          int64_t targetdim, uint64_t* out_labels, int64_t* out_counts, double* out_vecs,
                          int64_t* n_out);

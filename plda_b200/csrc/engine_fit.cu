@@ -65,8 +65,10 @@ void PldaEngine::joint_diagonalise(int64_t d, bool warm, bool final_pass) {
   em_c.reserve(dd); em_t1.reserve(dd); em_bp.reserve(dd); em_u.reserve(dd); em_a.reserve(dd); em_ainv.reserve(dd);
   em_psi.reserve(d); em_tmp.reserve(dd); em_info.reserve(1);
   PB_CUDA(cudaMemcpyAsync(em_c.get(), model.within.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
-  cholesky_lower(ctx, em_c.get(), d, em_info.get());
-  tri_inverse_lower(ctx, em_c.get(), em_t1.get(), d);
+  if (!cholesky_inverse_fused(ctx, em_c.get(), em_t1.get(), d, em_info.get())) {
+    cholesky_lower(ctx, em_c.get(), d, em_info.get());
+    tri_inverse_lower(ctx, em_c.get(), em_t1.get(), d);
+  }
   // B' = T1 B T1^T
   gemm_f64(ctx, false, false, d, d, d, 1.0, em_t1.get(), d, model.between.get(), d, 0.0, em_tmp.get(), d);
   gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp.get(), d, em_t1.get(), d, 0.0, em_bp.get(), d);
@@ -189,9 +191,16 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
     throw Error(kValueError,
                 "Number of speakers is 1. Aborting PLDA esimation, at least two speakers are required!");
   }
-  DevBuf<double> means(static_cast<size_t>(k) * d);
-  DevBuf<int32_t> counts(k);
-  DevBuf<double> scatter(dd);
+  // grow-only workspaces owned by the handle: a cudaMalloc / cudaFree pair per fit costs milliseconds at C4 sizes
+  // (200 MB of class means) and cudaFree synchronises the device in the middle of the pass
+  fit_means.reserve(static_cast<size_t>(k) * d);
+  fit_counts.reserve(k);
+  fit_scatter.reserve(dd);
+  fit_scalars.reserve(2);
+  fit_mc.reserve(static_cast<size_t>(k) * d);
+  DevBuf<double>& means = fit_means;
+  DevBuf<int32_t>& counts = fit_counts;
+  DevBuf<double>& scatter = fit_scatter;
   static const char* stats_mode = getenv("PLDA_B200_STATS");    // "legacy": round-1 materialised-operand path (A/B)
   const bool fused = precision != 1 && d <= scatter_fused_max_dim() &&
                      !(stats_mode != nullptr && strcmp(stats_mode, "legacy") == 0);
@@ -220,25 +229,25 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   }
   lap("scatter SYRK");
   // sum_ = sum_s w_s m_s, class_weight = sum_s w_s ; mu = sum_/class_weight
-  DevBuf<double> class_weight(1);
+  double* class_weight = fit_scalars.get();
   model.d = d;
   model.mean.reserve(d);
-  class_weighted_sum(ctx, means.get(), counts.get(), k, d, model.mean.get(), class_weight.get());
+  class_weighted_sum(ctx, means.get(), counts.get(), k, d, model.mean.get(), class_weight);
   // sharded fit (whole speakers per rank): S, sum_, class_weight and the class count are the only quantities
   // exchanged by the stats pass
-  DevBuf<double> k_dev(1);
+  double* k_dev = fit_scalars.get() + 1;
   const double k_local = static_cast<double>(k);
-  PB_CUDA(cudaMemcpyAsync(k_dev.get(), &k_local, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
-  allreduce_parts({{scatter.get(), static_cast<int64_t>(dd)}, {model.mean.get(), d}, {class_weight.get(), 1},
-                   {k_dev.get(), 1}});
+  PB_CUDA(cudaMemcpyAsync(k_dev, &k_local, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  allreduce_parts({{scatter.get(), static_cast<int64_t>(dd)}, {model.mean.get(), d}, {class_weight, 1},
+                   {k_dev, 1}});
   scale_vec_kernel<<<static_cast<unsigned>(ceil_div(d, 128)), 128, 0, ctx.stream>>>(model.mean.get(), static_cast<int>(d),
-                                                                                  class_weight.get());
+                                                                                  class_weight);
   ctx.count_launch();
   double h_cw = 0.0, h_k = 0.0;
-  PB_CUDA(cudaMemcpyAsync(&h_cw, class_weight.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(&h_k, k_dev.get(), sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(&h_cw, class_weight, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(&h_k, k_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   // centred class means (constant across iterations)
-  DevBuf<double> mc(static_cast<size_t>(k) * d);
+  DevBuf<double>& mc = fit_mc;
   convert_to_f64(ctx, means.get(), false, k, d, d, mc.get(), d, model.mean.get());
   if (precision != 1) split_rows(ctx, mc.get(), false, k, d, d, nullptr, nullptr, nullptr, ws_mc);
   PB_CUDA(cudaEventRecord(ev[1], ctx.stream));
@@ -328,6 +337,11 @@ void PldaEngine::test_linalg(int op, const double* a, int64_t d, double* out, do
     ctx.sync();
     for (int64_t p = 0; p < d; ++p)
       for (int64_t i = 0; i < d; ++i) out[i * d + p] = vt[p * d + i];
+  } else if (op == 3 || op == 4) {
+    // fused cluster Cholesky + inverse: op 3 returns L, op 4 returns L^-1
+    PB_CHECK(cholesky_inverse_fused(ctx, da.get(), db.get(), d, info.get()), kInvalidArg,
+             "test_linalg: the fused Cholesky / inverse kernel is not available for this size");
+    PB_CUDA(cudaMemcpyAsync(out, op == 3 ? da.get() : db.get(), dd * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   } else {
     throw Error(kInvalidArg, "test_linalg: unknown op");
   }

@@ -162,6 +162,9 @@ void set_identity(Context& ctx, double* a, int64_t d);
 // ---- d x d fp64 factorizations (K8) ------------------------------------------------- //
 // In-place lower Cholesky of a (row-major, ld = d); upper triangle zeroed.  *info (device int) = 0 or failing column+1.
 void cholesky_lower(Context& ctx, double* a, int64_t d, int* info_dev);
+// a <- chol(a) (lower, upper zeroed) and inv <- a^-1 in ONE cluster launch (d <= 512); false: not available on this
+// device / size (the caller uses cholesky_lower + tri_inverse_lower)
+bool cholesky_inverse_fused(Context& ctx, double* a, double* inv, int64_t d, int* info_dev);
 // inv = L^-1 (lower triangular), row-major
 void tri_inverse_lower(Context& ctx, const double* l, double* inv, int64_t d);
 // Symmetric eigendecomposition by one-sided (Hestenes) Jacobi, cooperative grid kernel.

@@ -76,6 +76,156 @@ __global__ void zero_upper_kernel(double* __restrict__ a, int d) {
 }
 
 // ------------------------------------------------------------------------- //
+// Cholesky + triangular inverse of a d x d SPD matrix (d <= 512) in ONE launch: a single thread-block cluster, CTA i
+// owns the 32-row block i.  Left-looking by block column k:
+//     every CTA i >= k :  S_i = A[i,k] - sum_{p<k} L[i,p] L[k,p]^T            (32 x 32 tile, kept in shared memory)
+//     CTA k            :  L[k,k] = chol(S_k)                                    -> cluster barrier
+//     every CTA i >  k :  L[i,k] = S_i L[k,k]^-T                                -> cluster barrier
+// then the inverse by block columns: X[j,j] = L[j,j]^-1 (barrier), X[i,j] = -X[i,i] sum_{j<=k<i} L[i,k] X[k,j].
+// Replaces ~3 launches per panel + a column-sequential inverse (22 + 1 launches at d = 200) on the EM critical path.
+// ------------------------------------------------------------------------- //
+constexpr int CB = 32;          // block size
+constexpr int CKC = 64;         // K chunk of the tile products
+constexpr int CP = CKC + 1;     // shared-memory row pitch (doubles): conflict-free strided reads
+
+__device__ __forceinline__ void cluster_barrier_all() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// acc(r, c) += sum_kk P[r][kk] * Q[c][kk] over K columns of two row-major 32-row panels in global memory (L2), staged
+// through shared memory in chunks of CKC columns.  Thread (r = threadIdx.x >> 5, c = lane).
+__device__ __forceinline__ double tile_dot(const double* __restrict__ p, const double* __restrict__ q, long long ld,
+                                           int rows_p, int rows_q, int k, double* sp, double* sq) {
+  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < k; k0 += CKC) {
+    const int kc = min(CKC, k - k0);
+    for (int idx = threadIdx.x; idx < CB * CKC; idx += blockDim.x) {
+      const int rr = idx / CKC, kk = idx - rr * CKC;
+      sp[rr * CP + kk] = (rr < rows_p && kk < kc) ? __ldcg(p + rr * ld + k0 + kk) : 0.0;
+      sq[rr * CP + kk] = (rr < rows_q && kk < kc) ? __ldcg(q + rr * ld + k0 + kk) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < CKC; ++kk) acc = fma(sp[r * CP + kk], sq[c * CP + kk], acc);
+    __syncthreads();
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, int d, int* __restrict__ info) {
+  extern __shared__ double csm[];
+  double* sp = csm;                  // [32][CP]
+  double* sq = sp + CB * CP;         // [32][CP]
+  double* st = sq + CB * CP;         // [32][33] the CTA's current tile
+  double* sl = st + CB * 33;         // [32][33] a diagonal block (L_kk or X_ii)
+  __shared__ int s_fail;
+  const int nb = gridDim.x;
+  const int bi = blockIdx.x;                                   // row block this CTA owns
+  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+  const int rows_i = min(CB, d - bi * CB);
+  const long long ld = d;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  // ---------------- Cholesky ----------------
+  for (int k = 0; k < nb; ++k) {
+    const int rows_k = min(CB, d - k * CB);
+    if (bi >= k) {
+      const double dot = tile_dot(a + static_cast<long long>(bi) * CB * ld, a + static_cast<long long>(k) * CB * ld, ld,
+                                  rows_i, rows_k, k * CB, sp, sq);
+      double v = 0.0;
+      if (r < rows_i && c < rows_k) v = __ldcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c) - dot;
+      st[r * 33 + c] = v;
+      __syncthreads();
+      if (bi == k) {
+        // factor the diagonal tile in place (thread (r, c) owns st[r][c]); rows / columns beyond rows_k are padding
+        for (int j = 0; j < rows_k; ++j) {
+          const double ajj = st[j * 33 + j];
+          if (!(ajj > 0.0)) {
+            if (threadIdx.x == 0) { *info = k * CB + j + 1; s_fail = 1; }
+            break;                                              // uniform: every thread read the same pivot
+          }
+          const double rs = rsqrt(ajj);
+          __syncthreads();
+          if (c == j && r >= j) st[r * 33 + j] = (r == j) ? sqrt(ajj) : st[r * 33 + j] * rs;
+          __syncthreads();
+          if (c > j && r >= c) st[r * 33 + c] -= st[r * 33 + j] * st[c * 33 + j];
+          __syncthreads();
+        }
+        if (r < rows_k && c < rows_k)
+          __stcg(a + (static_cast<long long>(k) * CB + r) * ld + k * CB + c, c <= r ? st[r * 33 + c] : 0.0);
+      }
+    }
+    cluster_barrier_all();
+    if (bi > k) {
+      // X L_kk^T = S: row r of the tile by forward substitution, one warp per row (lane = column)
+      sl[r * 33 + c] = (r < rows_k && c < rows_k) ? __ldcg(a + (static_cast<long long>(k) * CB + r) * ld + k * CB + c) : (r == c ? 1.0 : 0.0);
+      __syncthreads();
+      double x = 0.0;
+      for (int j = 0; j < rows_k; ++j) {
+        // x_j = (s_j - sum_{q<j} x_q L[j][q]) / L[j][j]; lane q holds x_q
+        double part = (c < j) ? x * sl[j * 33 + c] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const double xj = (st[r * 33 + j] - part) / sl[j * 33 + j];
+        if (c == j) x = xj;
+      }
+      if (r < rows_i && c < rows_k) __stcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c, x);
+    } else if (bi < k) {
+      // blocks above the diagonal of column k: zero (the caller gets a clean lower-triangular factor)
+      if (r < rows_i && c < rows_k) __stcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c, 0.0);
+    }
+    cluster_barrier_all();
+  }
+  // ---------------- inverse: CTA bi computes block column bi of X = L^-1 ----------------
+  {
+    // X[bi,bi] = L[bi,bi]^-1: warp r solves L x = e_r ... column r of the inverse; lane = row
+    sl[r * 33 + c] = (r < rows_i && c < rows_i) ? __ldcg(a + (static_cast<long long>(bi) * CB + r) * ld + bi * CB + c) : (r == c ? 1.0 : 0.0);
+    __syncthreads();
+    double x = 0.0;      // lane c holds x_c of column r
+    for (int j = 0; j < CB; ++j) {
+      double part = (c < j) ? sl[j * 33 + c] * x : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const double xj = ((j == r ? 1.0 : 0.0) - part) / sl[j * 33 + j];
+      if (c == j) x = xj;
+    }
+    // x is entry (row c, column r) of the block inverse
+    if (c < rows_i && r < rows_i) __stcg(inv + (static_cast<long long>(bi) * CB + c) * ld + bi * CB + r, x);
+    for (int i = 0; i < bi; ++i) {                              // blocks above the diagonal: zero
+      const int rows_u = min(CB, d - i * CB);
+      if (r < rows_u && c < rows_i) __stcg(inv + (static_cast<long long>(i) * CB + r) * ld + bi * CB + c, 0.0);
+    }
+  }
+  cluster_barrier_all();
+  for (int i = bi + 1; i < nb; ++i) {
+    const int rows_u = min(CB, d - i * CB);
+    // T = sum_{bi <= k < i} L[i,k] X[k,bi]  (K = 32 (i - bi) columns of L's row block i against X's column block bi)
+    double t = 0.0;
+    for (int k0 = bi; k0 < i; ++k0) {
+      const int rows_k = min(CB, d - k0 * CB);
+      sp[r * 33 + c] = (r < rows_u && c < rows_k) ? __ldcg(a + (static_cast<long long>(i) * CB + r) * ld + k0 * CB + c) : 0.0;
+      sq[r * 33 + c] = (r < rows_k && c < rows_i) ? __ldcg(inv + (static_cast<long long>(k0) * CB + r) * ld + bi * CB + c) : 0.0;
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < CB; ++kk) t = fma(sp[r * 33 + kk], sq[kk * 33 + c], t);
+      __syncthreads();
+    }
+    st[r * 33 + c] = t;
+    sl[r * 33 + c] = (r < rows_u && c < rows_u) ? __ldcg(inv + (static_cast<long long>(i) * CB + r) * ld + i * CB + c) : 0.0;   // X[i,i]
+    __syncthreads();
+    double x = 0.0;
+#pragma unroll 8
+    for (int kk = 0; kk < CB; ++kk) x = fma(sl[r * 33 + kk], st[kk * 33 + c], x);
+    if (r < rows_u && c < rows_i) __stcg(inv + (static_cast<long long>(i) * CB + r) * ld + bi * CB + c, -x);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------- //
 // inv = L^-1: warp j solves L x = e_j by forward substitution (x in smem), writes column j.
 // ------------------------------------------------------------------------- //
 __global__ void __launch_bounds__(256)
@@ -156,6 +306,12 @@ __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __
 // barrier (release / acquire at cluster scope orders the __stcg / __ldcg column exchange through L2) instead of an
 // atomic counter polled through L2.  big2: a sweep whose largest rotation satisfied gamma^2 <= big2 alpha beta is
 // the last one (quadratic convergence: the remaining couplings are ~big2 relative).
+//
+// One sweep = one INTRA round (CTA c orthogonalises the columns inside its blocks 2c and 2c+1: bw - 1 steps of bw
+// disjoint rotations) followed by nblk_pad - 1 CROSS rounds of the round-robin block tournament, in which only the
+// bw x bw pairs (x in block I, y in block J) are rotated (bw steps of bw disjoint rotations): every column pair is
+// visited exactly once per sweep -- a cyclic-by-blocks Jacobi sweep -- instead of re-rotating the intra-block pairs
+// in every round (2 bw - 1 steps per round).
 template <bool CLUSTER>
 __global__ void __launch_bounds__(1024, 1)
 block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, double big2, int max_sweeps,
@@ -169,23 +325,27 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
   double* gl = cols + m2 * dp;                // [m2][gp]
   double* qm = gl + m2 * gp;                  // [m2][gp]
   __shared__ int s_rot;
-  __shared__ int s_big;                       // a pair with |gamma|/sqrt(alpha beta) >= 1e-7 was seen
+  __shared__ int s_big;                       // a rotation above the stop threshold was seen
   __shared__ double s_abs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nthreads = blockDim.x;
-  const int half = m2 >> 1;
+  const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+  const int half = m2 >> 1;                   // == bw: rotations per tournament step
   unsigned int target = 0;
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
-    for (int r = 0; r < nblk_pad - 1; ++r) {
+    for (int r = -1; r < nblk_pad - 1; ++r) {
       int bi, bj;
       const int k = blockIdx.x;
-      if (k == 0) { bi = nblk_pad - 1; bj = r; }
+      if (r < 0) { bi = 2 * k; bj = 2 * k + 1; }                                  // intra round
+      else if (k == 0) { bi = nblk_pad - 1; bj = r; }
       else { bi = (r + k) % (nblk_pad - 1); bj = (r - k + (nblk_pad - 1)) % (nblk_pad - 1); }
-      for (int idx = threadIdx.x; idx < m2 * d; idx += nthreads) {
-        const int slot = idx / d, i = idx - slot * d;
+      // ---- 0. load the 2 bw columns (a warp per column, lanes along it)
+      for (int slot = warp; slot < m2; slot += nwarps) {
         const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
-        cols[slot * dp + i] = col < d ? __ldcg(gt + static_cast<long long>(col) * d + i) : 0.0;
+        const double* src = gt + static_cast<long long>(col) * d;
+        double* dst = cols + slot * dp;
+        if (col < d) { for (int i = lane; i < d; i += 32) dst[i] = __ldcg(src + i); }
+        else { for (int i = lane; i < d; i += 32) dst[i] = 0.0; }
       }
       for (int idx = threadIdx.x; idx < m2 * m2; idx += nthreads) {
         const int i = idx / m2, j = idx - i * m2;
@@ -224,14 +384,26 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       __syncthreads();
       const double abs_tol = s_abs;
-      // ---- 2. two-sided Jacobi tournament on the Gram matrix
-      for (int lr = 0; lr < m2 - 1; ++lr) {
+      // ---- 2. two-sided Jacobi on the Gram matrix: intra pairs (r < 0) or cross pairs
+      const int nsteps = r < 0 ? bw - 1 : bw;
+      for (int lr = 0; lr < nsteps; ++lr) {
         int x = 0, y = 0;
         double c = 1.0, sn = 0.0;
         bool rot = false;
         if (warp < half) {
-          if (warp == 0) { x = m2 - 1; y = lr; }
-          else { x = (lr + warp) % (m2 - 1); y = (lr - warp + (m2 - 1)) % (m2 - 1); }
+          if (r < 0) {
+            // round-robin over the bw columns of one block; warps [0, bw/2) take block I, the rest block J
+            const int hb = bw >> 1;
+            const int w = warp < hb ? warp : warp - hb;
+            const int off = warp < hb ? 0 : bw;
+            if (w == 0) { x = bw - 1; y = lr; }
+            else { x = (lr + w) % (bw - 1); y = (lr - w + (bw - 1)) % (bw - 1); }
+            x += off;
+            y += off;
+          } else {
+            x = warp;
+            y = bw + (warp + lr) % bw;
+          }
           const double alpha = gl[x * gp + x], beta = gl[y * gp + y], gamma = gl[x * gp + y];
           if (lane == 0 && gamma * gamma > big2 * alpha * beta) s_big = 1;
           if (gamma * gamma > tol * tol * alpha * beta && fabs(gamma) > abs_tol) {
@@ -273,29 +445,30 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       // ---- 3. C <- C Q, written back to global: new column x' = sum_x Q[x][x'] * old column x
       if (s_rot) {
         const int groups = m2 >> 2;
-        for (int idx = threadIdx.x; idx < groups * d; idx += nthreads) {
-          const int xg = idx / d, i = idx - xg * d;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int xg = warp; xg < groups; xg += nwarps) {
           const double* qrow = qm + xg * 4;
+          for (int i = lane; i < d; i += 32) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 4
-          for (int x = 0; x < m2; ++x) {
-            const double v = cols[x * dp + i];
-            a0 = fma(v, qrow[x * gp + 0], a0);
-            a1 = fma(v, qrow[x * gp + 1], a1);
-            a2 = fma(v, qrow[x * gp + 2], a2);
-            a3 = fma(v, qrow[x * gp + 3], a3);
-          }
-          const double out[4] = {a0, a1, a2, a3};
+            for (int x = 0; x < m2; ++x) {
+              const double v = cols[x * dp + i];
+              a0 = fma(v, qrow[x * gp + 0], a0);
+              a1 = fma(v, qrow[x * gp + 1], a1);
+              a2 = fma(v, qrow[x * gp + 2], a2);
+              a3 = fma(v, qrow[x * gp + 3], a3);
+            }
+            const double out[4] = {a0, a1, a2, a3};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int slot = xg * 4 + j;
-            const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
-            if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, out[j]);
+            for (int j = 0; j < 4; ++j) {
+              const int slot = xg * 4 + j;
+              const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+              if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, out[j]);
+            }
           }
         }
-        // bit 0: something rotated; bit 1: a rotation larger than 1e-7 (relative) happened.  Jacobi converges
-        // quadratically, so a sweep whose largest rotation was < 1e-7 leaves every pair below ~1e-14: converged
-        // without paying for a verification sweep.
+        // bit 0: something rotated; bit 1: a rotation above the stop threshold happened.  Jacobi converges
+        // quadratically, so a sweep whose largest rotation was below the threshold leaves every pair below its
+        // square: converged without paying for a verification sweep.
         if (threadIdx.x == 0) atomicOr(rotated + sweep, s_big ? 3 : 1);
       }
       if (CLUSTER) {
@@ -349,6 +522,40 @@ void cholesky_lower(Context& ctx, double* a, int64_t d, int* info_dev) {
   zero_upper_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(a, di);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
+}
+
+bool cholesky_inverse_fused(Context& ctx, double* a, double* inv, int64_t d, int* info_dev) {
+  static const char* mode = getenv("PLDA_B200_CHOL");
+  if (mode != nullptr && strcmp(mode, "legacy") == 0) return false;
+  const int nb = static_cast<int>(ceil_div(d, 32));
+  if (d < 1 || nb > 16) return false;
+  const size_t smem = (2 * 32 * 65 + 2 * 32 * 33) * sizeof(double);
+  static std::once_flag once;
+  std::call_once(once, [&] {
+    cudaFuncSetAttribute(chol_inverse_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(chol_inverse_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  });
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(nb);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx.stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nb;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, chol_inverse_cluster_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  PB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx.stream));
+  PB_CUDA(cudaLaunchKernelEx(&cfg, chol_inverse_cluster_kernel, a, inv, static_cast<int>(d), info_dev));
+  ctx.count_launch();
+  return true;
 }
 
 void tri_inverse_lower(Context& ctx, const double* l, double* inv, int64_t d) {

@@ -91,6 +91,21 @@ def test_cholesky_and_inverse(plda, d):
     assert np.allclose(np.triu(inv, 1), 0.0)
 
 
+@pytest.mark.parametrize("d", [1, 4, 31, 32, 33, 200, 256, 257, 480, 512])
+def test_fused_cholesky_inverse(plda, d):
+    """The single-launch cluster kernel (Cholesky + triangular inverse, one 32-row block per CTA) vs numpy."""
+    rng = np.random.RandomState(d + 7)
+    g = rng.randn(d, 2 * d + 3)
+    a = g @ g.T / (2 * d) + 0.1 * np.eye(d)
+    ref = np.linalg.cholesky(a)
+    l, _ = plda._test_linalg(3, a)
+    assert np.allclose(l, ref, rtol=1e-10, atol=1e-12)
+    assert np.allclose(np.triu(l, 1), 0.0)
+    inv, _ = plda._test_linalg(4, a)
+    assert np.allclose(inv @ ref, np.eye(d), atol=1e-9)
+    assert np.allclose(np.triu(inv, 1), 0.0)
+
+
 @pytest.mark.parametrize("d", [2, 7, 64, 200, 201, 512])
 def test_jacobi_eig(plda, d):
     rng = np.random.RandomState(d + 1)
