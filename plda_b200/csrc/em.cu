@@ -121,6 +121,44 @@ __global__ void add_diag_scale_kernel(double* __restrict__ x, const double* __re
   x[idx] = v;
 }
 
+// B_stats / W_stats in the diagonalising basis from the split-K partials of ONE stacked SYRK ([P ; Q] [P ; Q]^T,
+// 2d x 2d: the diagonal blocks are P^T P and Q^T Q), symmetrised, plus the diagonal terms -- one launch instead of
+// two reductions and two diagonal updates.
+__global__ void em_stats_reduce_kernel(const float* __restrict__ partial, int ksplit, int d, long long mpad,
+                                       long long npad, const double* __restrict__ db, const double* __restrict__ dw,
+                                       double* __restrict__ bs, double* __restrict__ ws) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(d) * d) return;
+  const int i = static_cast<int>(idx / d), j = static_cast<int>(idx % d);
+  double sb = 0.0, sw = 0.0;
+  for (int k = 0; k < ksplit; ++k) {
+    const float* pl = partial + k * mpad * npad;
+    sb += static_cast<double>(pl[i * npad + j]) + static_cast<double>(pl[j * npad + i]);
+    sw += static_cast<double>(pl[(d + i) * npad + d + j]) + static_cast<double>(pl[(d + j) * npad + d + i]);
+  }
+  sb *= 0.5;
+  sw *= 0.5;
+  if (i == j) { sb += db[i]; sw += dw[i]; }
+  bs[idx] = sb;
+  ws[idx] = sw;
+}
+
+// EstimateFromStats on the back-transformed statistics: B = sym(B) / B_count ; W = (sym(W) + S) / W_count
+__global__ void em_finalize_kernel(double* __restrict__ between, double* __restrict__ within,
+                                   const double* __restrict__ scatter, double inv_b, double inv_w, int d) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(d) * d) return;
+  const int i = static_cast<int>(idx / d), j = static_cast<int>(idx % d);
+  if (j > i) return;
+  const long long tr = static_cast<long long>(j) * d + i;
+  const double b = 0.5 * (between[idx] + between[tr]) * inv_b;
+  const double w = (0.5 * (within[idx] + within[tr]) + 0.5 * (scatter[idx] + scatter[tr])) * inv_w;
+  between[idx] = b;
+  between[tr] = b;
+  within[idx] = w;
+  within[tr] = w;
+}
+
 __global__ void set_identity_kernel(double* __restrict__ a, int d) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(d) * d) return;
@@ -144,6 +182,41 @@ void em_posterior_t(Context& ctx, const float* u, int64_t ldu, int64_t k, int64_
   dim3 grid(static_cast<unsigned>(kpad / 32), static_cast<unsigned>(ceil_div(d, 32)));
   em_posterior_t_kernel<<<grid, 256, 0, ctx.stream>>>(u, ldu, k, static_cast<int>(d), counts, psi, pt.hi.get(),
                                                       pt.lo.get(), qt.hi.get(), qt.lo.get(), kpad, db, dw);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void em_posterior_stacked(Context& ctx, const float* u, int64_t ldu, int64_t k, int64_t d, const int32_t* counts,
+                          const double* psi, SplitBuf& pq, double* db, double* dw) {
+  const int64_t kpad = round_up(k, 64);
+  pq.rows = 2 * d;
+  pq.k = k;
+  pq.ld = kpad;
+  pq.hi.reserve(static_cast<size_t>(2 * d) * kpad);
+  pq.lo.reserve(static_cast<size_t>(2 * d) * kpad);
+  PB_CUDA(cudaMemsetAsync(db, 0, d * sizeof(double), ctx.stream));
+  PB_CUDA(cudaMemsetAsync(dw, 0, d * sizeof(double), ctx.stream));
+  dim3 grid(static_cast<unsigned>(kpad / 32), static_cast<unsigned>(ceil_div(d, 32)));
+  em_posterior_t_kernel<<<grid, 256, 0, ctx.stream>>>(u, ldu, k, static_cast<int>(d), counts, psi, pq.hi.get(),
+                                                      pq.lo.get(), pq.hi.get() + d * kpad, pq.lo.get() + d * kpad, kpad,
+                                                      db, dw);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void em_stats_reduce(Context& ctx, const float* partial, int ksplit, int64_t d, const double* db, const double* dw,
+                     double* bs, double* ws) {
+  const long long mpad = round_up(2 * d, 128), npad = round_up(2 * d, 4);
+  em_stats_reduce_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(
+      partial, ksplit, static_cast<int>(d), mpad, npad, db, dw, bs, ws);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
+}
+
+void em_finalize(Context& ctx, double* between, double* within, const double* scatter, double inv_b, double inv_w,
+                 int64_t d) {
+  em_finalize_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(between, within, scatter, inv_b,
+                                                                                         inv_w, static_cast<int>(d));
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

@@ -80,9 +80,9 @@ void PldaEngine::joint_diagonalise(int64_t d, bool warm, bool final_pass) {
   // Inside the EM loop the basis only has to diagonalise (W, B) to ~1e-7 relative: the statistics of the iteration
   // inherit that error linearly (the E-step formulas are exact for an exactly diagonalising basis), far below the
   // 1e-3 parity tolerance, and it does not accumulate -- every iteration re-diagonalises the new (W, B).  GetOutput
-  // (the model the caller sees) is solved to full fp64 accuracy.
+  // (the model the caller sees) and the exact fp64 mode are solved to full fp64 accuracy.
   static const char* eig_exact = getenv("PLDA_B200_EIG_EXACT");
-  const double stop_rotation = (final_pass || eig_exact != nullptr) ? 1e-7 : 3e-4;
+  const double stop_rotation = (final_pass || precision == 1 || eig_exact != nullptr) ? 1e-7 : 3e-4;
   eig_sym_jacobi(ctx, em_bp.get(), d, (warm && em_have_basis) ? em_u.get() : nullptr, em_psi.get(), em_tmp.get(), eig,
                  dbg ? &sweeps : nullptr, stop_rotation);
   if (dbg) fprintf(stderr, "plda_b200: joint_diagonalise d=%lld warm=%d sweeps=%d\n", static_cast<long long>(d),
@@ -119,36 +119,32 @@ void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const
     epi.out = ws_u.get();
     epi.ldo = ldu;
     gemm_bf16x3(ctx, mc_split.view(), a_split.view(), k, d, d, epi);
-    em_posterior_t(ctx, ws_u.get(), ldu, k, d, counts_dev, em_psi.get(), ws_pt, ws_qt, em_db.get(), em_dw.get());
-    // two weighted SYRKs over the class axis (split-K), fp64 reduction of the partials
-    const int ks = choose_ksplit(ctx, d, d, k);
-    const int eff = effective_ksplit(ctx, d, d, k, ks);
-    const int64_t mpad = round_up(d, 128), npad = round_up(d, 4);
+    // P and Q stacked in one operand: ONE split-K SYRK ([P ; Q][P ; Q]^T, the diagonal blocks are the two statistics)
+    // and one fp64 reduction that also symmetrises and adds the diagonal terms
+    em_posterior_stacked(ctx, ws_u.get(), ldu, k, d, counts_dev, em_psi.get(), ws_pt, em_db.get(), em_dw.get());
+    const int ks = choose_ksplit(ctx, 2 * d, 2 * d, k);
+    const int eff = effective_ksplit(ctx, 2 * d, 2 * d, k, ks);
+    const int64_t mpad = round_up(2 * d, 128), npad = round_up(2 * d, 4);
     ws_partial.reserve(static_cast<size_t>(eff) * mpad * npad);
-    gemm_bf16x3_splitk(ctx, ws_pt.view(), ws_pt.view(), d, d, k, ks, ws_partial.get());
-    reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, em_bs.get(), d, 1.0, true);
-    gemm_bf16x3_splitk(ctx, ws_qt.view(), ws_qt.view(), d, d, k, ks, ws_partial.get());
-    reduce_partials_f64(ctx, ws_partial.get(), eff, d, d, em_ws.get(), d, 1.0, true);
+    gemm_bf16x3_splitk(ctx, ws_pt.view(), ws_pt.view(), 2 * d, 2 * d, k, ks, ws_partial.get());
+    em_stats_reduce(ctx, ws_partial.get(), eff, d, em_db.get(), em_dw.get(), em_bs.get(), em_ws.get());
   }
-  // add the diagonal terms (no scaling yet)
-  add_diag_scale(ctx, em_bs.get(), em_db.get(), d, 1.0, nullptr);
-  add_diag_scale(ctx, em_ws.get(), em_dw.get(), d, 1.0, nullptr);
+  if (precision == 1) {
+    // add the diagonal terms (no scaling yet)
+    add_diag_scale(ctx, em_bs.get(), em_db.get(), d, 1.0, nullptr);
+    add_diag_scale(ctx, em_ws.get(), em_dw.get(), d, 1.0, nullptr);
+  }
   // sharded fit: every rank holds a shard of the classes and the same (A, psi); the two d x d statistics are
   // the only per-iteration exchange
   allreduce_parts({{em_bs.get(), static_cast<int64_t>(dd)}, {em_ws.get(), static_cast<int64_t>(dd)}});
-  // back to the original basis:  X -> A^-1 X A^-T
-  gemm_f64(ctx, false, false, d, d, d, 1.0, em_ainv.get(), d, em_bs.get(), d, 0.0, em_tmp2.get(), d);
-  gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp2.get(), d, em_ainv.get(), d, 0.0, model.between.get(), d);
-  gemm_f64(ctx, false, false, d, d, d, 1.0, em_ainv.get(), d, em_ws.get(), d, 0.0, em_tmp2.get(), d);
-  gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp2.get(), d, em_ainv.get(), d, 0.0, model.within.get(), d);
-  // W = (S + .)/W_count ;  B = ./B_count      (EstimateFromStats)
-  add_diag_scale(ctx, model.between.get(), nullptr, d, 1.0 / b_count, nullptr);
-  add_diag_scale(ctx, model.within.get(), nullptr, d, 1.0, scatter);
-  add_diag_scale(ctx, model.within.get(), nullptr, d, 1.0 / w_count, nullptr);
-  const unsigned sb = static_cast<unsigned>(ceil_div(d * d, 256));
-  symmetrise_kernel<<<sb, 256, 0, ctx.stream>>>(model.between.get(), static_cast<int>(d));
-  symmetrise_kernel<<<sb, 256, 0, ctx.stream>>>(model.within.get(), static_cast<int>(d));
-  ctx.count_launch(2);
+  // back to the original basis:  X -> A^-1 X A^-T  (the two statistics side by side: two launches, not four)
+  em_tmp.reserve(dd);
+  gemm_f64_pair(ctx, false, false, d, d, d, 1.0, em_ainv.get(), em_bs.get(), em_tmp2.get(), em_ainv.get(), em_ws.get(),
+                em_tmp.get(), d, d, 0.0, d);
+  gemm_f64_pair(ctx, false, true, d, d, d, 1.0, em_tmp2.get(), em_ainv.get(), model.between.get(), em_tmp.get(),
+                em_ainv.get(), model.within.get(), d, d, 0.0, d);
+  // W = (S + .)/W_count ;  B = ./B_count      (EstimateFromStats), symmetrised
+  em_finalize(ctx, model.between.get(), model.within.get(), scatter, 1.0 / b_count, 1.0 / w_count, d);
 }
 
 void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,

@@ -153,6 +153,15 @@ void class_weighted_sum(Context& ctx, const double* means, const int32_t* counts
 //   r = psi/(1+n psi), g = n r;  P = sqrt(w) g u;  Q = sqrt(w n) (1-g) u;  db = sum_s w r;  dw = sum_s w n r
 void em_posterior_t(Context& ctx, const float* u, int64_t ldu, int64_t k, int64_t d, const int32_t* counts,
                     const double* psi, SplitBuf& pt, SplitBuf& qt, double* db, double* dw);
+// the same with P and Q stacked in ONE operand ([P ; Q], 2d rows): a single SYRK launch yields both statistics
+void em_posterior_stacked(Context& ctx, const float* u, int64_t ldu, int64_t k, int64_t d, const int32_t* counts,
+                          const double* psi, SplitBuf& pq, double* db, double* dw);
+// bs / ws [d x d] from the split-K partials of the stacked SYRK (+ symmetrise + diagonal terms), one launch
+void em_stats_reduce(Context& ctx, const float* partial, int ksplit, int64_t d, const double* db, const double* dw,
+                     double* bs, double* ws);
+// B = sym(B) / B_count ; W = (sym(W) + S) / W_count   (EstimateFromStats), one launch
+void em_finalize(Context& ctx, double* between, double* within, const double* scatter, double inv_b, double inv_w,
+                 int64_t d);
 void em_posterior_f64(Context& ctx, const double* u, int64_t k, int64_t d, const int32_t* counts, const double* psi,
                       double* p, double* q, double* db, double* dw);
 // out = (base? base:0) + scale * x ; adds diag (if diag) before scaling:  out = base + scale*(x + diag(dg))

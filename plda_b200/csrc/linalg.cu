@@ -94,20 +94,34 @@ __device__ __forceinline__ void cluster_barrier_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// acc(r, c) += sum_kk P[r][kk] * Q[c][kk] over K columns of two row-major 32-row panels in global memory (L2), staged
-// through shared memory in chunks of CKC columns.  Thread (r = threadIdx.x >> 5, c = lane).
+// acc(r, c) = sum_kk P[r][kk] * Q[c][kk] over K columns of two row-major 32-row panels in global memory (L2), staged
+// through shared memory in chunks of CKC columns; the next chunk travels global -> registers while the current one
+// is consumed.  Thread (r = threadIdx.x >> 5, c = lane); 1024 threads.
 __device__ __forceinline__ double tile_dot(const double* __restrict__ p, const double* __restrict__ q, long long ld,
                                            int rows_p, int rows_q, int k, double* sp, double* sq) {
   const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
   double acc = 0.0;
+  // element (rr, kk) of a chunk: thread t loads (t >> 6, t & 63) and (t >> 6) + 16
+  const int lr = threadIdx.x >> 6, lk = threadIdx.x & 63;
+  double pa[2], qa[2];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rr = lr + 16 * h;
+      const bool kin = k0 + lk < k;
+      pa[h] = (rr < rows_p && kin) ? __ldcg(p + rr * ld + k0 + lk) : 0.0;
+      qa[h] = (rr < rows_q && kin) ? __ldcg(q + rr * ld + k0 + lk) : 0.0;
+    }
+  };
+  if (k > 0) fetch(0);
   for (int k0 = 0; k0 < k; k0 += CKC) {
-    const int kc = min(CKC, k - k0);
-    for (int idx = threadIdx.x; idx < CB * CKC; idx += blockDim.x) {
-      const int rr = idx / CKC, kk = idx - rr * CKC;
-      sp[rr * CP + kk] = (rr < rows_p && kk < kc) ? __ldcg(p + rr * ld + k0 + kk) : 0.0;
-      sq[rr * CP + kk] = (rr < rows_q && kk < kc) ? __ldcg(q + rr * ld + k0 + kk) : 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      sp[(lr + 16 * h) * CP + lk] = pa[h];
+      sq[(lr + 16 * h) * CP + lk] = qa[h];
     }
     __syncthreads();
+    if (k0 + CKC < k) fetch(k0 + CKC);
 #pragma unroll 8
     for (int kk = 0; kk < CKC; ++kk) acc = fma(sp[r * CP + kk], sq[c * CP + kk], acc);
     __syncthreads();
@@ -121,89 +135,86 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
   double* sp = csm;                  // [32][CP]
   double* sq = sp + CB * CP;         // [32][CP]
   double* st = sq + CB * CP;         // [32][33] the CTA's current tile
-  double* sl = st + CB * 33;         // [32][33] a diagonal block (L_kk or X_ii)
-  __shared__ int s_fail;
+  double* sl = st + CB * 33;         // [32][33] a diagonal block's inverse
+  __shared__ double s_rd[CB];        // reciprocal diagonal of the factored block
   const int nb = gridDim.x;
   const int bi = blockIdx.x;                                   // row block this CTA owns
   const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
   const int rows_i = min(CB, d - bi * CB);
   const long long ld = d;
-  if (threadIdx.x == 0) s_fail = 0;
-  __syncthreads();
-  // ---------------- Cholesky ----------------
+  // ---------------- Cholesky (left-looking by block column k) ----------------
   for (int k = 0; k < nb; ++k) {
     const int rows_k = min(CB, d - k * CB);
     if (bi >= k) {
       const double dot = tile_dot(a + static_cast<long long>(bi) * CB * ld, a + static_cast<long long>(k) * CB * ld, ld,
                                   rows_i, rows_k, k * CB, sp, sq);
-      double v = 0.0;
+      double v = (r == c && r >= rows_k) ? 1.0 : 0.0;             // identity padding keeps the factor regular
       if (r < rows_i && c < rows_k) v = __ldcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c) - dot;
       st[r * 33 + c] = v;
       __syncthreads();
       if (bi == k) {
-        // factor the diagonal tile in place (thread (r, c) owns st[r][c]); rows / columns beyond rows_k are padding
-        for (int j = 0; j < rows_k; ++j) {
-          const double ajj = st[j * 33 + j];
-          if (!(ajj > 0.0)) {
-            if (threadIdx.x == 0) { *info = k * CB + j + 1; s_fail = 1; }
-            break;                                              // uniform: every thread read the same pivot
+        // (a) factor the diagonal tile: ONE warp, lane = row, no block barriers on the 32-step critical path
+        if (r == 0) {
+          const int row = c;
+          for (int j = 0; j < CB; ++j) {
+            const double ajj = st[j * 33 + j];
+            if (!(ajj > 0.0)) {                                    // uniform across the warp
+              if (row == 0) *info = k * CB + j + 1;
+              break;
+            }
+            const double piv = sqrt(ajj), rp = 1.0 / piv;
+            if (row == j) { st[j * 33 + j] = piv; s_rd[j] = rp; }
+            else if (row > j) st[row * 33 + j] *= rp;
+            __syncwarp();
+            const double lrj = st[row * 33 + j];
+            for (int cc = j + 1; cc <= row; ++cc) st[row * 33 + cc] = fma(-lrj, st[cc * 33 + j], st[row * 33 + cc]);
+            __syncwarp();
           }
-          const double rs = rsqrt(ajj);
-          __syncthreads();
-          if (c == j && r >= j) st[r * 33 + j] = (r == j) ? sqrt(ajj) : st[r * 33 + j] * rs;
-          __syncthreads();
-          if (c > j && r >= c) st[r * 33 + c] -= st[r * 33 + j] * st[c * 33 + j];
-          __syncthreads();
         }
-        if (r < rows_k && c < rows_k)
-          __stcg(a + (static_cast<long long>(k) * CB + r) * ld + k * CB + c, c <= r ? st[r * 33 + c] : 0.0);
+        __syncthreads();
+        // (b) its inverse: warp r solves L x = e_r (lane c holds x_c), reciprocal diagonal, no divisions
+        {
+          double x = 0.0;
+          for (int j = 0; j < CB; ++j) {
+            double part = (c < j) ? st[j * 33 + c] * x : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const double xj = ((j == r ? 1.0 : 0.0) - part) * s_rd[j];
+            if (c == j) x = xj;
+          }
+          sl[c * 33 + r] = x;                                      // entry (row c, column r) of L_kk^-1
+        }
+        __syncthreads();
+        if (r < rows_k && c < rows_k) {
+          const long long o = (static_cast<long long>(k) * CB + r) * ld + k * CB + c;
+          __stcg(a + o, c <= r ? st[r * 33 + c] : 0.0);
+          __stcg(inv + o, c <= r ? sl[r * 33 + c] : 0.0);
+        }
       }
     }
     cluster_barrier_all();
     if (bi > k) {
-      // X L_kk^T = S: row r of the tile by forward substitution, one warp per row (lane = column)
-      sl[r * 33 + c] = (r < rows_k && c < rows_k) ? __ldcg(a + (static_cast<long long>(k) * CB + r) * ld + k * CB + c) : (r == c ? 1.0 : 0.0);
+      // L[i,k] = S_i L_kk^-T : a 32 x 32 x 32 product against the inverse CTA k just published
+      sl[r * 33 + c] = (r < rows_k && c < rows_k) ? __ldcg(inv + (static_cast<long long>(k) * CB + r) * ld + k * CB + c) : 0.0;
       __syncthreads();
       double x = 0.0;
-      for (int j = 0; j < rows_k; ++j) {
-        // x_j = (s_j - sum_{q<j} x_q L[j][q]) / L[j][j]; lane q holds x_q
-        double part = (c < j) ? x * sl[j * 33 + c] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        const double xj = (st[r * 33 + j] - part) / sl[j * 33 + j];
-        if (c == j) x = xj;
-      }
+#pragma unroll 8
+      for (int q = 0; q < CB; ++q) x = fma(st[r * 33 + q], sl[c * 33 + q], x);
       if (r < rows_i && c < rows_k) __stcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c, x);
     } else if (bi < k) {
-      // blocks above the diagonal of column k: zero (the caller gets a clean lower-triangular factor)
-      if (r < rows_i && c < rows_k) __stcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c, 0.0);
+      // blocks above the diagonal of column k: zero (clean triangular factor and inverse for the caller)
+      if (r < rows_i && c < rows_k) {
+        const long long o = (static_cast<long long>(bi) * CB + r) * ld + k * CB + c;
+        __stcg(a + o, 0.0);
+        __stcg(inv + o, 0.0);
+      }
     }
     cluster_barrier_all();
   }
-  // ---------------- inverse: CTA bi computes block column bi of X = L^-1 ----------------
-  {
-    // X[bi,bi] = L[bi,bi]^-1: warp r solves L x = e_r ... column r of the inverse; lane = row
-    sl[r * 33 + c] = (r < rows_i && c < rows_i) ? __ldcg(a + (static_cast<long long>(bi) * CB + r) * ld + bi * CB + c) : (r == c ? 1.0 : 0.0);
-    __syncthreads();
-    double x = 0.0;      // lane c holds x_c of column r
-    for (int j = 0; j < CB; ++j) {
-      double part = (c < j) ? sl[j * 33 + c] * x : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      const double xj = ((j == r ? 1.0 : 0.0) - part) / sl[j * 33 + j];
-      if (c == j) x = xj;
-    }
-    // x is entry (row c, column r) of the block inverse
-    if (c < rows_i && r < rows_i) __stcg(inv + (static_cast<long long>(bi) * CB + c) * ld + bi * CB + r, x);
-    for (int i = 0; i < bi; ++i) {                              // blocks above the diagonal: zero
-      const int rows_u = min(CB, d - i * CB);
-      if (r < rows_u && c < rows_i) __stcg(inv + (static_cast<long long>(i) * CB + r) * ld + bi * CB + c, 0.0);
-    }
-  }
-  cluster_barrier_all();
+  // ---------------- inverse: CTA bi computes block column bi of X = L^-1 (X[bi,bi] is already there) ----------------
   for (int i = bi + 1; i < nb; ++i) {
     const int rows_u = min(CB, d - i * CB);
-    // T = sum_{bi <= k < i} L[i,k] X[k,bi]  (K = 32 (i - bi) columns of L's row block i against X's column block bi)
+    // T = sum_{bi <= k < i} L[i,k] X[k,bi]
     double t = 0.0;
     for (int k0 = bi; k0 < i; ++k0) {
       const int rows_k = min(CB, d - k0 * CB);

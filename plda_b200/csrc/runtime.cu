@@ -72,47 +72,71 @@ void Context::profile_collect(double* total_ms, int64_t* count) {
 // ------------------------------------------------------------------------- //
 namespace {
 
+// One problem of a (possibly batched) launch: blockIdx.z selects it.
+struct GemmF64Problem {
+  const double* a;
+  const double* b;
+  double* c;
+};
+struct GemmF64Batch {
+  GemmF64Problem p[2];
+};
+
 template <bool TA, bool TB, int TILE>   // TILE = 64 (4x4 per thread) or 32 (2x2 per thread: more CTAs for d x d work)
 __global__ void __launch_bounds__(256)
-gemm_f64_kernel(int m, int n, int k, double alpha, const double* __restrict__ a, long long lda,
-                const double* __restrict__ b, long long ldb, double beta, double* __restrict__ c, long long ldc) {
+gemm_f64_kernel(int m, int n, int k, double alpha, const GemmF64Batch batch, long long lda, long long ldb, double beta,
+                long long ldc) {
   constexpr int MT = TILE / 16;
+  constexpr int NL = TILE * 16 / 256;        // elements per thread per operand and k-chunk
   __shared__ double sa[16][TILE + 1];
   __shared__ double sb[16][TILE + 1];
+  const double* __restrict__ a = batch.p[blockIdx.z].a;
+  const double* __restrict__ b = batch.p[blockIdx.z].b;
+  double* __restrict__ c = batch.p[blockIdx.z].c;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
   double acc[MT][MT] = {};
-  for (int k0 = 0; k0 < k; k0 += 16) {
-    // A tile: element (mm, kk) = TA ? a[kk*lda + mm] : a[mm*lda + kk]
-    for (int i = threadIdx.x; i < TILE * 16; i += 256) {
+  // the next k-chunk travels global -> registers while the current one is consumed from shared memory
+  double ra[NL], rb[NL];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int i = threadIdx.x + l * 256;
       int mm, kk;
       if (TA) { mm = i % TILE; kk = i / TILE; } else { kk = i & 15; mm = i >> 4; }
       const int gm = m0 + mm, gk = k0 + kk;
-      double v = 0.0;
-      if (gm < m && gk < k) v = TA ? a[gk * lda + gm] : a[gm * lda + gk];
-      sa[kk][mm] = v;
+      ra[l] = (gm < m && gk < k) ? (TA ? a[gk * lda + gm] : a[gm * lda + gk]) : 0.0;
+      int nn, kb;
+      if (TB) { kb = i & 15; nn = i >> 4; } else { nn = i % TILE; kb = i / TILE; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      rb[l] = (gn < n && gkb < k) ? (TB ? b[gn * ldb + gkb] : b[gkb * ldb + gn]) : 0.0;
     }
-    // B tile: element (kk, nn) = TB ? b[nn*ldb + kk] : b[kk*ldb + nn]
-    for (int i = threadIdx.x; i < TILE * 16; i += 256) {
-      int nn, kk;
-      if (TB) { kk = i & 15; nn = i >> 4; } else { nn = i % TILE; kk = i / TILE; }
-      const int gn = n0 + nn, gk = k0 + kk;
-      double v = 0.0;
-      if (gn < n && gk < k) v = TB ? b[gn * ldb + gk] : b[gk * ldb + gn];
-      sb[kk][nn] = v;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < k; k0 += 16) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int i = threadIdx.x + l * 256;
+      int mm, kk;
+      if (TA) { mm = i % TILE; kk = i / TILE; } else { kk = i & 15; mm = i >> 4; }
+      sa[kk][mm] = ra[l];
+      int nn, kb;
+      if (TB) { kb = i & 15; nn = i >> 4; } else { nn = i % TILE; kb = i / TILE; }
+      sb[kb][nn] = rb[l];
     }
     __syncthreads();
+    if (k0 + 16 < k) fetch(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      double ra[MT], rb[MT];
+      double va[MT], vb[MT];
 #pragma unroll
-      for (int i = 0; i < MT; ++i) ra[i] = sa[kk][ty + 16 * i];
+      for (int i = 0; i < MT; ++i) va[i] = sa[kk][ty + 16 * i];
 #pragma unroll
-      for (int j = 0; j < MT; ++j) rb[j] = sb[kk][tx + 16 * j];
+      for (int j = 0; j < MT; ++j) vb[j] = sb[kk][tx + 16 * j];
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < MT; ++j) acc[i][j] = fma(ra[i], rb[j], acc[i][j]);
+        for (int j = 0; j < MT; ++j) acc[i][j] = fma(va[i], vb[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -131,28 +155,45 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double* __restrict__ a,
 }
 
 template <int TILE>
-void launch_gemm_f64(Context& ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* a, int64_t lda,
-                     const double* b, int64_t ldb, double beta, double* c, int64_t ldc) {
-  dim3 grid(static_cast<unsigned>(ceil_div(n, TILE)), static_cast<unsigned>(ceil_div(m, TILE)));
-  if (ta && tb) gemm_f64_kernel<true, true, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
-  else if (ta) gemm_f64_kernel<true, false, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
-  else if (tb) gemm_f64_kernel<false, true, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
-  else gemm_f64_kernel<false, false, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+void launch_gemm_f64(Context& ctx, bool ta, bool tb, int m, int n, int k, double alpha, const GemmF64Batch& batch,
+                     int count, int64_t lda, int64_t ldb, double beta, int64_t ldc) {
+  dim3 grid(static_cast<unsigned>(ceil_div(n, TILE)), static_cast<unsigned>(ceil_div(m, TILE)), static_cast<unsigned>(count));
+  if (ta && tb) gemm_f64_kernel<true, true, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, batch, lda, ldb, beta, ldc);
+  else if (ta) gemm_f64_kernel<true, false, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, batch, lda, ldb, beta, ldc);
+  else if (tb) gemm_f64_kernel<false, true, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, batch, lda, ldb, beta, ldc);
+  else gemm_f64_kernel<false, false, TILE><<<grid, 256, 0, ctx.stream>>>(m, n, k, alpha, batch, lda, ldb, beta, ldc);
+}
+
+void gemm_f64_any(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const GemmF64Batch& batch,
+                  int count, int64_t lda, int64_t ldb, double beta, int64_t ldc) {
+  PB_CHECK(m > 0 && n > 0 && k > 0, kInvalidArg, "gemm_f64: empty problem");
+  const int mi = static_cast<int>(m), ni = static_cast<int>(n), ki = static_cast<int>(k);
+  // d x d algebra (a handful of 64x64 tiles) is latency bound: use 32x32 tiles to spread over more SMs
+  if (ceil_div(m, 64) * ceil_div(n, 64) * count < 2 * ctx.num_sms)
+    launch_gemm_f64<32>(ctx, ta, tb, mi, ni, ki, alpha, batch, count, lda, ldb, beta, ldc);
+  else
+    launch_gemm_f64<64>(ctx, ta, tb, mi, ni, ki, alpha, batch, count, lda, ldb, beta, ldc);
+  PB_CUDA(cudaGetLastError());
+  ctx.count_launch();
 }
 
 }  // namespace
 
 void gemm_f64(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a,
               int64_t lda, const double* b, int64_t ldb, double beta, double* c, int64_t ldc) {
-  PB_CHECK(m > 0 && n > 0 && k > 0, kInvalidArg, "gemm_f64: empty problem");
-  const int mi = static_cast<int>(m), ni = static_cast<int>(n), ki = static_cast<int>(k);
-  // d x d algebra (a handful of 64x64 tiles) is latency bound: use 32x32 tiles to spread over more SMs
-  if (ceil_div(m, 64) * ceil_div(n, 64) < 2 * ctx.num_sms)
-    launch_gemm_f64<32>(ctx, ta, tb, mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
-  else
-    launch_gemm_f64<64>(ctx, ta, tb, mi, ni, ki, alpha, a, lda, b, ldb, beta, c, ldc);
-  PB_CUDA(cudaGetLastError());
-  ctx.count_launch();
+  GemmF64Batch batch;
+  batch.p[0] = GemmF64Problem{a, b, c};
+  batch.p[1] = batch.p[0];
+  gemm_f64_any(ctx, ta, tb, m, n, k, alpha, batch, 1, lda, ldb, beta, ldc);
+}
+
+void gemm_f64_pair(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a0,
+                   const double* b0, double* c0, const double* a1, const double* b1, double* c1, int64_t lda,
+                   int64_t ldb, double beta, int64_t ldc) {
+  GemmF64Batch batch;
+  batch.p[0] = GemmF64Problem{a0, b0, c0};
+  batch.p[1] = GemmF64Problem{a1, b1, c1};
+  gemm_f64_any(ctx, ta, tb, m, n, k, alpha, batch, 2, lda, ldb, beta, ldc);
 }
 
 }  // namespace pb

@@ -187,4 +187,10 @@ void reduce_partials_f64(Context& ctx, const float* partial, int ksplit, int64_t
 void gemm_f64(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a,
               int64_t lda, const double* b, int64_t ldb, double beta, double* c, int64_t ldc);
 
+// two independent products of the same shape / transposition / pitches in ONE launch (d x d algebra of the EM
+// iteration: halves the launch count on a latency-bound chain)
+void gemm_f64_pair(Context& ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* a0,
+                   const double* b0, double* c0, const double* a1, const double* b1, double* c1, int64_t lda,
+                   int64_t ldb, double beta, int64_t ldc);
+
 }  // namespace pb
