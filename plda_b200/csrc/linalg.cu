@@ -162,7 +162,7 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
               if (row == 0) *info = k * CB + j + 1;
               break;
             }
-            const double piv = sqrt(ajj), rp = 1.0 / piv;
+            const double rp = rsqrt(ajj), piv = ajj * rp;          // no fp64 sqrt / divide on the 32-step critical path
             if (row == j) { st[j * 33 + j] = piv; s_rd[j] = rp; }
             else if (row > j) st[row * 33 + j] *= rp;
             __syncwarp();

@@ -123,9 +123,15 @@ class PLDA(object):
         stream = torch.cuda.Stream(device=dev)
         failure = []
 
+        events = []
+
         def _cb(_user, count):
             try:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
                 dist.all_reduce(scratch[:count], group=group)
+                e1.record(stream)
+                events.append((e0, e1))
                 return 0
             except Exception as e:  # surfaced as PLDA_E_INTERNAL by the library
                 failure.append(e)
@@ -145,6 +151,9 @@ class PLDA(object):
         stream.synchronize()
         if failure:
             raise failure[0]
+        # device time spent in the exchanges of this fit: one after the stats pass, one per EM iteration
+        self.last_allreduce_ms = float(sum(a.elapsed_time(b) for a, b in events))
+        self.last_allreduce_count = len(events)
         return None
 
     def fit_timings(self):
