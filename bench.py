@@ -684,6 +684,13 @@ def run_sharded_extras(torch, dist, dev, pk, rank, world, steps):
         del xt
         torch.cuda.empty_cache()
         out = torch.empty((ne4, nt4), dtype=torch.float32, device=dev)
+        # library kernels, timing events and the cross-check on ONE stream (plda_set_stream), like the headline
+        from plda_b200 import _ffi
+        lib = _ffi.lib()
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        _ffi.check(lib.plda_set_stream(p4._h, C.c_void_p(stream.cuda_stream)))
         peer = pdist.PeerShardedScorer(p4, nt4, d4)
         reps = max(2, min(steps, 5))
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -691,9 +698,9 @@ def run_sharded_extras(torch, dist, dev, pk, rank, world, steps):
         dist.barrier()
         torch.cuda.synchronize()
         for a, b in evs:
-            a.record()
+            a.record(stream)
             peer.score(enrol_t, ENROL_UTTS, test_shard, out=out, sync=False)
-            b.record()
+            b.record(stream)
         peer.check()
         dist.barrier()
         torch.cuda.synchronize()
@@ -704,9 +711,12 @@ def run_sharded_extras(torch, dist, dev, pk, rank, world, steps):
         # cross-check a corner of the slab against the all-gather path
         full = pdist.all_gather_rows(test_shard, nt4)
         chk = p4.score_grid(enrol_t[:512], ENROL_UTTS, full)
+        torch.cuda.synchronize()
         ok = torch.tensor([1 if torch.equal(chk, out[:512]) else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         peer.close()
+        _ffi.check(lib.plda_set_stream(p4._h, C.c_void_p(None)))
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
         flops = 2.0 * d4 * ne4 * nt4
         rec["c4_slab"] = {"enrol_per_gpu": ne4, "test_total": nt4, "d": d4, "ms_per_step": ms,
                           "trials_per_sec_all_gpus": ne4 * nt4 * world / (ms * 1e-3),

@@ -251,6 +251,7 @@ class LdaEngine {
   void refresh_transform_operands();
   SplitBuf ws_x;
   DevBuf<float> ws_out[2], ws_lmax, ws_lsum, ws_neglse;
+  ScatterWork scat;
   DevBuf<double> ws_gram;
   DevBuf<uint8_t> ws_in;
 };

@@ -6,6 +6,9 @@
 #include <algorithm>
 #include <cmath>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "engine.h"
 
 namespace pb {
@@ -144,23 +147,31 @@ void LdaEngine::class_stats(const void* x, int64_t n, int64_t d_, int64_t ldx, i
   }
   DevBuf<double> means(static_cast<size_t>(kk) * d_);
   DevBuf<int32_t> counts(kk);
-  segment_sums(ctx, xd, is_f32, d_, ld, segs, means.get());
-  segment_finalize_means(ctx, means.get(), d_, segs, counts.get());
   // within scatter  Sw = xc^T xc  (unscaled)
   const size_t dd = static_cast<size_t>(d_) * d_;
   DevBuf<double> sw(dd);
-  if (precision == 1) {
-    ws_gram.reserve(static_cast<size_t>(n) * d_);
-    center_scale_f64(ctx, xd, is_f32, d_, ld, segs, means.get(), false, ws_gram.get());
-    gemm_f64(ctx, true, false, d_, d_, n, 1.0, ws_gram.get(), d_, ws_gram.get(), d_, 0.0, sw.get(), d_);
+  static const char* stats_mode = getenv("PLDA_B200_STATS");    // "legacy": round-1 materialised-operand path (A/B)
+  const bool fused = precision != 1 && d_ <= scatter_fused_max_dim() &&
+                     !(stats_mode != nullptr && strcmp(stats_mode, "legacy") == 0);
+  if (fused) {
+    // class means and the class-centred Gram (lda.py:183-191) in ONE read of the rows (csrc/scatter_tc.cu)
+    scatter_fused(ctx, xd, is_f32, d_, ld, segs, /*scale_by_count=*/false, sw.get(), means.get(), counts.get(), scat);
   } else {
-    SplitBuf xt;
-    center_scale_split_t(ctx, xd, is_f32, d_, ld, segs, means.get(), false, xt);
-    const int ks = choose_ksplit(ctx, d_, d_, n);
-    const int eff = effective_ksplit(ctx, d_, d_, n, ks);
-    DevBuf<float> partial(static_cast<size_t>(eff) * round_up(d_, 128) * round_up(d_, 4));
-    gemm_bf16x3_splitk(ctx, xt.view(), xt.view(), d_, d_, n, ks, partial.get());
-    reduce_partials_f64(ctx, partial.get(), eff, d_, d_, sw.get(), d_, 1.0, true);
+    segment_sums(ctx, xd, is_f32, d_, ld, segs, means.get());
+    segment_finalize_means(ctx, means.get(), d_, segs, counts.get());
+    if (precision == 1) {
+      ws_gram.reserve(static_cast<size_t>(n) * d_);
+      center_scale_f64(ctx, xd, is_f32, d_, ld, segs, means.get(), false, ws_gram.get());
+      gemm_f64(ctx, true, false, d_, d_, n, 1.0, ws_gram.get(), d_, ws_gram.get(), d_, 0.0, sw.get(), d_);
+    } else {
+      SplitBuf xt;
+      center_scale_split_t(ctx, xd, is_f32, d_, ld, segs, means.get(), false, xt);
+      const int ks = choose_ksplit(ctx, d_, d_, n);
+      const int eff = effective_ksplit(ctx, d_, d_, n, ks);
+      DevBuf<float> partial(static_cast<size_t>(eff) * round_up(d_, 128) * round_up(d_, 4));
+      gemm_bf16x3_splitk(ctx, xt.view(), xt.view(), d_, d_, n, ks, partial.get());
+      reduce_partials_f64(ctx, partial.get(), eff, d_, d_, sw.get(), d_, 1.0, true);
+    }
   }
   out.k = kk;
   out.sw.resize(dd);
