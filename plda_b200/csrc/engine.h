@@ -149,6 +149,8 @@ class PldaEngine {
   void produce_score_operands(const Staged& se, int64_t ne, const Staged& st, int64_t nt, int64_t dim,
                               const ScoreGroups& g, int64_t col_ld);
   std::vector<int32_t> ragged_key;   // distinct counts ws_tables was built for
+  DevBuf<int32_t> rg_counts, rg_grp, rg_gcounts;   // device copies owned by the ragged-count cache
+  std::vector<int32_t> last_counts;  // the ragged counts whose device copies (ws_counts / ws_grp) are current
   int64_t ragged_dim = 0;
   DevBuf<float4> ws_mom;
   DevBuf<unsigned long long> ws_hist;

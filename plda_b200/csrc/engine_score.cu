@@ -141,6 +141,7 @@ const double* PldaEngine::score_consts_for(int count, int64_t dim) {
 void PldaEngine::refresh_model_operands() {
   score_consts.clear();
   ragged_key.clear();
+  last_counts.clear();
   const int64_t d = model.d;
   split_rows(ctx, model.transform.get(), false, d, d, d, nullptr, nullptr, nullptr, model.a_split);
   model.h_psi.resize(d);
@@ -333,22 +334,45 @@ PldaEngine::ScoreGroups PldaEngine::prepare_groups(const int32_t* counts, int64_
     g.tables = score_consts_for(g.uniform_count, dim);
     return g;
   }
-  std::vector<int32_t> gcounts(counts, counts + ne);
-  std::sort(gcounts.begin(), gcounts.end());
-  gcounts.erase(std::unique(gcounts.begin(), gcounts.end()), gcounts.end());
+  // the device copies (counts, group index per row) are reused while the caller keeps passing the same counts
+  const bool same_counts = static_cast<int64_t>(last_counts.size()) == ne &&
+                           memcmp(last_counts.data(), counts, ne * sizeof(int32_t)) == 0 && !ragged_key.empty();
+  std::vector<int32_t> gcounts;
+  if (same_counts) {
+    gcounts = ragged_key;
+  } else {
+    // distinct counts in ascending order + group index per row: a direct table when the counts are small (they
+    // are utterance counts), a sort otherwise
+    int32_t mx = 0;
+    for (int64_t i = 0; i < ne; ++i) mx = std::max(mx, counts[i]);
+    std::vector<int32_t> grp(ne);
+    if (mx <= (1 << 20)) {
+      std::vector<int32_t> tab(static_cast<size_t>(mx) + 1, -1);
+      for (int64_t i = 0; i < ne; ++i) tab[counts[i]] = 0;
+      for (int32_t c = 1; c <= mx; ++c)
+        if (tab[c] == 0) { tab[c] = static_cast<int32_t>(gcounts.size()); gcounts.push_back(c); }
+      for (int64_t i = 0; i < ne; ++i) grp[i] = tab[counts[i]];
+    } else {
+      gcounts.assign(counts, counts + ne);
+      std::sort(gcounts.begin(), gcounts.end());
+      gcounts.erase(std::unique(gcounts.begin(), gcounts.end()), gcounts.end());
+      for (int64_t i = 0; i < ne; ++i)
+        grp[i] = static_cast<int32_t>(std::lower_bound(gcounts.begin(), gcounts.end(), counts[i]) - gcounts.begin());
+    }
+    rg_counts.reserve(ne);
+    rg_grp.reserve(ne);
+    rg_gcounts.reserve(gcounts.size());
+    PB_CUDA(cudaMemcpyAsync(rg_counts.get(), counts, ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(rg_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+    PB_CUDA(cudaMemcpyAsync(rg_gcounts.get(), gcounts.data(), gcounts.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            ctx.stream));
+    last_counts.assign(counts, counts + ne);
+    if (ragged_key != gcounts) ragged_key.clear();       // forces the tables to be rebuilt below
+  }
   g.ng = static_cast<int>(gcounts.size());
-  std::vector<int32_t> grp(ne);
-  for (int64_t i = 0; i < ne; ++i)
-    grp[i] = static_cast<int32_t>(std::lower_bound(gcounts.begin(), gcounts.end(), counts[i]) - gcounts.begin());
-  ws_counts.reserve(ne);
-  ws_grp.reserve(ne);
-  ws_gcounts.reserve(g.ng);
-  PB_CUDA(cudaMemcpyAsync(ws_counts.get(), counts, ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(ws_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-  PB_CUDA(cudaMemcpyAsync(ws_gcounts.get(), gcounts.data(), g.ng * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
-  g.counts_dev = ws_counts.get();
-  g.grp_dev = ws_grp.get();
-  g.gcounts_dev = ws_gcounts.get();
+  g.counts_dev = rg_counts.get();
+  g.grp_dev = rg_grp.get();
+  g.gcounts_dev = rg_gcounts.get();
   if (ragged_key != gcounts || ragged_dim != dim) {
     std::vector<double> tabs(static_cast<size_t>(g.ng) * kScoreConstsSize, 0.0);
     for (int i = 0; i < g.ng; ++i)

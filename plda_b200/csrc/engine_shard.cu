@@ -6,6 +6,7 @@
 // bf16 planes + column terms) into the operand buffer of EVERY rank through peer mappings and raises a ready flag;
 // the tcgen05 GEMM consumes the local buffer and waits per column tile for the flag of the rank that owns the
 // rows (gemm_tc.cu, GemmShard), starting with its own rows.  No NCCL, no host synchronisation per step.
+#include <stdlib.h>
 #include <string.h>
 
 #include "engine.h"
@@ -131,6 +132,8 @@ void PldaEngine::shard_produce(const void* test_shard, int64_t nt_local, int64_t
   }
   sig.counter = reinterpret_cast<unsigned*>(shard.region + kCounterOff);
   sig.epoch = shard.epoch;
+  static const char* fence_mode = getenv("PLDA_B200_FENCE");
+  sig.fence_per_thread = (fence_mode != nullptr && strcmp(fence_mode, "thread") == 0) ? 1 : 0;
   if (ne > 0) ws_row.reserve(ne);
   score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, ne > 0 ? &ws_l : nullptr, ne > 0 ? ws_row.get() : nullptr,
                            test_shard, nt_local, ld_test, row0, row0 + nt_local, dst, shard.ldk, dtype == 1, shard.dim,

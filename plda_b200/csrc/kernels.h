@@ -56,6 +56,7 @@ struct PrepSignal {
   unsigned* flag[kMaxPeers];        // ready flag of THIS source rank inside each destination region
   int n = 0;
   unsigned epoch = 0;
+  int fence_per_thread = 0;         // A/B switch (env PLDA_B200_FENCE=thread): system fence in every thread
 };
 void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, SplitBuf* l_out,
                               float* row_term, const void* test, int64_t nt, int64_t ld_t, int64_t test_row0,

@@ -333,9 +333,13 @@ score_prep_uniform_kernel(const T* __restrict__ enrol, long long ne, long long l
     // of this source rank in every destination region -- one thread per destination, so the NVLink round trips of
     // the flag stores overlap instead of adding up (block-uniform branch: the barriers are safe)
     __shared__ int s_last;
-    __threadfence_system();
+    // Release pattern of the block: the barrier orders every thread's peer stores before thread 0, whose ONE
+    // system-scope fence (cumulative) then publishes them ahead of the counter / flag -- the same shape NCCL's
+    // primitives use -- instead of a system fence in each of the 256 threads.  (sig.fence_per_thread: A/B switch.)
+    if (sig.fence_per_thread) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();
       const unsigned prev = atomicAdd(sig.counter, 1u);
       s_last = prev == test_blocks - 1 ? 1 : 0;
       if (s_last) atomicExch(sig.counter, 0u);
