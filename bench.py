@@ -893,6 +893,8 @@ def run_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_stats = {}
+
     def timed_region(profile):
         """Exactly K steps, device timed per step, L2 flushed between steps.  `profile`: CUDA events around every
         launch of the Gram kernel as well (roofline pass)."""
@@ -906,7 +908,10 @@ def run_main(args):
             step(i)
             ev[i][1].record(stream)
         barrier()
-        total = float(sum(a.elapsed_time(b) for a, b in ev))
+        per_step = [a.elapsed_time(b) for a, b in ev]
+        total = float(sum(per_step))
+        step_stats["median_ms"] = float(np.median(per_step))
+        step_stats["max_ms"] = float(np.max(per_step))
         g_ms, g_n = C.c_double(), C.c_int64()
         if profile:
             _ffi.check(lib.plda_profile_collect(plda._h, C.byref(g_ms), C.byref(g_n)))
@@ -929,12 +934,17 @@ def run_main(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return int(t.item()) == 1
 
+    # the NVML sampler thread initialises before the warm-up (its start-up must not steal the GIL from the enqueue
+    # loop of the timed region: at N > 1 a host hiccup on one rank shows up as flag-wait time on all the others)
+    sampler = ClockSampler(local).start()
+    import gc
+    gc.collect()
+    gc.disable()
     for i in range(args.warmup):
         step(i)
     barrier()
 
     # ---- timed region (value), then the same K steps again with events around the Gram kernel (roofline) ----
-    sampler = ClockSampler(local).start()
     total_ms, launches, _, _ = timed_region(profile=False)
     peer_used = peer is not None
     if peer is not None and not peer_ok():
@@ -949,7 +959,9 @@ def run_main(args):
             step(i)
         barrier()
         total_ms, launches, _, _ = timed_region(profile=False)
+    value_step_stats = dict(step_stats)
     _, _, gemm_ms_total, gemm_n = timed_region(profile=True)
+    gc.enable()
     if peer is not None:
         peer.close()
     trials_per_step = ne_local * nt_total * world
@@ -1043,7 +1055,8 @@ def run_main(args):
     cfg = bench_config(world)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "ms_per_step_median": value_step_stats.get("median_ms"),
+        "ms_per_step_max": value_step_stats.get("max_ms"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate, fp32 scores)", "data": "synthetic",
         "config": cfg,
         "parallelism": ("single GPU" if world == 1 else
