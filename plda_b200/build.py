@@ -20,7 +20,7 @@ OBJDIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(LIBDIR, "libplda_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["runtime.cu", "gemm_tc.cu", "prep.cu", "segments.cu", "scatter_tc.cu", "em.cu", "linalg.cu", "dvector.cu", "sinks.cu",
+SOURCES = ["runtime.cu", "gemm_tc.cu", "gemm_ts.cu", "prep.cu", "segments.cu", "scatter_tc.cu", "em.cu", "linalg.cu", "dvector.cu", "sinks.cu",
            "engine_score.cu", "engine_sinks.cu", "engine_shard.cu", "engine_fit.cu", "engine_lda.cu", "c_api.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -964,6 +964,18 @@ void encode_tmap_2d(CUtensorMap* out, TmaType type, const void* base, uint64_t i
 
 void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
                  const GemmEpilogue& epi, const GemmShard* shard) {
+  if (shard != nullptr && shard->flags != nullptr) {
+    PB_CHECK(shard->world >= 1 && shard->world <= 16 && shard->rank >= 0 && shard->rank < shard->world &&
+                 shard->err != nullptr && shard->bounds[0] == 0 && shard->bounds[shard->world] == n,
+             kInvalidArg, "gemm: bad shard description");
+  }
+  if (epi.col_add != nullptr) {
+    PB_CHECK(epi.col_ld % 4 == 0 && epi.col_ld >= round_up(n, 32) &&
+                 (reinterpret_cast<uintptr_t>(epi.col_add) & 15) == 0,
+             kInvalidArg, "gemm: col_add must be 16B aligned with pitch >= round_up(n,32)");
+  }
+  // small-K score grids: enrol operand in tensor memory (no A traffic through shared memory)
+  if (gemm_ts_score(ctx, a, b, m, n, k, epi, shard)) return;
   Plan pl = make_plan(ctx, m, n, k, 1);
   pl.p.epi = epi;
   if (shard != nullptr && shard->flags != nullptr) {

@@ -40,6 +40,8 @@ Context::Context(int dev) : device(dev) {
   if (pdl && pdl[0] == '0') pdl_enabled = false;
   const char* gm = getenv("PLDA_B200_GEMM");
   gemm_two_cta = !(gm != nullptr && strcmp(gm, "1cta") == 0);
+  const char* ts = getenv("PLDA_B200_TS");
+  if (ts != nullptr) gemm_ts = ts[0] == '1';
 }
 
 Context::~Context() {

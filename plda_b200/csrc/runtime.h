@@ -65,6 +65,7 @@ struct Context {
   bool k_tail_boxes = true;          // env PLDA_B200_KTAIL=0 disables the narrow K-tail boxes
   DevBuf<long long> gemm_dbg;        // env PLDA_B200_DBG=1: stall counters written by CTA 0/1 of the last GEMM launch
   bool gemm_two_cta = true;          // env PLDA_B200_GEMM=1cta forces the single-CTA (cta_group::1) kernel
+  bool gemm_ts = false;              // score grid with the enrol operand in TMEM (gemm_ts.cu); env PLDA_B200_TS=0/1
   // optional per-launch timing of the tensor-core GEMM (CUDA events on the launching stream); bench roofline
   // programmatic dependent launch: set by a producer kernel that executes griddepcontrol.launch_dependents; the
   // next tensor GEMM launch then carries the programmatic-serialization attribute, so its prologue (barrier init,
@@ -171,6 +172,10 @@ void shard_wait_all(Context& ctx, const GemmShard& shard);
 // the caller reduces them (reduce_partials_f64).
 void gemm_bf16x3(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
                  const GemmEpilogue& epi, const GemmShard* shard = nullptr);
+// Score-grid form with the A operand in tensor memory (gemm_ts.cu): k <= 256, plain store epilogue with row / uniform
+// column / z-norm terms.  Returns false when the problem does not qualify (nothing launched).
+bool gemm_ts_score(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
+                   const GemmEpilogue& epi, const GemmShard* shard);
 void gemm_bf16x3_splitk(Context& ctx, const SplitOperand& a, const SplitOperand& b, int64_t m, int64_t n, int64_t k,
                         int ksplit, float* partial);
 int choose_ksplit(const Context& ctx, int64_t m, int64_t n, int64_t k);
