@@ -57,6 +57,8 @@ struct TsParams {
   long long lda;
   GemmEpilogue epi;
   GemmShard shard;
+  long long* dbg;     // optional stall counters (env PLDA_B200_DBG=1)
+  int skip_store;     // debug (PLDA_B200_EPI=skip): no epilogue stores -> isolates the TMA / MMA loop
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
@@ -225,22 +227,30 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constan
         uint32_t acc_phase = 0, a_phase = 0;
         int cur_rb = -1;
         const uint32_t idesc = umma_idesc_bf16_f32(2 * TS_BM, TS_BN);
+        long long dbg_full = 0, dbg_tempty = 0, dbg_a = 0;
+        const long long t_start = clock64();
         for (int t = t0; t < t1; ++t) {
           const int rb = t / p.n_tiles;
           if (rb != cur_rb) {
             // the loaders may overwrite A once every MMA issued so far has retired; then wait for the new rows
             if (cur_rb >= 0) umma_commit_2cta(a_free, 3);
+            const long long ta = clock64();
             mbar_wait(a_ready, a_phase);
             mbar_wait_acq_cluster(a_ready_x, a_phase);
+            dbg_a += clock64() - ta;
             a_phase ^= 1;
             tc_fence_after();
             cur_rb = rb;
           }
+          long long tw = clock64();
           mbar_wait(&tempty[acc], acc_phase ^ 1);
+          dbg_tempty += clock64() - tw;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TS_BN;
           for (int kb = 0; kb < p.nkb; ++kb) {
+            tw = clock64();
             mbar_wait(&full[stage], phase);
+            dbg_full += clock64() - tw;
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * TS_STAGE_BYTES);
             const uint64_t b_hi = umma_desc_kmajor(sa, 128);
@@ -259,6 +269,13 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constan
           }
           umma_commit_2cta(&tfull[acc], 3);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (p.dbg != nullptr && blockIdx.x < 2) {
+          p.dbg[blockIdx.x * 16 + 2] = dbg_full;
+          p.dbg[blockIdx.x * 16 + 3] = dbg_tempty;
+          p.dbg[blockIdx.x * 16 + 4] = clock64() - t_start;
+          p.dbg[blockIdx.x * 16 + 5] = t1 - t0;
+          p.dbg[blockIdx.x * 16 + 13] = dbg_a;
         }
       }
     } else if (warp == 2) {
@@ -329,6 +346,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constan
     uint32_t acc_phase = 0;
     const bool col_cached = e.col_add != nullptr;
     const bool col_late = p.shard.flags != nullptr;
+    long long dbg_tfull = 0;
+    const long long t_start = clock64();
     for (int t = t0; t < t1; ++t) {
       const int rb = t / p.n_tiles;
       int nb = t - rb * p.n_tiles + p.n_rot;
@@ -359,7 +378,9 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constan
       // tile i-2's slot) before the slot is rewritten (see gemm_tc.cu)
       if (col_cached) asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * TS_BN;
+      const long long tw = clock64();
       mbar_wait(&tfull[acc], acc_phase);
+      dbg_tfull += clock64() - tw;
       tc_fence_after();
       if (col_cached && col_late) {
 #pragma unroll
@@ -405,7 +426,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constan
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (v[j] + radd) * zi;
-        if (warp_rows_valid) {
+        if (warp_rows_valid && !p.skip_store) {
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
 #pragma unroll
@@ -425,6 +446,11 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constan
       }
     }
     if (lane == 0) tma_store_wait<0>();
+    if (p.dbg != nullptr && blockIdx.x < 2 && lane == 0 && (ew == 0 || ew == 7)) {
+      const int o = blockIdx.x * 16 + (ew == 0 ? 6 : 9);
+      p.dbg[o + 0] = dbg_tfull;
+      p.dbg[o + 2] = clock64() - t_start;
+    }
   }
 
   tc_fence_before();
@@ -451,7 +477,7 @@ bool gemm_ts_score(Context& ctx, const SplitOperand& a, const SplitOperand& b, i
   if (((reinterpret_cast<uintptr_t>(a.hi) | reinterpret_cast<uintptr_t>(a.lo) | reinterpret_cast<uintptr_t>(b.hi) |
         reinterpret_cast<uintptr_t>(b.lo)) & 15) != 0)
     return false;
-  if (ctx.epi_mode != 0 || ctx.epi_sector || !ctx.gemm_two_cta) return false;
+  if ((ctx.epi_mode != 0 && ctx.epi_mode != 2) || ctx.epi_sector || !ctx.gemm_two_cta) return false;
   TsParams p{};
   p.m = static_cast<int>(m);
   p.n = static_cast<int>(n);
@@ -464,6 +490,8 @@ bool gemm_ts_score(Context& ctx, const SplitOperand& a, const SplitOperand& b, i
   p.a_lo = a.lo;
   p.lda = a.ld;
   p.epi = epi;
+  p.dbg = ctx.gemm_dbg.size() >= 32 ? ctx.gemm_dbg.get() : nullptr;
+  p.skip_store = ctx.epi_mode == 2 ? 1 : 0;
   if (shard != nullptr && shard->flags != nullptr) {
     p.shard = *shard;
     const int first = shard->bounds[shard->rank] < n ? shard->bounds[shard->rank] : 0;

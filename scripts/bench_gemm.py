@@ -40,14 +40,15 @@ _ffi.check(lib.plda_profile_collect(p._h, C.byref(ms), C.byref(n)))
 k_ms = ms.value / n.value
 k16 = (d + 15) // 16 * 16
 print("mode=%s ne=%d nt=%d d=%d  gemm %.4f ms  step %.4f ms  %.3e trials/s (kernel)  issued %.0f TFLOP/s  write %.0f GB/s"
-      % (os.environ.get("PLDA_B200_EPI", "default") + "/" + os.environ.get("PLDA_B200_GEMM", "2cta"), ne, nt, d, k_ms, ev0.elapsed_time(ev1) / reps, ne * nt / k_ms * 1e3,
+      % (os.environ.get("PLDA_B200_EPI", "default") + "/" + os.environ.get("PLDA_B200_GEMM", "2cta") + "/ts" + os.environ.get("PLDA_B200_TS", "-"), ne, nt, d, k_ms, ev0.elapsed_time(ev1) / reps, ne * nt / k_ms * 1e3,
          3 * 2 * k16 * ne * nt / k_ms / 1e9, 4.0 * ne * nt / k_ms / 1e6))
 
 if os.environ.get("PLDA_B200_DBG") == "1":
     c = np.zeros(32, dtype=np.int64)
     _ffi.check(lib.plda_debug_counters(p._h, _ffi.ptr(c), 32))
     names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tempty", "mma_total", "tiles",
-             "epi0_wait_tfull", "epi0_wait_store", "epi0_total", "epi7_wait_tfull", "epi7_wait_store", "epi7_total", "epi0_tmem_load"]
+             "epi0_wait_tfull", "epi0_wait_store", "epi0_total", "epi7_wait_tfull", "epi7_wait_store", "epi7_total", "epi0_tmem_load",
+             "mma_wait_a"]
     for b in range(2):
         print("  cta%d: " % b + "  ".join("%s=%d" % (n, c[b * 16 + i]) for i, n in enumerate(names)))
 
