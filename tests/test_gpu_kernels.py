@@ -134,3 +134,40 @@ def test_jacobi_degenerate_spectrum(plda):
     v, w = plda._test_linalg(2, a)
     assert np.allclose(w, lam, rtol=1e-8, atol=1e-13)
     assert np.allclose(v.T @ v, np.eye(d), atol=1e-10)
+
+
+def test_gram_kernel_with_enrol_operand_in_tmem_matches_default():
+    """The opt-in TS form of the score-grid kernel (csrc/gemm_ts.cu: enrol operand in tensor memory, PLDA_B200_TS=1)
+    issues the same three products per k-step in the same order: its grid is bit-identical to the default kernel's,
+    with and without the z-norm affine, at tile-edge shapes."""
+    import os
+    import torch
+    from plda_b200 import PLDA
+    d = 200
+    rs = np.random.RandomState(5)
+    q, _ = np.linalg.qr(rs.randn(d, d))
+    model = (np.full(d, 0.5), q, 2.0 * np.exp(-np.arange(d) / (0.15 * d)))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    ne, nt = 1300, 1111
+    e = torch.randn(ne, d, device="cuda", generator=g)
+    t = torch.randn(nt, d, device="cuda", generator=g)
+    zm = torch.randn(ne, device="cuda", generator=g).double()
+    zs = (1.0 + torch.rand(ne, device="cuda", generator=g)).double()
+    outs = {}
+    old = os.environ.get("PLDA_B200_TS")
+    try:
+        for mode in ("0", "1"):
+            os.environ["PLDA_B200_TS"] = mode          # read when the handle is created
+            p = PLDA()
+            p.set_model(*model)
+            outs[mode] = (p.score_grid(e, 3, t).clone(), p.score_grid(e, 3, t, znorm=(zm, zs)).clone())
+            del p
+    finally:
+        if old is None:
+            os.environ.pop("PLDA_B200_TS", None)
+        else:
+            os.environ["PLDA_B200_TS"] = old
+    assert torch.equal(outs["0"][0], outs["1"][0])
+    assert torch.equal(outs["0"][1], outs["1"][1])
+    assert float(outs["0"][0].abs().max()) > 1.0
