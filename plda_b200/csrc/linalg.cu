@@ -364,26 +364,45 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
       __syncthreads();
-      // ---- 1. Gram: thread owns the strided 2x2 tile {ti, ti+half} x {tj, tj+half}
-      for (int t = threadIdx.x; t < half * half; t += nthreads) {
-        const int ti = t / half, tj = t - ti * half;
-        const double* a0 = cols + ti * dp;
-        const double* a1 = cols + (ti + half) * dp;
-        const double* b0 = cols + tj * dp;
-        const double* b1 = cols + (tj + half) * dp;
-        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+      // ---- 1. Gram: a thread owns the strided 2x2 tile {ti, ti+half} x {tj, tj+half} over one of KS slices of the
+      //         column length (all 1024 threads busy); the slices are summed through shared memory
+      {
+        const int tiles2 = half * half;
+        const int ks_n = max(1, min(nthreads / tiles2, 4));
+        const int slice = (d + ks_n - 1) / ks_n;
+        double* part = qm + m2 * gp;                 // [ks_n - 1][m2][gp] scratch behind qm
+        for (int t = threadIdx.x; t < tiles2 * ks_n; t += nthreads) {
+          const int ks = t / tiles2, tt = t - ks * tiles2;
+          const int ti = tt / half, tj = tt - ti * half;
+          const double* a0 = cols + ti * dp;
+          const double* a1 = cols + (ti + half) * dp;
+          const double* b0 = cols + tj * dp;
+          const double* b1 = cols + (tj + half) * dp;
+          double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+          const int i1 = min(d, (ks + 1) * slice);
 #pragma unroll 4
-        for (int i = 0; i < d; ++i) {
-          const double x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
-          c00 = fma(x0, y0, c00);
-          c01 = fma(x0, y1, c01);
-          c10 = fma(x1, y0, c10);
-          c11 = fma(x1, y1, c11);
+          for (int i = ks * slice; i < i1; ++i) {
+            const double x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
+            c00 = fma(x0, y0, c00);
+            c01 = fma(x0, y1, c01);
+            c10 = fma(x1, y0, c10);
+            c11 = fma(x1, y1, c11);
+          }
+          double* dst = ks == 0 ? gl : part + (ks - 1) * m2 * gp;
+          dst[ti * gp + tj] = c00;
+          dst[ti * gp + tj + half] = c01;
+          dst[(ti + half) * gp + tj] = c10;
+          dst[(ti + half) * gp + tj + half] = c11;
         }
-        gl[ti * gp + tj] = c00;
-        gl[ti * gp + tj + half] = c01;
-        gl[(ti + half) * gp + tj] = c10;
-        gl[(ti + half) * gp + tj + half] = c11;
+        __syncthreads();
+        if (ks_n > 1) {
+          for (int idx = threadIdx.x; idx < m2 * m2; idx += nthreads) {
+            const int i = idx / m2, j = idx - i * m2;
+            double v = gl[i * gp + j];
+            for (int ks = 1; ks < ks_n; ++ks) v += part[(ks - 1) * m2 * gp + i * gp + j];
+            gl[i * gp + j] = v;
+          }
+        }
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -608,7 +627,8 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   int nblk_pad = nblk + (nblk & 1);
   const int blocks = nblk_pad / 2;
   const int m2 = 2 * bw;
-  const size_t smem = (static_cast<size_t>(m2) * (d | 1) + 2 * static_cast<size_t>(m2) * (m2 + 1)) * sizeof(double);
+  // columns + Gram + rotation accumulator + 3 partial Gram slices
+  const size_t smem = (static_cast<size_t>(m2) * (d | 1) + 5 * static_cast<size_t>(m2) * (m2 + 1)) * sizeof(double);
   PB_CHECK(smem <= 200 * 1024, kInvalidArg, "eig: dimension too large");
   PB_CHECK(blocks <= ctx.num_sms, kInvalidArg, "eig: too many blocks for a cooperative launch");
   static std::once_flag once;
@@ -629,7 +649,7 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   cudaLaunchAttribute attr[1];
   if (use_cluster) {
     cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(512);
+    cfg.blockDim = dim3(1024);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx.stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -651,7 +671,7 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   } else {
     void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &big2, &ms, &counter, &rotated, &sweeps_done};
     PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(block_jacobi_gram_kernel<false>), dim3(blocks),
-                                        dim3(512), args, smem, ctx.stream));
+                                        dim3(1024), args, smem, ctx.stream));
   }
   ctx.count_launch();
   eig_normalise_kernel<<<static_cast<unsigned>(ceil_div(d, 8)), 256, 0, ctx.stream>>>(w.g.get(), di, w.lam.get(),

@@ -3,7 +3,7 @@ class) against the CPU fp64 oracle (oracle/kaldi_plda.py) on identical seeded in
 the committed regression fixture and the reference's own test call sequences
 (tests/pldatest.py) as API-conformance tests.
 
-Tolerances (stated by BASELINE.json north_star: scores <= 1e-3 rel, EER identical):
+Tolerances (stated by BASELINE.json north_star: scores <= 1e-3 rel, EER identical) -- every assertion below holds them:
   * scores:   |d| <= 1e-3 * max(|s|, 1)            (SURVEY hard part 2)
   * psi:      rel 1e-3 for the default bf16x3 mode, 1e-8 for the exact fp64 mode
   * EER:      +-0.01 % absolute
@@ -19,11 +19,8 @@ from oracle import kaldi_plda as kp
 pytestmark = pytest.mark.gpu
 
 
-def TOL(loose):
-    """Tolerance looser than the north star's 1e-3 (see DESIGN.md section 2 for why); PLDA_TIGHT=1 runs the same
-    assertion at 1e-3 to show which of them the current kernels would also pass."""
-    import os
-    return 1e-3 if os.environ.get("PLDA_TIGHT") == "1" else loose
+# the ONE tolerance of this file looser than the north star's 1e-3 (see test_reference_call_sequence_pldatest)
+LOOSE_ZNORM_RAND = 5e-3
 
 
 def score_tol_ok(got, ref, tol=1e-3):
@@ -64,7 +61,7 @@ def test_fit_matches_oracle(small_problem, precision):
     assert g.fit(p["x"], p["labels"], p["iters"]) is None
     mean, a, psi = g.get_model()
     w, b = g.get_covariances()
-    rtol = 1e-8 if precision == "fp64" else TOL(2e-3)
+    rtol = 1e-8 if precision == "fp64" else 1e-3
     assert np.allclose(mean, ref.plda.mean, rtol=1e-12, atol=1e-12)
     assert np.allclose(psi, ref.plda.psi, rtol=rtol, atol=rtol * 1e-3)
     est = ref.estimator
@@ -131,7 +128,7 @@ def test_znorm_matches_oracle(small_problem, precision):
     ek, tk = sorted(te), sorted(tt)
     got = np.array([[g.score(k, te[k], tt[j]) for j in tk[:5]] for k in ek[:6]])
     want = np.array([[ref.score(k, te_ref[k], tt_ref[j]) for j in tk[:5]] for k in ek[:6]])
-    assert score_tol_ok(got, want, TOL(2e-3) if precision == "bf16x3" else 1e-5)
+    assert score_tol_ok(got, want, 1e-3 if precision == "bf16x3" else 1e-5)
     # z-normalised grid
     e = np.stack([te[k][1] for k in ek])
     n = np.array([te[k][0] for k in ek])
@@ -139,7 +136,7 @@ def test_znorm_matches_oracle(small_problem, precision):
     zgrid = g.score_grid(e, n, t, enrol_ids=np.array(ek, dtype=np.uint64))
     raw = kp.score_grid(ref.plda, np.stack([te_ref[k][1] for k in ek]), n, np.stack([tt_ref[k][1] for k in tk]))
     want_z = (raw - np.array([ref.meanz[k] for k in ek])[:, None]) / np.array([ref.stdvz[k] for k in ek])[:, None]
-    assert score_tol_ok(zgrid, want_z, TOL(2e-3) if precision == "bf16x3" else 1e-4)
+    assert score_tol_ok(zgrid, want_z, 1e-3 if precision == "bf16x3" else 1e-4)
     # a second norm() never overwrites (insert semantics, src/pldamodule.cpp:245,250)
     g.norm(p["bkg"][:10], te)
     ids2, zm2, _ = g.znorm_tables()
@@ -152,7 +149,7 @@ def test_regression_fixture(golden_dir):
     g = PLDA()
     g.fit(f["x"], f["labels"], int(f["iters"]))
     _, _, psi = g.get_model()
-    assert np.allclose(psi, f["psi"], rtol=TOL(2e-3), atol=1e-6)
+    assert np.allclose(psi, f["psi"], rtol=1e-3, atol=1e-6)
     te, tt = g.transform(f["xe"], f["le"]), g.transform(f["xt"], f["lt"])
     e = np.stack([te[k][1] for k in sorted(te)])
     t = np.stack([tt[k][1] for k in sorted(tt)])
@@ -160,7 +157,7 @@ def test_regression_fixture(golden_dir):
     assert score_tol_ok(grid, f["scores"])
     g.norm(f["bkg"], te)
     z = g.score_grid(e, f["enrol_counts"], t, enrol_ids=np.array(sorted(te), dtype=np.uint64))
-    assert score_tol_ok(z, f["zscores"], TOL(2e-3))
+    assert score_tol_ok(z, f["zscores"], 1e-3)
 
 
 def test_config1_readme_shape():
@@ -173,7 +170,7 @@ def test_config1_readme_shape():
     g = PLDA()
     assert g.fit(x, y, 10) is None
     _, _, psi = g.get_model()
-    assert np.allclose(psi, ref.plda.psi, rtol=TOL(5e-3), atol=1e-6)
+    assert np.allclose(psi, ref.plda.psi, rtol=1e-3, atol=1e-6)
     xe = rng.rand(500, 200)
     xt = rng.rand(500, 200)
     ids = np.arange(500, dtype="uint")
@@ -242,7 +239,9 @@ def test_reference_call_sequence_pldatest():
     ref.norm(rng.rand(100, 10), t_ref)
     got = np.array([[m.score(k, transformed[k], transformedtest[j]) for j in range(20)] for k in range(10)])
     want = np.array([[ref.score(k, t_ref[k], tt_ref[j]) for j in range(20)] for k in range(10)])
-    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) <= TOL(5e-3)
+    # z-normalised scores of rand() data: the cohort std is ~3e-4 of the raw score range, so the 1e-4 absolute error
+    # of a raw LLR (bf16x3 Gram, d = 1024) is amplified into the z-score; every other assertion of this file holds 1e-3
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) <= LOOSE_ZNORM_RAND
 
 
 def test_error_behaviour():
@@ -349,7 +348,7 @@ def test_fit_operand_kernels_agree(dtype):
         assert np.allclose(pa, pb_, rtol=3e-5, atol=1e-9) and np.allclose(ma, mb, rtol=1e-6, atol=1e-7)
         assert np.allclose(ta.T @ ta, tb.T @ tb, rtol=1e-4, atol=1e-5)
     ref = oracle_fit(x_al.double().cpu().numpy(), labels, 3)
-    assert np.max(np.abs(pa - ref.plda.psi) / np.maximum(ref.plda.psi, 1e-12)) <= TOL(2e-3)
+    assert np.max(np.abs(pa - ref.plda.psi) / np.maximum(ref.plda.psi, 1e-12)) <= 1e-3
 
 
 def test_norm_batch_equals_dict_norm(small_problem):
