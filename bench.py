@@ -1024,7 +1024,7 @@ def run_main(args):
 
     # DRAM traffic of the same kernel / shape from the committed ncu --set full capture (profiles/), per launch
     traffic, traffic_src = None, None
-    for name in ("r02_ncu_prof_gemm.json", "r01_ncu_prof_gemm.json"):
+    for name in ("r02_ncu_gemm.json", "r01_ncu_prof_gemm.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 nc = json.load(f)

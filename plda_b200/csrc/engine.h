@@ -148,6 +148,11 @@ class PldaEngine {
                     const float** zmean, const float** zinv);
   void produce_score_operands(const Staged& se, int64_t ne, const Staged& st, int64_t nt, int64_t dim,
                               const ScoreGroups& g, int64_t col_ld);
+  // set by produce_score_operands: reduction length of the score GEMM (dim, or dim + 2 * groups when the ragged
+  // column terms ride inside the operands) and the epilogue's column-term binding
+  int64_t score_k = 0;
+  bool score_cols_embedded = false;
+  void bind_col_terms(GemmEpilogue& epi, const ScoreGroups& g, int64_t r0, int64_t col_ld) const;
   std::vector<int32_t> ragged_key;   // distinct counts ws_tables was built for
   DevBuf<int32_t> rg_counts, rg_grp, rg_gcounts;   // device copies owned by the ragged-count cache
   std::vector<int32_t> last_counts;  // the ragged counts whose device copies (ws_counts / ws_grp) are current
@@ -193,6 +198,10 @@ class PldaEngine {
   DevBuf<double> em_c, em_t1, em_bp, em_u, em_a, em_ainv, em_psi, em_tmp, em_tmp2, em_bs, em_ws, em_db, em_dw;
   DevBuf<int> em_info;
   bool em_have_basis = false;
+  // PLDA_B200_EM_PROFILE=1: CUDA events between the phases of the EM loop, averaged per phase when fit returns
+  std::vector<std::pair<const char*, cudaEvent_t>> em_marks;
+  void em_mark(const char* what);
+  void em_report();
 };
 
 class LdaEngine {

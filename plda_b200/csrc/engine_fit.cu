@@ -4,6 +4,7 @@
 //   MPlda_fit (src/pldamodule.cpp:42-109)
 //     -> PldaStats::AddSamples per speaker with weight 1/n_s (:94-98), Sort (:100)
 //     -> PldaEstimator::Estimate (:102-106): EstimateOneIter x iters, GetOutput
+#include <algorithm>
 #include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
@@ -58,22 +59,52 @@ void PldaEngine::allreduce_parts(const std::vector<std::pair<double*, int64_t>>&
   }
 }
 
+void PldaEngine::em_mark(const char* what) {
+  static const bool on = getenv("PLDA_B200_EM_PROFILE") != nullptr;
+  if (!on) return;
+  cudaEvent_t e;
+  PB_CUDA(cudaEventCreate(&e));
+  PB_CUDA(cudaEventRecord(e, ctx.stream));
+  em_marks.emplace_back(what, e);
+}
+
+// phase = the work between the previous mark and this one
+void PldaEngine::em_report() {
+  if (em_marks.empty()) return;
+  ctx.sync();
+  std::vector<std::pair<const char*, std::pair<double, int>>> acc;
+  for (size_t i = 1; i < em_marks.size(); ++i) {
+    const double ms = ms_between(em_marks[i - 1].second, em_marks[i].second);
+    auto it = std::find_if(acc.begin(), acc.end(), [&](const auto& a) { return strcmp(a.first, em_marks[i].first) == 0; });
+    if (it == acc.end()) acc.push_back({em_marks[i].first, {ms, 1}});
+    else { it->second.first += ms; it->second.second += 1; }
+  }
+  for (const auto& a : acc)
+    fprintf(stderr, "plda_b200 em phase: %-28s %8.4f ms avg over %d\n", a.first, a.second.first / a.second.second,
+            a.second.second);
+  for (auto& m : em_marks) cudaEventDestroy(m.second);
+  em_marks.clear();
+}
+
 // C = chol(W); T1 = C^-1; B' = T1 B T1^T; B' = U diag(psi) U^T; A = U^T T1; A^-1 = C U
 // (PldaEstimator::GetOutput / ComputeNormalizingTransform).  Leaves A in em_a, A^-1 in em_ainv, psi in em_psi.
 void PldaEngine::joint_diagonalise(int64_t d, bool warm, bool final_pass) {
   const size_t dd = static_cast<size_t>(d) * d;
   em_c.reserve(dd); em_t1.reserve(dd); em_bp.reserve(dd); em_u.reserve(dd); em_a.reserve(dd); em_ainv.reserve(dd);
   em_psi.reserve(d); em_tmp.reserve(dd); em_info.reserve(1);
+  em_mark("(iteration start)");
   PB_CUDA(cudaMemcpyAsync(em_c.get(), model.within.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
   if (!cholesky_inverse_fused(ctx, em_c.get(), em_t1.get(), d, em_info.get())) {
     cholesky_lower(ctx, em_c.get(), d, em_info.get());
     tri_inverse_lower(ctx, em_c.get(), em_t1.get(), d);
   }
+  em_mark("cholesky + inverse");
   // B' = T1 B T1^T
   gemm_f64(ctx, false, false, d, d, d, 1.0, em_t1.get(), d, model.between.get(), d, 0.0, em_tmp.get(), d);
   gemm_f64(ctx, false, true, d, d, d, 1.0, em_tmp.get(), d, em_t1.get(), d, 0.0, em_bp.get(), d);
   symmetrise_kernel<<<static_cast<unsigned>(ceil_div(d * d, 256)), 256, 0, ctx.stream>>>(em_bp.get(), static_cast<int>(d));
   ctx.count_launch();
+  em_mark("B' = T1 B T1^T");
   // eigenvectors as ROWS of em_u (= U^T), eigenvalues descending, floored at 0
   int sweeps = 0;
   const bool dbg = getenv("PLDA_B200_DBG") != nullptr;
@@ -87,6 +118,7 @@ void PldaEngine::joint_diagonalise(int64_t d, bool warm, bool final_pass) {
                  dbg ? &sweeps : nullptr, stop_rotation);
   if (dbg) fprintf(stderr, "plda_b200: joint_diagonalise d=%lld warm=%d sweeps=%d\n", static_cast<long long>(d),
                    static_cast<int>(warm && em_have_basis), sweeps);
+  em_mark("eigensolver");
   PB_CUDA(cudaMemcpyAsync(em_u.get(), em_tmp.get(), dd * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
   em_have_basis = true;
   gemm_f64(ctx, false, false, d, d, d, 1.0, em_u.get(), d, em_t1.get(), d, 0.0, em_a.get(), d);     // A = U^T T1
@@ -119,6 +151,7 @@ void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const
     epi.out = ws_u.get();
     epi.ldo = ldu;
     gemm_bf16x3(ctx, mc_split.view(), a_split.view(), k, d, d, epi);
+    em_mark("U = Mc A^T");
     // P and Q stacked in one operand: ONE split-K SYRK ([P ; Q][P ; Q]^T, the diagonal blocks are the two statistics)
     // and one fp64 reduction that also symmetrises and adds the diagonal terms
     em_posterior_stacked(ctx, ws_u.get(), ldu, k, d, counts_dev, em_psi.get(), ws_pt, em_db.get(), em_dw.get());
@@ -128,6 +161,7 @@ void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const
     ws_partial.reserve(static_cast<size_t>(eff) * mpad * npad);
     gemm_bf16x3_splitk(ctx, ws_pt.view(), ws_pt.view(), 2 * d, 2 * d, k, ks, ws_partial.get());
     em_stats_reduce(ctx, ws_partial.get(), eff, d, em_db.get(), em_dw.get(), em_bs.get(), em_ws.get());
+    em_mark("posterior + class SYRK");
   }
   if (precision == 1) {
     // add the diagonal terms (no scaling yet)
@@ -145,6 +179,7 @@ void PldaEngine::em_iteration(int64_t k, int64_t d, const double* scatter, const
                 em_ainv.get(), model.within.get(), d, d, 0.0, d);
   // W = (S + .)/W_count ;  B = ./B_count      (EstimateFromStats), symmetrised
   em_finalize(ctx, model.between.get(), model.within.get(), scatter, 1.0 / b_count, 1.0 / w_count, d);
+  em_mark("back-transform + finalize");
 }
 
 void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype, int loc, const uint64_t* labels,
@@ -283,6 +318,7 @@ void PldaEngine::fit(const void* x, int64_t n, int64_t d, int64_t ldx, int dtype
   fit_ms[2] = ms_between(ev[2], ev[3]);
   fit_ms[3] = ms_between(ev[0], ev[3]);
   fit_ms[4] = iters;
+  em_report();
   for (auto& e : ev) cudaEventDestroy(e);
   PB_CHECK(h_info == 0, kInternal, "within-class covariance is not positive definite (Cholesky failed at column " +
                                       std::to_string(h_info) + ")");

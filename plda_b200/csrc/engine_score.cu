@@ -441,13 +441,18 @@ void PldaEngine::produce_score_operands(const Staged& se, int64_t ne, const Stag
                                         const ScoreGroups& g, int64_t col_ld) {
   ws_row.reserve(ne);
   ws_col.reserve(static_cast<size_t>(g.ng) * col_ld);
+  score_k = dim;
+  score_cols_embedded = false;
   if (g.uniform) {
     score_prep_uniform(ctx, se.ptr, ne, se.ld, st.ptr, nt, st.ld, se.is_f32, dim, g.tables, ws_l, ws_r, ws_row.get(),
                        ws_col.get(), col_ld);
     return;
   }
-  PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(g.ng) * col_ld * sizeof(float), ctx.stream));
   static const char* mode = getenv("PLDA_B200_RAGGED");
+  // producers below write every column term they own; the [nt, col_ld) padding is only read for columns that are
+  // never stored
+  if (mode != nullptr)
+    PB_CUDA(cudaMemsetAsync(ws_col.get(), 0, static_cast<size_t>(g.ng) * col_ld * sizeof(float), ctx.stream));
   if (mode != nullptr && strcmp(mode, "old") == 0) {            // A/B switch: per-element log / divide producers
     score_prep_enrol(ctx, se.ptr, se.is_f32, ne, dim, se.ld, g.counts_dev, g.uniform_count, model.psi.get(), &ws_l,
                      nullptr, ws_row.get(), nullptr);
@@ -457,9 +462,23 @@ void PldaEngine::produce_score_operands(const Staged& se, int64_t ne, const Stag
     score_prep_grouped(ctx, se.ptr, ne, se.ld, g.grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, g.ng, g.tables, ws_l, ws_r,
                        ws_row.get(), ws_col.get(), col_ld);
   } else {
+    // up to 8 distinct counts: their column terms travel inside the operands (at most one more 16-wide k-step) and
+    // the grid runs the uniform-count kernel; more: per-row group vectors in the epilogue
+    const bool embed = g.ng <= 8 && !(mode != nullptr && strcmp(mode, "epilogue") == 0);
     score_prep_grouped_vec(ctx, se.ptr, ne, se.ld, g.grp_dev, st.ptr, nt, st.ld, se.is_f32, dim, g.ng, g.tables, ws_l,
-                           ws_r, ws_row.get(), ws_col.get(), col_ld);
+                           ws_r, ws_row.get(), ws_col.get(), col_ld, embed);
+    if (embed) {
+      score_k = dim + 2 * g.ng;
+      score_cols_embedded = true;
+    }
   }
+}
+
+void PldaEngine::bind_col_terms(GemmEpilogue& epi, const ScoreGroups& g, int64_t r0, int64_t col_ld) const {
+  if (score_cols_embedded) return;
+  epi.col_add = ws_col.get();
+  epi.col_ld = col_ld;
+  epi.grp = g.grp_dev ? g.grp_dev + r0 : nullptr;
 }
 
 void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, const int32_t* counts,
@@ -544,12 +563,10 @@ void PldaEngine::score_grid(const void* enrol, int64_t ne, int64_t ld_enrol, con
       epi.out = dst;
       epi.ldo = ldo_dev;
       epi.row_add = ws_row.get() + r0;
-      epi.col_add = ws_col.get();
-      epi.col_ld = col_ld;
-      epi.grp = g.grp_dev ? g.grp_dev + r0 : nullptr;
+      bind_col_terms(epi, g, r0, col_ld);
       epi.zmean = zmean ? zmean + r0 : nullptr;
       epi.zinv = zinv ? zinv + r0 : nullptr;
-      gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, dim, epi);
+      gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, score_k, epi);
     }
     if (out_loc == 0) PB_CUDA(cudaEventRecord(ev_done[b], ctx.stream));
   };

@@ -75,12 +75,10 @@ void PldaEngine::score_trials(const void* enrol, int64_t ne, int64_t ld_enrol, c
       epi.out = ws_out[0].get();
       epi.ldo = ld_slab;
       epi.row_add = ws_row.get() + r0;
-      epi.col_add = ws_col.get();
-      epi.col_ld = col_ld;
-      epi.grp = g.grp_dev ? g.grp_dev + r0 : nullptr;
+      bind_col_terms(epi, g, r0, col_ld);
       epi.zmean = zmean ? zmean + r0 : nullptr;
       epi.zinv = zinv ? zinv + r0 : nullptr;
-      gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, dim, epi);
+      gemm_bf16x3(ctx, a, ws_r.view(), rows, nt, score_k, epi);
       gather_trials(ctx, ws_out[0].get(), ld_slab, r0, rows, te_d, tt_d, n_trials, out_d);
     }
   }

@@ -32,6 +32,7 @@
 // griddepcontrol.wait overlaps the producer's tail); sharded B operand (GemmShard): the TMA producer polls the
 // owner rank's ready flag before the first tile that touches its rows and the column tiles start at the rank's own.
 #include <algorithm>
+#include <cstdlib>
 
 #include "runtime.h"
 
@@ -143,7 +144,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tt_a_hi, const __grid_constant__ CUtensorMap tt_a_lo,
                    const __grid_constant__ CUtensorMap tt_b_hi, const __grid_constant__ CUtensorMap tt_b_lo,
                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
-  constexpr bool FAST = EPI == 1;
+  constexpr bool RAG = EPI == 6;    // score-grid path with per-row column-term groups (ragged enrol counts)
+  constexpr bool FAST = EPI == 1 || RAG;
   constexpr bool LSE = EPI == 2;
   constexpr bool SECT = EPI == 3;   // score-grid path, accumulators stored straight from registers (no smem staging)
   constexpr bool MOM = EPI == 4;    // z-norm sink: per-row shifted moments of the scores, nothing stored
@@ -409,6 +411,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
       float* colslot = colc + acc * BN_MAX;
+      // ragged counts: the column terms of a row come from its group's vector (rows of one warp may differ)
+      float cbuf[RAG ? 32 : 1];
+      auto load_cols = [&](int cc, float* dst) {
+        const float4* cp = reinterpret_cast<const float4*>(colp + cc * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = __ldg(cp + j4);
+          dst[4 * j4 + 0] = t.x; dst[4 * j4 + 1] = t.y; dst[4 * j4 + 2] = t.z; dst[4 * j4 + 3] = t.w;
+        }
+      };
+      if (RAG && h < nchunks) load_cols(h, cbuf);
       // The accumulator stage is handed back BEFORE process() reads the column cache, so tfull of tile i+2 alone
       // does not prove that the three sibling warps (same chunk parity h, other lane quarters) are done reading
       // this slot for tile i: the four warps that share a slot half meet here once per tile (after this point
@@ -416,7 +429,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (col_cached) asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN_MAX;
 
-      auto process = [&](uint32_t (&r)[32], int c) {
+      auto process = [&](uint32_t (&r)[32], int c, float* cadd, int next_c) {
         const int nbase = n0 + c * 32;
         float v[32];
 #pragma unroll
@@ -428,6 +441,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             const float4 t = cp[j4];
             v[4 * j4 + 0] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
           }
+        } else if (RAG) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += cadd[j];
+          // the next chunk's terms travel while this chunk is staged and stored
+          if (next_c >= 0) load_cols(next_c, cadd);
         } else if (!FAST && !LSE && colp != nullptr && mvalid) {
           const float4* cp = reinterpret_cast<const float4*>(colp + c * 32);
 #pragma unroll
@@ -711,10 +729,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         __syncwarp();     // the next item's speaker ids overwrite the staging box
         continue;
       }
+      if constexpr (RAG) {
+        // the thread's own group vector, one chunk ahead of the chunk being stored (first chunk fetched above,
+        // behind the accumulator wait)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int cc = h + 2 * i;
-        if (cc < nchunks) process(r[i], cc);
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc < nchunks) process(r[i], cc, cbuf, (i + 1 < 4 && cc + 2 < nchunks) ? cc + 2 : -1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc < nchunks) process(r[i], cc, nullptr, -1);
+        }
       }
 
       if (!FAST && mvalid) {
@@ -907,6 +935,10 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
   int epi = 0;
   if (out != nullptr && p.direct_store == 3 && ep.rsum == nullptr && ep.lse_max == nullptr && ep.grp == nullptr) epi = 1;
   // register-direct sector stores (PLDA_B200_EPI=sector): same preconditions as the TMA path (8-byte aligned rows)
+  static const bool ragged_generic = getenv("PLDA_B200_RAGGED_EPI") != nullptr;   // A/B switch: generic epilogue
+  if (out != nullptr && p.direct_store == 3 && ep.rsum == nullptr && ep.lse_max == nullptr && ep.grp != nullptr &&
+      ep.col_add != nullptr && !ragged_generic)
+    epi = 6;
   if (epi == 1 && ctx.epi_sector) epi = 3;
   else if (out == nullptr && ep.lse_max != nullptr && ep.rsum == nullptr && ep.grp == nullptr) epi = 2;
   else if (out == nullptr && ep.mom != nullptr) epi = 4;
@@ -930,6 +962,7 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     case 3: launch_epi<3>(ctx, pl, tm, pdl); break;
     case 4: launch_epi<4>(ctx, pl, tm, pdl); break;
     case 5: launch_epi<5>(ctx, pl, tm, pdl); break;
+    case 6: launch_epi<6>(ctx, pl, tm, pdl); break;
     default: launch_epi<0>(ctx, pl, tm, pdl); break;
   }
   PB_CUDA(cudaGetLastError());

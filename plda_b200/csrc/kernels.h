@@ -92,11 +92,13 @@ void score_trials_direct(Context& ctx, const void* enrol, int64_t ld_e, const vo
 // out[i] = slab[(te[i] - r0) * ld + tt[i]] for the trials with r0 <= te[i] < r0 + rows (others untouched)
 void gather_trials(Context& ctx, const float* slab, int64_t ld, int64_t r0, int64_t rows, const int32_t* te,
                    const int32_t* tt, int64_t n_trials, float* out);
-// Vectorised operand producer for ragged enrol counts (16-byte loads / stores, per-row constants table)
+// Vectorised operand producer for ragged enrol counts (16-byte loads / stores, per-row constants table).
+// embed: the operands get 2 * ng extra K columns that carry the column terms through the product itself (enrol
+// rows: one-hot pair of their group; test rows: the group's term in four bf16 pieces) -> K = d + 2 * ng.
 void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
                             const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
                             const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term,
-                            float* col_term, int64_t col_ld);
+                            float* col_term, int64_t col_ld, bool embed);
 
 // ---- label segmentation (K1) + segmented sums (K2/K4) --------------------------- //
 struct Segments {

@@ -474,10 +474,13 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       // ---- 3. C <- C Q, written back to global: new column x' = sum_x Q[x][x'] * old column x
       if (s_rot) {
+        // a warp owns 4 output columns over one of `parts` interleaved slices of the column length (all warps busy)
         const int groups = m2 >> 2;
-        for (int xg = warp; xg < groups; xg += nwarps) {
+        const int parts = max(1, nwarps / groups);
+        for (int wi = warp; wi < groups * parts; wi += nwarps) {
+          const int xg = wi % groups, part = wi / groups;
           const double* qrow = qm + xg * 4;
-          for (int i = lane; i < d; i += 32) {
+          for (int i = lane + 32 * part; i < d; i += 32 * parts) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 4
             for (int x = 0; x < m2; ++x) {

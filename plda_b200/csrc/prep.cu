@@ -216,6 +216,14 @@ struct Group8F32 {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
     part = p;
   }
+  // sum_j w[j] v[j]^2 over the first `valid` columns, in the arithmetic of run()
+  __device__ __forceinline__ double weighted_squares(const double* w, const float (&v)[8], int valid) const {
+    double p = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < valid) p = fma(__ldg(w + j), static_cast<double>(v[j] * v[j]), p);
+    return p;
+  }
 };
 struct Group8F64 {
   double sq[8], scale[8];
@@ -247,6 +255,13 @@ struct Group8F64 {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
     part = p;
+  }
+  __device__ __forceinline__ double weighted_squares(const double* w, const double (&v)[8], int valid) const {
+    double p = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < valid) p += __ldg(w + j) * v[j] * v[j];
+    return p;
   }
 };
 template <typename T> struct Group8Of;
@@ -413,7 +428,7 @@ score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long lo
                               __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo,
                               __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo, int ld_out,
                               float* __restrict__ row_term, float* __restrict__ col_term, long long col_ld,
-                              unsigned enrol_blocks, int vec_e, int vec_t) {
+                              unsigned enrol_blocks, int vec_e, int vec_t, int embed) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typename Group8Of<T>::type g;
   if (blockIdx.x < enrol_blocks) {
@@ -434,27 +449,66 @@ score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long lo
     }
     acc = warp_sum(acc);
     if (lane == 0) row_term[r] = static_cast<float>(0.5 * (__ldg(tab + kScoreConstsLogdet) - acc));
+    if (embed) {
+      // column terms inside the product: a one-hot pair of extra K columns selects the row's group (see below)
+      __syncwarp();                       // the zero fill of the padding columns above is by other lanes
+      if (lane == 0) {
+        const long long o = r * ld_out + d + 2 * __ldg(grp + r);
+        l_hi[o] = __float2bfloat16(1.0f);
+        l_hi[o + 1] = __float2bfloat16(1.0f);
+      }
+    }
   } else {
     const long long r = static_cast<long long>(blockIdx.x - enrol_blocks) * kWarpsPerBlock + warp;
     if (r >= nt) return;
     const T* src = test + r * ld_t;
-    for (int gi = 0; gi < ng; ++gi) {
-      const double* tab = tables + static_cast<long long>(gi) * kScoreConstsSize;
-      double acc = 0.0;
+    // one pass over the row: it is split once (unit scale) and every group's weighted sum of squares is taken from
+    // the same registers, eight groups per pass
+    for (int g0 = 0; g0 < ng; g0 += 8) {
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       for (int c = lane * 8; c < ld_out; c += 256) {
+        const double* tab = tables + static_cast<long long>(g0) * kScoreConstsSize;
         g.load_consts(tab + kScoreConstsTestSq, tab + kScoreConstsScale, false, c, d);
         T v[8];
         load8<T>(src, c, d, vec_t != 0, v);
         uint4 hi, lo;
-        g.run(v, hi, lo);
-        acc += g.part;
-        if (gi == 0) {
+        g.run(v, hi, lo);                 // leaves v unchanged (x 1) inside the row, 0 in the padding columns
+        acc[0] += g.part;
+        if (g0 == 0) {
           *reinterpret_cast<uint4*>(r_hi + r * ld_out + c) = hi;
           *reinterpret_cast<uint4*>(r_lo + r * ld_out + c) = lo;
         }
+#pragma unroll
+        for (int gi = 1; gi < 8; ++gi) {
+          if (g0 + gi >= ng) break;
+          const double* tq = tables + static_cast<long long>(g0 + gi) * kScoreConstsSize + kScoreConstsTestSq + c;
+          acc[gi] += g.weighted_squares(tq, v, d - c);
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) col_term[gi * col_ld + r] = static_cast<float>(acc);
+      if (g0 == 0 && embed) __syncwarp();   // the zero fill of the padding columns above is by other lanes
+#pragma unroll
+      for (int gi = 0; gi < 8; ++gi) {
+        if (g0 + gi >= ng) break;
+        const double a = warp_sum(acc[gi]);
+        if (lane != 0) continue;
+        col_term[(g0 + gi) * col_ld + r] = static_cast<float>(a);
+        if (embed) {
+          // The group's column term rides in two extra K columns of the test operand, as four bf16 pieces that add
+          // up to the fp32 value (hi/lo of the term, hi/lo of what those two left): against the enrol row's one-hot
+          // pair the hi*hi + hi*lo products of the bf16x3 scheme deliver exactly that sum into the fp32 accumulator,
+          // so the GEMM epilogue needs no per-row column vector (ragged counts run the uniform-count kernel).
+          const float cf = static_cast<float>(a);
+          const __nv_bfloat16 h1 = __float2bfloat16(cf);
+          const float r1 = cf - __bfloat162float(h1);
+          const __nv_bfloat16 l1 = __float2bfloat16(r1);
+          const float r2 = r1 - __bfloat162float(l1);
+          const __nv_bfloat16 h2 = __float2bfloat16(r2);
+          const __nv_bfloat16 l2 = __float2bfloat16(r2 - __bfloat162float(h2));
+          const long long o = r * ld_out + d + 2 * (g0 + gi);
+          r_hi[o] = h1; r_lo[o] = l1;
+          r_hi[o + 1] = h2; r_lo[o + 1] = l2;
+        }
+      }
     }
   }
 }
@@ -702,10 +756,11 @@ void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
 void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
                             const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
                             const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term,
-                            float* col_term, int64_t col_ld) {
+                            float* col_term, int64_t col_ld, bool embed) {
   PB_CHECK(d <= 1024 && ng >= 1, kInvalidArg, "score: dimension above 1024 is not supported");
-  l_out.reserve(ne, d);
-  r_out.reserve(nt, d);
+  const int64_t kk = embed ? d + 2 * ng : d;      // embed: two extra K columns per distinct count
+  l_out.reserve(ne, kk);
+  r_out.reserve(nt, kk);
   const unsigned eb = row_blocks(ne), tb = row_blocks(nt);
   if (eb + tb == 0) return;
   const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
@@ -714,12 +769,12 @@ void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t
     score_prep_grouped_vec_kernel<float><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
         static_cast<const float*>(enrol), ne, ld_e, grp_dev, static_cast<const float*>(test), nt, ld_t,
         static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
-        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t);
+        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t, embed ? 1 : 0);
   else
     score_prep_grouped_vec_kernel<double><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
         static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
         static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
-        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t);
+        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t, embed ? 1 : 0);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

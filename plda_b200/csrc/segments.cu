@@ -24,23 +24,33 @@ __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, long long n
   if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
-// seg_of_pos = inclusive_scan(flags) - 1 (done in place by the caller via cub); this scatters the heads.
-__global__ void scatter_heads_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ seg_of_pos,
-                                     long long n, uint64_t* __restrict__ seg_label, int32_t* __restrict__ seg_start,
-                                     long long nseg) {
+// Head flags on the rows as given + the identity order; *unsorted is raised when a label is smaller than its
+// predecessor (the caller then falls back to the radix sort).
+__global__ void head_flags_order_kernel(const uint64_t* __restrict__ keys, long long n, int32_t* __restrict__ flags,
+                                        int32_t* __restrict__ order, int32_t* __restrict__ unsorted) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
-  const int32_t s = seg_of_pos[i];
-  if (i == 0 || seg_of_pos[i - 1] != s) {
+  const uint64_t k = keys[i];
+  const uint64_t prev = i == 0 ? k : keys[i - 1];
+  flags[i] = (i == 0 || k != prev) ? 1 : 0;
+  order[i] = static_cast<int32_t>(i);
+  if (k < prev) *unsorted = 1;
+}
+
+// seg_of_pos holds inclusive_scan(flags): this makes it zero-based (each thread its own element) and scatters the
+// heads (label and first position of every segment).
+__global__ void scatter_heads_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ flags,
+                                     int32_t* __restrict__ seg_of_pos, long long n, uint64_t* __restrict__ seg_label,
+                                     int32_t* __restrict__ seg_start, long long nseg) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int32_t s = seg_of_pos[i] - 1;
+  seg_of_pos[i] = s;
+  if (flags[i] != 0) {
     seg_label[s] = keys[i];
     seg_start[s] = static_cast<int32_t>(i);
   }
   if (i == n - 1) seg_start[nseg] = static_cast<int32_t>(n);
-}
-
-__global__ void dec_kernel(int32_t* __restrict__ v, long long n) {
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i < n) v[i] -= 1;
 }
 
 // Balanced segmented sum: each warp owns kRowsPerWarp consecutive SORTED positions, keeps a running
@@ -331,37 +341,52 @@ inline unsigned blocks_for(long long n, int t) { return static_cast<unsigned>(ce
 void build_segments(Context& ctx, const uint64_t* labels_dev, int64_t n, Segments& seg) {
   PB_CHECK(n > 0 && n < (1ll << 31), kInvalidArg, "labels: need 1 <= n < 2^31 rows");
   seg.n = n;
-  seg.keys_out.reserve(n);
   seg.vals_in.reserve(n);
   seg.order.reserve(n);
   seg.seg_of_pos.reserve(n);
-  iota_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.vals_in.get(), n);
-  ctx.count_launch();
+  seg.flags.reserve(2);
   size_t tmp_bytes = 0, tmp2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, labels_dev, seg.keys_out.get(), seg.vals_in.get(),
                                   seg.order.get(), static_cast<int>(n), 0, 64, ctx.stream);
-  cub::DeviceScan::InclusiveSum(nullptr, tmp2, seg.seg_of_pos.get(), seg.seg_of_pos.get(), static_cast<int>(n),
-                                ctx.stream);
+  cub::DeviceScan::InclusiveSum(nullptr, tmp2, seg.vals_in.get(), seg.seg_of_pos.get(), static_cast<int>(n), ctx.stream);
   seg.cub_tmp.reserve(std::max(tmp_bytes, tmp2));
+  // Pass 1 assumes what callers nearly always hand over -- rows already grouped by ascending label: head flags and
+  // the identity order in one kernel, which also records whether any label is smaller than its predecessor.
+  PB_CUDA(cudaMemsetAsync(seg.flags.get(), 0, 2 * sizeof(int32_t), ctx.stream));
+  head_flags_order_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(labels_dev, n, seg.vals_in.get(),
+                                                                     seg.order.get(), seg.flags.get());
   size_t avail = seg.cub_tmp.size();
-  PB_CUDA(cub::DeviceRadixSort::SortPairs(seg.cub_tmp.get(), avail, labels_dev, seg.keys_out.get(), seg.vals_in.get(),
-                                          seg.order.get(), static_cast<int>(n), 0, 64, ctx.stream));
-  head_flags_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.keys_out.get(), n, seg.seg_of_pos.get());
-  ctx.count_launch();
-  avail = seg.cub_tmp.size();
-  PB_CUDA(cub::DeviceScan::InclusiveSum(seg.cub_tmp.get(), avail, seg.seg_of_pos.get(), seg.seg_of_pos.get(),
+  PB_CUDA(cub::DeviceScan::InclusiveSum(seg.cub_tmp.get(), avail, seg.vals_in.get(), seg.seg_of_pos.get(),
                                         static_cast<int>(n), ctx.stream));
-  int32_t last = 0;
+  ctx.count_launch(2);
+  int32_t last = 0, unsorted = 0;
   PB_CUDA(cudaMemcpyAsync(&last, seg.seg_of_pos.get() + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(&unsorted, seg.flags.get(), sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
   ctx.sync();
+  const uint64_t* keys = labels_dev;
+  if (unsorted != 0) {
+    // general case: stable radix sort of (label, row), then the same flags / scan on the sorted keys
+    seg.keys_out.reserve(n);
+    iota_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.vals_in.get(), n);
+    avail = seg.cub_tmp.size();
+    PB_CUDA(cub::DeviceRadixSort::SortPairs(seg.cub_tmp.get(), avail, labels_dev, seg.keys_out.get(),
+                                            seg.vals_in.get(), seg.order.get(), static_cast<int>(n), 0, 64, ctx.stream));
+    head_flags_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.keys_out.get(), n, seg.vals_in.get());
+    avail = seg.cub_tmp.size();
+    PB_CUDA(cub::DeviceScan::InclusiveSum(seg.cub_tmp.get(), avail, seg.vals_in.get(), seg.seg_of_pos.get(),
+                                          static_cast<int>(n), ctx.stream));
+    ctx.count_launch(4);
+    PB_CUDA(cudaMemcpyAsync(&last, seg.seg_of_pos.get() + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    keys = seg.keys_out.get();
+  }
   seg.nseg = last;
-  dec_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.seg_of_pos.get(), n);
   seg.seg_label.reserve(seg.nseg);
   seg.seg_start.reserve(seg.nseg + 1);
-  scatter_heads_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(seg.keys_out.get(), seg.seg_of_pos.get(), n,
+  scatter_heads_kernel<<<blocks_for(n, 256), 256, 0, ctx.stream>>>(keys, seg.vals_in.get(), seg.seg_of_pos.get(), n,
                                                                   seg.seg_label.get(), seg.seg_start.get(), seg.nseg);
   PB_CUDA(cudaGetLastError());
-  ctx.count_launch(2);
+  ctx.count_launch();
 }
 
 void segment_sums(Context& ctx, const void* x, bool is_f32, int64_t d, int64_t ld, const Segments& seg, double* sums) {

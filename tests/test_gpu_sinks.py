@@ -253,3 +253,28 @@ def test_stream_order_with_pending_torch_work(fitted):
             t = t_host.to(dev, non_blocking=True) * 1.0
             got = g.score_grid(e, 3, t)
         assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("groups", [4, 8, 13])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_ragged_count_grid_vs_oracle(fitted, groups, dtype):
+    """Ragged enrol counts in one grid (scoring/scorePLDA.py enrols speakers with differing numbers of utterances):
+    up to 8 distinct counts ride inside the operands as extra K columns, more take the per-row column vectors in the
+    epilogue -- both against the oracle's per-pair LLR, with and without a z-norm affine."""
+    import torch
+    f = fitted
+    ne, nt = f["e"].shape[0], f["t"].shape[0]
+    rng = np.random.RandomState(100 + groups)
+    counts = rng.randint(1, groups + 1, ne).astype(np.int32)
+    counts[:groups] = np.arange(1, groups + 1)
+    want = kp.score_grid(f["ref"].plda, f["e"], counts, f["t"])
+    e, t = f["e"].astype(dtype), f["t"].astype(dtype)
+    got = f["g"].score_grid(e, counts, t)
+    assert got.shape == (ne, nt)
+    tol = 1e-3
+    assert tol_err(got, want).max() <= tol
+    dev = torch.device("cuda", 0)
+    zm = rng.randn(ne)
+    zs = 0.5 + rng.rand(ne)
+    got_z = f["g"].score_grid(torch.from_numpy(e).to(dev), counts, torch.from_numpy(t).to(dev), znorm=(zm, zs))
+    assert tol_err(got_z.cpu().numpy(), (want - zm[:, None]) / zs[:, None]).max() <= tol
