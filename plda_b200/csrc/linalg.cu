@@ -153,34 +153,46 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
       st[r * 33 + c] = v;
       __syncthreads();
       if (bi == k) {
-        // (a) factor the diagonal tile: ONE warp, lane = row, no block barriers on the 32-step critical path
-        if (r == 0) {
-          const int row = c;
+        // (a) factor the diagonal tile: thread (r, c) keeps S[r][c] in a register; per step the pivot column is
+        //     published through a double-buffered shared-memory vector -> ONE block barrier per step, and every
+        //     thread derives rsqrt(pivot) itself (no fp64 sqrt / divide, no serial trailing update)
+        {
+          double v = st[r * 33 + c];
+          double* colbuf = sp;                                     // [2][32], the K-chunk staging is idle here
+          if (c == 0) colbuf[r] = v;
+          __syncthreads();
+          bool failed = false;
           for (int j = 0; j < CB; ++j) {
-            const double ajj = st[j * 33 + j];
-            if (!(ajj > 0.0)) {                                    // uniform across the warp
-              if (row == 0) *info = k * CB + j + 1;
+            const double* col = colbuf + (j & 1) * CB;
+            const double piv2 = col[j];
+            if (!(piv2 > 0.0)) {                                   // uniform across the block
+              if (threadIdx.x == 0) *info = k * CB + j + 1;
+              failed = true;
               break;
             }
-            const double rp = rsqrt(ajj), piv = ajj * rp;          // no fp64 sqrt / divide on the 32-step critical path
-            if (row == j) { st[j * 33 + j] = piv; s_rd[j] = rp; }
-            else if (row > j) st[row * 33 + j] *= rp;
-            __syncwarp();
-            const double lrj = st[row * 33 + j];
-            for (int cc = j + 1; cc <= row; ++cc) st[row * 33 + cc] = fma(-lrj, st[cc * 33 + j], st[row * 33 + cc]);
-            __syncwarp();
+            const double rp = rsqrt(piv2);
+            const double lr = col[r] * rp, lc = col[c] * rp;       // L[r][j], L[c][j] for r, c > j
+            if (c == j) {
+              if (r == j) { v = piv2 * rp; s_rd[j] = rp; }
+              else if (r > j) v = lr;
+            } else if (c > j && r >= c) {
+              v = fma(-lr, lc, v);
+            }
+            if (c == j + 1) colbuf[((j + 1) & 1) * CB + r] = v;
+            __syncthreads();
           }
+          st[r * 33 + c] = v;
+          if (failed && r == c) s_rd[r] = 1.0;                     // keep what follows finite; info reports the failure
         }
         __syncthreads();
-        // (b) its inverse: warp r solves L x = e_r (lane c holds x_c), reciprocal diagonal, no divisions
+        // (b) its inverse: warp r solves L x = e_r column-wise (lane c holds the running right-hand side b_c): one
+        //     broadcast + one FMA per step instead of a 5-level shuffle reduction
         {
-          double x = 0.0;
+          double b = c == r ? 1.0 : 0.0, x = 0.0;
           for (int j = 0; j < CB; ++j) {
-            double part = (c < j) ? st[j * 33 + c] * x : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            const double xj = ((j == r ? 1.0 : 0.0) - part) * s_rd[j];
+            const double xj = __shfl_sync(0xffffffffu, b, j) * s_rd[j];
             if (c == j) x = xj;
+            else if (c > j) b = fma(-st[c * 33 + j], xj, b);
           }
           sl[c * 33 + r] = x;                                      // entry (row c, column r) of L_kk^-1
         }
@@ -212,27 +224,44 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
     cluster_barrier_all();
   }
   // ---------------- inverse: CTA bi computes block column bi of X = L^-1 (X[bi,bi] is already there) ----------------
-  for (int i = bi + 1; i < nb; ++i) {
-    const int rows_u = min(CB, d - i * CB);
-    // T = sum_{bi <= k < i} L[i,k] X[k,bi]
-    double t = 0.0;
-    for (int k0 = bi; k0 < i; ++k0) {
-      const int rows_k = min(CB, d - k0 * CB);
-      sp[r * 33 + c] = (r < rows_u && c < rows_k) ? __ldcg(a + (static_cast<long long>(i) * CB + r) * ld + k0 * CB + c) : 0.0;
-      sq[r * 33 + c] = (r < rows_k && c < rows_i) ? __ldcg(inv + (static_cast<long long>(k0) * CB + r) * ld + bi * CB + c) : 0.0;
-      __syncthreads();
+  // The X tiles of the column stay in shared memory (xs[k] = X[k,bi]); the L tiles (final since the last barrier) and
+  // the diagonal inverses travel global -> registers one step ahead of their use.
+  {
+    double* xs = sl + CB * 33;                                     // [nb][32][33]
+    xs[(bi * CB + r) * 33 + c] = (r < rows_i && c < rows_i) ? __ldcg(inv + (static_cast<long long>(bi) * CB + r) * ld + bi * CB + c) : 0.0;
+    auto l_tile = [&](int i, int k0) -> double {                   // element (r, c) of L[i,k0]
+      return (i * CB + r < d && k0 * CB + c < d) ? __ldcg(a + (static_cast<long long>(i) * CB + r) * ld + k0 * CB + c) : 0.0;
+    };
+    auto x_diag = [&](int i) -> double {                           // element (r, c) of X[i,i]
+      return (i * CB + r < d && i * CB + c < d) ? __ldcg(inv + (static_cast<long long>(i) * CB + r) * ld + i * CB + c) : 0.0;
+    };
+    double l_next = bi + 1 < nb ? l_tile(bi + 1, bi) : 0.0;
+    for (int i = bi + 1; i < nb; ++i) {
+      const int rows_u = min(CB, d - i * CB);
+      const double xd = x_diag(i);
+      // T = sum_{bi <= k < i} L[i,k] X[k,bi]
+      double t = 0.0;
+      for (int k0 = bi; k0 < i; ++k0) {
+        sp[r * 33 + c] = l_next;
+        __syncthreads();
+        if (k0 + 1 < i) l_next = l_tile(i, k0 + 1);
+        else if (i + 1 < nb) l_next = l_tile(i + 1, bi);
+        const double* xk = xs + k0 * CB * 33;
 #pragma unroll 8
-      for (int kk = 0; kk < CB; ++kk) t = fma(sp[r * 33 + kk], sq[kk * 33 + c], t);
+        for (int kk = 0; kk < CB; ++kk) t = fma(sp[r * 33 + kk], xk[kk * 33 + c], t);
+        __syncthreads();
+      }
+      st[r * 33 + c] = t;
+      sq[r * 33 + c] = xd;
+      __syncthreads();
+      double x = 0.0;
+#pragma unroll 8
+      for (int kk = 0; kk < CB; ++kk) x = fma(sq[r * 33 + kk], st[kk * 33 + c], x);
+      x = (r < rows_u && c < rows_i) ? -x : 0.0;
+      xs[(i * CB + r) * 33 + c] = x;
+      if (r < rows_u && c < rows_i) __stcg(inv + (static_cast<long long>(i) * CB + r) * ld + bi * CB + c, x);
       __syncthreads();
     }
-    st[r * 33 + c] = t;
-    sl[r * 33 + c] = (r < rows_u && c < rows_u) ? __ldcg(inv + (static_cast<long long>(i) * CB + r) * ld + i * CB + c) : 0.0;   // X[i,i]
-    __syncthreads();
-    double x = 0.0;
-#pragma unroll 8
-    for (int kk = 0; kk < CB; ++kk) x = fma(sl[r * 33 + kk], st[kk * 33 + c], x);
-    if (r < rows_u && c < rows_i) __stcg(inv + (static_cast<long long>(i) * CB + r) * ld + bi * CB + c, -x);
-    __syncthreads();
   }
 }
 
@@ -324,7 +353,7 @@ __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __
 // visited exactly once per sweep -- a cyclic-by-blocks Jacobi sweep -- instead of re-rotating the intra-block pairs
 // in every round (2 bw - 1 steps per round).
 template <bool CLUSTER>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, double big2, int max_sweeps,
                          unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated,
                          int* __restrict__ sweeps_done) {
@@ -364,35 +393,49 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
       __syncthreads();
-      // ---- 1. Gram: a thread owns the strided 2x2 tile {ti, ti+half} x {tj, tj+half} over one of KS slices of the
-      //         column length (all 1024 threads busy); the slices are summed through shared memory
+      // ---- 1. Gram (symmetric: tiles on or above the diagonal only): a thread owns the strided 4x4 tile
+      //         {ti + q a} x {tj + q b} (q = m2 / 4) over one of up to 4 slices of the column length -- 8 shared-memory
+      //         loads per 16 FMAs, lanes of a warp read at most 8 distinct addresses per load (broadcast); the slices
+      //         are summed through shared memory
       {
-        const int tiles2 = half * half;
+        const int q4 = m2 >> 2;
+        const int tiles2 = q4 * (q4 + 1) / 2;
         const int ks_n = max(1, min(nthreads / tiles2, 4));
         const int slice = (d + ks_n - 1) / ks_n;
+        const int qs = q4 * dp;
         double* part = qm + m2 * gp;                 // [ks_n - 1][m2][gp] scratch behind qm
         for (int t = threadIdx.x; t < tiles2 * ks_n; t += nthreads) {
-          const int ks = t / tiles2, tt = t - ks * tiles2;
-          const int ti = tt / half, tj = tt - ti * half;
-          const double* a0 = cols + ti * dp;
-          const double* a1 = cols + (ti + half) * dp;
-          const double* b0 = cols + tj * dp;
-          const double* b1 = cols + (tj + half) * dp;
-          double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+          const int ks = t / tiles2;
+          int rem = t - ks * tiles2, ti = 0;
+          while (rem >= q4 - ti) { rem -= q4 - ti; ++ti; }
+          const int tj = ti + rem;
+          const double* ap = cols + ti * dp;
+          const double* bp = cols + tj * dp;
+          double acc[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
           const int i1 = min(d, (ks + 1) * slice);
-#pragma unroll 4
+#pragma unroll 2
           for (int i = ks * slice; i < i1; ++i) {
-            const double x0 = a0[i], x1 = a1[i], y0 = b0[i], y1 = b1[i];
-            c00 = fma(x0, y0, c00);
-            c01 = fma(x0, y1, c01);
-            c10 = fma(x1, y0, c10);
-            c11 = fma(x1, y1, c11);
+            double x[4], y[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { x[a] = ap[a * qs + i]; y[a] = bp[a * qs + i]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
           }
           double* dst = ks == 0 ? gl : part + (ks - 1) * m2 * gp;
-          dst[ti * gp + tj] = c00;
-          dst[ti * gp + tj + half] = c01;
-          dst[(ti + half) * gp + tj] = c10;
-          dst[(ti + half) * gp + tj + half] = c11;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int rr = ti + q4 * a, cc = tj + q4 * b;
+              dst[rr * gp + cc] = acc[a][b];
+              if (ti != tj) dst[cc * gp + rr] = acc[a][b];
+            }
         }
         __syncthreads();
         if (ks_n > 1) {
@@ -474,28 +517,41 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       // ---- 3. C <- C Q, written back to global: new column x' = sum_x Q[x][x'] * old column x
       if (s_rot) {
-        // a warp owns 4 output columns over one of `parts` interleaved slices of the column length (all warps busy)
+        // a warp owns 4 output columns x 128 rows (lane: rows i0 + 32 m): 4 column loads + 4 broadcast loads of Q per
+        // 16 FMAs
         const int groups = m2 >> 2;
-        const int parts = max(1, nwarps / groups);
-        for (int wi = warp; wi < groups * parts; wi += nwarps) {
+        const int rparts = (d + 127) >> 7;
+        for (int wi = warp; wi < groups * rparts; wi += nwarps) {
           const int xg = wi % groups, part = wi / groups;
           const double* qrow = qm + xg * 4;
-          for (int i = lane + 32 * part; i < d; i += 32 * parts) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 4
-            for (int x = 0; x < m2; ++x) {
-              const double v = cols[x * dp + i];
-              a0 = fma(v, qrow[x * gp + 0], a0);
-              a1 = fma(v, qrow[x * gp + 1], a1);
-              a2 = fma(v, qrow[x * gp + 2], a2);
-              a3 = fma(v, qrow[x * gp + 3], a3);
-            }
-            const double out[4] = {a0, a1, a2, a3};
+          const int i0 = part * 128 + lane;
+          double acc[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int slot = xg * 4 + j;
-              const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
-              if (col < d) __stcg(gt + static_cast<long long>(col) * d + i, out[j]);
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[m][j] = 0.0;
+#pragma unroll 2
+          for (int x = 0; x < m2; ++x) {
+            // rows past d read the next column / the Gram area: finite or not, those accumulators are never stored
+            double v[4], qv[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) v[m] = cols[x * dp + i0 + 32 * m];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qv[j] = qrow[x * gp + j];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[m][j] = fma(v[m], qv[j], acc[m][j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int slot = xg * 4 + j;
+            const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+            if (col >= d) continue;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int i = i0 + 32 * m;
+              if (i < d) __stcg(gt + static_cast<long long>(col) * d + i, acc[m][j]);
             }
           }
         }
@@ -562,10 +618,11 @@ bool cholesky_inverse_fused(Context& ctx, double* a, double* inv, int64_t d, int
   if (mode != nullptr && strcmp(mode, "legacy") == 0) return false;
   const int nb = static_cast<int>(ceil_div(d, 32));
   if (d < 1 || nb > 16) return false;
-  const size_t smem = (2 * 32 * 65 + 2 * 32 * 33) * sizeof(double);
+  const size_t smem = (2 * 32 * 65 + 2 * 32 * 33 + static_cast<size_t>(nb) * 32 * 33) * sizeof(double);
   static std::once_flag once;
   std::call_once(once, [&] {
-    cudaFuncSetAttribute(chol_inverse_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(chol_inverse_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>((2 * 32 * 65 + 2 * 32 * 33 + 16 * 32 * 33) * sizeof(double)));
     cudaFuncSetAttribute(chol_inverse_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   });
   cudaLaunchConfig_t cfg = {};
@@ -652,7 +709,7 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   cudaLaunchAttribute attr[1];
   if (use_cluster) {
     cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(1024);
+    cfg.blockDim = dim3(512);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx.stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -674,7 +731,7 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   } else {
     void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &big2, &ms, &counter, &rotated, &sweeps_done};
     PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(block_jacobi_gram_kernel<false>), dim3(blocks),
-                                        dim3(1024), args, smem, ctx.stream));
+                                        dim3(512), args, smem, ctx.stream));
   }
   ctx.count_launch();
   eig_normalise_kernel<<<static_cast<unsigned>(ceil_div(d, 8)), 256, 0, ctx.stream>>>(w.g.get(), di, w.lam.get(),

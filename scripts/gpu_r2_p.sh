@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2: Cholesky/inverse cluster kernel (parallel diagonal factor, smem-resident inverse columns), Jacobi 4x4 tiles
+mkdir -p gpurun_out
+export PLDA_B200_CUBLAS=0
+echo "== gpu tests"; timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 2>&1 | tail -n 8
+echo "== EM phases C2"; PLDA_B200_EM_PROFILE=1 timeout 300 python scripts/r2_stats_probe.py 100000 200 1000 10 f32 2>&1 | grep -E "em phase|stats_ms" | tail -n 9
+echo "== EM phases C3"; PLDA_B200_EM_PROFILE=1 timeout 300 python scripts/r2_stats_probe.py 1000000 256 10000 5 f32 2>&1 | grep -E "em phase|stats_ms" | tail -n 9
+echo "== EM phases C4"; PLDA_B200_EM_PROFILE=1 timeout 300 python scripts/r2_stats_probe.py 5000000 512 50000 5 f32 2>&1 | grep -E "em phase|stats_ms" | tail -n 9
+echo "== C2 fp64 rows"; timeout 300 python scripts/r2_stats_probe.py 100000 200 1000 10 f64 2>&1 | grep stats_ms

@@ -112,6 +112,8 @@ if __name__ == "__main__":
                             "ncu --metrics gpu__time_duration.sum --clock-control none --csv python scripts/fit_once.py 200 1000 100 10"),
                            (tag + "_stats_launches.csv", "ncu launch list of PLDA.fit (2M x 512 fp32, 20k speakers, 1 EM iter, run twice)",
                             "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python scripts/r2_stats_probe.py 2000000 512 20000 1 f32"),
+                           (tag + "_ragged_launches.csv", "ncu launch list of score_grid with ragged enrol counts (10k x 10k, d = 160, counts 1..5), then uniform counts",
+                            "ncu --metrics gpu__time_duration.sum --clock-control none --csv python scripts/r2_sink_probe.py ragged"),
                            (tag + "_bench_launches.csv", "ncu launch list of the bench (scoring steps)",
                             "ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 3 --warmup 3 --no-cpu --skip-em --headline-only")):
         path = os.path.join(GO, fn)
