@@ -72,16 +72,21 @@ void PldaEngine::em_mark(const char* what) {
 void PldaEngine::em_report() {
   if (em_marks.empty()) return;
   ctx.sync();
-  std::vector<std::pair<const char*, std::pair<double, int>>> acc;
+  std::vector<std::pair<const char*, std::vector<double>>> acc;
   for (size_t i = 1; i < em_marks.size(); ++i) {
     const double ms = ms_between(em_marks[i - 1].second, em_marks[i].second);
     auto it = std::find_if(acc.begin(), acc.end(), [&](const auto& a) { return strcmp(a.first, em_marks[i].first) == 0; });
-    if (it == acc.end()) acc.push_back({em_marks[i].first, {ms, 1}});
-    else { it->second.first += ms; it->second.second += 1; }
+    if (it == acc.end()) acc.push_back({em_marks[i].first, {ms}});
+    else it->second.push_back(ms);
   }
-  for (const auto& a : acc)
-    fprintf(stderr, "plda_b200 em phase: %-28s %8.4f ms avg over %d\n", a.first, a.second.first / a.second.second,
-            a.second.second);
+  for (auto& a : acc) {
+    std::vector<double>& v = a.second;
+    double sum = 0.0;
+    for (double x : v) sum += x;
+    std::sort(v.begin(), v.end());
+    fprintf(stderr, "plda_b200 em phase: %-28s avg %8.4f  median %8.4f  min %8.4f ms over %d\n", a.first,
+            sum / v.size(), v[v.size() / 2], v[0], static_cast<int>(v.size()));
+  }
   for (auto& m : em_marks) cudaEventDestroy(m.second);
   em_marks.clear();
 }

@@ -94,13 +94,63 @@ __device__ __forceinline__ void cluster_barrier_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// 32 x 32 x K tile products of the cluster kernel run on 512 of the 1024 threads as 4 x 2 register tiles over four
+// K slices (6 shared-memory loads per 8 FMAs; a thread-per-output loop needs 2 loads per FMA and is bound by the
+// shared-memory port): thread t < 512 -> slice t >> 7, rows {ti + 8 a}, columns {tj + 16 b}.
+struct Tile42 {
+  double acc[4][2];
+  int ks, ti, tj;
+  bool active;
+  __device__ __forceinline__ void init() {
+    active = threadIdx.x < 512;
+    ks = threadIdx.x >> 7;
+    const int tt = threadIdx.x & 127;
+    ti = tt >> 4;
+    tj = tt & 15;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { acc[a][0] = 0.0; acc[a][1] = 0.0; }
+  }
+  // acc += A[row][kk] * B(kk, col) for kk in this thread's quarter of [0, klen): A row-major with pitch lda, B element
+  // (kk, col) at b[kk * sbk + col * sbc]
+  __device__ __forceinline__ void fma_slice(const double* a, int lda, const double* b, int sbk, int sbc, int klen) {
+    if (!active) return;
+    const int q = klen >> 2;
+    const double* ap = a + ti * lda;
+    const double* bp = b + tj * sbc;
+#pragma unroll 4
+    for (int kk = ks * q; kk < (ks + 1) * q; ++kk) {
+      const double y0 = bp[kk * sbk], y1 = bp[kk * sbk + 16 * sbc];
+#pragma unroll
+      for (int a4 = 0; a4 < 4; ++a4) {
+        const double x = ap[a4 * 8 * lda + kk];
+        acc[a4][0] = fma(x, y0, acc[a4][0]);
+        acc[a4][1] = fma(x, y1, acc[a4][1]);
+      }
+    }
+  }
+  // sum of the four slices for output (r, c) of thread (r = threadIdx.x >> 5, c = lane); red: [4][32][32] scratch that
+  // no thread is still reading; ends with a block barrier (red reusable)
+  __device__ __forceinline__ double reduce(double* red) {
+    if (active) {
+#pragma unroll
+      for (int a4 = 0; a4 < 4; ++a4) {
+        red[(ks * 32 + ti + 8 * a4) * 32 + tj] = acc[a4][0];
+        red[(ks * 32 + ti + 8 * a4) * 32 + tj + 16] = acc[a4][1];
+      }
+    }
+    __syncthreads();
+    const int o = (threadIdx.x >> 5) * 32 + (threadIdx.x & 31);
+    const double v = (red[o] + red[1024 + o]) + (red[2048 + o] + red[3072 + o]);
+    __syncthreads();
+    return v;
+  }
+};
+
 // acc(r, c) = sum_kk P[r][kk] * Q[c][kk] over K columns of two row-major 32-row panels in global memory (L2), staged
 // through shared memory in chunks of CKC columns; the next chunk travels global -> registers while the current one
 // is consumed.  Thread (r = threadIdx.x >> 5, c = lane); 1024 threads.
 __device__ __forceinline__ double tile_dot(const double* __restrict__ p, const double* __restrict__ q, long long ld,
                                            int rows_p, int rows_q, int k, double* sp, double* sq) {
-  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
-  double acc = 0.0;
   // element (rr, kk) of a chunk: thread t loads (t >> 6, t & 63) and (t >> 6) + 16
   const int lr = threadIdx.x >> 6, lk = threadIdx.x & 63;
   double pa[2], qa[2];
@@ -113,7 +163,10 @@ __device__ __forceinline__ double tile_dot(const double* __restrict__ p, const d
       qa[h] = (rr < rows_q && kin) ? __ldcg(q + rr * ld + k0 + lk) : 0.0;
     }
   };
-  if (k > 0) fetch(0);
+  if (k <= 0) return 0.0;
+  Tile42 tl;
+  tl.init();
+  fetch(0);
   for (int k0 = 0; k0 < k; k0 += CKC) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -122,11 +175,10 @@ __device__ __forceinline__ double tile_dot(const double* __restrict__ p, const d
     }
     __syncthreads();
     if (k0 + CKC < k) fetch(k0 + CKC);
-#pragma unroll 8
-    for (int kk = 0; kk < CKC; ++kk) acc = fma(sp[r * CP + kk], sq[c * CP + kk], acc);
+    tl.fma_slice(sp, CP, sq, 1, CP, CKC);
     __syncthreads();
   }
-  return acc;
+  return tl.reduce(sp);            // sp and sq are contiguous: [4][32][32] fits in their 2 x 32 x 65 doubles
 }
 
 __global__ void __launch_bounds__(1024, 1)
@@ -209,9 +261,10 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
       // L[i,k] = S_i L_kk^-T : a 32 x 32 x 32 product against the inverse CTA k just published
       sl[r * 33 + c] = (r < rows_k && c < rows_k) ? __ldcg(inv + (static_cast<long long>(k) * CB + r) * ld + k * CB + c) : 0.0;
       __syncthreads();
-      double x = 0.0;
-#pragma unroll 8
-      for (int q = 0; q < CB; ++q) x = fma(st[r * 33 + q], sl[c * 33 + q], x);
+      Tile42 tl;
+      tl.init();
+      tl.fma_slice(st, 33, sl, 1, 33, CB);
+      const double x = tl.reduce(sp);
       if (r < rows_i && c < rows_k) __stcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c, x);
     } else if (bi < k) {
       // blocks above the diagonal of column k: zero (clean triangular factor and inverse for the caller)
@@ -239,24 +292,24 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
     for (int i = bi + 1; i < nb; ++i) {
       const int rows_u = min(CB, d - i * CB);
       const double xd = x_diag(i);
-      // T = sum_{bi <= k < i} L[i,k] X[k,bi]
-      double t = 0.0;
+      // T = sum_{bi <= k < i} L[i,k] X[k,bi]   (accumulated in the register tiles across the k loop)
+      Tile42 tl;
+      tl.init();
       for (int k0 = bi; k0 < i; ++k0) {
-        sp[r * 33 + c] = l_next;
+        sq[r * 33 + c] = l_next;
         __syncthreads();
         if (k0 + 1 < i) l_next = l_tile(i, k0 + 1);
         else if (i + 1 < nb) l_next = l_tile(i + 1, bi);
-        const double* xk = xs + k0 * CB * 33;
-#pragma unroll 8
-        for (int kk = 0; kk < CB; ++kk) t = fma(sp[r * 33 + kk], xk[kk * 33 + c], t);
+        tl.fma_slice(sq, 33, xs + k0 * CB * 33, 33, 1, CB);
         __syncthreads();
       }
-      st[r * 33 + c] = t;
-      sq[r * 33 + c] = xd;
+      st[r * 33 + c] = tl.reduce(sp);
+      sl[r * 33 + c] = xd;                 // (operands outside the reduction scratch, which spans sp and sq)
       __syncthreads();
-      double x = 0.0;
-#pragma unroll 8
-      for (int kk = 0; kk < CB; ++kk) x = fma(sq[r * 33 + kk], st[kk * 33 + c], x);
+      Tile42 tx;
+      tx.init();
+      tx.fma_slice(sl, 33, st, 33, 1, CB);
+      double x = tx.reduce(sp);
       x = (r < rows_u && c < rows_i) ? -x : 0.0;
       xs[(i * CB + r) * 33 + c] = x;
       if (r < rows_u && c < rows_i) __stcg(inv + (static_cast<long long>(i) * CB + r) * ld + bi * CB + c, x);
@@ -482,8 +535,11 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
           if (gamma * gamma > tol * tol * alpha * beta && fabs(gamma) > abs_tol) {
             // rotation angle in fp32 (a 1e-7 relative error in the angle only leaves a 1e-7 * gamma residual),
             // but (c, s) exactly orthonormal in fp64: c = rsqrt(1 + t^2) by two Newton steps, s = c t
-            const float zf = static_cast<float>(beta - alpha) / (2.0f * static_cast<float>(gamma));
-            const float tf = copysignf(1.0f, zf) / (fabsf(zf) + sqrtf(1.0f + zf * zf));
+            // (approximate divide / square root: they sit on the critical path of every tournament step)
+            const float zf = __fdividef(static_cast<float>(beta - alpha), 2.0f * static_cast<float>(gamma));
+            float rt;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(fmaf(zf, zf, 1.0f)));
+            const float tf = copysignf(__fdividef(1.0f, fabsf(zf) + rt), zf);
             const double t = static_cast<double>(tf);
             const double xx = fma(t, t, 1.0);
             double c0 = static_cast<double>(rsqrtf(static_cast<float>(xx)));
