@@ -145,7 +145,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tt_b_hi, const __grid_constant__ CUtensorMap tt_b_lo,
                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   constexpr bool RAG = EPI == 6;    // score-grid path with per-row column-term groups (ragged enrol counts)
-  constexpr bool FAST = EPI == 1 || RAG;
+  constexpr bool HYB = EPI == 7;    // score-grid path, every other chunk stored straight from registers (sector stores)
+  constexpr bool FAST = EPI == 1 || RAG || HYB;
   constexpr bool LSE = EPI == 2;
   constexpr bool SECT = EPI == 3;   // score-grid path, accumulators stored straight from registers (no smem staging)
   constexpr bool MOM = EPI == 4;    // z-norm sink: per-row shifted moments of the scores, nothing stored
@@ -645,6 +646,79 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
         continue;
       }
+      if constexpr (HYB) {
+        // Hybrid store path: the warp's 1st and 3rd chunk go through the swizzled staging box and a TMA store, the
+        // 2nd and 4th are read in the 16x256b shape (four threads hold 8 consecutive columns of a row) and stored
+        // straight from registers as full 32-byte sectors.  The shared-memory port -- the measured bound of this
+        // kernel at d = 200 -- carries half of the epilogue traffic; the LSU / L2 request path, idle in the TMA
+        // variant, carries the other half.
+        uint32_t ra[2][32];
+        uint32_t rs[2][2][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc >= nchunks) continue;
+          if ((i & 1) == 0) {
+            tmem_ld_32x32b_x32(tbase + cc * 32, ra[i >> 1]);
+          } else {
+            tmem_ld_16x256b_x4(tbase + cc * 32, rs[i >> 1][0]);
+            tmem_ld_16x256b_x4(tbase + (16u << 16) + cc * 32, rs[i >> 1][1]);
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));
+          else mbar_arrive(&tempty[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // the four rows of this thread in the sector shape: lane/4 + {0, 8, 16, 24} inside the warp's 32-row quarter
+        float radd4[4], zi4[4];
+        float* orow[4];
+        bool rok[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int mr = m0 + q * 32 + s4 * 8 + (lane >> 2);
+          rok[s4] = mr < p.m;
+          float ra4 = 0.f, zm4 = 0.f;
+          zi4[s4] = 1.f;
+          if (rok[s4]) {
+            if (e.row_add) ra4 = __ldg(e.row_add + mr);
+            if (e.zmean) { zm4 = __ldg(e.zmean + mr); zi4[s4] = __ldg(e.zinv + mr); }
+          }
+          radd4[s4] = ra4 - zm4;
+          orow[s4] = e.out + (static_cast<long long>(w.ks) * p.mpad + mr) * e.ldo + n0 + 2 * (lane & 3);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = h + 2 * i;
+          if (cc >= nchunks) continue;
+          if ((i & 1) == 0) {
+            process(ra[i >> 1], cc, nullptr, -1);
+          } else {
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+              const int cl = cc * 32 + rep * 8 + 2 * (lane & 3);     // column inside the tile
+              float2 ct = make_float2(0.f, 0.f);
+              if (col_cached) ct = *reinterpret_cast<const float2*>(colslot + cl);
+#pragma unroll
+              for (int s4 = 0; s4 < 4; ++s4) {
+                const int h2 = s4 >> 1, half = s4 & 1;
+                float2 v;
+                v.x = (__uint_as_float(rs[i >> 1][h2][rep * 4 + half * 2 + 0]) + ct.x + radd4[s4]) * zi4[s4];
+                v.y = (__uint_as_float(rs[i >> 1][h2][rep * 4 + half * 2 + 1]) + ct.y + radd4[s4]) * zi4[s4];
+                if (rok[s4]) {
+                  const int col = n0 + cl;
+                  if (col + 1 < p.n) *reinterpret_cast<float2*>(orow[s4] + cc * 32 + rep * 8) = v;
+                  else if (col < p.n) orow[s4][cc * 32 + rep * 8] = v.x;
+                }
+              }
+            }
+          }
+        }
+        continue;
+      }
       // all of this warp's chunks are fetched with the TMEM loads in flight together (one ~1k-cycle latency per
       // tile instead of one per chunk), then the accumulator stage is handed back BEFORE the post-processing
       // and the stores, so the MMA warp never waits for the store path
@@ -940,6 +1014,7 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
       ep.col_add != nullptr && !ragged_generic)
     epi = 6;
   if (epi == 1 && ctx.epi_sector) epi = 3;
+  else if (epi == 1 && ctx.epi_hybrid) epi = 7;
   else if (out == nullptr && ep.lse_max != nullptr && ep.rsum == nullptr && ep.grp == nullptr) epi = 2;
   else if (out == nullptr && ep.mom != nullptr) epi = 4;
   else if (out == nullptr && ep.hist_n != nullptr) epi = 5;
@@ -963,6 +1038,7 @@ void launch(Context& ctx, const SplitOperand& a, const SplitOperand& b, Plan& pl
     case 4: launch_epi<4>(ctx, pl, tm, pdl); break;
     case 5: launch_epi<5>(ctx, pl, tm, pdl); break;
     case 6: launch_epi<6>(ctx, pl, tm, pdl); break;
+    case 7: launch_epi<7>(ctx, pl, tm, pdl); break;
     default: launch_epi<0>(ctx, pl, tm, pdl); break;
   }
   PB_CUDA(cudaGetLastError());

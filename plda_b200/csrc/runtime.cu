@@ -27,6 +27,7 @@ Context::Context(int dev) : device(dev) {
   epi_mode = epi == nullptr ? 0
              : (strcmp(epi, "direct") == 0 ? 1 : (strcmp(epi, "skip") == 0 ? 2 : (strcmp(epi, "lsu") == 0 ? 3 : 0)));
   epi_sector = epi != nullptr && strcmp(epi, "sector") == 0;
+  epi_hybrid = epi != nullptr && strcmp(epi, "hybrid") == 0;
   const char* kt = getenv("PLDA_B200_KTAIL");
   k_tail_boxes = !(kt != nullptr && strcmp(kt, "0") == 0);
   const char* dbg = getenv("PLDA_B200_DBG");

@@ -58,6 +58,7 @@ struct Context {
   bool owns_stream = true;
   std::atomic<long long> launches{0};   // number of OUR kernels launched (bench "gpu_launches")
   int epi_mode = 0;                  // debug (env PLDA_B200_EPI): 0 default (TMA store), 1 "direct" register stores, 2 "skip", 3 "lsu"
+  bool epi_hybrid = false;           // env PLDA_B200_EPI=hybrid: every other chunk of the score-grid epilogue as register sector stores
   bool epi_sector = false;           // env PLDA_B200_EPI=sector: register-direct sector stores in the score-grid epilogue
   int dbg_skip_a = 0;                // debug (env PLDA_B200_DBGSKIPA=1): timing experiment, the TMA producer loads the A
                                      // tiles only for the first item of a CTA (WRONG results) -> upper bound of an
