@@ -207,6 +207,17 @@ int plda_shard_score(plda_handle_t h, const void* enrol, int64_t ne, int64_t ld_
 int plda_shard_step(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol,
                     int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* enrol_ids, int dtype, float* out,
                     int64_t ldo);
+/* Ragged enrol counts on the sharded grid (scoring/scorePLDA.py enrols speakers with differing numbers of utterances;
+ * the reference scores them pair by pair, src/pldamodule.cpp:258-277).  open_ragged = open with room in the operand
+ * rows for `max_groups` (<= 8) distinct enrol counts; step_ragged = plda_shard_step with a count per enrol row
+ * (host int32[ne]) and `group_counts`: the distinct counts over ALL ranks, strictly ascending, the SAME list on
+ * every rank (n_groups <= max_groups).  The column terms of every group travel inside the pushed operand rows, so
+ * the grid runs the same kernel as for one uniform count.  Uniform steps remain valid on such a session.           */
+int plda_shard_open_ragged(plda_handle_t h, int world, int rank, const int64_t* bounds, int64_t dim, int max_groups,
+                           unsigned char* ipc_handle_out, void** region_out);
+int plda_shard_step_ragged(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol,
+                           int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts, const int32_t* group_counts,
+                           int n_groups, const uint64_t* enrol_ids, int dtype, float* out, int64_t ldo);
 int plda_shard_status(plda_handle_t h, int64_t* epoch, int64_t* timeouts);
 int plda_shard_close(plda_handle_t h);
 

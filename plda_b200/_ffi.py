@@ -67,6 +67,8 @@ SIGNATURES = {
     "plda_shard_push": [_vp, _vp, _i64, _i64, _int, _int],
     "plda_shard_score": [_vp, _vp, _i64, _i64, _int, _vp, _int, _vp, _i64],
     "plda_shard_step": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _i64],
+    "plda_shard_open_ragged": [_vp, _int, _int, _vp, _i64, _int, _vp, C.POINTER(_vp)],
+    "plda_shard_step_ragged": [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _int, _vp, _int, _vp, _i64],
     "plda_shard_status": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "plda_shard_close": [_vp],
     "plda_dvector_pool": [_vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _i64, _int, _int, _vp, _i64, _int],

@@ -274,6 +274,20 @@ int plda_shard_open(plda_handle_t h, int world, int rank, const int64_t* bounds,
                     unsigned char* ipc_handle_out, void** region_out) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.shard_open(world, rank, bounds, dim, ipc_handle_out, region_out); });
 }
+int plda_shard_open_ragged(plda_handle_t h, int world, int rank, const int64_t* bounds, int64_t dim, int max_groups,
+                           unsigned char* ipc_handle_out, void** region_out) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.shard_open(world, rank, bounds, dim, ipc_handle_out, region_out, max_groups);
+  });
+}
+int plda_shard_step_ragged(plda_handle_t h, const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol,
+                           int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts, const int32_t* group_counts,
+                           int n_groups, const uint64_t* enrol_ids, int dtype, float* out, int64_t ldo) {
+  return with_handle(h, [&](pb::PldaEngine& e) {
+    e.shard_step_ragged(test_shard, nt_local, ld_test, enrol, ne, ld_enrol, enrol_counts, group_counts, n_groups,
+                        enrol_ids, dtype, out, ldo);
+  });
+}
 int plda_shard_connect(plda_handle_t h, int peer_rank, const unsigned char* ipc_handle, void* same_process_region) {
   return with_handle(h, [&](pb::PldaEngine& e) { e.shard_connect(peer_rank, ipc_handle, same_process_region); });
 }

@@ -47,6 +47,7 @@ struct ShardSession {
   std::vector<bool> peer_ipc;           // mapped with cudaIpcOpenMemHandle (to be closed)
   unsigned epoch = 0;                   // number of pushes so far (same on every rank)
   int push_count = 0;                   // enrol count the column terms of the current generation were built for
+  int max_groups = 0;                   // distinct enrol counts a ragged step may carry (room in the operand pitch)
 };
 
 // rows of the background set used by norm(numutts, seed): defined splitmix64 Fisher-Yates (engine_score.cu)
@@ -106,7 +107,7 @@ class PldaEngine {
   // sharded score grid (engine_shard.cu)
   ShardSession shard;
   void shard_open(int world, int rank, const int64_t* bounds, int64_t dim, unsigned char* ipc_handle_out,
-                  void** region_out);
+                  void** region_out, int max_groups = 0);
   void shard_connect(int peer_rank, const unsigned char* ipc_handle, void* same_process_region);
   void shard_push(const void* test_shard, int64_t nt_local, int64_t ld, int dtype, int enrol_count);
   void shard_score(const void* enrol, int64_t ne, int64_t ld_enrol, int enrol_count, const uint64_t* ids, int dtype,
@@ -114,6 +115,11 @@ class PldaEngine {
   // push + score with the enrol-side producer fused into the push kernel (one launch less per step)
   void shard_step(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
                   int64_t ld_enrol, int enrol_count, const uint64_t* ids, int dtype, float* out, int64_t ldo);
+  // ragged enrol counts on the sharded grid: group_counts = the distinct counts of ALL ranks (ascending, the same list
+  // on every rank, at most the session's max_groups); their column terms travel inside the pushed operand rows
+  void shard_step_ragged(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol, int64_t ne,
+                         int64_t ld_enrol, const int32_t* enrol_counts, const int32_t* group_counts, int n_groups,
+                         const uint64_t* ids, int dtype, float* out, int64_t ldo);
   void shard_status(int64_t* epoch, int64_t* timeouts);
   void shard_close();
   ~PldaEngine();
@@ -123,6 +129,7 @@ class PldaEngine {
                      int64_t ld_enrol, int enrol_count, int dtype);
   void shard_gemm(int64_t ne, const uint64_t* ids, float* out, int64_t ldo);
   GemmShard shard_desc() const;
+  void shard_targets(PrepDst& dst, PrepSignal& sig);
 
  public:
   void test_gemm(const double* a, const double* b, int64_t m, int64_t n, int64_t k, int ksplit, float* out);

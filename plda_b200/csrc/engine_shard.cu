@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "engine.h"
 
 namespace pb {
@@ -36,7 +38,7 @@ PldaEngine::~PldaEngine() {
 }
 
 void PldaEngine::shard_open(int world, int rank, const int64_t* bounds, int64_t dim, unsigned char* ipc_handle_out,
-                            void** region_out) {
+                            void** region_out, int max_groups) {
   require_model();
   PB_CHECK(!shard.open, kInvalidArg, "shard_open: a session is already open on this handle");
   PB_CHECK(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, kInvalidArg, "shard_open: bad world/rank");
@@ -51,7 +53,10 @@ void PldaEngine::shard_open(int world, int rank, const int64_t* bounds, int64_t 
   s.bounds.assign(bounds, bounds + world + 1);
   s.nt_total = bounds[world];
   s.dim = dim;
-  s.ldk = round_up(dim, 16);
+  PB_CHECK(max_groups >= 0 && max_groups <= 8, kInvalidArg, "shard_open: at most 8 distinct enrol counts per session");
+  s.max_groups = max_groups;
+  // ragged steps carry two extra K columns per distinct enrol count inside the operand rows (prep.cu)
+  s.ldk = round_up(dim + 2 * max_groups, 16);
   s.col_ld = round_up(s.nt_total, 32);
   const size_t plane = align_up(static_cast<size_t>(s.nt_total) * s.ldk * sizeof(__nv_bfloat16), 1024);
   const size_t colb = align_up(static_cast<size_t>(s.col_ld) * sizeof(float), 1024);
@@ -118,10 +123,20 @@ void PldaEngine::shard_produce(const void* test_shard, int64_t nt_local, int64_t
   shard.epoch += 1;
   shard.push_count = enrol_count;
   const size_t gen = shard.off_gen[shard.epoch & 1u];
+  (void)gen;
   PrepDst dst;
   PrepSignal sig;
+  shard_targets(dst, sig);
+  if (ne > 0) ws_row.reserve(ne);
+  score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, ne > 0 ? &ws_l : nullptr, ne > 0 ? ws_row.get() : nullptr,
+                           test_shard, nt_local, ld_test, row0, row0 + nt_local, dst, shard.ldk, dtype == 1, shard.dim,
+                           consts, sig);
+}
+
+// Destinations of the current generation in every region (0 = this rank's own) and the ready flags of this source rank.
+void PldaEngine::shard_targets(PrepDst& dst, PrepSignal& sig) {
+  const size_t gen = shard.off_gen[shard.epoch & 1u];
   dst.n = sig.n = shard.world;
-  // destination 0 is this rank's own region (the kernel keeps it in registers)
   for (int i = 0; i < shard.world; ++i) {
     const int r = (shard.rank + i) % shard.world;
     uint8_t* base = shard.peer[r];
@@ -134,10 +149,80 @@ void PldaEngine::shard_produce(const void* test_shard, int64_t nt_local, int64_t
   sig.epoch = shard.epoch;
   static const char* fence_mode = getenv("PLDA_B200_FENCE");
   sig.fence_per_thread = (fence_mode != nullptr && strcmp(fence_mode, "thread") == 0) ? 1 : 0;
-  if (ne > 0) ws_row.reserve(ne);
-  score_prep_uniform_multi(ctx, enrol, ne, ld_enrol, ne > 0 ? &ws_l : nullptr, ne > 0 ? ws_row.get() : nullptr,
-                           test_shard, nt_local, ld_test, row0, row0 + nt_local, dst, shard.ldk, dtype == 1, shard.dim,
-                           consts, sig);
+}
+
+// One sharded step with RAGGED enrol counts: the producer writes this rank's test rows, with the column terms of
+// every group of `group_counts` in their extra K columns, into every region; the enrol rows get the one-hot pair of
+// their group; the GEMM is the uniform-count kernel over K = dim + 2 * n_groups.
+void PldaEngine::shard_step_ragged(const void* test_shard, int64_t nt_local, int64_t ld_test, const void* enrol,
+                                   int64_t ne, int64_t ld_enrol, const int32_t* enrol_counts,
+                                   const int32_t* group_counts, int n_groups, const uint64_t* ids, int dtype,
+                                   float* out, int64_t ldo) {
+  require_model();
+  PB_CHECK(shard.open, kInvalidArg, "shard: no open session");
+  for (int r = 0; r < shard.world; ++r) PB_CHECK(shard.peer[r] != nullptr, kInvalidArg, "shard: a peer is not connected");
+  PB_CHECK(dtype == 0 || dtype == 1, kInvalidArg, "dtype must be PLDA_F64 or PLDA_F32");
+  const int64_t row0 = shard.bounds[shard.rank];
+  PB_CHECK(nt_local == shard.bounds[shard.rank + 1] - row0, kInvalidArg, "shard: shard size does not match the bounds");
+  PB_CHECK(nt_local == 0 || (test_shard != nullptr && ld_test >= shard.dim), kInvalidArg, "shard: bad test rows");
+  PB_CHECK(ne >= 0 && (ne == 0 || (enrol != nullptr && enrol_counts != nullptr && out != nullptr && ld_enrol >= shard.dim)),
+           kInvalidArg, "shard: bad enrol rows");
+  PB_CHECK(ne == 0 || ldo >= shard.nt_total, kInvalidArg, "shard_step: output pitch too small");
+  PB_CHECK(group_counts != nullptr && n_groups >= 1 && n_groups <= shard.max_groups, kInvalidArg,
+           "shard: the session was opened for fewer distinct enrol counts (plda_shard_open_ragged max_groups)");
+  for (int i = 0; i < n_groups; ++i)
+    PB_CHECK(group_counts[i] > 0 && (i == 0 || group_counts[i] > group_counts[i - 1]), kInvalidArg,
+             "shard: group counts must be positive and strictly ascending");
+  // group of every local enrol row
+  std::vector<int32_t> grp(static_cast<size_t>(ne));
+  for (int64_t i = 0; i < ne; ++i) {
+    const int32_t* it = std::lower_bound(group_counts, group_counts + n_groups, enrol_counts[i]);
+    PB_CHECK(it != group_counts + n_groups && *it == enrol_counts[i], kInvalidArg,
+             "shard: an enrol count is missing from the group list");
+    grp[i] = static_cast<int32_t>(it - group_counts);
+  }
+  // the ragged caches of score_grid describe other rows / tables from here on
+  ragged_key.clear();
+  last_counts.clear();
+  rg_grp.reserve(std::max<int64_t>(ne, 1));
+  if (ne > 0)
+    PB_CUDA(cudaMemcpyAsync(rg_grp.get(), grp.data(), ne * sizeof(int32_t), cudaMemcpyHostToDevice, ctx.stream));
+  std::vector<double> tabs(static_cast<size_t>(n_groups) * kScoreConstsSize, 0.0);
+  for (int i = 0; i < n_groups; ++i)
+    fill_score_consts(model.h_psi.data(), shard.dim, group_counts[i], tabs.data() + static_cast<size_t>(i) * kScoreConstsSize);
+  ws_tables.reserve(tabs.size());
+  PB_CUDA(cudaMemcpyAsync(ws_tables.get(), tabs.data(), tabs.size() * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+  shard.epoch += 1;
+  shard.push_count = -n_groups;
+  PrepDst dst;
+  PrepSignal sig;
+  shard_targets(dst, sig);
+  ws_row.reserve(std::max<int64_t>(ne, 1));
+  score_prep_grouped_vec(ctx, enrol, ne, ld_enrol, rg_grp.get(), test_shard, nt_local, ld_test, dtype == 1, shard.dim,
+                         n_groups, ws_tables.get(), ws_l, ws_r, ws_row.get(), nullptr, 0, /*embed=*/true, &dst, row0,
+                         shard.ldk, &sig);
+  if (ne == 0) {
+    shard_wait_all(ctx, shard_desc());     // an empty enrol block must not run ahead of its peers
+    return;
+  }
+  const float* zmean = nullptr;
+  const float* zinv = nullptr;
+  znorm_affine(ids, ne, nullptr, nullptr, 0, &zmean, &zinv);
+  const size_t gen = shard.off_gen[shard.epoch & 1u];
+  SplitOperand b;
+  b.hi = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen);
+  b.lo = reinterpret_cast<const __nv_bfloat16*>(shard.region + gen + shard.off_lo);
+  b.rows = shard.nt_total;
+  b.k = shard.dim + 2 * n_groups;
+  b.ld = shard.ldk;
+  GemmEpilogue epi;
+  epi.out = out;
+  epi.ldo = ldo;
+  epi.row_add = ws_row.get();
+  epi.zmean = zmean;
+  epi.zinv = zinv;
+  const GemmShard gs = shard_desc();
+  gemm_bf16x3(ctx, ws_l.view(), b, ne, shard.nt_total, shard.dim + 2 * n_groups, epi, &gs);
 }
 
 // The grid of this rank's enrol block (operand already in ws_l / ws_row) against the current generation.

@@ -95,10 +95,13 @@ void gather_trials(Context& ctx, const float* slab, int64_t ld, int64_t r0, int6
 // Vectorised operand producer for ragged enrol counts (16-byte loads / stores, per-row constants table).
 // embed: the operands get 2 * ng extra K columns that carry the column terms through the product itself (enrol
 // rows: one-hot pair of their group; test rows: the group's term in four bf16 pieces) -> K = d + 2 * ng.
+// shard_dst (sharded grid, embed only): the test rows are written at row offset test_row0 into every destination
+// (pitch shard_ld) instead of r_out and `sig` raises the ready flags; col_term may then be null.
 void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
                             const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
                             const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term,
-                            float* col_term, int64_t col_ld, bool embed);
+                            float* col_term, int64_t col_ld, bool embed, const PrepDst* shard_dst = nullptr,
+                            int64_t test_row0 = 0, int64_t shard_ld = 0, const PrepSignal* sig = nullptr);
 
 // ---- label segmentation (K1) + segmented sums (K2/K4) --------------------------- //
 struct Segments {

@@ -418,34 +418,37 @@ score_prep_grouped_kernel(const T* __restrict__ enrol, long long ne, long long l
 
 // Vectorised form of the ragged-count producer: one warp per row, a lane owns 8-column groups (16-byte loads, one
 // 16-byte store per plane), constants read from the row's table (L1 / L2 resident: 24 KB per distinct count).
-// Test rows: the split row is written once together with the column term of group 0; the other groups re-read the
-// row from L1.
+// Test rows: the row is split once (unit scale) and every group's column term is taken from the same registers.
+// Test blocks come FIRST in the grid and write to every destination of `tdst` at row offset test_row0 (one
+// destination on a single GPU; on a sharded grid the peers' operand buffers, followed by the ready flags of `sig`);
+// the enrol rows (pitch ld_l) stay local.
 template <typename T>
 __global__ void __launch_bounds__(256)
 score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long long ld_e,
                               const int32_t* __restrict__ grp, const T* __restrict__ test, long long nt,
                               long long ld_t, int d, int ng, const double* __restrict__ tables,
-                              __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo,
-                              __nv_bfloat16* __restrict__ r_hi, __nv_bfloat16* __restrict__ r_lo, int ld_out,
-                              float* __restrict__ row_term, float* __restrict__ col_term, long long col_ld,
-                              unsigned enrol_blocks, int vec_e, int vec_t, int embed) {
+                              __nv_bfloat16* __restrict__ l_hi, __nv_bfloat16* __restrict__ l_lo, int ld_l,
+                              const PrepDst tdst, long long test_row0, int ld_out, float* __restrict__ row_term,
+                              float* __restrict__ col_term, long long col_ld, unsigned test_blocks, int vec_e,
+                              int vec_t, int embed, const PrepSignal sig) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   typename Group8Of<T>::type g;
-  if (blockIdx.x < enrol_blocks) {
-    const long long r = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
+  const bool is_enrol = blockIdx.x >= test_blocks;
+  if (is_enrol) {
+    const long long r = static_cast<long long>(blockIdx.x - test_blocks) * kWarpsPerBlock + warp;
     if (r >= ne) return;
     const double* tab = tables + static_cast<long long>(__ldg(grp + r)) * kScoreConstsSize;
     const T* src = enrol + r * ld_e;
     double acc = 0.0;
-    for (int c = lane * 8; c < ld_out; c += 256) {
+    for (int c = lane * 8; c < ld_l; c += 256) {
       g.load_consts(tab + kScoreConstsEnrolSq, tab + kScoreConstsScale, true, c, d);
       T v[8];
       load8<T>(src, c, d, vec_e != 0, v);
       uint4 hi, lo;
       g.run(v, hi, lo);
       acc += g.part;
-      *reinterpret_cast<uint4*>(l_hi + r * ld_out + c) = hi;
-      *reinterpret_cast<uint4*>(l_lo + r * ld_out + c) = lo;
+      *reinterpret_cast<uint4*>(l_hi + r * ld_l + c) = hi;
+      *reinterpret_cast<uint4*>(l_lo + r * ld_l + c) = lo;
     }
     acc = warp_sum(acc);
     if (lane == 0) row_term[r] = static_cast<float>(0.5 * (__ldg(tab + kScoreConstsLogdet) - acc));
@@ -453,15 +456,17 @@ score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long lo
       // column terms inside the product: a one-hot pair of extra K columns selects the row's group (see below)
       __syncwarp();                       // the zero fill of the padding columns above is by other lanes
       if (lane == 0) {
-        const long long o = r * ld_out + d + 2 * __ldg(grp + r);
+        const long long o = r * ld_l + d + 2 * __ldg(grp + r);
         l_hi[o] = __float2bfloat16(1.0f);
         l_hi[o + 1] = __float2bfloat16(1.0f);
       }
     }
-  } else {
-    const long long r = static_cast<long long>(blockIdx.x - enrol_blocks) * kWarpsPerBlock + warp;
-    if (r >= nt) return;
+    return;
+  }
+  const long long r = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp;
+  if (r < nt) {
     const T* src = test + r * ld_t;
+    const long long orow = (test_row0 + r) * ld_out;
     // one pass over the row: it is split once (unit scale) and every group's weighted sum of squares is taken from
     // the same registers, eight groups per pass
     for (int g0 = 0; g0 < ng; g0 += 8) {
@@ -475,8 +480,10 @@ score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long lo
         g.run(v, hi, lo);                 // leaves v unchanged (x 1) inside the row, 0 in the padding columns
         acc[0] += g.part;
         if (g0 == 0) {
-          *reinterpret_cast<uint4*>(r_hi + r * ld_out + c) = hi;
-          *reinterpret_cast<uint4*>(r_lo + r * ld_out + c) = lo;
+          for (int w = 0; w < tdst.n; ++w) {
+            *reinterpret_cast<uint4*>(tdst.hi[w] + orow + c) = hi;
+            *reinterpret_cast<uint4*>(tdst.lo[w] + orow + c) = lo;
+          }
         }
 #pragma unroll
         for (int gi = 1; gi < 8; ++gi) {
@@ -491,7 +498,7 @@ score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long lo
         if (g0 + gi >= ng) break;
         const double a = warp_sum(acc[gi]);
         if (lane != 0) continue;
-        col_term[(g0 + gi) * col_ld + r] = static_cast<float>(a);
+        if (col_term != nullptr) col_term[(g0 + gi) * col_ld + r] = static_cast<float>(a);
         if (embed) {
           // The group's column term rides in two extra K columns of the test operand, as four bf16 pieces that add
           // up to the fp32 value (hi/lo of the term, hi/lo of what those two left): against the enrol row's one-hot
@@ -504,11 +511,31 @@ score_prep_grouped_vec_kernel(const T* __restrict__ enrol, long long ne, long lo
           const float r2 = r1 - __bfloat162float(l1);
           const __nv_bfloat16 h2 = __float2bfloat16(r2);
           const __nv_bfloat16 l2 = __float2bfloat16(r2 - __bfloat162float(h2));
-          const long long o = r * ld_out + d + 2 * (g0 + gi);
-          r_hi[o] = h1; r_lo[o] = l1;
-          r_hi[o + 1] = h2; r_lo[o + 1] = l2;
+          const long long o = orow + d + 2 * (g0 + gi);
+          for (int w = 0; w < tdst.n; ++w) {
+            tdst.hi[w][o] = h1; tdst.lo[w][o] = l1;
+            tdst.hi[w][o + 1] = h2; tdst.lo[w][o + 1] = l2;
+          }
         }
       }
+    }
+  }
+  if (sig.counter != nullptr) {
+    // publish (same release pattern as score_prep_uniform_kernel): block barrier, one system fence, block counter;
+    // the LAST test block raises this source rank's ready flag in every destination region
+    __shared__ int s_last;
+    if (sig.fence_per_thread) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned prev = atomicAdd(sig.counter, 1u);
+      s_last = prev == test_blocks - 1 ? 1 : 0;
+      if (s_last) atomicExch(sig.counter, 0u);
+    }
+    __syncthreads();
+    if (s_last && static_cast<int>(threadIdx.x) < sig.n) {
+      __threadfence_system();
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sig.flag[threadIdx.x]), "r"(sig.epoch) : "memory");
     }
   }
 }
@@ -678,8 +705,7 @@ void score_prep_uniform_multi(Context& ctx, const void* enrol, int64_t ne, int64
   PB_CHECK(d <= 1024, kInvalidArg, "score: dimension above 1024 is not supported");
   PB_CHECK(ld_out % 16 == 0 && ld_out >= d, kInvalidArg, "score prep: operand pitch must be a multiple of 16");
   PB_CHECK(tdst.n >= 0 && tdst.n <= kMaxPeers && sig.n <= kMaxPeers, kInvalidArg, "score prep: too many destinations");
-  if (l_out) l_out->reserve(ne, d);
-  PB_CHECK(l_out == nullptr || l_out->ld == ld_out || nt == 0, kInvalidArg, "score prep: operand pitches differ");
+  if (l_out) l_out->reserve(ne, d, ld_out);      // one pitch for both sides (a session may leave room for group columns)
   const int ldo = static_cast<int>(l_out ? l_out->ld : ld_out);
   // two resident blocks per SM, split between the sides in proportion to their rows; a small side gets one block
   // per 32 rows (one round of four rows per warp).  When the test rows travel to peers (tdst.n > 1) the test side
@@ -756,25 +782,44 @@ void score_prep_grouped(Context& ctx, const void* enrol, int64_t ne, int64_t ld_
 void score_prep_grouped_vec(Context& ctx, const void* enrol, int64_t ne, int64_t ld_e, const int32_t* grp_dev,
                             const void* test, int64_t nt, int64_t ld_t, bool is_f32, int64_t d, int ng,
                             const double* tables_dev, SplitBuf& l_out, SplitBuf& r_out, float* row_term,
-                            float* col_term, int64_t col_ld, bool embed) {
+                            float* col_term, int64_t col_ld, bool embed, const PrepDst* shard_dst, int64_t test_row0,
+                            int64_t shard_ld, const PrepSignal* sig) {
   PB_CHECK(d <= 1024 && ng >= 1, kInvalidArg, "score: dimension above 1024 is not supported");
   const int64_t kk = embed ? d + 2 * ng : d;      // embed: two extra K columns per distinct count
   l_out.reserve(ne, kk);
-  r_out.reserve(nt, kk);
+  PrepDst dst;
+  int64_t ld_out = 0;
+  if (shard_dst != nullptr) {
+    // sharded grid: the test rows go to the peers' operand buffers (pitch shard_ld), not to r_out
+    PB_CHECK(embed && shard_ld >= round_up(kk, 16) && shard_ld % 8 == 0, kInvalidArg,
+             "score: the sharded operand pitch has no room for the group columns");
+    dst = *shard_dst;
+    ld_out = shard_ld;
+  } else {
+    r_out.reserve(nt, kk);
+    dst.n = 1;
+    dst.hi[0] = r_out.hi.get();
+    dst.lo[0] = r_out.lo.get();
+    dst.term[0] = nullptr;
+    ld_out = r_out.ld;
+  }
   const unsigned eb = row_blocks(ne), tb = row_blocks(nt);
-  if (eb + tb == 0) return;
+  // a sharded producer with no test rows still has to raise its flags: one (empty) test block
+  const unsigned tb_launch = (sig != nullptr && sig->counter != nullptr && tb == 0) ? 1u : tb;
+  if (eb + tb_launch == 0) return;
   const int vec_e = enrol && rows_vectorisable(enrol, ld_e, is_f32) ? 1 : 0;
   const int vec_t = test && rows_vectorisable(test, ld_t, is_f32) ? 1 : 0;
+  const PrepSignal sg = sig != nullptr ? *sig : PrepSignal{};
   if (is_f32)
-    score_prep_grouped_vec_kernel<float><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
+    score_prep_grouped_vec_kernel<float><<<eb + tb_launch, kWarpsPerBlock * 32, 0, ctx.stream>>>(
         static_cast<const float*>(enrol), ne, ld_e, grp_dev, static_cast<const float*>(test), nt, ld_t,
-        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
-        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t, embed ? 1 : 0);
+        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), static_cast<int>(l_out.ld), dst, test_row0,
+        static_cast<int>(ld_out), row_term, col_term, col_ld, tb_launch, vec_e, vec_t, embed ? 1 : 0, sg);
   else
-    score_prep_grouped_vec_kernel<double><<<eb + tb, kWarpsPerBlock * 32, 0, ctx.stream>>>(
+    score_prep_grouped_vec_kernel<double><<<eb + tb_launch, kWarpsPerBlock * 32, 0, ctx.stream>>>(
         static_cast<const double*>(enrol), ne, ld_e, grp_dev, static_cast<const double*>(test), nt, ld_t,
-        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), r_out.hi.get(), r_out.lo.get(),
-        static_cast<int>(l_out.ld), row_term, col_term, col_ld, eb, vec_e, vec_t, embed ? 1 : 0);
+        static_cast<int>(d), ng, tables_dev, l_out.hi.get(), l_out.lo.get(), static_cast<int>(l_out.ld), dst, test_row0,
+        static_cast<int>(ld_out), row_term, col_term, col_ld, tb_launch, vec_e, vec_t, embed ? 1 : 0, sg);
   PB_CUDA(cudaGetLastError());
   ctx.count_launch();
 }

@@ -105,8 +105,8 @@ struct SplitOperand {
 struct SplitBuf {           // owning version
   DevBuf<__nv_bfloat16> hi, lo;
   int64_t rows = 0, k = 0, ld = 0;
-  void reserve(int64_t r, int64_t kk) {
-    rows = r; k = kk; ld = round_up(kk, 16);
+  void reserve(int64_t r, int64_t kk, int64_t pitch = 0) {
+    rows = r; k = kk; ld = pitch > 0 ? pitch : round_up(kk, 16);
     size_t n = static_cast<size_t>(r > 0 ? r : 1) * ld;
     hi.reserve(n); lo.reserve(n);
   }

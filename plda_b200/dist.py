@@ -97,14 +97,15 @@ class PeerShardedScorer:
 
     One instance per process (rank); ``torch.distributed`` is used once, at construction, to exchange the 64-byte
     CUDA-IPC handles of the regions -- no collective runs on the data path.  ``score`` must be called the same
-    number of times on every rank.  Uniform enrol counts only (ragged counts: ``ShardedScorer``).
+    number of times on every rank.  ``score`` takes one enrol count for the block, ``score_ragged`` a count per
+    row (scorer opened with ``max_groups``).
 
     ``peers``: same-process alternative to ``torch.distributed`` (tests, several handles in one process): a list of
     all ranks' ``PeerShardedScorer`` objects is connected with ``PeerShardedScorer.connect_local``.
     """
 
     def __init__(self, plda, n_test_total: int, dim: int, group=None, world: Optional[int] = None,
-                 rank: Optional[int] = None):
+                 rank: Optional[int] = None, max_groups: int = 0):
         import ctypes as C
         from . import _ffi
         self._ffi, self._C = _ffi, C
@@ -117,6 +118,7 @@ class PeerShardedScorer:
             world, rank = dist.get_world_size(group), dist.get_rank(group)
         self.world, self.rank = int(world), int(rank)
         self.n_test_total, self.dim = int(n_test_total), int(dim)
+        self.max_groups = int(max_groups)     # > 0: room for that many distinct enrol counts (score_ragged)
         self.bounds = np.array([block_bounds(self.n_test_total, self.world, r)[0] for r in range(self.world)]
                                + [self.n_test_total], dtype=np.int64)
         self._handle = (C.c_ubyte * 64)()
@@ -124,8 +126,13 @@ class PeerShardedScorer:
         self._open = False
         err = None
         try:
-            _ffi.check(self._lib.plda_shard_open(plda._h, self.world, self.rank, _ffi.ptr(self.bounds), self.dim,
-                                                 C.cast(self._handle, C.c_void_p), C.byref(self._region)))
+            if self.max_groups > 0:
+                _ffi.check(self._lib.plda_shard_open_ragged(plda._h, self.world, self.rank, _ffi.ptr(self.bounds),
+                                                            self.dim, self.max_groups,
+                                                            C.cast(self._handle, C.c_void_p), C.byref(self._region)))
+            else:
+                _ffi.check(self._lib.plda_shard_open(plda._h, self.world, self.rank, _ffi.ptr(self.bounds), self.dim,
+                                                     C.cast(self._handle, C.c_void_p), C.byref(self._region)))
             self._open = True
         except Exception as e:          # decided collectively below: a rank must not leave the others in a collective
             err = e
@@ -223,6 +230,57 @@ class PeerShardedScorer:
             self.plda._h, C.c_void_p(tt.data_ptr()), tt.shape[0], tt.stride(0) if tt.shape[0] else self.dim,
             C.c_void_p(et.data_ptr()), ne, et.stride(0) if ne else self.dim, int(enrol_count), self._ffi.ptr(ids), dtype,
             C.c_void_p(out.data_ptr()), out.stride(0)))
+        if sync:
+            self.check()
+        return out
+
+    def group_counts(self, enrol_counts):
+        """The distinct enrol counts over ALL ranks, ascending (one small all-gather; the list every rank must pass to
+        ``score_ragged``).  Same-process scorers (tests) pass the list themselves."""
+        import torch
+        import torch.distributed as dist
+        mine = np.unique(np.asarray(enrol_counts, dtype=np.int64))
+        if mine.size > self.max_groups:
+            mine = mine[: self.max_groups + 1]           # enough to make the check below fail on every rank
+        pad = np.zeros(self.max_groups + 1, dtype=np.int64)
+        pad[: mine.size] = mine
+        dev = _coll_device(self.group)
+        allc = torch.empty((self.world, pad.size), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, torch.from_numpy(pad).to(dev), group=self.group)
+        allc = np.unique(allc.cpu().numpy())
+        allc = allc[allc > 0]
+        if allc.size > self.max_groups:
+            raise ValueError("score_ragged: %d distinct enrol counts over all ranks, the session has room for %d"
+                             % (allc.size, self.max_groups))
+        return allc.astype(np.int32)
+
+    def score_ragged(self, enrol_block, enrol_counts, test_shard, group_counts=None, out=None, enrol_ids=None,
+                     sync: bool = True):
+        """One sharded scoring step with a count PER ENROL ROW (``plda_shard_step_ragged``): the column terms of
+        every distinct count travel inside the pushed operand rows, the grid is the uniform-count kernel.  Needs a
+        scorer opened with ``max_groups`` >= the number of distinct counts over all ranks."""
+        import torch
+        tt, dtype = _cuda_matrix(test_shard)
+        et, dtype_e = _cuda_matrix(enrol_block)
+        if dtype != dtype_e:
+            raise ValueError("enrol and test dtypes differ")
+        ne = et.shape[0]
+        cnt = np.ascontiguousarray(enrol_counts, dtype=np.int32).reshape(-1)
+        if cnt.shape[0] != ne:
+            raise ValueError("score_ragged: enrol_counts length mismatch")
+        if group_counts is None:
+            group_counts = self.group_counts(cnt)
+        groups = np.ascontiguousarray(group_counts, dtype=np.int32).reshape(-1)
+        if out is None:
+            ldo = (self.n_test_total + 3) // 4 * 4
+            out = torch.empty((ne, ldo), dtype=torch.float32, device=et.device)[:, : self.n_test_total]
+        ids = None if enrol_ids is None else np.ascontiguousarray(enrol_ids, dtype=np.uint64).reshape(-1)
+        C = self._C
+        self.plda._after_torch(tt)
+        self._ffi.check(self._lib.plda_shard_step_ragged(
+            self.plda._h, C.c_void_p(tt.data_ptr()), tt.shape[0], tt.stride(0) if tt.shape[0] else self.dim,
+            C.c_void_p(et.data_ptr()), ne, et.stride(0) if ne else self.dim, self._ffi.ptr(cnt), self._ffi.ptr(groups),
+            int(groups.shape[0]), self._ffi.ptr(ids), dtype, C.c_void_p(out.data_ptr()), out.stride(0)))
         if sync:
             self.check()
         return out

@@ -52,5 +52,25 @@ if rank == 0:
     print("peer-sharded grid == all-gather grid on every rank: %s (max abs diff %.3g, timeouts %d)"
           % (bool(flag.item()), worst, timeouts))
 peer.close()
+# ragged enrol counts: a count per row, different count sets per rank; the group list is agreed with one all-gather
+rag = PeerShardedScorer(p, nt_total, d, max_groups=6)
+counts = np.random.RandomState(7 + rank).choice([1 + rank, 2, 5], size=ne).astype(np.int32)
+ok_r, worst_r = True, 0.0
+for step in range(3):
+    got = rag.score_ragged(e_dev, counts, t_shard)
+    torch.cuda.synchronize()
+    want_r = p.score_grid(e_dev, counts, test_all)
+    torch.cuda.synchronize()
+    diff = float((got - want_r).abs().max().item())
+    worst_r = max(worst_r, diff)
+    ok_r = ok_r and diff <= 1e-4 * max(1.0, float(want_r.abs().max().item()))
+ok_r = ok_r and rag.status() == (3, 0)
+flag_r = torch.tensor([1 if ok_r else 0], device="cuda")
+dist.all_reduce(flag_r, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("ragged peer-sharded grid == single-GPU ragged grid on every rank: %s (max abs diff %.3g)"
+          % (bool(flag_r.item()), worst_r))
+rag.close()
+flag = torch.minimum(flag, flag_r)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)

@@ -35,4 +35,5 @@ def test_peer_sharded_grid_over_ipc_matches_allgather():
            "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "scripts", "dist_shard_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "on every rank: True" in r.stdout
+    assert "peer-sharded grid == all-gather grid on every rank: True" in r.stdout
+    assert "ragged peer-sharded grid == single-GPU ragged grid on every rank: True" in r.stdout

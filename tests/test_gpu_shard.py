@@ -23,7 +23,7 @@ def _model(d, seed=5):
     return np.full(d, 0.5), q, psi
 
 
-def _ranks(world, d, nt_total, model):
+def _ranks(world, d, nt_total, model, max_groups=0):
     from plda_b200 import PLDA
     from plda_b200.dist import PeerShardedScorer
     hs, scorers = [], []
@@ -31,7 +31,7 @@ def _ranks(world, d, nt_total, model):
         p = PLDA()
         p.set_model(*model)
         hs.append(p)
-        scorers.append(PeerShardedScorer(p, nt_total, d, world=world, rank=r))
+        scorers.append(PeerShardedScorer(p, nt_total, d, world=world, rank=r, max_groups=max_groups))
     PeerShardedScorer.connect_local(scorers)
     return hs, scorers
 
@@ -148,6 +148,64 @@ def test_fused_step_equals_push_then_grid(world):
                 ref = _oracle_grid(model[2], enrol[r], count, test)
                 got = fused[r].cpu().numpy()
                 assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) <= 1e-3
+    finally:
+        for sc in scorers:
+            sc.close()
+
+
+@pytest.mark.parametrize("world,d,nt_total", [(2, 200, 700), (3, 64, 333)])
+def test_ragged_counts_on_the_sharded_grid(world, d, nt_total):
+    """plda_shard_step_ragged: a count per enrol row, different count sets on different ranks; the column terms of
+    every group travel inside the pushed operand rows.  Checked against the oracle's per-pair LLR and the single-GPU
+    ragged grid; a uniform step on the same (ragged-capable) session still equals the plain sharded grid."""
+    import torch
+    from plda_b200 import PLDA
+    from plda_b200.dist import block_bounds
+    model = _model(d)
+    hs, scorers = _ranks(world, d, nt_total, model, max_groups=4)
+    single = PLDA()
+    single.set_model(*model)
+    rng = np.random.RandomState(21)
+    ref = kp.Plda()
+    ref.psi = np.asarray(model[2], dtype=np.float64)
+    rank_counts = [[1, 2], [2, 5], [1, 7]][:world]
+    groups = np.unique(np.concatenate(rank_counts)).astype(np.int32)
+    try:
+        for step in range(2):
+            test = rng.randn(nt_total, d).astype(np.float32)
+            enrol = [rng.randn(150 + 20 * r, d).astype(np.float32) for r in range(world)]
+            counts = [rng.choice(rank_counts[r], size=enrol[r].shape[0]).astype(np.int32) for r in range(world)]
+            t_dev = torch.from_numpy(test).cuda()
+            e_dev = [torch.from_numpy(e).cuda() for e in enrol]
+            torch.cuda.synchronize()
+            outs = []
+            for r, sc in enumerate(scorers):
+                lo, hi = block_bounds(nt_total, world, r)
+                outs.append(sc.score_ragged(e_dev[r], counts[r], t_dev[lo:hi], group_counts=groups, sync=False))
+            torch.cuda.synchronize()
+            for r, sc in enumerate(scorers):
+                assert sc.status() == (2 * step + 1, 0)
+                got = outs[r].cpu().numpy()
+                want = kp.score_grid(ref, enrol[r].astype(np.float64), counts[r], test.astype(np.float64))
+                assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) <= 1e-3
+                one = single.score_grid(e_dev[r], counts[r], t_dev).cpu().numpy()
+                assert np.max(np.abs(got - one)) <= 1e-4 * max(1.0, np.abs(one).max())
+            # a uniform step on the ragged-capable session (wider operand pitch, same kernels)
+            uni = []
+            for r, sc in enumerate(scorers):
+                lo, hi = block_bounds(nt_total, world, r)
+                uni.append(sc.score(e_dev[r], 3, t_dev[lo:hi], sync=False))
+            torch.cuda.synchronize()
+            for r, sc in enumerate(scorers):
+                assert sc.status() == (2 * step + 2, 0)
+                want = single.score_grid(e_dev[r], np.full(enrol[r].shape[0], 3, np.int32), t_dev)
+                assert torch.equal(uni[r], want)
+        with pytest.raises(ValueError):              # a count outside the agreed group list
+            scorers[0].score_ragged(e_dev[0], np.full(enrol[0].shape[0], 9, np.int32), t_dev[:block_bounds(nt_total, world, 0)[1]],
+                                    group_counts=groups, sync=False)
+        with pytest.raises(ValueError):              # more groups than the session has room for
+            scorers[0].score_ragged(e_dev[0], counts[0], t_dev[:block_bounds(nt_total, world, 0)[1]],
+                                    group_counts=np.arange(1, 7, dtype=np.int32), sync=False)
     finally:
         for sc in scorers:
             sc.close()
