@@ -731,6 +731,65 @@ def run_sharded_extras(torch, dist, dev, pk, rank, world, steps):
         rec["fit_c4_or_slab_error"] = repr(e)
     torch.cuda.empty_cache()
 
+    # ---- ragged enrol counts on the peer-memory grid (C2-shaped slab, 5 distinct counts over the ranks) ----
+    try:
+        d = D
+        rs = np.random.RandomState(5)
+        qq, _ = np.linalg.qr(rs.randn(d, d))
+        pr = PLDA(device=dev.index)
+        pr.set_model(np.full(d, 0.5), qq, 2.0 * np.exp(-np.arange(d) / (0.15 * d)))
+        ne_r, nt_r = NE, NT
+        lo, hi = pdist.block_bounds(nt_r, world, rank)
+        g = torch.Generator(device=dev)
+        g.manual_seed(77)                                  # the same test set on every rank
+        test_all = torch.randn(nt_r, d, device=dev, generator=g)
+        g.manual_seed(78 + rank)
+        enrol_r = torch.randn(ne_r, d, device=dev, generator=g)
+        cnt = np.random.RandomState(79 + rank).choice([1 + (rank % 2), 3, 4, 5], size=ne_r).astype(np.int32)
+        out = torch.empty((ne_r, nt_r), dtype=torch.float32, device=dev)
+        from plda_b200 import _ffi
+        lib = _ffi.lib()
+        torch.cuda.synchronize()
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        _ffi.check(lib.plda_set_stream(pr._h, C.c_void_p(stream.cuda_stream)))
+        peer = pdist.PeerShardedScorer(pr, nt_r, d, max_groups=8)
+        groups = peer.group_counts(cnt)
+        shard_t = test_all[lo:hi].contiguous()
+        reps = max(5, min(steps, 20))
+        for _ in range(3):
+            peer.score_ragged(enrol_r, cnt, shard_t, group_counts=groups, out=out, sync=False)
+        peer.check()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(reps):
+            peer.score_ragged(enrol_r, cnt, shard_t, group_counts=groups, out=out, sync=False)
+        ev1.record(stream)
+        peer.check()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t_ms = torch.tensor([ev0.elapsed_time(ev1) / reps], device=dev)
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        want = pr.score_grid(enrol_r[:512], cnt[:512], test_all)
+        torch.cuda.synchronize()
+        diff = float((out[:512] - want).abs().max().item())
+        ok = torch.tensor([1 if diff <= 1e-4 * max(1.0, float(want.abs().max().item())) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        peer.close()
+        _ffi.check(lib.plda_set_stream(pr._h, C.c_void_p(None)))
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
+        rec["ragged"] = {"enrol_per_gpu": ne_r, "test_total": nt_r, "d": d, "distinct_counts_all_ranks": [int(c) for c in groups],
+                         "ms_per_step": float(t_ms.item()), "trials_per_sec_all_gpus": ne_r * nt_r * world / (float(t_ms.item()) * 1e-3),
+                         "max_abs_diff_vs_single_gpu_ragged_grid": diff, "matches_single_gpu": bool(ok.item()),
+                         "note": "plda_shard_step_ragged: the column terms of every count travel inside the pushed operand "
+                                 "rows (2 extra K columns per distinct count); back-to-back steps, no L2 flush"}
+        del out, test_all, enrol_r, pr
+    except Exception as e:
+        rec["ragged"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
     # ---- sharded z-norm (enrol-block ownership, cohort all-gathered) ----
     try:
         d = 64

@@ -90,6 +90,30 @@ class ShardedScorer:
         return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
 
 
+def agree_group_counts(enrol_counts, max_groups: int, group=None) -> np.ndarray:
+    """Collective: the distinct (positive) enrol counts over all ranks of ``group``, ascending, as int32 -- the list
+    ``plda_shard_step_ragged`` needs to be the same everywhere.  Raises ``ValueError`` on EVERY rank when there are more
+    than ``max_groups`` of them."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = np.unique(np.asarray(enrol_counts, dtype=np.int64).reshape(-1))
+    if mine.size and mine[0] <= 0:
+        raise ValueError("enrol counts must be positive")
+    width = int(max_groups) + 1                       # one more than fits, so that an overflow is seen by every rank
+    pad = np.zeros(width, dtype=np.int64)
+    pad[: min(mine.size, width)] = mine[:width]
+    dev = _coll_device(group)
+    allc = torch.empty(world * width, dtype=torch.int64, device=dev)      # flat: gloo accepts no other shape
+    dist.all_gather_into_tensor(allc, torch.from_numpy(pad).to(dev), group=group)
+    allc = np.unique(allc.cpu().numpy())
+    allc = allc[allc > 0]
+    if allc.size > max_groups:
+        raise ValueError("%d or more distinct enrol counts over all ranks, the session has room for %d"
+                         % (allc.size, max_groups))
+    return allc.astype(np.int32)
+
+
 class PeerShardedScorer:
     """Enrol-block sharded scoring WITHOUT a collective: the operand producer of every rank writes its test rows
     straight into the operand buffer of every other rank over NVLink peer memory and the tcgen05 GEMM waits, per
@@ -237,22 +261,7 @@ class PeerShardedScorer:
     def group_counts(self, enrol_counts):
         """The distinct enrol counts over ALL ranks, ascending (one small all-gather; the list every rank must pass to
         ``score_ragged``).  Same-process scorers (tests) pass the list themselves."""
-        import torch
-        import torch.distributed as dist
-        mine = np.unique(np.asarray(enrol_counts, dtype=np.int64))
-        if mine.size > self.max_groups:
-            mine = mine[: self.max_groups + 1]           # enough to make the check below fail on every rank
-        pad = np.zeros(self.max_groups + 1, dtype=np.int64)
-        pad[: mine.size] = mine
-        dev = _coll_device(self.group)
-        allc = torch.empty((self.world, pad.size), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allc, torch.from_numpy(pad).to(dev), group=self.group)
-        allc = np.unique(allc.cpu().numpy())
-        allc = allc[allc > 0]
-        if allc.size > self.max_groups:
-            raise ValueError("score_ragged: %d distinct enrol counts over all ranks, the session has room for %d"
-                             % (allc.size, self.max_groups))
-        return allc.astype(np.int32)
+        return agree_group_counts(enrol_counts, self.max_groups, self.group)
 
     def score_ragged(self, enrol_block, enrol_counts, test_shard, group_counts=None, out=None, enrol_ids=None,
                      sync: bool = True):

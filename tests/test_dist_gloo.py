@@ -179,3 +179,33 @@ def test_peer_scorer_failure_is_collective(tmp_path):
     mp.spawn(_peer_fail_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert (tmp_path / ("peer_%d.txt" % r)).read_text() == "RuntimeError"
+
+
+def _group_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from plda_b200.dist import agree_group_counts
+        mine = [[1, 2, 2, 1], [5, 2, 5], [7]][rank]
+        got = agree_group_counts(np.array(mine, dtype=np.int32), 4)
+        over = "no error"
+        try:
+            agree_group_counts(np.array(mine, dtype=np.int32), 3)       # 4 distinct counts, room for 3: every rank raises
+        except ValueError:
+            over = "ValueError"
+        empty = agree_group_counts(np.zeros(0, dtype=np.int32) if rank == 1 else np.array([3]), 2)   # a rank without rows
+        dist.barrier()
+        with open(os.path.join(result_dir, "groups_%d.txt" % rank), "w") as f:
+            f.write("%s|%s|%s|%s" % (got.tolist(), got.dtype, over, empty.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_group_list_is_agreed_collectively(tmp_path):
+    """The sharded ragged grid needs the SAME ascending list of distinct enrol counts on every rank
+    (plda_shard_step_ragged); too many counts must fail on every rank, not on one."""
+    world = 3
+    mp.spawn(_group_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / ("groups_%d.txt" % r)).read_text() == "[1, 2, 5, 7]|int32|ValueError|[3]"
