@@ -24,3 +24,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_ragged_launches.csv python scripts/r2_sink_probe.py ragged > gpurun_out/ncu_ragged.log 2>&1; echo "exit=$?"
 echo "== bench ours"; timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit=$?"; tail -n 3 gpurun_out/bench.err; cut -c 1-400 gpurun_out/bench.json
 echo "== bench reference"; timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit=$?"; cut -c 1-300 gpurun_out/bench_ref.json
+echo "== sanitizer (small fit: Cholesky / Jacobi cluster kernels, fused stats kernel)"
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis python scripts/fit_once.py 72 60 10 2 > gpurun_out/sanitizer_race_fit.log 2>&1; echo "racecheck exit=$?"; grep -E "RACECHECK SUMMARY|ERROR SUMMARY|hazard" gpurun_out/sanitizer_race_fit.log | tail -n 5
+timeout 900 compute-sanitizer --tool memcheck python scripts/fit_once.py 72 60 10 2 > gpurun_out/sanitizer_mem_fit.log 2>&1; echo "memcheck exit=$?"; grep -E "ERROR SUMMARY" gpurun_out/sanitizer_mem_fit.log | tail -n 2
