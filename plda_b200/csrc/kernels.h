@@ -189,6 +189,7 @@ struct EigWork {
   DevBuf<double> g, v, lam, tmp;
   DevBuf<int> flags;
   DevBuf<int32_t> perm;
+  DevBuf<long long> dbg;     // PLDA_B200_DBG=1: SM cycles of CTA 1 per phase (load, Gram, tournament, apply, barrier, rounds)
 };
 // stop_rotation: the solve ends after the first sweep whose largest rotation |gamma| / sqrt(alpha beta) stayed below
 // it; Jacobi converges quadratically, so the couplings left are ~stop_rotation^2 relative (1e-7 -> full fp64

@@ -405,15 +405,29 @@ __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __
 // bw x bw pairs (x in block I, y in block J) are rotated (bw steps of bw disjoint rotations): every column pair is
 // visited exactly once per sweep -- a cyclic-by-blocks Jacobi sweep -- instead of re-rotating the intra-block pairs
 // in every round (2 bw - 1 steps per round).
-template <bool CLUSTER>
+// D(8x8) += A(8x4) B(4x8) on the fp64 tensor cores.  Fragments: a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// (c0, c1) = D[lane/4][2*(lane%4) + {0, 1}].
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// TEAM (cluster form only): 1 or 2 CTAs share a block pair.  With 2, each CTA holds HALF of the column length: it
+// loads, forms a partial Gram matrix of, and applies the rotations to its own rows only; the partials are exchanged
+// through distributed shared memory (one more cluster barrier per round) and both CTAs run the identical rotation
+// tournament on the identical sum.  The d-proportional phases of a round are fp64-FMA bound on one SM.
+template <bool CLUSTER, int BW, int TEAM>
 __global__ void __launch_bounds__(512, 1)
-block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, double tol, double big2, int max_sweeps,
+block_jacobi_gram_kernel(double* __restrict__ gt, int d, int /*bw*/, int nblk_pad, double tol, double big2, int max_sweeps,
                          unsigned int* __restrict__ barrier_counter, int* __restrict__ rotated,
-                         int* __restrict__ sweeps_done) {
+                         int* __restrict__ sweeps_done, long long* __restrict__ dbg, int variant) {
   extern __shared__ double sm[];
-  const int m2 = 2 * bw;
+  constexpr int bw = BW;                      // compile-time block width: the tournament's index arithmetic (% bw,
+                                              // % (bw - 1)) sits on the critical path of every step
+  constexpr int m2 = 2 * bw;
   const int dp = d | 1;                       // odd pitch: strided column reads are bank-conflict free
-  const int gp = m2 + 1;
+  constexpr int gp = m2 + 1;
   double* cols = sm;                          // [m2][dp]
   double* gl = cols + m2 * dp;                // [m2][gp]
   double* qm = gl + m2 * gp;                  // [m2][gp]
@@ -422,23 +436,32 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
   __shared__ double s_abs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
-  const int half = m2 >> 1;                   // == bw: rotations per tournament step
+  constexpr int half = m2 >> 1;               // == bw: rotations per tournament step
   unsigned int target = 0;
   int sweep = 0;
+  long long t_ph[6] = {0, 0, 0, 0, 0, 0};
+  // CTA 0's team holds the padding block: profile the next team
+  const bool prof = dbg != nullptr && blockIdx.x == (gridDim.x > TEAM ? static_cast<unsigned>(TEAM) : 0u) && threadIdx.x == 0;
+  // rows of the columns this CTA works on
+  const int team_h = TEAM == 2 ? static_cast<int>(blockIdx.x & 1u) : 0;
+  const int dh = TEAM == 2 ? (((d + 1) / 2 + 7) & ~7) : d;
+  const int row0 = team_h * dh;
+  const int nloc = max(0, min(d, row0 + dh) - row0);
   for (; sweep < max_sweeps; ++sweep) {
     for (int r = -1; r < nblk_pad - 1; ++r) {
+      long long t0 = prof ? clock64() : 0;
       int bi, bj;
-      const int k = blockIdx.x;
+      const int k = blockIdx.x / TEAM;
       if (r < 0) { bi = 2 * k; bj = 2 * k + 1; }                                  // intra round
       else if (k == 0) { bi = nblk_pad - 1; bj = r; }
       else { bi = (r + k) % (nblk_pad - 1); bj = (r - k + (nblk_pad - 1)) % (nblk_pad - 1); }
       // ---- 0. load the 2 bw columns (a warp per column, lanes along it)
       for (int slot = warp; slot < m2; slot += nwarps) {
         const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
-        const double* src = gt + static_cast<long long>(col) * d;
+        const double* src = gt + static_cast<long long>(col) * d + row0;
         double* dst = cols + slot * dp;
-        if (col < d) { for (int i = lane; i < d; i += 32) dst[i] = __ldcg(src + i); }
-        else { for (int i = lane; i < d; i += 32) dst[i] = 0.0; }
+        if (col < d) { for (int i = lane; i < nloc; i += 32) dst[i] = __ldcg(src + i); }
+        else { for (int i = lane; i < nloc; i += 32) dst[i] = 0.0; }
       }
       for (int idx = threadIdx.x; idx < m2 * m2; idx += nthreads) {
         const int i = idx / m2, j = idx - i * m2;
@@ -446,57 +469,50 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
       __syncthreads();
-      // ---- 1. Gram (symmetric: tiles on or above the diagonal only): a thread owns the strided 4x4 tile
-      //         {ti + q a} x {tj + q b} (q = m2 / 4) over one of up to 4 slices of the column length -- 8 shared-memory
-      //         loads per 16 FMAs, lanes of a warp read at most 8 distinct addresses per load (broadcast); the slices
-      //         are summed through shared memory
+      if (prof) { const long long t1 = clock64(); t_ph[0] += t1 - t0; t0 = t1; }
+      // ---- 1. Gram on the fp64 tensor cores: a warp owns one 8 x 8 tile of C^T C and walks the column length in
+      //         DMMA.8x8x4 steps (A and B fragments are the same access pattern: lane -> column i0 + lane/4, row
+      //         r + lane%4).  The plain-FMA form of this phase was bound by the fp64 FMA rate of the SM.
       {
-        const int q4 = m2 >> 2;
-        const int tiles2 = q4 * (q4 + 1) / 2;
-        const int ks_n = max(1, min(nthreads / tiles2, 4));
-        const int slice = (d + ks_n - 1) / ks_n;
-        const int qs = q4 * dp;
-        double* part = qm + m2 * gp;                 // [ks_n - 1][m2][gp] scratch behind qm
-        for (int t = threadIdx.x; t < tiles2 * ks_n; t += nthreads) {
-          const int ks = t / tiles2;
-          int rem = t - ks * tiles2, ti = 0;
-          while (rem >= q4 - ti) { rem -= q4 - ti; ++ti; }
-          const int tj = ti + rem;
-          const double* ap = cols + ti * dp;
-          const double* bp = cols + tj * dp;
-          double acc[4][4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-          const int i1 = min(d, (ks + 1) * slice);
-#pragma unroll 2
-          for (int i = ks * slice; i < i1; ++i) {
-            double x[4], y[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) { x[a] = ap[a * qs + i]; y[a] = bp[a * qs + i]; }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int b = 0; b < 4; ++b) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+        const int nt8 = m2 >> 3;
+        const int lr = lane >> 2, lk = lane & 3;
+        double* gdst = TEAM == 2 ? qm + m2 * gp : gl;   // team: partial Gram in the scratch behind qm
+        for (int t = warp; t < nt8 * nt8; t += nwarps) {
+          const int ti = t / nt8, tj = t - ti * nt8;
+          if (tj < ti) continue;                       // symmetric: mirrored below
+          const double* ap = cols + (ti * 8 + lr) * dp + lk;
+          const double* bp = cols + (tj * 8 + lr) * dp + lk;
+          double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator pairs: independent DMMA chains
+          int r = 0;
+          for (; r + 8 <= nloc; r += 8) {
+            dmma_8x8x4(c0, c1, ap[r], bp[r]);
+            dmma_8x8x4(e0, e1, ap[r + 4], bp[r + 4]);
           }
-          double* dst = ks == 0 ? gl : part + (ks - 1) * m2 * gp;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int rr = ti + q4 * a, cc = tj + q4 * b;
-              dst[rr * gp + cc] = acc[a][b];
-              if (ti != tj) dst[cc * gp + rr] = acc[a][b];
-            }
+          for (; r < nloc; r += 4) {
+            const bool in = r + lk < nloc;
+            dmma_8x8x4(c0, c1, in ? ap[r] : 0.0, in ? bp[r] : 0.0);
+          }
+          c0 += e0;
+          c1 += e1;
+          const int gi = ti * 8 + lr, gj = tj * 8 + 2 * lk;
+          gdst[gi * gp + gj] = c0;
+          gdst[gi * gp + gj + 1] = c1;
+          if (ti != tj) {
+            gdst[gj * gp + gi] = c0;
+            gdst[(gj + 1) * gp + gi] = c1;
+          }
         }
-        __syncthreads();
-        if (ks_n > 1) {
+        if (TEAM == 2) {
+          // exchange: own partial + the partner's (read through distributed shared memory); a + b == b + a exactly,
+          // so both CTAs of the team continue with bit-identical Gram matrices
+          asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+          asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+          const uint32_t remote = mapa_shared(smem_u32(gdst), blockIdx.x ^ 1u);
           for (int idx = threadIdx.x; idx < m2 * m2; idx += nthreads) {
             const int i = idx / m2, j = idx - i * m2;
-            double v = gl[i * gp + j];
-            for (int ks = 1; ks < ks_n; ++ks) v += part[(ks - 1) * m2 * gp + i * gp + j];
-            gl[i * gp + j] = v;
+            double other;
+            asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(other) : "r"(remote + (i * gp + j) * 8) : "memory");
+            gl[i * gp + j] = gdst[i * gp + j] + other;
           }
         }
       }
@@ -510,6 +526,7 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       }
       __syncthreads();
       const double abs_tol = s_abs;
+      if (prof) { const long long t1 = clock64(); t_ph[1] += t1 - t0; t0 = t1; }
       // ---- 2. two-sided Jacobi on the Gram matrix: intra pairs (r < 0) or cross pairs
       const int nsteps = r < 0 ? bw - 1 : bw;
       for (int lr = 0; lr < nsteps; ++lr) {
@@ -571,12 +588,43 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
         }
         __syncthreads();
       }
+      if (prof) { const long long t1 = clock64(); t_ph[2] += t1 - t0; t0 = t1; }
       // ---- 3. C <- C Q, written back to global: new column x' = sum_x Q[x][x'] * old column x
       if (s_rot) {
+        if ((variant & 2) != 0) {
+        // fp64 tensor cores again: a warp owns 8 rows x 8 output columns per tile, K = the m2 old columns
+        {
+          const int nt8 = m2 >> 3;
+          const int mt8 = (nloc + 7) >> 3;
+          const int lr = lane >> 2, lk = lane & 3;
+          for (int t = warp; t < mt8 * nt8; t += nwarps) {
+            const int rt = t / nt8, ct = t - rt * nt8;
+            // rows past d (last tile only) read the next column / the Gram area: those outputs are never stored
+            const double* ap = cols + lk * dp + rt * 8 + lr;          // A[i][k] = old column k0 + k, row rt*8 + i
+            const double* bp = qm + lk * gp + ct * 8 + lr;            // B[k][j] = Q[k0 + k][ct*8 + j]
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            for (int k0 = 0; k0 < m2; k0 += 8) {
+              dmma_8x8x4(c0, c1, ap[k0 * dp], bp[k0 * gp]);
+              dmma_8x8x4(e0, e1, ap[(k0 + 4) * dp], bp[(k0 + 4) * gp]);
+            }
+            c0 += e0;
+            c1 += e1;
+            const int i = rt * 8 + lr;
+            if (i < nloc) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int slot = ct * 8 + 2 * lk + j;
+                const int col = (slot < bw ? bi : bj) * bw + (slot < bw ? slot : slot - bw);
+                if (col < d) __stcg(gt + static_cast<long long>(col) * d + row0 + i, j == 0 ? c0 : c1);
+              }
+            }
+          }
+        }
+        } else {
         // a warp owns 4 output columns x 128 rows (lane: rows i0 + 32 m): 4 column loads + 4 broadcast loads of Q per
         // 16 FMAs
         const int groups = m2 >> 2;
-        const int rparts = (d + 127) >> 7;
+        const int rparts = (nloc + 127) >> 7;
         for (int wi = warp; wi < groups * rparts; wi += nwarps) {
           const int xg = wi % groups, part = wi / groups;
           const double* qrow = qm + xg * 4;
@@ -607,15 +655,17 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const int i = i0 + 32 * m;
-              if (i < d) __stcg(gt + static_cast<long long>(col) * d + i, acc[m][j]);
+              if (i < nloc) __stcg(gt + static_cast<long long>(col) * d + row0 + i, acc[m][j]);
             }
           }
+        }
         }
         // bit 0: something rotated; bit 1: a rotation above the stop threshold happened.  Jacobi converges
         // quadratically, so a sweep whose largest rotation was below the threshold leaves every pair below its
         // square: converged without paying for a verification sweep.
         if (threadIdx.x == 0) atomicOr(rotated + sweep, s_big ? 3 : 1);
       }
+      if (prof) { const long long t1 = clock64(); t_ph[3] += t1 - t0; t0 = t1; }
       if (CLUSTER) {
         __threadfence();
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -623,11 +673,14 @@ block_jacobi_gram_kernel(double* __restrict__ gt, int d, int bw, int nblk_pad, d
       } else {
         grid_barrier(barrier_counter, target, gridDim.x);
       }
+      if (prof) { t_ph[4] += clock64() - t0; t_ph[5] += 1; }
     }
     const int flags = *reinterpret_cast<volatile int*>(rotated + sweep);
     if ((flags & 2) == 0) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *sweeps_done = sweep;
+  if (prof)
+    for (int i = 0; i < 6; ++i) dbg[i] = t_ph[i];
 }
 
 // lambda_p = |g_p| ; v_p = g_p / |g_p|  (zero vector if the column vanished)
@@ -749,11 +802,25 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   PB_CHECK(blocks <= ctx.num_sms, kInvalidArg, "eig: too many blocks for a cooperative launch");
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(block_jacobi_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(block_jacobi_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(block_jacobi_gram_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<false, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<true, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<true, 16, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<true, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(block_jacobi_gram_kernel<true, 16, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   });
   double* gp = w.g.get();
+  // A/B switch (PLDA_B200_JACOBI): 2 = apply phase on DMMA as well (default: Gram on DMMA, apply on plain FMAs --
+  // measured at d = 200: DMMA.8x8x4 sustains ~20 FMA/clk/SM against 64 for DFMA, but the Gram phase's plain-FMA form
+  // is load-bound and gains from the tensor-core fragments, the apply phase does not)
+  static const char* var_env = getenv("PLDA_B200_JACOBI");
+  int variant = var_env != nullptr ? atoi(var_env) : 0;
+  static const bool dbg_on = getenv("PLDA_B200_DBG") != nullptr;
+  long long* dbgp = nullptr;
+  if (dbg_on) {
+    w.dbg.reserve(8);
+    dbgp = w.dbg.get();
+  }
   unsigned int* counter = reinterpret_cast<unsigned int*>(w.flags.get());
   int* sweeps_done = w.flags.get() + 1;
   int* rotated = w.flags.get() + 2;
@@ -763,31 +830,52 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   bool use_cluster = blocks <= 16 && !(getenv("PLDA_B200_EIG") != nullptr && strcmp(getenv("PLDA_B200_EIG"), "grid") == 0);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  if (use_cluster) {
-    cfg.gridDim = dim3(blocks);
+  // two CTAs per block pair (each half of the column length) when the doubled cluster still fits: d <= 256
+  static const char* team_env = getenv("PLDA_B200_JACOBI_TEAM");
+  int team = (use_cluster && bw == 16 && 2 * blocks <= 16 && d >= 64 && !(team_env != nullptr && atoi(team_env) == 1)) ? 2 : 1;
+  auto configure = [&](int t) {
+    cfg.gridDim = dim3(blocks * t);
     cfg.blockDim = dim3(512);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx.stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = blocks;
+    attr[0].val.clusterDim.x = blocks * t;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+  };
+  if (use_cluster) {
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, block_jacobi_gram_kernel<true>, &cfg) != cudaSuccess ||
-        max_clusters < 1) {
-      cudaGetLastError();
-      use_cluster = false;
+    if (bw != 16) use_cluster = false;
+    if (use_cluster && team == 2) {
+      configure(2);
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, block_jacobi_gram_kernel<true, 16, 2>, &cfg) != cudaSuccess ||
+          max_clusters < 1) {
+        cudaGetLastError();
+        team = 1;
+      }
+    }
+    if (use_cluster && team == 1) {
+      configure(1);
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, block_jacobi_gram_kernel<true, 16, 1>, &cfg) != cudaSuccess ||
+          max_clusters < 1) {
+        cudaGetLastError();
+        use_cluster = false;
+      }
     }
   }
-  if (use_cluster) {
-    PB_CUDA(cudaLaunchKernelEx(&cfg, block_jacobi_gram_kernel<true>, gp, di, bw, nblk_pad, tol, big2, ms, counter, rotated,
-                               sweeps_done));
+  if (use_cluster && team == 2) {
+    PB_CUDA(cudaLaunchKernelEx(&cfg, block_jacobi_gram_kernel<true, 16, 2>, gp, di, bw, nblk_pad, tol, big2, ms, counter,
+                               rotated, sweeps_done, dbgp, variant));
+  } else if (use_cluster) {
+    PB_CUDA(cudaLaunchKernelEx(&cfg, block_jacobi_gram_kernel<true, 16, 1>, gp, di, bw, nblk_pad, tol, big2, ms, counter,
+                               rotated, sweeps_done, dbgp, variant));
   } else {
-    void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &big2, &ms, &counter, &rotated, &sweeps_done};
-    PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(block_jacobi_gram_kernel<false>), dim3(blocks),
-                                        dim3(512), args, smem, ctx.stream));
+    void* args[] = {&gp, &di, &bw, &nblk_pad, &tol, &big2, &ms, &counter, &rotated, &sweeps_done, &dbgp, &variant};
+    const void* fn = bw == 16 ? reinterpret_cast<const void*>(block_jacobi_gram_kernel<false, 16, 1>)
+                              : reinterpret_cast<const void*>(block_jacobi_gram_kernel<false, 8, 1>);
+    PB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(512), args, smem, ctx.stream));
   }
   ctx.count_launch();
   eig_normalise_kernel<<<static_cast<unsigned>(ceil_div(d, 8)), 256, 0, ctx.stream>>>(w.g.get(), di, w.lam.get(),
@@ -798,6 +886,14 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   if (sweeps_out) {
     PB_CUDA(cudaMemcpyAsync(sweeps_out, sweeps_done, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
+  }
+  if (dbgp != nullptr) {
+    long long h[6];
+    PB_CUDA(cudaMemcpyAsync(h, dbgp, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    const double n = h[5] > 0 ? static_cast<double>(h[5]) : 1.0;
+    fprintf(stderr, "plda_b200 jacobi d=%d: %lld rounds; SM cycles per round: load %.0f  gram %.0f  tournament %.0f  apply %.0f  barrier %.0f\n",
+            di, h[5], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n);
   }
 }
 
