@@ -106,7 +106,9 @@ def test_fused_cholesky_inverse(plda, d):
     assert np.allclose(np.triu(inv, 1), 0.0)
 
 
-@pytest.mark.parametrize("d", [2, 7, 64, 200, 201, 512])
+# 64 .. 256: two CTAs per block pair (halves of the column length, partial Gram matrices over distributed shared
+# memory); 63 and below / above 256: one CTA per pair; 600: grid-barrier form with 8-column blocks
+@pytest.mark.parametrize("d", [2, 7, 63, 64, 77, 130, 200, 201, 255, 256, 257, 512, 600])
 def test_jacobi_eig(plda, d):
     rng = np.random.RandomState(d + 1)
     q, _ = np.linalg.qr(rng.randn(d, d))
