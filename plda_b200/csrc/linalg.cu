@@ -182,7 +182,8 @@ __device__ __forceinline__ double tile_dot(const double* __restrict__ p, const d
 }
 
 __global__ void __launch_bounds__(1024, 1)
-chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, int d, int* __restrict__ info) {
+chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, int d, int* __restrict__ info,
+                            long long* __restrict__ dbg) {
   extern __shared__ double csm[];
   double* sp = csm;                  // [32][CP]
   double* sq = sp + CB * CP;         // [32][CP]
@@ -194,6 +195,13 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
   const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
   const int rows_i = min(CB, d - bi * CB);
   const long long ld = d;
+  // PLDA_B200_DBG=1: SM cycles of the LAST row block's CTA per phase (it takes part in every panel)
+  const bool prof = dbg != nullptr && bi == nb - 1 && threadIdx.x == 0;
+  long long t_ph[5] = {0, 0, 0, 0, 0};
+  long long t0 = prof ? clock64() : 0;
+  auto lap = [&](int i) {
+    if (prof) { const long long t1 = clock64(); t_ph[i] += t1 - t0; t0 = t1; }
+  };
   // ---------------- Cholesky (left-looking by block column k) ----------------
   for (int k = 0; k < nb; ++k) {
     const int rows_k = min(CB, d - k * CB);
@@ -256,7 +264,9 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
         }
       }
     }
+    lap(0);                 // tile update (+ the diagonal factor and its inverse in the last panel)
     cluster_barrier_all();
+    lap(1);                 // barrier: the diagonal CTA's factor + inverse, then the cluster barrier itself
     if (bi > k) {
       // L[i,k] = S_i L_kk^-T : a 32 x 32 x 32 product against the inverse CTA k just published
       sl[r * 33 + c] = (r < rows_k && c < rows_k) ? __ldcg(inv + (static_cast<long long>(k) * CB + r) * ld + k * CB + c) : 0.0;
@@ -274,8 +284,14 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
         __stcg(inv + o, 0.0);
       }
     }
+    lap(2);                 // panel product
     cluster_barrier_all();
+    lap(3);
   }
+  if (prof) {
+    for (int i = 0; i < 4; ++i) dbg[i] = t_ph[i];
+  }
+  const long long t_inv0 = (dbg != nullptr && bi == 0 && threadIdx.x == 0) ? clock64() : 0;
   // ---------------- inverse: CTA bi computes block column bi of X = L^-1 (X[bi,bi] is already there) ----------------
   // The X tiles of the column stay in shared memory (xs[k] = X[k,bi]); the L tiles (final since the last barrier) and
   // the diagonal inverses travel global -> registers one step ahead of their use.
@@ -316,6 +332,7 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
       __syncthreads();
     }
   }
+  if (dbg != nullptr && bi == 0 && threadIdx.x == 0) dbg[4] = clock64() - t_inv0;   // the longest inverse column
 }
 
 // ------------------------------------------------------------------------- //
@@ -752,8 +769,19 @@ bool cholesky_inverse_fused(Context& ctx, double* a, double* inv, int64_t d, int
     return false;
   }
   PB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx.stream));
-  PB_CUDA(cudaLaunchKernelEx(&cfg, chol_inverse_cluster_kernel, a, inv, static_cast<int>(d), info_dev));
+  static const bool dbg_on = getenv("PLDA_B200_DBG") != nullptr;
+  static long long* dbgp = nullptr;
+  if (dbg_on && dbgp == nullptr) PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&dbgp), 8 * sizeof(long long)));
+  PB_CUDA(cudaLaunchKernelEx(&cfg, chol_inverse_cluster_kernel, a, inv, static_cast<int>(d), info_dev, dbgp));
   ctx.count_launch();
+  if (dbgp != nullptr) {
+    long long h[5];
+    PB_CUDA(cudaMemcpyAsync(h, dbgp, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    fprintf(stderr, "plda_b200 cholesky d=%d (%d panels), SM cycles of the last row block's CTA: tile update %lld  wait for the "
+            "diagonal + barrier %lld  panel product %lld  barrier %lld | inverse (column 0) %lld\n",
+            static_cast<int>(d), nb, h[0], h[1], h[2], h[3], h[4]);
+  }
   return true;
 }
 
