@@ -406,11 +406,11 @@ __global__ void eig_sort_kernel(const double* __restrict__ lam, const double* __
 //   gt[p,:] = column p of G = B V (rows contiguous).  Columns are grouped in blocks of `bw`; a CTA owns one
 //   PAIR of blocks per global round (round-robin tournament over blocks, one device-wide barrier per round)
 //   and orthogonalises its 2*bw columns through their small Gram matrix:
-//   1. Gl = C^T C            (m2 x m2, register-tiled dot products out of shared memory)
+//   1. Gl = C^T C            (m2 x m2; DMMA.8x8x4 fragments out of shared memory, a warp per 8 x 8 tile)
 //   2. one two-sided Jacobi tournament on Gl (m2 - 1 rounds of m2/2 disjoint rotations, rows then columns),
 //      accumulating the rotations in Q -- rotation angles come from 3 Gram entries, no d-length reductions
 //   3. C <- C Q              (written straight back to global memory)
-// Steps 1 and 3 are GEMM-shaped and use every thread; only step 2 is sequential, on a 32x32 / 64x64 matrix.
+// Steps 1 and 3 are GEMM-shaped and use every thread; only step 2 is sequential, on a 32 x 32 (16 x 16) matrix.
 // ------------------------------------------------------------------------- //
 // CLUSTER: the whole grid is ONE thread-block cluster (<= 16 CTAs): the per-round barrier is the hardware cluster
 // barrier (release / acquire at cluster scope orders the __stcg / __ldcg column exchange through L2) instead of an
@@ -824,8 +824,9 @@ void eig_sym_jacobi(Context& ctx, const double* b, int64_t d, const double* v0_t
   int nblk_pad = nblk + (nblk & 1);
   const int blocks = nblk_pad / 2;
   const int m2 = 2 * bw;
-  // columns + Gram + rotation accumulator + 3 partial Gram slices
-  const size_t smem = (static_cast<size_t>(m2) * (d | 1) + 5 * static_cast<size_t>(m2) * (m2 + 1)) * sizeof(double);
+  // columns + Gram + rotation accumulator + scratch (the team partner's view of the partial Gram matrix)
+  // (with two CTAs per pair each CTA stages only its half of the column length; sized for the one-CTA form)
+  const size_t smem = (static_cast<size_t>(m2) * (d | 1) + 3 * static_cast<size_t>(m2) * (m2 + 1)) * sizeof(double);
   PB_CHECK(smem <= 200 * 1024, kInvalidArg, "eig: dimension too large");
   PB_CHECK(blocks <= ctx.num_sms, kInvalidArg, "eig: too many blocks for a cooperative launch");
   static std::once_flag once;
