@@ -21,7 +21,8 @@
 //               barrier collects the bytes of both CTAs; narrow boxes for a 16/32-column K tail
 //   warp 1      TMEM allocator; in the leader CTA a single thread issues tcgen05.mma.cta_group::2 (M = 256);
 //               multicast tcgen05.commit releases smem stages and publishes accumulators in both CTAs
-//   warps 2-3   idle (they complete warpgroup 0, which donates registers via setmaxnreg)
+//   warp 2      sharded B: watches the peers' ready flags (all ranks in parallel) for the TMA producer; else idle
+//   warp 3      idle (warps 2-3 complete warpgroup 0, which donates registers via setmaxnreg)
 //   warps 4..11 epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks): all tcgen05.ld of a
 //               tile in flight together -> accumulator stage released -> fused row/col/z-norm terms -> swizzled
 //               smem staging -> TMA store (or fused row reductions, no store)
@@ -166,6 +167,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint64_t* tfull = empty + 3;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // sharded B: per source rank, set by the flag-watcher warp once the rank's push of this epoch has been observed
+  uint32_t* shard_seen = reinterpret_cast<uint32_t*>(epi_base + EPI_BYTES + COLC_BYTES + 128);   // [16] + "all seen"
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +208,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       }
       mbar_fence_init();
     }
+    if (lane < 17) shard_seen[lane] = 0u;
     __syncwarp();
     if (TWO) {
       tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -252,7 +256,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           for (int r = 0; r < p.shard.world; ++r) {
             if ((shard_ready >> r) & 1u) continue;
             if (p.shard.bounds[r] >= b_hi || p.shard.bounds[r + 1] <= b_lo) continue;
-            shard_wait(p.shard.flags + r, p.shard.epoch, p.shard.err);
+            // the flag-watcher warp polls every rank's flag concurrently (system-scope acquire loads cost ~1 us each;
+            // taken one after the other on this thread they stalled the operand ring once per source rank)
+            uint32_t seen;
+            do {
+              asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(shard_seen + r)) : "memory");
+            } while (seen == 0u);
             shard_ready |= 1u << r;
             waited = true;
           }
@@ -359,6 +368,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         p.dbg[blockIdx.x * 16 + 5] = dbg_tiles;
       }
     }
+  } else if (warp == 2) {
+    // ===================== flag watcher (sharded B only) ===================== //
+    // lane r waits (bounded, see shard_wait) for source rank r's push of this epoch -- all ranks in parallel -- and
+    // publishes it to the TMA producer through shared memory: peer stores -> system fence -> flag (producer kernel)
+    // -> acquire.sys here -> release.cta -> acquire.cta + fence.proxy.async in the TMA thread -> TMA loads.
+    if (p.shard.flags != nullptr) {
+      if (lane < p.shard.world) {
+        shard_wait(p.shard.flags + lane, p.shard.epoch, p.shard.err);
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(shard_seen + lane)), "r"(1u) : "memory");
+      }
+      __syncwarp();
+      // every rank has pushed: from here on the epilogue may fetch its column terms ahead of the accumulator
+      if (lane == 0)
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(shard_seen + 16)), "r"(1u) : "memory");
+    }
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
@@ -402,9 +426,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const bool col_cached = e.col_add != nullptr && e.grp == nullptr;
       // sharded B: the column terms travel with the operand rows, so they are only valid once the accumulator is
       // (producer saw the owner's flag -> TMA -> MMA -> tfull): fetched after the tfull wait, L1 bypassed
-      const bool col_late = p.shard.flags != nullptr;
+      bool col_late = p.shard.flags != nullptr;
+      if (col_late) {
+        // ... unless the flag watcher has already seen every rank's push: then they are as final as on one GPU
+        uint32_t all_seen;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(all_seen) : "r"(smem_u32(shard_seen + 16)) : "memory");
+        if (all_seen != 0u) col_late = false;
+      }
       float cpre[4] = {0.f, 0.f, 0.f, 0.f};
       if (col_cached && !col_late) {
+        // (sharded: this SM has not read these words earlier in the launch -- the late path bypasses L1 -- and L1 is
+        // invalidated at every launch boundary, so the read-only path cannot return a previous generation)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int cc = h + 2 * i;

@@ -1,0 +1,12 @@
+#!/bin/bash
+# headline-only scaling points (peer-memory exchange): bash scripts/gpu_r2_h2.sh N
+mkdir -p gpurun_out
+N=${1:-8}
+echo "== multi tests"; timeout 900 python -m pytest tests/test_gpu_multi.py -q --timeout 600 2>&1 | tail -n 3
+for rep in 1 2; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$rep bench.py --gpus $N --steps 50 --warmup 5 --headline-only --no-cpu > gpurun_out/bench_g${N}_head$rep.json 2> gpurun_out/bench_g${N}_head$rep.err; echo "exit=$?"; python -c "
+import json
+j=json.loads(open('gpurun_out/bench_g${N}_head$rep.json').read().strip().splitlines()[-1])
+print({k:j[k] for k in ('value','ms_per_step','ms_per_step_median','ms_per_step_max','n_gpus') if k in j}, 'gemm kernel ms', j['roofline']['kernel_ms'])
+"
+done
