@@ -113,12 +113,14 @@ void PldaEngine::joint_diagonalise(int64_t d, bool warm, bool final_pass) {
   // eigenvectors as ROWS of em_u (= U^T), eigenvalues descending, floored at 0
   int sweeps = 0;
   const bool dbg = getenv("PLDA_B200_DBG") != nullptr;
-  // Inside the EM loop the basis only has to diagonalise (W, B) to ~1e-7 relative: the statistics of the iteration
-  // inherit that error linearly (the E-step formulas are exact for an exactly diagonalising basis), far below the
-  // 1e-3 parity tolerance, and it does not accumulate -- every iteration re-diagonalises the new (W, B).  GetOutput
-  // (the model the caller sees) and the exact fp64 mode are solved to full fp64 accuracy.
+  // Inside the EM loop the solve ends after the first sweep whose largest rotation stayed below 3e-3: Jacobi converges
+  // quadratically, so the couplings left are ~1e-5 relative.  The statistics of the iteration inherit that error
+  // linearly (the E-step formulas are exact for an exactly diagonalising basis) -- two orders below the 1e-3 parity
+  // tolerance -- and it does not accumulate: every iteration re-diagonalises the new (W, B).  GetOutput (the model the
+  // caller sees) and the exact fp64 mode are solved to full fp64 accuracy.  (3e-4 costs 2-3 more sweeps per 10-iteration
+  // fit at d = 200 for no measurable change of psi / W / B against the oracle.)
   static const char* eig_exact = getenv("PLDA_B200_EIG_EXACT");
-  const double stop_rotation = (final_pass || precision == 1 || eig_exact != nullptr) ? 1e-7 : 3e-4;
+  const double stop_rotation = (final_pass || precision == 1 || eig_exact != nullptr) ? 1e-7 : 3e-3;
   eig_sym_jacobi(ctx, em_bp.get(), d, (warm && em_have_basis) ? em_u.get() : nullptr, em_psi.get(), em_tmp.get(), eig,
                  dbg ? &sweeps : nullptr, stop_rotation);
   if (dbg) fprintf(stderr, "plda_b200: joint_diagonalise d=%lld warm=%d sweeps=%d\n", static_cast<long long>(d),

@@ -206,10 +206,13 @@ chol_inverse_cluster_kernel(double* __restrict__ a, double* __restrict__ inv, in
   for (int k = 0; k < nb; ++k) {
     const int rows_k = min(CB, d - k * CB);
     if (bi >= k) {
+      // (the tile's own element travels from L2 while the products run)
+      const bool in_tile = r < rows_i && c < rows_k;
+      const double a_rc = in_tile ? __ldcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c) : 0.0;
       const double dot = tile_dot(a + static_cast<long long>(bi) * CB * ld, a + static_cast<long long>(k) * CB * ld, ld,
                                   rows_i, rows_k, k * CB, sp, sq);
       double v = (r == c && r >= rows_k) ? 1.0 : 0.0;             // identity padding keeps the factor regular
-      if (r < rows_i && c < rows_k) v = __ldcg(a + (static_cast<long long>(bi) * CB + r) * ld + k * CB + c) - dot;
+      if (in_tile) v = a_rc - dot;
       st[r * 33 + c] = v;
       __syncthreads();
       if (bi == k) {

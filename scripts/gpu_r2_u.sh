@@ -1,6 +1,5 @@
 #!/bin/bash
-for i in 1 2 3; do
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --skip-em --headline-only 2>/dev/null | python -c "
-import json,sys
-j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(j['value'], j['ms_per_step'], j['ms_per_step_median'], j['ms_per_step_max'], j['roofline']['kernel_ms'])"
-done
+echo "== fit + kernel tests"; timeout 900 python -m pytest tests/test_gpu_plda.py tests/test_gpu_scale.py tests/test_gpu_lda.py tests/test_gpu_kernels.py -q -x --timeout 600 2>&1 | tail -n 3
+echo "== sweeps"; PLDA_B200_DBG=1 timeout 300 python scripts/em_bench_probe.py 2>&1 | grep -E "sweeps" | tail -n 11 | tr '\n' ';'
+echo; PLDA_B200_DBG=1 timeout 300 python scripts/em_bench_probe.py 2>&1 | grep -E "cholesky" | tail -n 1
+echo "== EM (bench data)"; timeout 300 python scripts/em_bench_probe.py 2>&1 | tail -n 1
