@@ -172,3 +172,28 @@ def test_emulated_fp32_row_producer_meets_parity_bar(d):
     # and the fp32 path stays close to the fp64-row path of the same design (the bench's parity_spot check)
     alt = device_grid(ref.plda, e32.astype(np.float64), ce, t32.astype(np.float64))
     assert np.max(np.abs(got - alt)) < 2e-4
+
+
+def test_ragged_column_terms_ride_exactly_inside_the_operands():
+    """The ragged-count producer (csrc/prep.cu, score_prep_grouped_vec_kernel) carries the column term c_g of every count
+    group in two extra K columns of the test operand, as four bf16 pieces -- hi/lo of the fp32 value, hi/lo of what those
+    two left -- against a one-hot pair (1, 1) in the enrol row.  The bf16x3 scheme then delivers hi*hi + hi*lo of both
+    columns: that sum must BE the fp32 value (so the grid equals the epilogue-added form), and a row of another group must
+    receive exactly zero."""
+    rng = np.random.RandomState(7)
+    for scale in (1e-6, 1e-2, 1.0, 37.5, 4.0e3, 2.5e6):
+        cf = (scale * rng.randn(2000)).astype(np.float32).astype(np.float64)
+        h1 = bf16(cf)
+        r1 = (cf - h1).astype(np.float32).astype(np.float64)            # exact in fp32
+        l1 = bf16(r1)
+        r2 = (r1 - l1).astype(np.float32).astype(np.float64)
+        h2 = bf16(r2)
+        l2 = bf16((r2 - h2).astype(np.float32).astype(np.float64))
+        # enrol one-hot pair: A_hi = (1, 1), A_lo = (0, 0); test columns: (h1 | l1) and (h2 | l2) as (B_hi | B_lo)
+        acc = (1.0 * h1 + 1.0 * l1 + 0.0 * h1) + (1.0 * h2 + 1.0 * l2 + 0.0 * h2)
+        assert np.array_equal(acc.astype(np.float32), cf.astype(np.float32))
+        # the pieces are bf16-representable (what the operand planes can hold)
+        for piece in (h1, l1, h2, l2):
+            assert np.array_equal(bf16(piece), piece)
+        # a row of another group multiplies the same columns by (0, 0)
+        assert np.all(0.0 * h1 + 0.0 * l1 + 0.0 * h2 + 0.0 * l2 == 0.0)
